@@ -1,0 +1,216 @@
+"""ctypes binding of libctd_b200.so (include/ctd_b200.h).  Thin: numpy arrays in/out, every
+non-zero return code becomes a Python exception carrying ctd_last_error().  There is no CPU
+fallback: if the library is missing or no sm_100 GPU is visible, construction raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libctd_b200.so")
+MAX_SRC = 3
+ABI_VERSION = 1
+PREC_FP16_TC, PREC_FP32_SIMT, PREC_FP16_SIMT = 0, 1, 2
+
+
+class CtdOp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_src", C.c_int32), ("src_buf", C.c_int32 * MAX_SRC),
+                ("src_coff", C.c_int32 * MAX_SRC), ("src_c", C.c_int32 * MAX_SRC), ("dst_buf", C.c_int32),
+                ("dst_coff", C.c_int32), ("cout", C.c_int32), ("cout_pad", C.c_int32), ("ksize", C.c_int32),
+                ("stride", C.c_int32), ("act", C.c_int32), ("residual", C.c_int32), ("aux", C.c_int32),
+                ("w16_off", C.c_int64), ("w32_off", C.c_int64), ("b_off", C.c_int64), ("p_off", C.c_int64)]
+
+
+class CtdBufDesc(C.Structure):
+    _fields_ = [("channels", C.c_int32), ("down", C.c_int32)]
+
+
+class CtdConfig(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("precision", C.c_int32), ("max_batch", C.c_int32),
+                ("max_h", C.c_int32), ("max_w", C.c_int32), ("nc", C.c_int32), ("use_graph", C.c_int32),
+                ("conf_thresh", C.c_float), ("nms_thresh", C.c_float), ("db_thresh", C.c_float),
+                ("debug_skip_postproc", C.c_int32)]
+
+
+EXPORTS = ["ctd_create", "ctd_destroy", "ctd_last_error", "ctd_forward", "ctd_get_net_outputs", "ctd_get_mask_u8",
+           "ctd_get_detections", "ctd_get_db_components", "ctd_last_forward_ms", "ctd_last_launch_count",
+           "ctd_debug_read_buffer", "ctd_debug_write_buffer", "ctd_connected_components", "ctd_nms"]
+
+_lib = None
+
+
+class CtdError(RuntimeError):
+    pass
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise CtdError("libctd_b200.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "-- there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32 = C.c_void_p, C.c_int32
+    lib.ctd_create.argtypes = [C.POINTER(vp), C.POINTER(CtdConfig), C.POINTER(CtdOp), i32, C.POINTER(CtdBufDesc), i32,
+                               vp, C.c_size_t]
+    lib.ctd_create.restype = C.c_int
+    lib.ctd_destroy.argtypes = [vp]
+    lib.ctd_destroy.restype = None
+    lib.ctd_last_error.argtypes = [vp]
+    lib.ctd_last_error.restype = C.c_char_p
+    lib.ctd_forward.argtypes = [vp, vp, i32, i32, i32, i32]
+    lib.ctd_get_net_outputs.argtypes = [vp, vp, vp, vp]
+    lib.ctd_get_mask_u8.argtypes = [vp, vp]
+    lib.ctd_get_detections.argtypes = [vp, vp, vp]
+    lib.ctd_get_db_components.argtypes = [vp, vp, vp, vp]
+    lib.ctd_last_forward_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.ctd_last_launch_count.argtypes = [vp, C.POINTER(i32)]
+    lib.ctd_debug_read_buffer.argtypes = [vp, i32, vp, C.c_size_t]
+    lib.ctd_debug_write_buffer.argtypes = [vp, i32, vp, i32, i32, i32]
+    lib.ctd_connected_components.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp]
+    lib.ctd_nms.argtypes = [vp, vp, i32, C.c_float, C.c_float, vp, vp]
+    for name in EXPORTS[3:]:
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One engine handle = one GPU + one stream + one compiled program."""
+
+    def __init__(self, program, device=0, precision=PREC_FP16_TC, max_batch=1, max_h=1024, max_w=1024, use_graph=False,
+                 conf_thresh=0.4, nms_thresh=0.35, db_thresh=0.3, skip_postproc=False):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        self.program = program
+        self.nc = int(getattr(program, "nc", 2))
+        ops = (CtdOp * len(program.ops))()
+        for o, d in zip(ops, program.ops):
+            for k, v in d.items():
+                if k in ("src_buf", "src_coff", "src_c"):
+                    for i in range(MAX_SRC):
+                        getattr(o, k)[i] = int(v[i])
+                else:
+                    setattr(o, k, int(v))
+        bufs = (CtdBufDesc * len(program.bufs))(*[CtdBufDesc(c, d) for c, d in program.bufs])
+        cfg = CtdConfig(ABI_VERSION, device, precision, max_batch, max_h, max_w, self.nc, int(use_graph), conf_thresh,
+                        nms_thresh, db_thresh, int(skip_postproc))
+        blob = (C.c_char * len(program.blob)).from_buffer(program.blob)
+        rc = self.lib.ctd_create(C.byref(self.h), C.byref(cfg), ops, len(program.ops), bufs, len(program.bufs),
+                                 C.cast(blob, C.c_void_p), len(program.blob))
+        if rc != 0:
+            raise CtdError("ctd_create failed (%d): %s" % (rc, self.lib.ctd_last_error(None).decode()))
+        self.shape = None
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise CtdError("ctd error %d: %s" % (rc, self.lib.ctd_last_error(self.h).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ctd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- forward ------------------------------------------------------------------------
+    def forward(self, pages):
+        """pages: uint8 [n][h][w][3] BGR (host numpy) -> runs the whole device pipeline."""
+        pages = np.ascontiguousarray(pages, dtype=np.uint8)
+        if pages.ndim == 3:
+            pages = pages[None]
+        n, h, w, c = pages.shape
+        assert c == 3
+        self._ck(self.lib.ctd_forward(self.h, _ptr(pages), n, h, w, 0))
+        self.shape = (n, h, w)
+
+    def forward_device(self, dev_ptr, n, h, w):
+        """pages already resident in HBM (device pointer as int)."""
+        self._ck(self.lib.ctd_forward(self.h, C.c_void_p(dev_ptr), n, h, w, 1))
+        self.shape = (n, h, w)
+
+    def rows_per_image(self):
+        n, h, w = self.shape
+        return 3 * ((h // 8) * (w // 8) + (h // 16) * (w // 16) + (h // 32) * (w // 32))
+
+    def net_outputs(self, want_blks=True, want_mask=True, want_lines=True):
+        n, h, w = self.shape
+        blks = np.empty((n, self.rows_per_image(), 5 + self.nc), np.float32) if want_blks else None
+        mask = np.empty((n, 1, h, w), np.float32) if want_mask else None
+        lines = np.empty((n, 2, h, w), np.float32) if want_lines else None
+        self._ck(self.lib.ctd_get_net_outputs(self.h, _ptr(blks), _ptr(mask), _ptr(lines)))
+        return blks, mask, lines
+
+    def mask_u8(self):
+        n, h, w = self.shape
+        m = np.empty((n, h, w), np.uint8)
+        self._ck(self.lib.ctd_get_mask_u8(self.h, _ptr(m)))
+        return m
+
+    def detections(self):
+        n = self.shape[0]
+        det = np.empty((n, 300, 6), np.float32)
+        cnt = np.empty((n,), np.int32)
+        self._ck(self.lib.ctd_get_detections(self.h, _ptr(det), _ptr(cnt)))
+        return [det[i, :cnt[i]].copy() for i in range(n)]
+
+    def db_components(self, want_bitmap=True, want_labels=True):
+        n, h, w = self.shape
+        bm = np.empty((n, h, w), np.uint8) if want_bitmap else None
+        lab = np.empty((n, h, w), np.int32) if want_labels else None
+        nl = np.empty((n,), np.int32)
+        self._ck(self.lib.ctd_get_db_components(self.h, _ptr(bm), _ptr(lab), _ptr(nl)))
+        return bm, lab, nl
+
+    def last_forward_ms(self):
+        ms = C.c_float()
+        self._ck(self.lib.ctd_last_forward_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def last_launch_count(self):
+        v = C.c_int32()
+        self._ck(self.lib.ctd_last_launch_count(self.h, C.byref(v)))
+        return v.value
+
+    def debug_read(self, tensor):
+        """tensor: dict(buf, coff, c, down) from the compiler -> float32 [n][h/down][w/down][c]."""
+        n, h, w = self.shape
+        ch = self.program.bufs[tensor["buf"]][0]
+        d = tensor["down"]
+        out = np.empty((n, h // d, w // d, ch), np.float32)
+        self._ck(self.lib.ctd_debug_read_buffer(self.h, tensor["buf"], _ptr(out), out.size))
+        return out[..., tensor["coff"]:tensor["coff"] + tensor["c"]]
+
+    def debug_write(self, tensor, arr, n, h, w):
+        """fill a whole buffer (all its channels) from float32 [n][h/down][w/down][channels]."""
+        arr = np.ascontiguousarray(arr, np.float32)
+        ch = self.program.bufs[tensor["buf"]][0]
+        assert arr.shape == (n, h // tensor["down"], w // tensor["down"], ch), arr.shape
+        self._ck(self.lib.ctd_debug_write_buffer(self.h, tensor["buf"], _ptr(arr), n, h, w))
+
+    # ---- stand-alone array kernels --------------------------------------------------------
+    def connected_components(self, img, stats_cap=0):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        labels = np.empty((h, w), np.int32)
+        nl = np.zeros((1,), np.int32)
+        stats = np.empty((stats_cap, 5), np.int32) if stats_cap else None
+        self._ck(self.lib.ctd_connected_components(self.h, _ptr(img), h, w, _ptr(labels), _ptr(stats), stats_cap, _ptr(nl)))
+        n = int(nl[0])
+        return n, labels, (stats[:n] if stats is not None else None)
+
+    def nms(self, pred, conf_thresh=0.4, iou_thresh=0.35):
+        pred = np.ascontiguousarray(pred, np.float32)
+        det = np.empty((300, 6), np.float32)
+        cnt = np.zeros((1,), np.int32)
+        self._ck(self.lib.ctd_nms(self.h, _ptr(pred), pred.shape[0], conf_thresh, iou_thresh, _ptr(det), _ptr(cnt)))
+        return det[:int(cnt[0])].copy()

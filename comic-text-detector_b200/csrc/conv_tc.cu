@@ -1,0 +1,342 @@
+// tcgen05 implicit-GEMM convolution for sm_100a.
+//
+//   D[128 pixels x BN couts] (fp32, TMEM) = sum over K blocks  A[128 x KB] * B[BN x KB]^T
+//
+// * A (activations, NHWC fp16) is fetched by 4-D tiled TMA: one box = 8 rows x 16 cols of
+//   pixels x KB channels of ONE filter tap, shifted by the tap offset; out-of-bounds pixels are
+//   zero-filled by the TMA unit, which implements the convolution padding.  The box lands in
+//   shared memory as 128 rows of KB*2 bytes with the 128B (or 64B) hardware swizzle, i.e.
+//   exactly the canonical K-major UMMA operand layout - there is no im2col buffer anywhere.
+//   torch.cat inputs are K-concatenated: each source buffer has its own tensor map.
+//   Stride-2 convolutions read through four "parity" maps (even/odd rows x even/odd columns).
+//   ConvTranspose 4x4 s2 p1 runs as 4 sub-pixel phases (blockIdx.z), each a 2x2-tap convolution.
+// * B (weights, packed [cout][tap][cin] fp16, BN folded) is fetched by 2-D tiled TMA.
+// * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread, tcgen05.mma
+//   cta_group::1 kind::f16, M=128,N=BN,K=16), warps 2-5 = epilogue (tcgen05.ld 32x32b ->
+//   bias + activation (+ residual) -> fp16 NHWC store at a channel offset, or the Detect decode).
+//   A multi-stage mbarrier ring (full/empty) couples TMA and MMA; tcgen05.commit frees slots.
+//
+// Reference semantics: Conv.forward_fuse (models/yolov5/common.py:48-49), Bottleneck add
+// (common.py:104), ConvTranspose2d+BN+ReLU (basemodel.py:26-28), Detect (yolo.py:23-44).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace ctd {
+
+constexpr int kTileW = 16, kTileH = 8;  // 128 grid pixels per CTA
+constexpr int kThreads = 192;
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 3 : 4);  // <=113 KB for BN<=128: 2 CTAs/SM
+  static constexpr int kABytes = 128 * 128;  // per stage (worst case 128-byte rows)
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  static constexpr size_t kSmem = 1024 /*align slack*/ + size_t(kStages) * (kABytes + kBBytes) + 256;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case CTD_ACT_SILU: return v / (1.0f + __expf(-v));
+    case CTD_ACT_LEAKY: return v > 0.f ? v : 0.1f * v;
+    case CTD_ACT_RELU: return fmaxf(v, 0.f);
+    case CTD_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-v));
+    default: return v;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + Cfg::kStages * Cfg::kABytes;
+  const uint32_t bar_base = b_base + Cfg::kStages * Cfg::kBBytes;
+  // barriers: full[s] at +8s, empty[s] at +8(S+s), tmem_full at +16S, tmem ptr at +16S+8
+  const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * Cfg::kStages;
+  const uint32_t tmem_full_bar = bar_base + 16 * Cfg::kStages;
+  const uint32_t tmem_ptr_addr = tmem_full_bar + 8;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kStages * (Cfg::kABytes + Cfg::kBBytes) + 16 * Cfg::kStages + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvGeom& g = p.g;
+
+  // ---- tile coordinates
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int img = blockIdx.x / tiles_per_img;
+  const int trem = blockIdx.x - img * tiles_per_img;
+  const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
+  const int y0 = ty * kTileH, x0 = tx * kTileW;
+  const int nblk = blockIdx.y;
+  const int phase = blockIdx.z;
+
+  const int kb = p.kb_elems;
+  const uint32_t row_bytes = kb * 2;
+  const uint32_t stage_tx = 128u * row_bytes + uint32_t(BN) * row_bytes;
+  int kblocks_per_tap = 0;
+  for (int s = 0; s < g.n_src; ++s) kblocks_per_tap += p.src_kblocks[s];
+  const int total_it = g.taps * kblocks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < g.n_src; ++s)
+      for (int q = 0; q < (g.in_stride == 2 ? 4 : 1); ++q) prefetch_tensormap(&p.a_map[s][q]);
+    prefetch_tensormap(&p.b_map);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (elect_one()) {
+      int it = 0;
+      for (int tap = 0; tap < g.taps; ++tap) {
+        const int dy = g.tap_dy[phase][tap], dx = g.tap_dx[phase][tap];
+        const int q = p.tap_map[phase][tap];
+        int kglob = tap * g.cin_total;
+        for (int s = 0; s < g.n_src; ++s) {
+          for (int cb = 0; cb < p.src_kblocks[s]; ++cb, ++it) {
+            const int stage = it % Cfg::kStages;
+            const uint32_t par = ((it / Cfg::kStages) & 1) ^ 1;
+            mbar_wait(empty_bar + 8 * stage, par);
+            mbar_arrive_expect_tx(full_bar + 8 * stage, stage_tx);
+            tma_load_4d(a_base + stage * Cfg::kABytes, &p.a_map[s][q], full_bar + 8 * stage, cb * kb, x0 + dx,
+                        y0 + dy, img);
+            tma_load_2d(b_base + stage * Cfg::kBBytes, &p.b_map, full_bar + 8 * stage, kglob + cb * kb,
+                        phase * g.cout_pad + nblk * BN);
+          }
+          kglob += g.src_c[s];
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    const uint32_t idesc = make_idesc_f16(BN);
+    for (int it = 0; it < total_it; ++it) {
+      const int stage = it % Cfg::kStages;
+      const uint32_t par = (it / Cfg::kStages) & 1;
+      mbar_wait(full_bar + 8 * stage, par);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = a_base + stage * Cfg::kABytes;
+        const uint32_t b_addr = b_base + stage * Cfg::kBBytes;
+        const int ksteps = kb / 16;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t ad = make_kmajor_desc(a_addr + k * 32, row_bytes);
+          const uint64_t bd = make_kmajor_desc(b_addr + k * 32, row_bytes);
+          umma_f16(tmem_d, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar + 8 * stage);
+        if (it == total_it - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================== epilogue ====================================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;
+    const int py = row / kTileW, px = row - py * kTileW;
+    const int gy = y0 + py, gx = x0 + px;
+    const bool valid = gy < g.gh && gx < g.gw;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int ph_y = phase >> 1, ph_x = phase & 1;
+    const int oy = gy * g.out_mul + ph_y, ox = gx * g.out_mul + ph_x;
+    constexpr int kChunk = BN >= 32 ? 32 : 16;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += kChunk) {
+      uint32_t v[kChunk];
+      const uint32_t taddr = tmem_d + (uint32_t(quad * 32) << 16) + uint32_t(c0);
+      if constexpr (kChunk == 32) {
+        tmem_ld_32x32(taddr, v);
+      } else {
+        tmem_ld_32x16(taddr, reinterpret_cast<uint32_t(&)[16]>(v));
+      }
+      tmem_ld_wait();
+      const int n0 = nblk * BN + c0;
+      if (!valid) continue;
+      if (p.dst != nullptr) {
+        __half* out = p.dst + (size_t(img) * g.dst_h * g.dst_w + size_t(oy) * g.dst_w + ox) * g.dst_cstride +
+                      g.dst_coff + n0;
+#pragma unroll
+        for (int j = 0; j < kChunk; j += 8) {
+          if (n0 + j >= g.cout) break;
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = apply_act(__uint_as_float(v[j + e]) + __ldg(p.bias + n0 + j + e), g.act);
+          if (g.residual) {
+            const uint4 r = *reinterpret_cast<const uint4*>(out + j);
+            const __half2* rh = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 rf = __half22float2(rh[e]);
+              f[2 * e] += rf.x;
+              f[2 * e + 1] += rf.y;
+            }
+          }
+          uint4 o;
+          __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+          *reinterpret_cast<uint4*>(out + j) = o;
+        }
+      } else {
+        // Detect decode (yolo.py:36-44): columns = anchor*(5+nc) + o
+        const int no = 5 + p.nc;
+        float* rows = p.blks + (size_t(img) * p.blks_rows_per_img + p.level_row0) * no;
+#pragma unroll 1
+        for (int j = 0; j < kChunk; ++j) {
+          const int col = n0 + j;
+          if (col >= g.cout) break;
+          const int a = col / no, o = col - a * no;
+          const float s = 1.0f / (1.0f + expf(-(__uint_as_float(v[j]) + __ldg(p.bias + col))));
+          float r;
+          if (o == 0) r = (s * 2.0f - 0.5f + float(gx)) * p.det_stride;
+          else if (o == 1) r = (s * 2.0f - 0.5f + float(gy)) * p.det_stride;
+          else if (o == 2) r = (s * 2.0f) * (s * 2.0f) * p.anchor_wh[2 * a];
+          else if (o == 3) r = (s * 2.0f) * (s * 2.0f) * p.anchor_wh[2 * a + 1];
+          else r = s;
+          rows[(size_t(a) * g.gh * g.gw + size_t(gy) * g.gw + gx) * no + o] = r;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, Cfg::kTmemCols);
+  }
+}
+
+// =========================================================================================
+// host side
+
+static const char* encode_map(PFN_encodeTiled enc, CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
+                              const cuuint64_t* strides_bytes, const cuuint32_t* box, int kb_elems) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = kb_elems == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                               : (kb_elems == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled failed";
+}
+
+static int pick_block_n(int cout_pad) {
+  if (cout_pad >= 256 && cout_pad % 256 == 0) return 256;
+  if (cout_pad >= 128 && cout_pad % 128 == 0) return 128;
+  if (cout_pad % 64 == 0) return 64;
+  if (cout_pad % 32 == 0) return 32;
+  return 16;
+}
+
+const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
+                         const int src_coff[], const void* w16, const float* bias, __half* dst) {
+  ConvTcParams& p = plan.p;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  int kb = 64;
+  for (int s = 0; s < g.n_src; ++s) {
+    if (g.src_c[s] % 64 != 0) kb = 32;
+    if (g.src_c[s] % 32 != 0) return "conv_tc: source channels must be a multiple of 32";
+    if (src_coff[s] % 8 != 0) return "conv_tc: source channel offset must be a multiple of 8";
+  }
+  if ((g.dst_coff % 8) != 0 || (g.dst_cstride % 8) != 0) return "conv_tc: destination slice must be 16-byte aligned";
+  p.kb_elems = kb;
+  for (int s = 0; s < g.n_src; ++s) p.src_kblocks[s] = g.src_c[s] / kb;
+  p.tiles_x = (g.gw + kTileW - 1) / kTileW;
+  p.tiles_y = (g.gh + kTileH - 1) / kTileH;
+  p.dst = dst;
+  p.bias = bias;
+  const int sh = g.src_h, sw = g.src_w;
+  for (int s = 0; s < g.n_src; ++s) {
+    const size_t cs = size_t(g.src_cstride[s]);
+    const char* base = static_cast<const char*>(src_ptr[s]) + size_t(src_coff[s]) * 2;
+    if (g.in_stride == 1) {
+      cuuint64_t dims[4] = {cuuint64_t(g.src_c[s]), cuuint64_t(sw), cuuint64_t(sh), cuuint64_t(g.n_img)};
+      cuuint64_t str[3] = {cs * 2, cs * 2 * sw, cs * 2 * sw * sh};
+      cuuint32_t box[4] = {cuuint32_t(kb), kTileW, kTileH, 1};
+      if (const char* e = encode_map(enc, &p.a_map[s][0], base, 4, dims, str, box, kb)) return e;
+    } else {
+      // parity views: pixel (2*yh+yp, 2*xh+xp)
+      for (int q = 0; q < 4; ++q) {
+        const int yp = q >> 1, xp = q & 1;
+        cuuint64_t dims[4] = {cuuint64_t(g.src_c[s]), cuuint64_t(sw / 2), cuuint64_t(sh / 2), cuuint64_t(g.n_img)};
+        cuuint64_t str[3] = {cs * 2 * 2, cs * 2 * sw * 2, cs * 2 * sw * sh};
+        cuuint32_t box[4] = {cuuint32_t(kb), kTileW, kTileH, 1};
+        const char* b2 = base + (size_t(yp) * sw + xp) * cs * 2;
+        if (const char* e = encode_map(enc, &p.a_map[s][q], b2, 4, dims, str, box, kb)) return e;
+      }
+    }
+  }
+  // tap -> (parity map, offset in map coordinates)
+  for (int ph = 0; ph < g.n_phase; ++ph)
+    for (int t = 0; t < g.taps; ++t) {
+      if (g.in_stride == 2) {
+        // source pixel = 2*o + d, d in {-1,0,1}: d=-1 -> (h=o-1, parity 1); d=0 -> (o,0); d=1 -> (o,1)
+        const int dy = g.tap_dy[ph][t], dx = g.tap_dx[ph][t];
+        const int yp = dy != 0, xp = dx != 0;
+        p.tap_map[ph][t] = int8_t(yp * 2 + xp);
+        p.g.tap_dy[ph][t] = int8_t(dy < 0 ? -1 : 0);
+        p.g.tap_dx[ph][t] = int8_t(dx < 0 ? -1 : 0);
+      } else {
+        p.tap_map[ph][t] = 0;
+      }
+    }
+  const int bn = pick_block_n(g.cout_pad);
+  plan.block_n = bn;
+  {
+    cuuint64_t dims[2] = {cuuint64_t(g.k_total), cuuint64_t(g.n_phase) * cuuint64_t(g.cout_pad)};
+    cuuint64_t str[1] = {cuuint64_t(g.k_total) * 2};
+    cuuint32_t box[2] = {cuuint32_t(kb), cuuint32_t(bn)};
+    if (const char* e = encode_map(enc, &p.b_map, w16, 2, dims, str, box, kb)) return e;
+  }
+  plan.grid = dim3(unsigned(g.n_img * p.tiles_x * p.tiles_y), unsigned(g.cout_pad / bn), unsigned(g.n_phase));
+  switch (bn) {
+    case 256: plan.smem_bytes = TcCfg<256>::kSmem; break;
+    case 128: plan.smem_bytes = TcCfg<128>::kSmem; break;
+    case 64: plan.smem_bytes = TcCfg<64>::kSmem; break;
+    case 32: plan.smem_bytes = TcCfg<32>::kSmem; break;
+    default: plan.smem_bytes = TcCfg<16>::kSmem; break;
+  }
+  return nullptr;
+}
+
+cudaError_t conv_tc_init() {
+  cudaError_t e;
+#define CTD_SET(BN)                                                                                   \
+  e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TcCfg<BN>::kSmem)); \
+  if (e != cudaSuccess) return e;
+  CTD_SET(256) CTD_SET(128) CTD_SET(64) CTD_SET(32) CTD_SET(16)
+#undef CTD_SET
+  return cudaSuccess;
+}
+
+cudaError_t conv_tc_launch(const ConvTcPlan& plan, cudaStream_t s) {
+  switch (plan.block_n) {
+    case 256: conv_tc_kernel<256><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p); break;
+    case 128: conv_tc_kernel<128><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p); break;
+    case 64: conv_tc_kernel<64><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p); break;
+    case 32: conv_tc_kernel<32><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p); break;
+    default: conv_tc_kernel<16><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p); break;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace ctd

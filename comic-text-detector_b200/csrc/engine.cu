@@ -1,0 +1,542 @@
+// libctd_b200.so: C-ABI engine (see include/ctd_b200.h).  Owns device buffers, the weight blob,
+// per-shape launch plans (tensor maps) and the optional CUDA graph; runs the op list emitted by
+// the Python host "compiler".  No CPU fallback: every entry point fails without an sm_100 GPU.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace ctd;
+
+namespace {
+thread_local std::string g_create_error;
+
+struct ShapePlan {
+  std::vector<ConvTcPlan> tc;  // index = op index (unused entries default)
+  std::vector<char> has_tc;
+  cudaGraphExec_t graph = nullptr;
+  int launches = 0;
+};
+}  // namespace
+
+struct ctd_handle {
+  ctd_config cfg{};
+  std::vector<ctd_op> ops;
+  std::vector<ctd_bufdesc> bufs;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  PFN_encodeTiled enc = nullptr;
+  char* d_blob = nullptr;
+  size_t blob_bytes = 0;
+  std::vector<void*> d_buf;
+  int elem = 2;  // bytes per activation element
+  uint8_t* d_pages = nullptr;
+  float* d_blks = nullptr;
+  float* d_mask = nullptr;
+  uint8_t* d_mask_u8 = nullptr;
+  float* d_lines = nullptr;
+  uint8_t* d_bitmap = nullptr;
+  float* d_det = nullptr;
+  int* d_det_count = nullptr;
+  int32_t* d_labels = nullptr;
+  int32_t* d_nlabels = nullptr;
+  int32_t* d_ccl_scratch = nullptr;
+  void* d_nms_ws = nullptr;
+  NmsWorkspace nms{};
+  std::map<std::tuple<int, int, int>, ShapePlan> plans;
+  // last forward
+  int n = 0, ph = 0, pw = 0;
+  int last_launches = 0;
+  bool have_forward = false;
+};
+
+static int fail(ctd_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+#define CK(expr)                                                                                      \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess) return fail(h, CTD_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static int rows_per_image(int ph, int pw) { return 3 * ((ph / 8) * (pw / 8) + (ph / 16) * (pw / 16) + (ph / 32) * (pw / 32)); }
+
+extern "C" const char* ctd_last_error(const ctd_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" void ctd_destroy(ctd_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  for (auto& kv : h->plans)
+    if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
+  for (void* p : h->d_buf) cudaFree(p);
+  cudaFree(h->d_blob); cudaFree(h->d_pages); cudaFree(h->d_blks); cudaFree(h->d_mask); cudaFree(h->d_mask_u8);
+  cudaFree(h->d_lines); cudaFree(h->d_bitmap); cudaFree(h->d_det); cudaFree(h->d_det_count); cudaFree(h->d_labels);
+  cudaFree(h->d_nlabels); cudaFree(h->d_ccl_scratch); cudaFree(h->d_nms_ws);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op* ops, int32_t n_ops,
+                          const ctd_bufdesc* bufs, int32_t n_bufs, const void* blob, size_t blob_bytes) {
+  ctd_handle* h = nullptr;
+  if (!out || !cfg || !ops || !bufs || !blob) return fail(nullptr, CTD_E_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != CTD_ABI_VERSION) return fail(nullptr, CTD_E_INVALID, "ABI version mismatch");
+  if (cfg->max_h % 64 || cfg->max_w % 64 || cfg->max_batch < 1) return fail(nullptr, CTD_E_SHAPE, "bad max shape");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device)
+    return fail(nullptr, CTD_E_NO_DEVICE, "no CUDA device %d (this engine has no CPU fallback)", cfg->device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+    return fail(nullptr, CTD_E_NO_DEVICE, "device %d is not sm_100 (compute %d.%d)", cfg->device, prop.major, prop.minor);
+  h = new ctd_handle();
+  h->cfg = *cfg;
+  h->ops.assign(ops, ops + n_ops);
+  h->bufs.assign(bufs, bufs + n_bufs);
+  h->elem = cfg->precision == CTD_PREC_FP32_SIMT ? 4 : 2;
+  auto bail = [&](int code) { std::string e = h->err; ctd_destroy(h); g_create_error = e; return code; };
+#define CKC(expr)                                                                                        \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) {                                                                             \
+      fail(h, CTD_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);          \
+      return bail(CTD_E_CUDA);                                                                           \
+    }                                                                                                    \
+  } while (0)
+  CKC(cudaSetDevice(cfg->device));
+  CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreate(&h->ev0));
+  CKC(cudaEventCreate(&h->ev1));
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CKC(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) {
+      fail(h, CTD_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+      return bail(CTD_E_CUDA);
+    }
+    h->enc = reinterpret_cast<PFN_encodeTiled>(fn);
+  }
+  CKC(conv_tc_init());
+  h->blob_bytes = blob_bytes;
+  CKC(cudaMalloc(&h->d_blob, blob_bytes));
+  CKC(cudaMemcpy(h->d_blob, blob, blob_bytes, cudaMemcpyHostToDevice));
+  const size_t nb = size_t(cfg->max_batch), mh = cfg->max_h, mw = cfg->max_w;
+  h->d_buf.assign(n_bufs, nullptr);
+  for (int i = 0; i < n_bufs; ++i) {
+    const size_t bytes = nb * (mh / bufs[i].down) * (mw / bufs[i].down) * bufs[i].channels * h->elem;
+    CKC(cudaMalloc(&h->d_buf[i], bytes));
+    CKC(cudaMemset(h->d_buf[i], 0, bytes));
+  }
+  const size_t px = nb * mh * mw;
+  const int no = 5 + cfg->nc;
+  CKC(cudaMalloc(&h->d_pages, px * 3));
+  CKC(cudaMalloc(&h->d_blks, nb * rows_per_image(mh, mw) * no * sizeof(float)));
+  CKC(cudaMalloc(&h->d_mask, px * 4));
+  CKC(cudaMalloc(&h->d_mask_u8, px));
+  CKC(cudaMalloc(&h->d_lines, px * 2 * 4));
+  CKC(cudaMalloc(&h->d_bitmap, px));
+  CKC(cudaMalloc(&h->d_det, nb * 300 * 6 * 4));
+  CKC(cudaMalloc(&h->d_det_count, nb * 4));
+  CKC(cudaMalloc(&h->d_labels, px * 4));
+  CKC(cudaMalloc(&h->d_nlabels, nb * 4));
+  CKC(cudaMalloc(&h->d_ccl_scratch, px * 4 * 3));
+  const int cap = 4096;
+  CKC(cudaMalloc(&h->d_nms_ws, nms_workspace_bytes(int(nb), cap)));
+  nms_workspace_bind(h->nms, h->d_nms_ws, int(nb), cap);
+  CKC(cudaDeviceSynchronize());
+#undef CKC
+  *out = h;
+  return CTD_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+static int op_geom(ctd_handle* h, const ctd_op& op, int n, int ph, int pw, ConvGeom& g) {
+  memset(&g, 0, sizeof(g));
+  fill_conv_geom_taps(g, op.kind == CTD_OP_DETECT ? CTD_OP_CONV : op.kind, op.ksize, op.stride);
+  g.n_img = n;
+  g.n_src = op.n_src;
+  const ctd_bufdesc& sb = h->bufs[op.src_buf[0]];
+  g.src_h = ph / sb.down;
+  g.src_w = pw / sb.down;
+  g.cin_total = 0;
+  for (int s = 0; s < op.n_src; ++s) {
+    const ctd_bufdesc& b = h->bufs[op.src_buf[s]];
+    if (b.down != sb.down) return fail(h, CTD_E_INVALID, "op sources differ in resolution");
+    g.src_c[s] = op.src_c[s];
+    g.src_cstride[s] = b.channels;
+    g.cin_total += op.src_c[s];
+  }
+  g.k_total = g.taps * g.cin_total;
+  g.gh = op.kind == CTD_OP_DECONV4 ? g.src_h : g.src_h / op.stride;
+  g.gw = op.kind == CTD_OP_DECONV4 ? g.src_w : g.src_w / op.stride;
+  g.dst_h = g.gh * g.out_mul;
+  g.dst_w = g.gw * g.out_mul;
+  g.cout = op.cout;
+  g.cout_pad = op.cout_pad;
+  if (op.dst_buf >= 0) {
+    g.dst_cstride = h->bufs[op.dst_buf].channels;
+    g.dst_coff = op.dst_coff;
+  }
+  g.act = op.act;
+  g.residual = op.residual;
+  return CTD_OK;
+}
+
+static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
+  sp.tc.resize(h->ops.size());
+  sp.has_tc.assign(h->ops.size(), 0);
+  if (h->cfg.precision != CTD_PREC_FP16_TC) return CTD_OK;
+  for (size_t i = 0; i < h->ops.size(); ++i) {
+    const ctd_op& op = h->ops[i];
+    if (op.kind != CTD_OP_CONV && op.kind != CTD_OP_DECONV4 && op.kind != CTD_OP_DETECT) continue;
+    ConvGeom g;
+    if (int rc = op_geom(h, op, n, ph, pw, g)) return rc;
+    const void* src[CTD_MAX_SRC];
+    int coff[CTD_MAX_SRC];
+    for (int s = 0; s < op.n_src; ++s) {
+      src[s] = h->d_buf[op.src_buf[s]];
+      coff[s] = op.src_coff[s];
+    }
+    __half* dst = op.kind == CTD_OP_DETECT ? nullptr : static_cast<__half*>(h->d_buf[op.dst_buf]);
+    const char* e = conv_tc_plan(sp.tc[i], h->enc, g, src, coff, h->d_blob + op.w16_off,
+                                 reinterpret_cast<const float*>(h->d_blob + op.b_off), dst);
+    if (e) return fail(h, CTD_E_INVALID, "op %zu: %s", i, e);
+    if (op.kind == CTD_OP_DETECT) {
+      ConvTcParams& p = sp.tc[i].p;
+      p.blks = h->d_blks;
+      p.blks_rows_per_img = rows_per_image(ph, pw);
+      int row0 = 0;
+      for (int l = 0; l < op.aux; ++l) row0 += 3 * (ph / (8 << l)) * (pw / (8 << l));
+      p.level_row0 = row0;
+      p.nc = h->cfg.nc;
+      float hp[7];
+      cudaMemcpy(hp, h->d_blob + op.p_off, sizeof(hp), cudaMemcpyDeviceToHost);
+      p.det_stride = hp[0];
+      for (int k = 0; k < 6; ++k) p.anchor_wh[k] = hp[1 + k];
+    }
+    sp.has_tc[i] = 1;
+  }
+  return CTD_OK;
+}
+
+template <typename T>
+static int run_op_simt(ctd_handle* h, const ctd_op& op, int n, int ph, int pw) {
+  cudaStream_t s = h->stream;
+  const bool f32 = sizeof(T) == 4;
+  switch (op.kind) {
+    case CTD_OP_CONV:
+    case CTD_OP_DECONV4:
+    case CTD_OP_DETECT: {
+      ConvSimtParams p;
+      memset(&p, 0, sizeof(p));
+      if (int rc = op_geom(h, op, n, ph, pw, p.g)) return rc;
+      for (int k = 0; k < op.n_src; ++k)
+        p.src[k] = static_cast<char*>(h->d_buf[op.src_buf[k]]) + size_t(op.src_coff[k]) * sizeof(T);
+      p.w = h->d_blob + (f32 ? op.w32_off : op.w16_off);
+      p.bias = reinterpret_cast<const float*>(h->d_blob + op.b_off);
+      if (op.kind == CTD_OP_DETECT) {
+        p.dst = nullptr;
+        p.blks = h->d_blks;
+        p.blks_rows_per_img = rows_per_image(ph, pw);
+        int row0 = 0;
+        for (int l = 0; l < op.aux; ++l) row0 += 3 * (ph / (8 << l)) * (pw / (8 << l));
+        p.level_row0 = row0;
+        p.nc = h->cfg.nc;
+        float hp[7];
+        cudaMemcpy(hp, h->d_blob + op.p_off, sizeof(hp), cudaMemcpyDeviceToHost);
+        p.det_stride = hp[0];
+        for (int k = 0; k < 6; ++k) p.anchor_wh[k] = hp[1 + k];
+      } else {
+        p.dst = h->d_buf[op.dst_buf];
+      }
+      CK(conv_simt_launch<T>(p, s));
+      return CTD_OK;
+    }
+    default: return fail(h, CTD_E_INVALID, "run_op_simt: bad kind %d", op.kind);
+  }
+}
+
+template <typename T>
+static int run_op_thin(ctd_handle* h, const ctd_op& op, int n, int ph, int pw) {
+  cudaStream_t s = h->stream;
+  const ctd_bufdesc* sb = op.kind == CTD_OP_STEM ? nullptr : &h->bufs[op.src_buf[0]];
+  const int sh = sb ? ph / sb->down : ph, sw = sb ? pw / sb->down : pw;
+  const T* src = sb ? static_cast<const T*>(h->d_buf[op.src_buf[0]]) + op.src_coff[0] : nullptr;
+  switch (op.kind) {
+    case CTD_OP_STEM:
+      CK(stem_launch<T>(h->d_pages, n, ph, pw, reinterpret_cast<const float*>(h->d_blob + op.w32_off),
+                        reinterpret_cast<const float*>(h->d_blob + op.b_off), static_cast<T*>(h->d_buf[op.dst_buf]),
+                        h->bufs[op.dst_buf].channels, op.dst_coff, op.cout, op.act, s));
+      return CTD_OK;
+    case CTD_OP_AVGPOOL2:
+      CK(avgpool2_launch<T>(src, n, sh, sw, op.src_c[0], sb->channels,
+                            static_cast<T*>(h->d_buf[op.dst_buf]) + op.dst_coff, h->bufs[op.dst_buf].channels, s));
+      return CTD_OK;
+    case CTD_OP_SPPF_POOL:
+      CK(sppf_pool_launch<T>(static_cast<T*>(h->d_buf[op.src_buf[0]]) + op.src_coff[0], n, sh, sw, op.src_c[0],
+                             sb->channels, s));
+      return CTD_OK;
+    case CTD_OP_UPSAMPLE2:
+      CK(upsample2_launch<T>(src, n, sh, sw, op.src_c[0], sb->channels,
+                             static_cast<T*>(h->d_buf[op.dst_buf]) + op.dst_coff, h->bufs[op.dst_buf].channels, s));
+      return CTD_OK;
+    case CTD_OP_SEG_TAIL:
+      CK(seg_tail_launch<T>(src, n, sh, sw, op.src_c[0], sb->channels,
+                            reinterpret_cast<const float*>(h->d_blob + op.p_off), h->d_mask, h->d_mask_u8, s));
+      return CTD_OK;
+    case CTD_OP_DB_TAIL:
+      CK(db_tail_launch<T>(src, n, sh, sw, sb->channels, reinterpret_cast<const float*>(h->d_blob + op.p_off),
+                           h->d_lines, h->d_bitmap, h->cfg.db_thresh, s));
+      return CTD_OK;
+    default: return fail(h, CTD_E_INVALID, "run_op_thin: bad kind %d", op.kind);
+  }
+}
+
+static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* launches) {
+  int cnt = 0;
+  for (size_t i = 0; i < h->ops.size(); ++i) {
+    const ctd_op& op = h->ops[i];
+    const bool gemm = op.kind == CTD_OP_CONV || op.kind == CTD_OP_DECONV4 || op.kind == CTD_OP_DETECT;
+    int rc;
+    if (gemm) {
+      if (h->cfg.precision == CTD_PREC_FP16_TC) {
+        cudaError_t e = conv_tc_launch(sp.tc[i], h->stream);
+        rc = e == cudaSuccess ? CTD_OK : fail(h, CTD_E_CUDA, "conv_tc op %zu: %s", i, cudaGetErrorString(e));
+      } else if (h->cfg.precision == CTD_PREC_FP32_SIMT) {
+        rc = run_op_simt<float>(h, op, n, ph, pw);
+      } else {
+        rc = run_op_simt<__half>(h, op, n, ph, pw);
+      }
+    } else {
+      rc = h->elem == 4 ? run_op_thin<float>(h, op, n, ph, pw) : run_op_thin<__half>(h, op, n, ph, pw);
+    }
+    if (rc) return rc;
+    ++cnt;
+  }
+  *launches = cnt;
+  if (h->cfg.debug_skip_postproc) return CTD_OK;
+  // post-processing on the same stream
+  const int rows = rows_per_image(ph, pw);
+  CK(nms_launch(h->d_blks, n, rows, h->cfg.nc, h->cfg.conf_thresh, h->cfg.nms_thresh, h->nms, h->d_det,
+                h->d_det_count, h->stream));
+  cnt += 4;
+  CK(ccl_launch(h->d_bitmap, n, ph, pw, h->d_labels, h->d_ccl_scratch, h->d_nlabels, h->stream));
+  cnt += 6;
+  *launches = cnt;
+  return CTD_OK;
+}
+
+extern "C" int ctd_forward(ctd_handle* h, const uint8_t* pages, int32_t n, int32_t ph, int32_t pw,
+                           int32_t pages_on_device) {
+  if (!h || !pages) return CTD_E_INVALID;
+  if (n < 1 || n > h->cfg.max_batch) return fail(h, CTD_E_CAPACITY, "batch %d exceeds max_batch %d", n, h->cfg.max_batch);
+  if (ph % 64 || pw % 64 || ph > h->cfg.max_h || pw > h->cfg.max_w || ph < 64 || pw < 64)
+    return fail(h, CTD_E_SHAPE, "page %dx%d must be a multiple of 64 and <= %dx%d", ph, pw, h->cfg.max_h, h->cfg.max_w);
+  CK(cudaSetDevice(h->cfg.device));
+  auto key = std::make_tuple(int(n), int(ph), int(pw));
+  auto it = h->plans.find(key);
+  if (it == h->plans.end()) {
+    ShapePlan sp;
+    if (int rc = build_plans(h, n, ph, pw, sp)) return rc;
+    it = h->plans.emplace(key, std::move(sp)).first;
+  }
+  ShapePlan& sp = it->second;
+  const size_t bytes = size_t(n) * ph * pw * 3;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  CK(cudaMemcpyAsync(h->d_pages, pages, bytes, pages_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                     h->stream));
+  if (h->cfg.use_graph) {
+    if (!sp.graph) {
+      // DETECT params are fetched with a blocking memcpy in the SIMT path: plans are already built, so
+      // capture only sees kernel launches (TC path).  SIMT paths run un-captured.
+      if (h->cfg.precision == CTD_PREC_FP16_TC) {
+        cudaGraph_t graph;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = run_ops(h, n, ph, pw, sp, &sp.launches);
+        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        if (rc) return rc;
+        CK(e);
+        CK(cudaGraphInstantiate(&sp.graph, graph, 0));
+        cudaGraphDestroy(graph);
+      }
+    }
+  }
+  if (sp.graph) {
+    CK(cudaGraphLaunch(sp.graph, h->stream));
+  } else {
+    if (int rc = run_ops(h, n, ph, pw, sp, &sp.launches)) return rc;
+  }
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->last_launches = sp.launches;
+  h->n = n; h->ph = ph; h->pw = pw;
+  h->have_forward = true;
+  return CTD_OK;
+}
+
+#define NEED_FWD()                                                                     \
+  if (!h) return CTD_E_INVALID;                                                        \
+  if (!h->have_forward) return fail(h, CTD_E_INVALID, "no forward pass has been run"); \
+  CK(cudaSetDevice(h->cfg.device));
+
+extern "C" int ctd_get_net_outputs(ctd_handle* h, float* blks, float* mask, float* lines) {
+  NEED_FWD();
+  const size_t px = size_t(h->n) * h->ph * h->pw;
+  if (blks)
+    CK(cudaMemcpyAsync(blks, h->d_blks, size_t(h->n) * rows_per_image(h->ph, h->pw) * (5 + h->cfg.nc) * 4,
+                       cudaMemcpyDeviceToHost, h->stream));
+  if (mask) CK(cudaMemcpyAsync(mask, h->d_mask, px * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (lines) CK(cudaMemcpyAsync(lines, h->d_lines, px * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return CTD_OK;
+}
+
+extern "C" int ctd_get_mask_u8(ctd_handle* h, uint8_t* mask_u8) {
+  NEED_FWD();
+  if (!mask_u8) return CTD_E_INVALID;
+  CK(cudaMemcpyAsync(mask_u8, h->d_mask_u8, size_t(h->n) * h->ph * h->pw, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return CTD_OK;
+}
+
+extern "C" int ctd_get_detections(ctd_handle* h, float* det, int32_t* det_count) {
+  NEED_FWD();
+  if (!det || !det_count) return CTD_E_INVALID;
+  CK(cudaMemcpyAsync(det, h->d_det, size_t(h->n) * 300 * 6 * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(det_count, h->d_det_count, size_t(h->n) * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return CTD_OK;
+}
+
+extern "C" int ctd_get_db_components(ctd_handle* h, uint8_t* bitmap, int32_t* labels, int32_t* n_labels) {
+  NEED_FWD();
+  const size_t px = size_t(h->n) * h->ph * h->pw;
+  if (bitmap) CK(cudaMemcpyAsync(bitmap, h->d_bitmap, px, cudaMemcpyDeviceToHost, h->stream));
+  if (labels) CK(cudaMemcpyAsync(labels, h->d_labels, px * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (n_labels) CK(cudaMemcpyAsync(n_labels, h->d_nlabels, size_t(h->n) * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return CTD_OK;
+}
+
+extern "C" int ctd_last_forward_ms(ctd_handle* h, float* ms) {
+  NEED_FWD();
+  if (!ms) return CTD_E_INVALID;
+  CK(cudaEventSynchronize(h->ev1));
+  CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return CTD_OK;
+}
+
+extern "C" int ctd_last_launch_count(ctd_handle* h, int32_t* launches) {
+  NEED_FWD();
+  if (!launches) return CTD_E_INVALID;
+  *launches = h->last_launches;
+  return CTD_OK;
+}
+
+template <typename T>
+__global__ void to_f32_kernel(const T* src, float* dst, size_t n) {
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i < n) dst[i] = float(src[i]);
+}
+
+extern "C" int ctd_debug_read_buffer(ctd_handle* h, int32_t buf, float* out, size_t out_elems) {
+  NEED_FWD();
+  if (buf < 0 || buf >= int(h->bufs.size()) || !out) return fail(h, CTD_E_INVALID, "bad buffer id");
+  const ctd_bufdesc& b = h->bufs[buf];
+  const size_t elems = size_t(h->n) * (h->ph / b.down) * (h->pw / b.down) * b.channels;
+  if (out_elems < elems) return fail(h, CTD_E_INVALID, "buffer %d holds %zu elements", buf, elems);
+  float* tmp = nullptr;
+  CK(cudaMalloc(&tmp, elems * 4));
+  if (h->elem == 4) to_f32_kernel<float><<<unsigned((elems + 255) / 256), 256, 0, h->stream>>>(static_cast<float*>(h->d_buf[buf]), tmp, elems);
+  else to_f32_kernel<__half><<<unsigned((elems + 255) / 256), 256, 0, h->stream>>>(static_cast<__half*>(h->d_buf[buf]), tmp, elems);
+  cudaError_t e = cudaMemcpyAsync(out, tmp, elems * 4, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(tmp);
+  CK(e);
+  return CTD_OK;
+}
+
+template <typename T>
+__global__ void from_f32_kernel(const float* src, T* dst, size_t n) {
+  size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i < n) dst[i] = T(src[i]);
+}
+
+extern "C" int ctd_debug_write_buffer(ctd_handle* h, int32_t buf, const float* in, int32_t n, int32_t ph, int32_t pw) {
+  if (!h || !in) return CTD_E_INVALID;
+  if (buf < 0 || buf >= int(h->bufs.size())) return fail(h, CTD_E_INVALID, "bad buffer id");
+  if (n < 1 || n > h->cfg.max_batch || ph > h->cfg.max_h || pw > h->cfg.max_w) return fail(h, CTD_E_CAPACITY, "shape");
+  CK(cudaSetDevice(h->cfg.device));
+  const ctd_bufdesc& b = h->bufs[buf];
+  const size_t elems = size_t(n) * (ph / b.down) * (pw / b.down) * b.channels;
+  float* tmp = nullptr;
+  CK(cudaMalloc(&tmp, elems * 4));
+  cudaError_t e = cudaMemcpyAsync(tmp, in, elems * 4, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) {
+    if (h->elem == 4) from_f32_kernel<float><<<unsigned((elems + 255) / 256), 256, 0, h->stream>>>(tmp, static_cast<float*>(h->d_buf[buf]), elems);
+    else from_f32_kernel<__half><<<unsigned((elems + 255) / 256), 256, 0, h->stream>>>(tmp, static_cast<__half*>(h->d_buf[buf]), elems);
+    e = cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(tmp);
+  CK(e);
+  return CTD_OK;
+}
+
+extern "C" int ctd_connected_components(ctd_handle* h, const uint8_t* img, int32_t ih, int32_t iw, int32_t* labels,
+                                        int32_t* stats, int32_t stats_cap, int32_t* n_labels) {
+  if (!h || !img || !labels || !n_labels) return CTD_E_INVALID;
+  if (size_t(ih) * iw > size_t(h->cfg.max_batch) * h->cfg.max_h * h->cfg.max_w)
+    return fail(h, CTD_E_CAPACITY, "image larger than the workspace");
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t px = size_t(ih) * iw;
+  // reuse the page-sized scratch: bitmap <- img
+  CK(cudaMemcpyAsync(h->d_bitmap, img, px, cudaMemcpyHostToDevice, h->stream));
+  CK(ccl_launch(h->d_bitmap, 1, ih, iw, h->d_labels, h->d_ccl_scratch, h->d_nlabels, h->stream));
+  CK(cudaMemcpyAsync(labels, h->d_labels, px * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(n_labels, h->d_nlabels, 4, cudaMemcpyDeviceToHost, h->stream));
+  if (stats && stats_cap > 0) {
+    int32_t* d_stats = reinterpret_cast<int32_t*>(h->d_ccl_scratch);  // scratch is free again after ccl_launch
+    if (size_t(stats_cap) * 5 > px * 3) return fail(h, CTD_E_CAPACITY, "stats_cap too large");
+    CK(ccl_stats_launch(h->d_labels, ih, iw, d_stats, stats_cap, h->stream));
+    CK(cudaMemcpyAsync(stats, d_stats, size_t(stats_cap) * 5 * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  h->have_forward = false;  // the page outputs were clobbered
+  return CTD_OK;
+}
+
+extern "C" int ctd_nms(ctd_handle* h, const float* pred, int32_t rows, float conf_thresh, float iou_thresh, float* det,
+                       int32_t* det_count) {
+  if (!h || !pred || !det || !det_count) return CTD_E_INVALID;
+  const int no = 5 + h->cfg.nc;
+  if (rows > rows_per_image(h->cfg.max_h, h->cfg.max_w) * h->cfg.max_batch)
+    return fail(h, CTD_E_CAPACITY, "too many prediction rows");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(h->d_blks, pred, size_t(rows) * no * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(nms_launch(h->d_blks, 1, rows, h->cfg.nc, conf_thresh, iou_thresh, h->nms, h->d_det, h->d_det_count, h->stream));
+  CK(cudaMemcpyAsync(det, h->d_det, 300 * 6 * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(det_count, h->d_det_count, 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->have_forward = false;
+  return CTD_OK;
+}

@@ -1,0 +1,136 @@
+// Launch-parameter structs and host entry points of every kernel in the engine.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ctd_b200.h"
+
+namespace ctd {
+
+constexpr int kMaxTaps = 9;
+constexpr int kMaxPhases = 4;
+
+// Geometry shared by the tensor-core and CUDA-core convolution kernels.  A "grid" pixel is an
+// output pixel for CONV and an input pixel (= one sub-pixel phase output) for DECONV4.
+struct ConvGeom {
+  int n_img;             // images in the batch
+  int gh, gw;            // grid height/width (see above)
+  int dst_h, dst_w;      // destination buffer spatial size
+  int out_mul;           // 1 (conv) or 2 (deconv): dst pixel = grid pixel * out_mul + phase
+  int n_phase;           // 1 or 4
+  int taps;              // taps per phase: 1, 9 or 4
+  int cin_total;         // sum of src_c
+  int k_total;           // taps * cin_total
+  int n_src;
+  int src_c[CTD_MAX_SRC];
+  int src_cstride[CTD_MAX_SRC];  // channels of the source buffer (element stride between pixels)
+  int src_h, src_w;              // source spatial size (all sources agree)
+  int in_stride;                 // 1 or 2 (conv stride)
+  // per phase, per tap: source pixel = grid pixel * in_stride + (dy, dx)
+  int8_t tap_dy[kMaxPhases][kMaxTaps];
+  int8_t tap_dx[kMaxPhases][kMaxTaps];
+  int cout, cout_pad;
+  int dst_cstride, dst_coff;
+  int act, residual;
+};
+
+// Fill taps/offset tables for an op (conv k=1/3 stride 1/2, deconv 4x4 s2 p1).
+void fill_conv_geom_taps(ConvGeom& g, int kind, int ksize, int stride);
+
+// ---------------------------------------------------------------------------------------
+// tcgen05 implicit-GEMM convolution (conv_tc.cu)
+struct alignas(64) ConvTcParams {
+  CUtensorMap a_map[CTD_MAX_SRC][4];  // [source][parity]: parity maps only for stride-2 convs
+  CUtensorMap b_map;                  // packed weights [n_phase*cout_pad][k_total], K-major
+  ConvGeom g;
+  int kb_elems;                       // channels per K block: 64 / 32 / 16 (swizzle 128/64/32 B)
+  int src_kblocks[CTD_MAX_SRC];
+  int tiles_x, tiles_y;               // 16x8-pixel tiles per image
+  int8_t tap_map[kMaxPhases][kMaxTaps];  // parity map index per tap (stride 2), else 0
+  __half* dst;
+  const float* bias;
+  // DETECT epilogue (dst == nullptr): decoded rows go to blks
+  float* blks;
+  int blks_rows_per_img;  // A
+  int level_row0;         // first row of this pyramid level
+  float det_stride;
+  float anchor_wh[6];     // pixels
+  int nc;
+};
+
+struct ConvTcPlan {
+  ConvTcParams p;
+  int block_n;
+  dim3 grid;
+  size_t smem_bytes;
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Builds tensor maps + launch shape.  Returns nullptr on success, else an error string.
+const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
+                         const int src_coff[], const void* w16, const float* bias, __half* dst);
+cudaError_t conv_tc_launch(const ConvTcPlan& plan, cudaStream_t s);
+cudaError_t conv_tc_init();  // sets max dynamic smem attributes once
+
+// ---------------------------------------------------------------------------------------
+// CUDA-core kernels (simt.cu): accurate/bisecting path and the thin layers.  T = float | __half.
+struct ConvSimtParams {
+  ConvGeom g;
+  const void* src[CTD_MAX_SRC];  // already offset to the first channel read
+  const void* w;                 // [n_phase*cout_pad][k_total] float (T=float) or __half (T=__half)
+  const float* bias;
+  void* dst;
+  float* blks;                   // DETECT
+  int blks_rows_per_img, level_row0, nc;
+  float det_stride;
+  float anchor_wh[6];
+};
+template <typename T>
+cudaError_t conv_simt_launch(const ConvSimtParams& p, cudaStream_t s);
+
+template <typename T>
+cudaError_t stem_launch(const uint8_t* pages, int n, int h, int w, const float* wgt /*[32][108] (ky,kx,c)*/,
+                        const float* bias, T* dst, int dst_cstride, int dst_coff, int cout, int act, cudaStream_t s);
+template <typename T>
+cudaError_t avgpool2_launch(const T* src, int n, int h, int w, int c, int src_cstride, T* dst, int dst_cstride,
+                            cudaStream_t s);
+template <typename T>
+cudaError_t sppf_pool_launch(T* buf, int n, int h, int w, int c, int cstride, cudaStream_t s);  // in-place slots
+template <typename T>
+cudaError_t upsample2_launch(const T* src, int n, int h, int w, int c, int src_cstride, T* dst, int dst_cstride,
+                             cudaStream_t s);
+// seg tail: ConvT4x4s2p1 C->1 + sigmoid; writes f32 mask [n][2h][2w] and u8 mask (p*255 truncated)
+template <typename T>
+cudaError_t seg_tail_launch(const T* src, int n, int h, int w, int c, int cstride, const float* wgt /*[c][4][4]*/,
+                            float* mask_f32, uint8_t* mask_u8, cudaStream_t s);
+// DB tail on the 32-channel (binarize|thresh) map at 1/4 resolution -> lines f32 [n][2][4h][4w]
+// and the thresholded bitmap u8 [n][4h][4w] (shrink > db_thresh).
+template <typename T>
+cudaError_t db_tail_launch(const T* src, int n, int h, int w, int cstride, const float* params, float* lines,
+                           uint8_t* bitmap, float db_thresh, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------
+// post-processing (postproc.cu)
+struct NmsWorkspace {
+  float* cand;     // [n][cap][6]
+  int* cand_count; // [n]
+  float* sorted;   // [n][cap][6]
+  unsigned long long* mask;  // [n][cap][cap/64]
+  int cap;
+};
+cudaError_t nms_launch(const float* blks, int n, int rows, int nc, float conf, float iou, NmsWorkspace& ws,
+                       float* det /*[n][300][6]*/, int* det_count, cudaStream_t s);
+size_t nms_workspace_bytes(int n, int cap);
+void nms_workspace_bind(NmsWorkspace& ws, void* base, int n, int cap);
+
+// 8-connectivity labelling with OpenCV's label numbering; labels i32, n_labels incl. background.
+cudaError_t ccl_launch(const uint8_t* img, int n, int h, int w, int32_t* labels, int32_t* scratch /*3*n*h*w ints*/,
+                       int32_t* n_labels, cudaStream_t s);
+cudaError_t ccl_stats_launch(const int32_t* labels, int h, int w, int32_t* stats, int cap, cudaStream_t s);
+
+}  // namespace ctd

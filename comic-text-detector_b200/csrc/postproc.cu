@@ -1,0 +1,384 @@
+// Post-processing kernels: YOLO candidate filter + NMS (utils/yolov5_utils.py:124-218 with
+// torchvision.ops.nms semantics) and 8-connectivity connected-components labelling with OpenCV's
+// label numbering (cv2.connectedComponentsWithStats as called from utils/textmask.py:93,113,138).
+#include <cuda_runtime.h>
+#include <limits.h>
+
+#include "kernels.h"
+
+namespace ctd {
+
+// =========================================================================================
+// NMS
+constexpr int kCandStride = 8;  // x1,y1,x2,y2,conf,cls,row(int bits),pad
+constexpr int kMaxDet = 300;    // max_det (yolov5_utils.py:125)
+constexpr float kMaxWh = 4096.f;  // class offset (yolov5_utils.py:143,198)
+
+size_t nms_workspace_bytes(int n, int cap) {
+  return size_t(n) * cap * kCandStride * 4 * 2 + size_t(n) * 4 * 4 + size_t(n) * cap * (cap / 64) * 8;
+}
+void nms_workspace_bind(NmsWorkspace& ws, void* base, int n, int cap) {
+  char* p = static_cast<char*>(base);
+  ws.cap = cap;
+  ws.mask = reinterpret_cast<unsigned long long*>(p);
+  p += size_t(n) * cap * (cap / 64) * 8;
+  ws.cand = reinterpret_cast<float*>(p);
+  p += size_t(n) * cap * kCandStride * 4;
+  ws.sorted = reinterpret_cast<float*>(p);
+  p += size_t(n) * cap * kCandStride * 4;
+  ws.cand_count = reinterpret_cast<int*>(p);
+}
+
+// yolov5_utils.py:136,152,169-182: obj > conf -> cls *= obj -> xywh2xyxy -> best class -> conf > thres
+__global__ void nms_filter_kernel(const float* __restrict__ blks, int rows, int no, float conf_thres,
+                                  float* __restrict__ cand, int* __restrict__ cand_count, int cap) {
+  const int img = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* x = blks + (size_t(img) * rows + r) * no;
+  const float obj = x[4];
+  if (!(obj > conf_thres)) return;
+  float best = -INFINITY;
+  int bj = 0;
+  for (int j = 5; j < no; ++j) {
+    const float c = __fmul_rn(x[j], obj);
+    if (c > best) {
+      best = c;
+      bj = j - 5;
+    }
+  }
+  if (!(best > conf_thres)) return;
+  const int slot = atomicAdd(&cand_count[img], 1);
+  if (slot >= cap) return;
+  float* o = cand + (size_t(img) * cap + slot) * kCandStride;
+  const float hw = x[2] / 2.f, hh = x[3] / 2.f;
+  o[0] = x[0] - hw;
+  o[1] = x[1] - hh;
+  o[2] = x[0] + hw;
+  o[3] = x[1] + hh;
+  o[4] = best;
+  o[5] = float(bj);
+  o[6] = __int_as_float(r);
+  o[7] = 0.f;
+}
+
+// stable descending sort by score (ties: original row order) -- torchvision nms_kernel sorts with
+// stable=true.  One CTA per page, bitonic network in shared memory.
+template <int P>
+__global__ void __launch_bounds__(1024) nms_sort_kernel(const float* __restrict__ cand, int* __restrict__ cand_count,
+                                                        float* __restrict__ sorted, int cap) {
+  __shared__ float skey[P];
+  __shared__ int srow[P];
+  __shared__ int sslot[P];
+  const int img = blockIdx.x;
+  int m = cand_count[img];
+  if (m > cap) m = cap;
+  const float* c = cand + size_t(img) * cap * kCandStride;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    if (i < m) {
+      skey[i] = c[i * kCandStride + 4];
+      srow[i] = __float_as_int(c[i * kCandStride + 6]);
+      sslot[i] = i;
+    } else {
+      skey[i] = -INFINITY;
+      srow[i] = INT_MAX;
+      sslot[i] = -1;
+    }
+  }
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool up = (i & k) == 0;  // ascending position order == "better first"
+          const float ka = skey[i], kb = skey[ixj];
+          const int ra = srow[i], rb = srow[ixj];
+          const bool a_first = (ka > kb) || (ka == kb && ra < rb);
+          if (a_first != up) {
+            skey[i] = kb; skey[ixj] = ka;
+            srow[i] = rb; srow[ixj] = ra;
+            const int t = sslot[i]; sslot[i] = sslot[ixj]; sslot[ixj] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  float* o = sorted + size_t(img) * cap * kCandStride;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const int sl = sslot[i];
+#pragma unroll
+    for (int e = 0; e < kCandStride; ++e) o[i * kCandStride + e] = c[sl * kCandStride + e];
+  }
+}
+
+// IoU bit matrix over class-offset boxes (yolov5_utils.py:198-200; torchvision nms_kernel arithmetic)
+__global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ sorted, const int* __restrict__ cand_count,
+                                                      unsigned long long* __restrict__ mask, int cap, float iou_thres) {
+  const int img = blockIdx.z;
+  int m = cand_count[img];
+  if (m > cap) m = cap;
+  const int rb = blockIdx.y, cb = blockIdx.x;
+  if (rb * 64 >= m || cb * 64 >= m || cb < rb) return;
+  __shared__ float cbox[64][5];
+  const float* s = sorted + size_t(img) * cap * kCandStride;
+  const int cj = cb * 64 + threadIdx.x;
+  if (cj < m) {
+    const float off = s[cj * kCandStride + 5] * kMaxWh;
+    cbox[threadIdx.x][0] = s[cj * kCandStride + 0] + off;
+    cbox[threadIdx.x][1] = s[cj * kCandStride + 1] + off;
+    cbox[threadIdx.x][2] = s[cj * kCandStride + 2] + off;
+    cbox[threadIdx.x][3] = s[cj * kCandStride + 3] + off;
+    cbox[threadIdx.x][4] = __fmul_rn(cbox[threadIdx.x][2] - cbox[threadIdx.x][0], cbox[threadIdx.x][3] - cbox[threadIdx.x][1]);
+  }
+  __syncthreads();
+  const int i = rb * 64 + threadIdx.x;
+  if (i >= m) return;
+  const float off = s[i * kCandStride + 5] * kMaxWh;
+  const float x1 = s[i * kCandStride + 0] + off, y1 = s[i * kCandStride + 1] + off;
+  const float x2 = s[i * kCandStride + 2] + off, y2 = s[i * kCandStride + 3] + off;
+  const float area = __fmul_rn(x2 - x1, y2 - y1);
+  unsigned long long bits = 0;
+  const int jmax = min(64, m - cb * 64);
+  for (int j = 0; j < jmax; ++j) {
+    if (cb * 64 + j <= i) continue;
+    const float xx1 = fmaxf(x1, cbox[j][0]), yy1 = fmaxf(y1, cbox[j][1]);
+    const float xx2 = fminf(x2, cbox[j][2]), yy2 = fminf(y2, cbox[j][3]);
+    const float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area, cbox[j][4]), inter));
+    if (ovr > iou_thres) bits |= 1ull << j;
+  }
+  mask[(size_t(img) * cap + i) * (cap / 64) + cb] = bits;
+}
+
+// greedy scan (one warp per page), keeps at most max_det rows
+__global__ void __launch_bounds__(32) nms_scan_kernel(const float* __restrict__ sorted, const int* __restrict__ cand_count,
+                                                      const unsigned long long* __restrict__ mask, int cap,
+                                                      float* __restrict__ det, int* __restrict__ det_count) {
+  extern __shared__ unsigned long long remv[];  // cap/64 words
+  const int img = blockIdx.x, lane = threadIdx.x;
+  int m = cand_count[img];
+  if (m > cap) m = cap;
+  const int words = cap / 64;
+  for (int w = lane; w < words; w += 32) remv[w] = 0ull;
+  __syncwarp();
+  const float* s = sorted + size_t(img) * cap * kCandStride;
+  float* o = det + size_t(img) * kMaxDet * 6;
+  int kept = 0;
+  for (int i = 0; i < m && kept < kMaxDet; ++i) {
+    const unsigned long long rw = remv[i >> 6];
+    if ((rw >> (i & 63)) & 1ull) continue;
+    if (lane < 6) o[kept * 6 + lane] = s[i * kCandStride + lane];
+    ++kept;
+    const unsigned long long* mrow = mask + (size_t(img) * cap + i) * words;
+    const int wlast = (m + 63) >> 6;
+    for (int w = (i >> 6) + lane; w < wlast; w += 32) remv[w] |= mrow[w];
+    __syncwarp();
+  }
+  if (lane == 0) det_count[img] = kept;
+}
+
+cudaError_t nms_launch(const float* blks, int n, int rows, int nc, float conf, float iou, NmsWorkspace& ws, float* det,
+                       int* det_count, cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(ws.cand_count, 0, sizeof(int) * n, s);
+  if (e != cudaSuccess) return e;
+  // rows of `mask` below the diagonal block are never read; words at/after are always written
+  nms_filter_kernel<<<dim3((rows + 255) / 256, n), 256, 0, s>>>(blks, rows, 5 + nc, conf, ws.cand, ws.cand_count, ws.cap);
+  if (ws.cap == 4096) nms_sort_kernel<4096><<<n, 1024, 0, s>>>(ws.cand, ws.cand_count, ws.sorted, ws.cap);
+  else if (ws.cap == 1024) nms_sort_kernel<1024><<<n, 1024, 0, s>>>(ws.cand, ws.cand_count, ws.sorted, ws.cap);
+  else return cudaErrorInvalidValue;
+  const int blocks = ws.cap / 64;
+  nms_mask_kernel<<<dim3(blocks, blocks, n), 64, 0, s>>>(ws.sorted, ws.cand_count, ws.mask, ws.cap, iou);
+  nms_scan_kernel<<<n, 32, (ws.cap / 64) * 8, s>>>(ws.sorted, ws.cand_count, ws.mask, ws.cap, det, det_count);
+  return cudaGetLastError();
+}
+
+// =========================================================================================
+// Connected components, 8-connectivity, OpenCV numbering.
+//
+// OpenCV's 8-connectivity labeller scans 2x2 blocks in raster order and, after flattening its
+// union-find, numbers components by their smallest provisional label, i.e. by the first 2x2
+// block (raster order over blocks) that holds one of the component's pixels (SURVEY section 7,
+// App. D #16).  All pixels of one 2x2 block are mutually 8-adjacent, so that block identifies the
+// component uniquely.  Here: union-find over pixels (Playne-Hawick atomicMin unions), per-root
+// minimum block index, a prefix sum over "is a first block" flags gives the final label.
+
+__device__ __forceinline__ int uf_find(const int* L, int a) {
+  int p = L[a];
+  while (p != a) {
+    a = p;
+    p = L[a];
+  }
+  return a;
+}
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+  bool done;
+  do {
+    a = uf_find(L, a);
+    b = uf_find(L, b);
+    if (a < b) {
+      const int old = atomicMin(&L[b], a);
+      done = old == b;
+      b = old;
+    } else if (b < a) {
+      const int old = atomicMin(&L[a], b);
+      done = old == a;
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+
+__global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int h, int w, int* __restrict__ L,
+                                int* __restrict__ keymin, int* __restrict__ bflag) {
+  const int page = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hw = h * w;
+  if (p >= hw) return;
+  const size_t o = size_t(page) * hw + p;
+  L[o] = img[o] ? p : -1;
+  keymin[o] = INT_MAX;
+  const int nb = ((h + 1) / 2) * ((w + 1) / 2);
+  if (p < nb) bflag[size_t(page) * hw + p] = 0;  // bflag shares the per-page stride hw (nb <= hw)
+}
+
+__global__ void ccl_merge_kernel(int h, int w, int* __restrict__ Lall) {
+  const int page = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hw = h * w;
+  if (p >= hw) return;
+  int* L = Lall + size_t(page) * hw;
+  if (L[p] < 0) return;
+  const int y = p / w, x = p - y * w;
+  if (x > 0 && L[p - 1] >= 0) uf_union(L, p, p - 1);
+  if (y > 0) {
+    if (L[p - w] >= 0) uf_union(L, p, p - w);
+    if (x > 0 && L[p - w - 1] >= 0) uf_union(L, p, p - w - 1);
+    if (x + 1 < w && L[p - w + 1] >= 0) uf_union(L, p, p - w + 1);
+  }
+}
+
+__global__ void ccl_flatten_key_kernel(int h, int w, int* __restrict__ Lall, int* __restrict__ keymin_all) {
+  const int page = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hw = h * w;
+  if (p >= hw) return;
+  int* L = Lall + size_t(page) * hw;
+  if (L[p] < 0) return;
+  const int r = uf_find(L, p);
+  L[p] = r;  // racing writers all store a valid ancestor; roots are fixed points
+  const int y = p / w, x = p - y * w;
+  const int bw = (w + 1) / 2;
+  atomicMin(&keymin_all[size_t(page) * hw + r], (y >> 1) * bw + (x >> 1));
+}
+
+__global__ void ccl_markfirst_kernel(int h, int w, const int* __restrict__ Lall, const int* __restrict__ keymin_all,
+                                     int* __restrict__ bflag_all) {
+  const int page = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hw = h * w;
+  if (p >= hw) return;
+  if (Lall[size_t(page) * hw + p] == p) bflag_all[size_t(page) * hw + keymin_all[size_t(page) * hw + p]] = 1;
+}
+
+// exclusive prefix sum of bflag (in place -> rank), one CTA per page; writes n_labels (incl. background)
+__global__ void __launch_bounds__(1024) ccl_scan_kernel(int h, int w, int* __restrict__ bflag_all, int* __restrict__ n_labels) {
+  __shared__ int part[1024];
+  const int page = blockIdx.x;
+  const int nb = ((h + 1) / 2) * ((w + 1) / 2);
+  int* f = bflag_all + size_t(page) * h * w;
+  const int chunk = (nb + 1023) / 1024;
+  const int b0 = threadIdx.x * chunk, b1 = min(nb, b0 + chunk);
+  int s = 0;
+  for (int i = b0; i < b1; ++i) s += f[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    int v = 0;
+    if (threadIdx.x >= off) v = part[threadIdx.x - off];
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  int run = part[threadIdx.x] - s;
+  for (int i = b0; i < b1; ++i) {
+    const int v = f[i];
+    f[i] = run;
+    run += v;
+  }
+  if (threadIdx.x == 1023) n_labels[page] = part[1023] + 1;
+}
+
+__global__ void ccl_relabel_kernel(int h, int w, const int* __restrict__ Lall, const int* __restrict__ keymin_all,
+                                   const int* __restrict__ rank_all, int32_t* __restrict__ labels) {
+  const int page = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hw = h * w;
+  if (p >= hw) return;
+  const size_t o = size_t(page) * hw;
+  const int r = Lall[o + p];
+  labels[o + p] = r < 0 ? 0 : rank_all[o + keymin_all[o + r]] + 1;
+}
+
+// scratch: 3 * n*h*w ints (L, keymin, bflag/rank)
+cudaError_t ccl_launch(const uint8_t* img, int n, int h, int w, int32_t* labels, int32_t* scratch, int32_t* n_labels,
+                       cudaStream_t s) {
+  const int hw = h * w;
+  int* L = scratch;
+  int* keymin = scratch + size_t(n) * hw;
+  int* bflag = scratch + size_t(2) * n * hw;
+  dim3 grid((hw + 255) / 256, n);
+  ccl_init_kernel<<<grid, 256, 0, s>>>(img, h, w, L, keymin, bflag);
+  ccl_merge_kernel<<<grid, 256, 0, s>>>(h, w, L);
+  ccl_flatten_key_kernel<<<grid, 256, 0, s>>>(h, w, L, keymin);
+  ccl_markfirst_kernel<<<grid, 256, 0, s>>>(h, w, L, keymin, bflag);
+  ccl_scan_kernel<<<n, 1024, 0, s>>>(h, w, bflag, n_labels);
+  ccl_relabel_kernel<<<grid, 256, 0, s>>>(h, w, L, keymin, bflag, labels);
+  return cudaGetLastError();
+}
+
+// stats rows: x, y, w, h, area (cv2.CC_STAT_*); single page
+__global__ void ccl_stats_init_kernel(int32_t* stats, int cap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  stats[i * 5 + 0] = INT_MAX;
+  stats[i * 5 + 1] = INT_MAX;
+  stats[i * 5 + 2] = -1;
+  stats[i * 5 + 3] = -1;
+  stats[i * 5 + 4] = 0;
+}
+__global__ void ccl_stats_acc_kernel(const int32_t* __restrict__ labels, int h, int w, int32_t* stats, int cap) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= h * w) return;
+  const int l = labels[p];
+  if (l >= cap) return;
+  const int y = p / w, x = p - y * w;
+  atomicMin(&stats[l * 5 + 0], x);
+  atomicMin(&stats[l * 5 + 1], y);
+  atomicMax(&stats[l * 5 + 2], x);
+  atomicMax(&stats[l * 5 + 3], y);
+  atomicAdd(&stats[l * 5 + 4], 1);
+}
+__global__ void ccl_stats_fin_kernel(int32_t* stats, int cap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap) return;
+  if (stats[i * 5 + 4] == 0) {
+    // OpenCV reports an empty label (only possible for background) as x=y=INT_MAX-ish; mirror cv2: zeros w/h
+    stats[i * 5 + 2] = 0;
+    stats[i * 5 + 3] = 0;
+  } else {
+    stats[i * 5 + 2] = stats[i * 5 + 2] - stats[i * 5 + 0] + 1;
+    stats[i * 5 + 3] = stats[i * 5 + 3] - stats[i * 5 + 1] + 1;
+  }
+}
+cudaError_t ccl_stats_launch(const int32_t* labels, int h, int w, int32_t* stats, int cap, cudaStream_t s) {
+  ccl_stats_init_kernel<<<(cap + 255) / 256, 256, 0, s>>>(stats, cap);
+  ccl_stats_acc_kernel<<<(h * w + 255) / 256, 256, 0, s>>>(labels, h, w, stats, cap);
+  ccl_stats_fin_kernel<<<(cap + 255) / 256, 256, 0, s>>>(stats, cap);
+  return cudaGetLastError();
+}
+
+}  // namespace ctd

@@ -1,0 +1,452 @@
+// CUDA-core kernels: the fp32-accurate / bisecting convolution path (same op descriptors and
+// weight packing as the tcgen05 path) and the thin layers that are HBM-bound by nature
+// (stem from u8, pools, nearest upsample, the seg/DB tails).  T = float or __half storage,
+// arithmetic always fp32.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace ctd {
+
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(__half* p, float v) { *p = __float2half_rn(v); }
+
+__device__ __forceinline__ float act_f(float v, int act) {
+  switch (act) {
+    case CTD_ACT_SILU: return v / (1.0f + expf(-v));
+    case CTD_ACT_LEAKY: return v > 0.f ? v : 0.1f * v;
+    case CTD_ACT_RELU: return fmaxf(v, 0.f);
+    case CTD_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+    default: return v;
+  }
+}
+
+void fill_conv_geom_taps(ConvGeom& g, int kind, int ksize, int stride) {
+  memset(g.tap_dy, 0, sizeof(g.tap_dy));
+  memset(g.tap_dx, 0, sizeof(g.tap_dx));
+  if (kind == CTD_OP_DECONV4) {
+    // out = 2*in - 1 + k  (k=4, s=2, p=1).  Output phase py: taps (ky, dy): py=0 -> (1,0),(3,-1); py=1 -> (0,+1),(2,0)
+    g.n_phase = 4;
+    g.taps = 4;
+    g.out_mul = 2;
+    g.in_stride = 1;
+    const int d[2][2] = {{0, -1}, {1, 0}};
+    for (int ph = 0; ph < 4; ++ph)
+      for (int t = 0; t < 4; ++t) {
+        g.tap_dy[ph][t] = int8_t(d[ph >> 1][t >> 1]);
+        g.tap_dx[ph][t] = int8_t(d[ph & 1][t & 1]);
+      }
+  } else {
+    g.n_phase = 1;
+    g.taps = ksize * ksize;
+    g.out_mul = 1;
+    g.in_stride = stride;
+    const int pad = ksize / 2;
+    for (int t = 0; t < g.taps; ++t) {
+      g.tap_dy[0][t] = int8_t(t / ksize - pad);
+      g.tap_dx[0][t] = int8_t(t % ksize - pad);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// generic implicit-GEMM convolution on CUDA cores: CTA = 64 grid pixels x 64 couts, K chunks of 16
+template <typename T>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const ConvSimtParams p) {
+  const ConvGeom& g = p.g;
+  __shared__ float As[16][64 + 4];
+  __shared__ float Ws[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int phase = blockIdx.z;
+  const long long npix = (long long)g.n_img * g.gh * g.gw;
+  const long long pix0 = (long long)blockIdx.x * 64;
+  const int co0 = blockIdx.y * 64;
+  const int tx = tid & 15, ty = tid >> 4;  // tx -> couts (4 each), ty -> pixels (4 each)
+
+  // loader roles
+  const int lp = tid >> 2;        // pixel within tile loaded by this thread (0..63)
+  const int lk = (tid & 3) * 4;   // first of 4 consecutive channels in the 16-chunk
+  const long long lpix = pix0 + lp;
+  int ln = 0, ly = 0, lx = 0;
+  const bool lvalid = lpix < npix;
+  if (lvalid) {
+    ln = int(lpix / (g.gh * g.gw));
+    const int r = int(lpix - (long long)ln * g.gh * g.gw);
+    ly = r / g.gw;
+    lx = r - ly * g.gw;
+  }
+  const int wco = tid >> 2;       // cout within tile whose weights this thread loads
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const T* wbase = static_cast<const T*>(p.w) + (size_t(phase) * g.cout_pad) * g.k_total;
+  for (int tap = 0; tap < g.taps; ++tap) {
+    const int sy = ly * g.in_stride + g.tap_dy[phase][tap];
+    const int sx = lx * g.in_stride + g.tap_dx[phase][tap];
+    const bool inb = lvalid && sy >= 0 && sy < g.src_h && sx >= 0 && sx < g.src_w;
+    int kglob = tap * g.cin_total;
+    for (int s = 0; s < g.n_src; ++s) {
+      const T* sp = static_cast<const T*>(p.src[s]);
+      const size_t poff = (size_t(ln) * g.src_h * g.src_w + size_t(sy) * g.src_w + sx) * g.src_cstride[s];
+      for (int c0 = 0; c0 < g.src_c[s]; c0 += 16) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) As[lk + e][lp] = inb ? ldf(sp + poff + c0 + lk + e) : 0.f;
+        const int co = co0 + wco;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          Ws[lk + e][wco] = co < g.cout_pad ? ldf(wbase + size_t(co) * g.k_total + kglob + c0 + lk + e) : 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          float a[4], w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) w[j] = Ws[k][tx * 4 + j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+      }
+      kglob += g.src_c[s];
+    }
+  }
+  // epilogue
+  const int ph_y = phase >> 1, ph_x = phase & 1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long pix = pix0 + ty * 4 + i;
+    if (pix >= npix) continue;
+    const int n = int(pix / (g.gh * g.gw));
+    const int r = int(pix - (long long)n * g.gh * g.gw);
+    const int gy = r / g.gw, gx = r - gy * g.gw;
+    const int oy = gy * g.out_mul + ph_y, ox = gx * g.out_mul + ph_x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tx * 4 + j;
+      if (co >= g.cout) continue;
+      float v = acc[i][j] + p.bias[co];
+      if (p.dst != nullptr) {
+        T* o = static_cast<T*>(p.dst) + (size_t(n) * g.dst_h * g.dst_w + size_t(oy) * g.dst_w + ox) * g.dst_cstride +
+               g.dst_coff + co;
+        v = act_f(v, g.act);
+        if (g.residual) v += ldf(o);
+        stf(o, v);
+      } else {
+        const int no = 5 + p.nc;
+        const int a = co / no, oo = co - a * no;
+        const float s = 1.0f / (1.0f + expf(-v));
+        float rr;
+        if (oo == 0) rr = (s * 2.0f - 0.5f + float(gx)) * p.det_stride;
+        else if (oo == 1) rr = (s * 2.0f - 0.5f + float(gy)) * p.det_stride;
+        else if (oo == 2) rr = (s * 2.0f) * (s * 2.0f) * p.anchor_wh[2 * a];
+        else if (oo == 3) rr = (s * 2.0f) * (s * 2.0f) * p.anchor_wh[2 * a + 1];
+        else rr = s;
+        float* rows = p.blks + (size_t(n) * p.blks_rows_per_img + p.level_row0) * no;
+        rows[(size_t(a) * g.gh * g.gw + size_t(gy) * g.gw + gx) * no + oo] = rr;
+      }
+    }
+  }
+}
+
+template <typename T>
+cudaError_t conv_simt_launch(const ConvSimtParams& p, cudaStream_t s) {
+  const long long npix = (long long)p.g.n_img * p.g.gh * p.g.gw;
+  dim3 grid(unsigned((npix + 63) / 64), unsigned((p.g.cout_pad + 63) / 64), unsigned(p.g.n_phase));
+  conv_simt_kernel<T><<<grid, 256, 0, s>>>(p);
+  return cudaGetLastError();
+}
+template cudaError_t conv_simt_launch<float>(const ConvSimtParams&, cudaStream_t);
+template cudaError_t conv_simt_launch<__half>(const ConvSimtParams&, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------
+// stem: Conv 6x6 s2 p2, 3 -> cout(32), reads the u8 BGR HWC page, fuses /255 (inference.py:78)
+template <typename T>
+__global__ void __launch_bounds__(256) stem_kernel(const uint8_t* __restrict__ pages, int n, int h, int w,
+                                                   const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                   T* __restrict__ dst, int dst_cstride, int dst_coff, int cout,
+                                                   int act) {
+  // CTA: 8x32 output pixels; input patch (2*8+4) x (2*32+4) x 3
+  constexpr int TH = 8, TW = 32;
+  constexpr int PH = 2 * TH + 4, PW = 2 * TW + 4;
+  __shared__ float patch[PH][PW * 3];
+  __shared__ float ws[108 * 32];
+  __shared__ float bs[32];
+  const int oh = h / 2, ow = w / 2;
+  const int tiles_x = (ow + TW - 1) / TW, tiles_y = (oh + TH - 1) / TH;
+  const int img = blockIdx.x / (tiles_x * tiles_y);
+  const int tr = blockIdx.x % (tiles_x * tiles_y);
+  const int oy0 = (tr / tiles_x) * TH, ox0 = (tr % tiles_x) * TW;
+  const int iy0 = oy0 * 2 - 2, ix0 = ox0 * 2 - 2;
+  for (int i = threadIdx.x; i < 108 * 32; i += 256) {
+    // ws[k][co] <- wgt[co][k]
+    const int co = i & 31, k = i >> 5;
+    ws[i] = co < cout ? wgt[co * 108 + k] : 0.f;
+  }
+  if (threadIdx.x < 32) bs[threadIdx.x] = threadIdx.x < cout ? bias[threadIdx.x] : 0.f;
+  const uint8_t* page = pages + size_t(img) * h * w * 3;
+  for (int i = threadIdx.x; i < PH * PW * 3; i += 256) {
+    const int py = i / (PW * 3), rem = i - py * (PW * 3);
+    const int px = rem / 3, c = rem - px * 3;
+    const int iy = iy0 + py, ix = ix0 + px;
+    float v = 0.f;
+    if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = float(page[(size_t(iy) * w + ix) * 3 + c]) / 255.0f;
+    patch[py][rem] = v;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float acc[32];
+#pragma unroll
+  for (int co = 0; co < 32; ++co) acc[co] = bs[co];
+  for (int ky = 0; ky < 6; ++ky)
+#pragma unroll
+    for (int kc = 0; kc < 18; ++kc) {  // kc = kx*3 + c
+      const float a = patch[ty * 2 + ky][tx * 6 + kc];
+      const float* wr = &ws[(ky * 18 + kc) * 32];
+#pragma unroll
+      for (int co = 0; co < 32; ++co) acc[co] = fmaf(a, wr[co], acc[co]);
+    }
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  if (oy < oh && ox < ow) {
+    T* o = dst + (size_t(img) * oh * ow + size_t(oy) * ow + ox) * dst_cstride + dst_coff;
+    for (int co = 0; co < cout; ++co) stf(o + co, act_f(acc[co], act));
+  }
+}
+
+template <typename T>
+cudaError_t stem_launch(const uint8_t* pages, int n, int h, int w, const float* wgt, const float* bias, T* dst,
+                        int dst_cstride, int dst_coff, int cout, int act, cudaStream_t s) {
+  if (cout > 32) return cudaErrorInvalidValue;
+  const int oh = h / 2, ow = w / 2;
+  const int tiles = ((ow + 31) / 32) * ((oh + 7) / 8);
+  stem_kernel<T><<<n * tiles, 256, 0, s>>>(pages, n, h, w, wgt, bias, dst, dst_cstride, dst_coff, cout, act);
+  return cudaGetLastError();
+}
+template cudaError_t stem_launch<float>(const uint8_t*, int, int, int, const float*, const float*, float*, int, int,
+                                        int, int, cudaStream_t);
+template cudaError_t stem_launch<__half>(const uint8_t*, int, int, int, const float*, const float*, __half*, int, int,
+                                         int, int, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void avgpool2_kernel(const T* __restrict__ src, int n, int h, int w, int c, int scs, T* __restrict__ dst,
+                                int dcs) {
+  const int oh = h / 2, ow = w / 2;
+  const long long total = (long long)n * oh * ow * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = int(i % c);
+    long long r = i / c;
+    const int ox = int(r % ow);
+    r /= ow;
+    const int oy = int(r % oh);
+    const int img = int(r / oh);
+    const T* s0 = src + ((size_t(img) * h + 2 * oy) * w + 2 * ox) * scs + ch;
+    const float v = (ldf(s0) + ldf(s0 + scs) + ldf(s0 + size_t(w) * scs) + ldf(s0 + size_t(w) * scs + scs)) * 0.25f;
+    stf(dst + ((size_t(img) * oh + oy) * ow + ox) * dcs + ch, v);
+  }
+}
+template <typename T>
+cudaError_t avgpool2_launch(const T* src, int n, int h, int w, int c, int scs, T* dst, int dcs, cudaStream_t s) {
+  const long long total = (long long)n * (h / 2) * (w / 2) * c;
+  avgpool2_kernel<T><<<unsigned((total + 255) / 256), 256, 0, s>>>(src, n, h, w, c, scs, dst, dcs);
+  return cudaGetLastError();
+}
+template cudaError_t avgpool2_launch<float>(const float*, int, int, int, int, int, float*, int, cudaStream_t);
+template cudaError_t avgpool2_launch<__half>(const __half*, int, int, int, int, int, __half*, int, cudaStream_t);
+
+// SPPF pools: buf[..., 0:c] = x (already written); writes y1=mp5(x), y2=mp5(y1)=mp9(x), y3=mp13(x)
+// into channel slots [c,2c), [2c,3c), [3c,4c).  Chained 5x5 s1 p2 max pools equal 9x9 / 13x13 windows.
+template <typename T>
+__global__ void sppf_pool_kernel(T* __restrict__ buf, int n, int h, int w, int c, int cs) {
+  const long long total = (long long)n * h * w * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = int(i % c);
+    long long r = i / c;
+    const int x = int(r % w);
+    r /= w;
+    const int y = int(r % h);
+    const int img = int(r / h);
+    const T* base = buf + size_t(img) * h * w * cs + ch;
+    float m5 = -INFINITY, m9 = -INFINITY, m13 = -INFINITY;
+    for (int dy = -6; dy <= 6; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= h) continue;
+      for (int dx = -6; dx <= 6; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= w) continue;
+        const float v = ldf(base + (size_t(yy) * w + xx) * cs);
+        const int ad = max(abs(dy), abs(dx));
+        m13 = fmaxf(m13, v);
+        if (ad <= 4) m9 = fmaxf(m9, v);
+        if (ad <= 2) m5 = fmaxf(m5, v);
+      }
+    }
+    T* o = buf + ((size_t(img) * h + y) * w + x) * cs + ch;
+    stf(o + c, m5);
+    stf(o + 2 * c, m9);
+    stf(o + 3 * c, m13);
+  }
+}
+template <typename T>
+cudaError_t sppf_pool_launch(T* buf, int n, int h, int w, int c, int cs, cudaStream_t s) {
+  const long long total = (long long)n * h * w * c;
+  sppf_pool_kernel<T><<<unsigned((total + 255) / 256), 256, 0, s>>>(buf, n, h, w, c, cs);
+  return cudaGetLastError();
+}
+template cudaError_t sppf_pool_launch<float>(float*, int, int, int, int, int, cudaStream_t);
+template cudaError_t sppf_pool_launch<__half>(__half*, int, int, int, int, int, cudaStream_t);
+
+template <typename T>
+__global__ void upsample2_kernel(const T* __restrict__ src, int n, int h, int w, int c, int scs, T* __restrict__ dst,
+                                 int dcs) {
+  const int oh = 2 * h, ow = 2 * w;
+  const long long total = (long long)n * oh * ow * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = int(i % c);
+    long long r = i / c;
+    const int ox = int(r % ow);
+    r /= ow;
+    const int oy = int(r % oh);
+    const int img = int(r / oh);
+    dst[((size_t(img) * oh + oy) * ow + ox) * dcs + ch] = src[((size_t(img) * h + oy / 2) * w + ox / 2) * scs + ch];
+  }
+}
+template <typename T>
+cudaError_t upsample2_launch(const T* src, int n, int h, int w, int c, int scs, T* dst, int dcs, cudaStream_t s) {
+  const long long total = (long long)n * 4 * h * w * c;
+  upsample2_kernel<T><<<unsigned((total + 255) / 256), 256, 0, s>>>(src, n, h, w, c, scs, dst, dcs);
+  return cudaGetLastError();
+}
+template cudaError_t upsample2_launch<float>(const float*, int, int, int, int, int, float*, int, cudaStream_t);
+template cudaError_t upsample2_launch<__half>(const __half*, int, int, int, int, int, __half*, int, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------
+// seg tail: ConvTranspose2d(C,1,4,2,1,bias=False) + Sigmoid (basemodel.py:57-60) and
+// postprocess_mask's (p*255).astype(uint8) (inference.py:96-99).  One thread per output pixel.
+template <typename T>
+__global__ void __launch_bounds__(256) seg_tail_kernel(const T* __restrict__ src, int n, int h, int w, int c, int cs,
+                                                       const float* __restrict__ wgt, float* __restrict__ mask_f32,
+                                                       uint8_t* __restrict__ mask_u8) {
+  extern __shared__ float wsm[];  // [16][c]: wsm[(ky*4+kx)*c + ci]
+  for (int i = threadIdx.x; i < 16 * c; i += blockDim.x) {
+    const int ci = i % c, t = i / c;
+    wsm[i] = wgt[ci * 16 + t];
+  }
+  __syncthreads();
+  const int oh = 2 * h, ow = 2 * w;
+  const long long total = (long long)n * oh * ow;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ox = int(i % ow);
+  const int oy = int((i / ow) % oh);
+  const int img = int(i / ((long long)ow * oh));
+  // oy = 2*iy - 1 + ky
+  const int py = oy & 1, px = ox & 1;
+  const int qy = oy >> 1, qx = ox >> 1;
+  const int kys[2] = {py ? 0 : 1, py ? 2 : 3};
+  const int iys[2] = {py ? qy + 1 : qy, py ? qy : qy - 1};
+  const int kxs[2] = {px ? 0 : 1, px ? 2 : 3};
+  const int ixs[2] = {px ? qx + 1 : qx, px ? qx : qx - 1};
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    if (iys[a] < 0 || iys[a] >= h) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      if (ixs[b] < 0 || ixs[b] >= w) continue;
+      const T* sp = src + ((size_t(img) * h + iys[a]) * w + ixs[b]) * cs;
+      const float* wr = wsm + (kys[a] * 4 + kxs[b]) * c;
+      for (int ci = 0; ci < c; ++ci) acc = fmaf(ldf(sp + ci), wr[ci], acc);
+    }
+  }
+  const float s = 1.0f / (1.0f + expf(-acc));
+  mask_f32[i] = s;
+  mask_u8[i] = (uint8_t)(s * 255.0f);
+}
+template <typename T>
+cudaError_t seg_tail_launch(const T* src, int n, int h, int w, int c, int cs, const float* wgt, float* mask_f32,
+                            uint8_t* mask_u8, cudaStream_t s) {
+  const long long total = (long long)n * 4 * h * w;
+  seg_tail_kernel<T><<<unsigned((total + 255) / 256), 256, 16 * c * sizeof(float), s>>>(src, n, h, w, c, cs, wgt,
+                                                                                       mask_f32, mask_u8);
+  return cudaGetLastError();
+}
+template cudaError_t seg_tail_launch<float>(const float*, int, int, int, int, int, const float*, float*, uint8_t*,
+                                            cudaStream_t);
+template cudaError_t seg_tail_launch<__half>(const __half*, int, int, int, int, int, const float*, float*, uint8_t*,
+                                             cudaStream_t);
+
+// ---------------------------------------------------------------------------------------
+// DB tail (basemodel.py:99-103 binarize[3..6] and 138-142 thresh[3..7]); input = 32 channels at
+// 1/4 resolution: [0,16) = ReLU(BN(binarize conv3x3)), [16,32) = ReLU(BN(thresh conv3x3)).
+// params (fp32), per branch b in {0: binarize, 1: thresh}, base = b*1105:
+//   w3[ci][co][dy][dx] (16*16*4, BN folded), b3[co] (16), w6[co][dy][dx] (16*4), b6 (1)
+// One thread per 1/4-res pixel: 16 in -> 2x2x16 -> 4x4 outputs per branch.
+// lines[n][0] = sigmoid(binarize) (shrink), lines[n][1] = sigmoid(thresh)  (basemodel.py:114-125)
+template <typename T>
+__global__ void __launch_bounds__(128) db_tail_kernel(const T* __restrict__ src, int n, int h, int w, int cs,
+                                                      const float* __restrict__ params, float* __restrict__ lines,
+                                                      uint8_t* __restrict__ bitmap, float db_thresh) {
+  __shared__ float prm[2 * 1105];
+  for (int i = threadIdx.x; i < 2 * 1105; i += blockDim.x) prm[i] = params[i];
+  __syncthreads();
+  const long long total = (long long)n * h * w;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = int(i % w), y = int((i / w) % h), img = int(i / ((long long)w * h));
+  const T* sp = src + i * cs;
+  const int H = 4 * h, W = 4 * w;
+  for (int b = 0; b < 2; ++b) {
+    const float* w3 = prm + b * 1105;
+    const float* b3 = w3 + 1024;
+    const float* w6 = b3 + 16;
+    const float b6 = w6[64];
+    float xin[16];
+#pragma unroll
+    for (int ci = 0; ci < 16; ++ci) xin[ci] = ldf(sp + b * 16 + ci);
+    float* outp = lines + ((size_t(img) * 2 + b) * H + 4 * y) * W + 4 * x;
+#pragma unroll
+    for (int d1 = 0; d1 < 4; ++d1) {  // first deconv position (dy1,dx1)
+      float t[16];
+#pragma unroll
+      for (int co = 0; co < 16; ++co) {
+        float a = b3[co];
+#pragma unroll
+        for (int ci = 0; ci < 16; ++ci) a = fmaf(xin[ci], w3[(ci * 16 + co) * 4 + d1], a);
+        t[co] = fmaxf(a, 0.f);
+      }
+#pragma unroll
+      for (int d2 = 0; d2 < 4; ++d2) {
+        float a = b6;
+#pragma unroll
+        for (int co = 0; co < 16; ++co) a = fmaf(t[co], w6[co * 4 + d2], a);
+        const float s = 1.0f / (1.0f + expf(-a));
+        const int oy = (d1 >> 1) * 2 + (d2 >> 1), ox = (d1 & 1) * 2 + (d2 & 1);
+        outp[size_t(oy) * W + ox] = s;
+        if (b == 0) bitmap[(size_t(img) * H + 4 * y + oy) * W + 4 * x + ox] = s > db_thresh ? 1 : 0;
+      }
+    }
+  }
+}
+template <typename T>
+cudaError_t db_tail_launch(const T* src, int n, int h, int w, int cs, const float* params, float* lines,
+                           uint8_t* bitmap, float db_thresh, cudaStream_t s) {
+  const long long total = (long long)n * h * w;
+  db_tail_kernel<T><<<unsigned((total + 127) / 128), 128, 0, s>>>(src, n, h, w, cs, params, lines, bitmap, db_thresh);
+  return cudaGetLastError();
+}
+template cudaError_t db_tail_launch<float>(const float*, int, int, int, int, const float*, float*, uint8_t*, float,
+                                           cudaStream_t);
+template cudaError_t db_tail_launch<__half>(const __half*, int, int, int, int, const float*, float*, uint8_t*, float,
+                                            cudaStream_t);
+
+}  // namespace ctd

@@ -1,0 +1,180 @@
+/*
+ * ctd_b200.h -- C ABI of libctd_b200.so, the B200 (sm_100a) engine behind the reference's
+ * inference path  page -> (block boxes, text-line map, segmentation mask).
+ *
+ * The reference is pure Python and has no FFI; the seam this library replaces is the
+ * backend object built in `inference.TextDetector.__init__` (reference inference.py:124-130:
+ * `self.net = TextDetBase(...)` / `TextDetBaseDNN(...)`, a callable
+ * `net(img_in) -> (blks, mask, lines_map)`, basemodel.py:240-244) plus the array-level
+ * post-processing calls made from `TextDetector.__call__` (inference.py:141-178).
+ * Each entry point cites the reference interface it stands in for.  Plain C types only:
+ * no torch, no C++ types, nothing thrown across the boundary.  Every function returns 0 on
+ * success or a negative CTD_E_* code; `ctd_last_error()` gives the message.
+ *
+ * Threading: a handle is bound to one CUDA device and one internal stream and is NOT
+ * thread-safe; independent handles (one per GPU / per process) are independent.
+ */
+#ifndef CTD_B200_H_
+#define CTD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTD_ABI_VERSION 1
+#if defined(__GNUC__)
+#define CTD_API __attribute__((visibility("default")))
+#else
+#define CTD_API
+#endif
+
+/* ---- error codes ---------------------------------------------------------------------- */
+#define CTD_OK 0
+#define CTD_E_INVALID (-1)   /* bad argument / malformed program                            */
+#define CTD_E_CUDA (-2)      /* CUDA runtime/driver error (message has the CUDA string)     */
+#define CTD_E_NO_DEVICE (-3) /* no sm_100 GPU visible: the engine has NO CPU fallback       */
+#define CTD_E_SHAPE (-4)     /* page size not a multiple of 64 (basemodel.py:62-78 stride)  */
+#define CTD_E_CAPACITY (-5)  /* batch larger than the reserved workspace                    */
+
+/* ---- network program ------------------------------------------------------------------
+ * The Python host (comic-text-detector_b200/compiler.py) plays the role of the reference's
+ * `parse_model` + `load_state_dict` + `fuse` (models/yolov5/yolo.py:208-259,285-311;
+ * utils/yolov5_utils.py:23-43; basemodel.py:211-220): it walks the checkpoint's cfg, folds
+ * every BatchNorm and emits a flat list of ops over numbered NHWC activation buffers plus one
+ * weight blob.  The engine owns no architecture knowledge beyond these op kinds.           */
+
+enum ctd_op_kind {
+  CTD_OP_STEM = 0,      /* 6x6 s2 p2 conv on the u8 BGR page (/255 fused), common.py:30-49 cfg L0 */
+  CTD_OP_CONV = 1,      /* k in {1,3}, stride in {1,2}, pad k/2; K-concatenated sources     */
+  CTD_OP_DECONV4 = 2,   /* ConvTranspose2d 4x4 s2 p1 (basemodel.py:26) as 4 sub-pixel phases */
+  CTD_OP_AVGPOOL2 = 3,  /* AvgPool2d(2,2)                (basemodel.py:38)                  */
+  CTD_OP_SPPF_POOL = 4, /* 3 chained MaxPool2d(5,1,2)    (common.py:188-196)                */
+  CTD_OP_UPSAMPLE2 = 5, /* nn.Upsample(x2, nearest)      (cfg layers 11,15)                 */
+  CTD_OP_DETECT = 6,    /* Detect 1x1 conv + sigmoid + box decode (yolo.py:23-44)           */
+  CTD_OP_SEG_TAIL = 7,  /* ConvT4x4s2 64->1 + sigmoid    (basemodel.py:57-60)               */
+  CTD_OP_DB_TAIL = 8    /* ConvT2x2s2+BN+ReLU -> ConvT2x2s2 -> sigmoid, both branches
+                           (basemodel.py:99-103,138-142)                                    */
+};
+
+enum ctd_act { CTD_ACT_NONE = 0, CTD_ACT_SILU = 1, CTD_ACT_LEAKY = 2, CTD_ACT_RELU = 3, CTD_ACT_SIGMOID = 4 };
+
+#define CTD_MAX_SRC 3
+
+typedef struct ctd_op {
+  int32_t kind;                  /* enum ctd_op_kind                                        */
+  int32_t n_src;                 /* 1..CTD_MAX_SRC K-concatenated inputs (torch.cat on dim 1) */
+  int32_t src_buf[CTD_MAX_SRC];  /* activation buffer ids                                   */
+  int32_t src_coff[CTD_MAX_SRC]; /* first channel read in that buffer                       */
+  int32_t src_c[CTD_MAX_SRC];    /* channels read                                           */
+  int32_t dst_buf;               /* activation buffer id (-1 for ops writing engine outputs) */
+  int32_t dst_coff;              /* first channel written                                   */
+  int32_t cout;                  /* true output channels                                    */
+  int32_t cout_pad;              /* rows in the packed weight matrix (multiple of 16)       */
+  int32_t ksize;                 /* 1, 3 (conv), 4 (deconv), 6 (stem)                       */
+  int32_t stride;                /* 1 or 2                                                  */
+  int32_t act;                   /* enum ctd_act                                            */
+  int32_t residual;              /* 1: dst = act(conv)+dst in place (Bottleneck.add, common.py:104) */
+  int32_t aux;                   /* DETECT: pyramid level (0,1,2)                           */
+  int64_t w16_off;               /* blob offset: fp16 weights [phase][cout_pad][taps*Cin] K-major */
+  int64_t w32_off;               /* blob offset: fp32 weights, same layout                  */
+  int64_t b_off;                 /* blob offset: fp32 bias[cout_pad] (BN folded)            */
+  int64_t p_off;                 /* blob offset: extra fp32 params (DETECT anchors, tails)  */
+} ctd_op;
+
+typedef struct ctd_bufdesc {
+  int32_t channels; /* total channels of the NHWC buffer                                   */
+  int32_t down;     /* spatial size = page size / down                                     */
+} ctd_bufdesc;
+
+enum ctd_precision {
+  CTD_PREC_FP16_TC = 0,   /* fp16 storage, tcgen05 implicit GEMM, fp32 accumulate (default) */
+  CTD_PREC_FP32_SIMT = 1, /* fp32 storage + CUDA-core fp32 kernels ("vs reference fp32" config) */
+  CTD_PREC_FP16_SIMT = 2  /* fp16 storage + CUDA-core kernels (bisecting aid)               */
+};
+
+typedef struct ctd_config {
+  int32_t abi_version; /* CTD_ABI_VERSION                                                  */
+  int32_t device;      /* CUDA device ordinal                                              */
+  int32_t precision;   /* enum ctd_precision                                               */
+  int32_t max_batch;   /* pages per ctd_infer call the workspace is sized for              */
+  int32_t max_h, max_w; /* largest page (multiples of 64)                                  */
+  int32_t nc;          /* classes of the Detect head (reference: 2, inference.py:117-118)  */
+  int32_t use_graph;   /* 1: capture the op list into a CUDA graph per (n,h,w)             */
+  float conf_thresh;   /* 0.4  (inference.py:120)                                          */
+  float nms_thresh;    /* 0.35 (inference.py:120)                                          */
+  float db_thresh;     /* 0.3  (inference.py:139 -> db_utils.py:71-72)                     */
+  int32_t debug_skip_postproc; /* 1: ctd_forward stops after the op list (kernel unit tests)  */
+} ctd_config;
+
+typedef struct ctd_handle ctd_handle;
+
+/* Replaces TextDetBase.__init__ / get_base_det_models (basemodel.py:211-227).
+ * `blob` is copied to the device; the arrays may be freed after the call.                 */
+CTD_API int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op* ops, int32_t n_ops,
+               const ctd_bufdesc* bufs, int32_t n_bufs, const void* blob, size_t blob_bytes);
+CTD_API void ctd_destroy(ctd_handle* h);
+CTD_API const char* ctd_last_error(const ctd_handle* h); /* h may be NULL: last create() error     */
+
+/* ---- the forward pass --------------------------------------------------------------------
+ * Replaces `TextDetBase.forward` (basemodel.py:240-244) fed by `preprocess_img` for
+ * net-sized pages (inference.py:72-83: BGR u8 HWC -> BGR f32 NCHW /255; the /255 and the
+ * layout change are fused into the stem kernel).
+ *
+ * pages : n*h*w*3 bytes, BGR, HWC, u8.  `pages_on_device` != 0 means a device pointer.
+ * The result stays on the device inside the handle; fetch what you need with ctd_get_*.   */
+CTD_API int ctd_forward(ctd_handle* h, const uint8_t* pages, int32_t n, int32_t ph, int32_t pw, int32_t pages_on_device);
+
+/* Net-level outputs (the tuple TextDetBase.forward returns), copied to HOST memory.
+ * blks  : f32 [n][A][5+nc], A = 3*(h/8*w/8 + h/16*w/16 + h/32*w/32)     (yolo.py:44)
+ * mask  : f32 [n][h][w] in (0,1)                                        (basemodel.py:57-60)
+ * lines : f32 [n][2][h][w] = (shrink, threshold)                        (basemodel.py:125)
+ * Any pointer may be NULL to skip it.                                                      */
+CTD_API int ctd_get_net_outputs(ctd_handle* h, float* blks, float* mask, float* lines);
+
+/* `postprocess_mask` (inference.py:85-99): (mask*255) truncated to u8, [n][h][w], HOST.   */
+CTD_API int ctd_get_mask_u8(ctd_handle* h, uint8_t* mask_u8);
+
+/* `postprocess_yolo` up to the numpy conversion (inference.py:101-105) =
+ * `non_max_suppression(det, conf, iou)[i]` (utils/yolov5_utils.py:124-218): rows
+ * [x1,y1,x2,y2,conf,cls] f32, score-descending, at most 300 per page.
+ * det: HOST f32 [n][300][6]; det_count: HOST i32 [n].                                      */
+CTD_API int ctd_get_detections(ctd_handle* h, float* det, int32_t* det_count);
+
+/* `SegDetectorRepresenter.binarize` + connected components of the shrink map
+ * (db_utils.py:71-72 and the labelling findContours/connectedComponents imply):
+ * bitmap u8 [n][h][w] (0/1), labels i32 [n][h][w] numbered like
+ * cv2.connectedComponents(connectivity=8) (0 = background), n_labels i32 [n] (incl. bg).
+ * Any pointer may be NULL.                                                                 */
+CTD_API int ctd_get_db_components(ctd_handle* h, uint8_t* bitmap, int32_t* labels, int32_t* n_labels);
+
+/* Device-side timing of the last ctd_forward (CUDA events on the engine stream), ms.       */
+CTD_API int ctd_last_forward_ms(ctd_handle* h, float* ms);
+/* Number of kernels the last ctd_forward launched (graph nodes when captured).             */
+CTD_API int ctd_last_launch_count(ctd_handle* h, int32_t* launches);
+/* Debug/bisect: copy activation buffer `buf` of the last forward to HOST as f32 NHWC.      */
+CTD_API int ctd_debug_read_buffer(ctd_handle* h, int32_t buf, float* out, size_t out_elems);
+/* Debug/unit tests: fill activation buffer `buf` (f32 NHWC on the host, converted to the engine's
+ * storage type) for a forward of shape (n, ph, pw); used with programs that have no STEM op.  */
+CTD_API int ctd_debug_write_buffer(ctd_handle* h, int32_t buf, const float* in, int32_t n, int32_t ph, int32_t pw);
+
+/* ---- stand-alone array kernels (stage-isolated parity; same kernels the pipeline uses) --
+ * cv2.connectedComponentsWithStats(img, connectivity=8, ltype=CV_32S) as the reference
+ * effectively calls it (utils/textmask.py:93,113,138).
+ * img u8 [h][w] (non-zero = foreground), HOST pointers.  labels i32 [h][w];
+ * stats i32 [n_labels][5] = x,y,w,h,area (row 0 = background); returns count in *n_labels.
+ * `stats_cap` = rows available in `stats`.                                                 */
+CTD_API int ctd_connected_components(ctd_handle* h, const uint8_t* img, int32_t ih, int32_t iw, int32_t* labels,
+                             int32_t* stats, int32_t stats_cap, int32_t* n_labels);
+
+/* utils/yolov5_utils.py:124-218 on a caller-supplied prediction tensor (HOST f32
+ * [rows][5+nc]); output as ctd_get_detections for one page.                                */
+CTD_API int ctd_nms(ctd_handle* h, const float* pred, int32_t rows, float conf_thresh, float iou_thresh, float* det,
+            int32_t* det_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTD_B200_H_ */
