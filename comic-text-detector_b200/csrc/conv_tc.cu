@@ -32,20 +32,94 @@ constexpr int kThreads = 192;
 
 template <int BN>
 struct TcCfg {
-  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 3 : 4);  // <=113 KB for BN<=128: 2 CTAs/SM
+  static constexpr int kStages = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);  // <=113 KB each: 2 CTAs/SM
   static constexpr int kABytes = 128 * 128;  // per stage (worst case 128-byte rows)
   static constexpr int kBBytes = BN * 128;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static constexpr size_t kSmem = 1024 /*align slack*/ + size_t(kStages) * (kABytes + kBBytes) + 256;
+  static constexpr size_t kSmem = 1024 /*align slack*/ + size_t(kStages) * (kABytes + kBBytes) + 256 + BN * 4;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case CTD_ACT_SILU: return v / (1.0f + __expf(-v));
-    case CTD_ACT_LEAKY: return v > 0.f ? v : 0.1f * v;
-    case CTD_ACT_RELU: return fmaxf(v, 0.f);
-    case CTD_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-v));
-    default: return v;
+template <int ACT>
+__device__ __forceinline__ float apply_act(float v) {
+  if constexpr (ACT == CTD_ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
+  else if constexpr (ACT == CTD_ACT_LEAKY) return fmaxf(v, 0.1f * v);
+  else if constexpr (ACT == CTD_ACT_RELU) return fmaxf(v, 0.f);
+  else if constexpr (ACT == CTD_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-v));
+  else return v;
+}
+
+// One 32-column chunk of the accumulator row owned by this thread: bias + activation (+ residual)
+// -> fp16 -> four 16-byte stores.  Straight-line code (no per-element branches), bias from smem.
+template <int ACT, bool RES>
+__device__ __forceinline__ void epilogue_chunk32(const uint32_t (&v)[32], const float* __restrict__ bias_s,
+                                                 __half* __restrict__ out, int ncols) {
+  uint4 r[4];
+  if constexpr (RES) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (q * 8 < ncols) r[q] = *reinterpret_cast<const uint4*>(out + q * 8);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (q * 8 >= ncols) break;
+    float f[8];
+    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + q * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + q * 8 + 4);
+    f[0] = apply_act<ACT>(__uint_as_float(v[q * 8 + 0]) + b0.x);
+    f[1] = apply_act<ACT>(__uint_as_float(v[q * 8 + 1]) + b0.y);
+    f[2] = apply_act<ACT>(__uint_as_float(v[q * 8 + 2]) + b0.z);
+    f[3] = apply_act<ACT>(__uint_as_float(v[q * 8 + 3]) + b0.w);
+    f[4] = apply_act<ACT>(__uint_as_float(v[q * 8 + 4]) + b1.x);
+    f[5] = apply_act<ACT>(__uint_as_float(v[q * 8 + 5]) + b1.y);
+    f[6] = apply_act<ACT>(__uint_as_float(v[q * 8 + 6]) + b1.z);
+    f[7] = apply_act<ACT>(__uint_as_float(v[q * 8 + 7]) + b1.w);
+    if constexpr (RES) {
+      const __half2* rh = reinterpret_cast<const __half2*>(&r[q]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 rf = __half22float2(rh[e]);
+        f[2 * e] += rf.x;
+        f[2 * e + 1] += rf.y;
+      }
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+    *reinterpret_cast<uint4*>(out + q * 8) = o;
+  }
+}
+
+template <int BN, int ACT, bool RES>
+__device__ __forceinline__ void epilogue_store(uint32_t tmem_row, const float* __restrict__ bias_s,
+                                               __half* __restrict__ out, int cout_left, bool valid) {
+  if constexpr (BN >= 64) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 64) {
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(tmem_row + uint32_t(c0), v0);
+      tmem_ld_32x32(tmem_row + uint32_t(c0 + 32), v1);
+      tmem_ld_wait();
+      if (valid) {
+        epilogue_chunk32<ACT, RES>(v0, bias_s + c0, out + c0, cout_left - c0);
+        epilogue_chunk32<ACT, RES>(v1, bias_s + c0 + 32, out + c0 + 32, cout_left - c0 - 32);
+      }
+    }
+  } else if constexpr (BN == 32) {
+    uint32_t v0[32];
+    tmem_ld_32x32(tmem_row, v0);
+    tmem_ld_wait();
+    if (valid) epilogue_chunk32<ACT, RES>(v0, bias_s, out, cout_left);
+  } else {
+    uint32_t v0[32];
+    uint32_t t16[16];
+    tmem_ld_32x16(tmem_row, t16);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v0[j] = t16[j];
+#pragma unroll
+    for (int j = 16; j < 32; ++j) v0[j] = 0u;
+    if (valid) epilogue_chunk32<ACT, RES>(v0, bias_s, out, cout_left < 16 ? cout_left : 16);
   }
 }
 
@@ -64,6 +138,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kStages * (Cfg::kABytes + Cfg::kBBytes) + 16 * Cfg::kStages + 8);
+
+  float* bias_s = reinterpret_cast<float*>(smem_gen + Cfg::kStages * (Cfg::kABytes + Cfg::kBBytes) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom& g = p.g;
@@ -96,6 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_addr, Cfg::kTmemCols);
+  for (int i = threadIdx.x; i < BN; i += kThreads) bias_s[i] = p.bias[nblk * BN + i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -157,61 +234,51 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     tc_fence_after();
     const int ph_y = phase >> 1, ph_x = phase & 1;
     const int oy = gy * g.out_mul + ph_y, ox = gx * g.out_mul + ph_x;
-    constexpr int kChunk = BN >= 32 ? 32 : 16;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += kChunk) {
-      uint32_t v[kChunk];
-      const uint32_t taddr = tmem_d + (uint32_t(quad * 32) << 16) + uint32_t(c0);
-      if constexpr (kChunk == 32) {
-        tmem_ld_32x32(taddr, v);
-      } else {
-        tmem_ld_32x16(taddr, reinterpret_cast<uint32_t(&)[16]>(v));
+    const uint32_t tmem_row = tmem_d + (uint32_t(quad * 32) << 16);
+    if (p.dst != nullptr) {
+      __half* out = p.dst + (size_t(img) * g.dst_h * g.dst_w + size_t(valid ? oy : 0) * g.dst_w + (valid ? ox : 0)) * g.dst_cstride +
+                    g.dst_coff + nblk * BN;
+      const int cout_left = g.cout - nblk * BN;
+#define CTD_EPI(ACT)                                                                              \
+  if (g.residual) epilogue_store<BN, ACT, true>(tmem_row, bias_s, out, cout_left, valid);         \
+  else epilogue_store<BN, ACT, false>(tmem_row, bias_s, out, cout_left, valid);
+      switch (g.act) {
+        case CTD_ACT_SILU: CTD_EPI(CTD_ACT_SILU) break;
+        case CTD_ACT_LEAKY: CTD_EPI(CTD_ACT_LEAKY) break;
+        case CTD_ACT_RELU: CTD_EPI(CTD_ACT_RELU) break;
+        case CTD_ACT_SIGMOID: CTD_EPI(CTD_ACT_SIGMOID) break;
+        default: CTD_EPI(CTD_ACT_NONE) break;
       }
-      tmem_ld_wait();
-      const int n0 = nblk * BN + c0;
-      if (!valid) continue;
-      if (p.dst != nullptr) {
-        __half* out = p.dst + (size_t(img) * g.dst_h * g.dst_w + size_t(oy) * g.dst_w + ox) * g.dst_cstride +
-                      g.dst_coff + n0;
-#pragma unroll
-        for (int j = 0; j < kChunk; j += 8) {
-          if (n0 + j >= g.cout) break;
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = apply_act(__uint_as_float(v[j + e]) + __ldg(p.bias + n0 + j + e), g.act);
-          if (g.residual) {
-            const uint4 r = *reinterpret_cast<const uint4*>(out + j);
-            const __half2* rh = reinterpret_cast<const __half2*>(&r);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 rf = __half22float2(rh[e]);
-              f[2 * e] += rf.x;
-              f[2 * e + 1] += rf.y;
-            }
-          }
-          uint4 o;
-          __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
-          *reinterpret_cast<uint4*>(out + j) = o;
-        }
-      } else {
-        // Detect decode (yolo.py:36-44): columns = anchor*(5+nc) + o
-        const int no = 5 + p.nc;
-        float* rows = p.blks + (size_t(img) * p.blks_rows_per_img + p.level_row0) * no;
+#undef CTD_EPI
+    } else {
+      // Detect decode (yolo.py:36-44): columns = anchor*(5+nc) + o
+      constexpr int kChunk = BN >= 32 ? 32 : 16;
+      const int no = 5 + p.nc;
+      float* rows = p.blks + (size_t(img) * p.blks_rows_per_img + p.level_row0) * no;
 #pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += kChunk) {
+        uint32_t v[kChunk];
+        if constexpr (kChunk == 32) {
+          tmem_ld_32x32(tmem_row + uint32_t(c0), v);
+        } else {
+          tmem_ld_32x16(tmem_row + uint32_t(c0), reinterpret_cast<uint32_t(&)[16]>(v));
+        }
+        tmem_ld_wait();
+        if (!valid) continue;
+#pragma unroll
         for (int j = 0; j < kChunk; ++j) {
-          const int col = n0 + j;
-          if (col >= g.cout) break;
-          const int a = col / no, o = col - a * no;
-          const float s = 1.0f / (1.0f + expf(-(__uint_as_float(v[j]) + __ldg(p.bias + col))));
-          float r;
-          if (o == 0) r = (s * 2.0f - 0.5f + float(gx)) * p.det_stride;
-          else if (o == 1) r = (s * 2.0f - 0.5f + float(gy)) * p.det_stride;
-          else if (o == 2) r = (s * 2.0f) * (s * 2.0f) * p.anchor_wh[2 * a];
-          else if (o == 3) r = (s * 2.0f) * (s * 2.0f) * p.anchor_wh[2 * a + 1];
-          else r = s;
-          rows[(size_t(a) * g.gh * g.gw + size_t(gy) * g.gw + gx) * no + o] = r;
+          const int col = nblk * BN + c0 + j;
+          if (col < g.cout) {
+            const int a = col / no, o = col - a * no;
+            const float s = 1.0f / (1.0f + expf(-(__uint_as_float(v[j]) + bias_s[c0 + j])));
+            float r;
+            if (o == 0) r = (s * 2.0f - 0.5f + float(gx)) * p.det_stride;
+            else if (o == 1) r = (s * 2.0f - 0.5f + float(gy)) * p.det_stride;
+            else if (o == 2) r = (s * 2.0f) * (s * 2.0f) * p.anchor_wh[2 * a];
+            else if (o == 3) r = (s * 2.0f) * (s * 2.0f) * p.anchor_wh[2 * a + 1];
+            else r = s;
+            rows[(size_t(a) * g.gh * g.gw + size_t(gy) * g.gw + gx) * no + o] = r;
+          }
         }
       }
     }

@@ -342,7 +342,7 @@ static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* lau
                 h->d_det_count, h->stream));
   cnt += 4;
   CK(ccl_launch(h->d_bitmap, n, ph, pw, h->d_labels, h->d_ccl_scratch, h->d_nlabels, h->stream));
-  cnt += 6;
+  cnt += 8;
   *launches = cnt;
   return CTD_OK;
 }

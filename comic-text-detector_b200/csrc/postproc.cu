@@ -232,35 +232,71 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
   } while (!done);
 }
 
-__global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int h, int w, int* __restrict__ L,
-                                int* __restrict__ keymin, int* __restrict__ bflag) {
-  const int page = blockIdx.y;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const int hw = h * w;
-  if (p >= hw) return;
-  const size_t o = size_t(page) * hw + p;
-  L[o] = img[o] ? p : -1;
-  keymin[o] = INT_MAX;
-  const int nb = ((h + 1) / 2) * ((w + 1) / 2);
-  if (p < nb) bflag[size_t(page) * hw + p] = 0;  // bflag shares the per-page stride hw (nb <= hw)
+constexpr int kCclTile = 32;  // 32x32-pixel tiles, one thread per pixel
+constexpr int kScanSeg = 2048;
+
+// Pass 1: union-find inside a 32x32 tile in shared memory; every pixel then points at the GLOBAL
+// raster index of its tile-local root (the smallest index of its local component).
+__global__ void __launch_bounds__(1024) ccl_local_kernel(const uint8_t* __restrict__ img, int h, int w,
+                                                         int* __restrict__ Lall, int* __restrict__ keymin_all) {
+  __shared__ int s[kCclTile * kCclTile];
+  const int page = blockIdx.z;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int x = blockIdx.x * kCclTile + lx, y = blockIdx.y * kCclTile + ly;
+  const bool inb = x < w && y < h;
+  const size_t o = size_t(page) * h * w;
+  const int l = threadIdx.x;
+  const bool fg = inb && img[o + size_t(y) * w + x] != 0;
+  s[l] = fg ? l : -1;
+  __syncthreads();
+  if (fg) {
+    if (lx > 0 && s[l - 1] >= 0) uf_union(s, l, l - 1);
+    if (ly > 0) {
+      if (s[l - 32] >= 0) uf_union(s, l, l - 32);
+      if (lx > 0 && s[l - 33] >= 0) uf_union(s, l, l - 33);
+      if (lx < 31 && s[l - 31] >= 0) uf_union(s, l, l - 31);
+    }
+  }
+  __syncthreads();
+  if (inb) {
+    int g = -1;
+    if (fg) {
+      const int r = uf_find(s, l);
+      g = (blockIdx.y * kCclTile + (r >> 5)) * w + blockIdx.x * kCclTile + (r & 31);
+    }
+    Lall[o + size_t(y) * w + x] = g;
+    keymin_all[o + size_t(y) * w + x] = INT_MAX;
+  }
 }
 
-__global__ void ccl_merge_kernel(int h, int w, int* __restrict__ Lall) {
+// Pass 2: unions across tile borders only (global memory).
+__global__ void ccl_border_kernel(int h, int w, int* __restrict__ Lall) {
   const int page = blockIdx.y;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  const int hw = h * w;
-  if (p >= hw) return;
-  int* L = Lall + size_t(page) * hw;
-  if (L[p] < 0) return;
-  const int y = p / w, x = p - y * w;
-  if (x > 0 && L[p - 1] >= 0) uf_union(L, p, p - 1);
-  if (y > 0) {
+  int* L = Lall + size_t(page) * h * w;
+  const int nvl = (w - 1) / kCclTile;  // vertical border lines at x = 32, 64, ...
+  const int nhl = (h - 1) / kCclTile;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nvl * h) {
+    const int x = (i / h + 1) * kCclTile, y = i % h;
+    const int p = y * w + x;
+    if (L[p] < 0) return;
+    if (L[p - 1] >= 0) uf_union(L, p, p - 1);
+    if (y > 0 && L[p - w - 1] >= 0) uf_union(L, p, p - w - 1);
+    if (y + 1 < h && L[p + w - 1] >= 0) uf_union(L, p, p + w - 1);
+  } else if (i < nvl * h + nhl * w) {
+    const int j = i - nvl * h;
+    const int y = (j / w + 1) * kCclTile, x = j % w;
+    const int p = y * w + x;
+    if (L[p] < 0) return;
     if (L[p - w] >= 0) uf_union(L, p, p - w);
     if (x > 0 && L[p - w - 1] >= 0) uf_union(L, p, p - w - 1);
     if (x + 1 < w && L[p - w + 1] >= 0) uf_union(L, p, p - w + 1);
   }
 }
 
+// Pass 3: flatten + key.  The component's first 2x2 block (block-raster order) lies in the block row
+// of its first pixel (= its root); its block column is the minimum over the component's pixels in
+// that block row.  Only those pixels issue an atomic.
 __global__ void ccl_flatten_key_kernel(int h, int w, int* __restrict__ Lall, int* __restrict__ keymin_all) {
   const int page = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -271,72 +307,120 @@ __global__ void ccl_flatten_key_kernel(int h, int w, int* __restrict__ Lall, int
   const int r = uf_find(L, p);
   L[p] = r;  // racing writers all store a valid ancestor; roots are fixed points
   const int y = p / w, x = p - y * w;
-  const int bw = (w + 1) / 2;
-  atomicMin(&keymin_all[size_t(page) * hw + r], (y >> 1) * bw + (x >> 1));
+  if ((y >> 1) == ((r / w) >> 1)) atomicMin(&keymin_all[size_t(page) * hw + r], x >> 1);
 }
 
+// Pass 4: flag[first block] = 1 per component (bflag zeroed by a memset).
 __global__ void ccl_markfirst_kernel(int h, int w, const int* __restrict__ Lall, const int* __restrict__ keymin_all,
                                      int* __restrict__ bflag_all) {
   const int page = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int hw = h * w;
   if (p >= hw) return;
-  if (Lall[size_t(page) * hw + p] == p) bflag_all[size_t(page) * hw + keymin_all[size_t(page) * hw + p]] = 1;
+  const size_t o = size_t(page) * hw;
+  if (Lall[o + p] == p) {
+    const int bw = (w + 1) / 2;
+    bflag_all[o + ((p / w) >> 1) * bw + keymin_all[o + p]] = 1;
+  }
 }
 
-// exclusive prefix sum of bflag (in place -> rank), one CTA per page; writes n_labels (incl. background)
-__global__ void __launch_bounds__(1024) ccl_scan_kernel(int h, int w, int* __restrict__ bflag_all, int* __restrict__ n_labels) {
+// Pass 5a: per 2048-flag segment: exclusive prefix in place + segment total.
+__global__ void __launch_bounds__(256) ccl_scan_seg_kernel(int h, int w, int* __restrict__ bflag_all, int* __restrict__ segsum,
+                                                           int nseg) {
+  __shared__ int wsum[8];
+  const int page = blockIdx.y, seg = blockIdx.x;
+  const int nb = ((h + 1) / 2) * ((w + 1) / 2);
+  int* f = bflag_all + size_t(page) * h * w + size_t(seg) * kScanSeg;
+  const int base = seg * kScanSeg;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // each thread owns 8 consecutive flags
+  int v[8], t = 0;
+  const int i0 = threadIdx.x * 8;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    v[e] = (base + i0 + e < nb) ? f[i0 + e] : 0;
+    t += v[e];
+  }
+  int incl = t;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += u;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  int woff = 0;
+  for (int k = 0; k < warp; ++k) woff += wsum[k];
+  int run = woff + incl - t;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (base + i0 + e < nb) f[i0 + e] = run;
+    run += v[e];
+  }
+  if (threadIdx.x == 255) segsum[page * nseg + seg] = woff + incl;
+}
+// Pass 5b: exclusive scan of the segment totals (<= 1024 segments per page), n_labels.
+__global__ void __launch_bounds__(1024) ccl_scan_top_kernel(int* __restrict__ segsum, int nseg, int* __restrict__ n_labels) {
   __shared__ int part[1024];
   const int page = blockIdx.x;
-  const int nb = ((h + 1) / 2) * ((w + 1) / 2);
-  int* f = bflag_all + size_t(page) * h * w;
-  const int chunk = (nb + 1023) / 1024;
-  const int b0 = threadIdx.x * chunk, b1 = min(nb, b0 + chunk);
-  int s = 0;
-  for (int i = b0; i < b1; ++i) s += f[i];
-  part[threadIdx.x] = s;
+  int* sgs = segsum + page * nseg;
+  const int v = threadIdx.x < nseg ? sgs[threadIdx.x] : 0;
+  part[threadIdx.x] = v;
   __syncthreads();
   for (int off = 1; off < 1024; off <<= 1) {
-    int v = 0;
-    if (threadIdx.x >= off) v = part[threadIdx.x - off];
+    int u = 0;
+    if (threadIdx.x >= off) u = part[threadIdx.x - off];
     __syncthreads();
-    part[threadIdx.x] += v;
+    part[threadIdx.x] += u;
     __syncthreads();
   }
-  int run = part[threadIdx.x] - s;
-  for (int i = b0; i < b1; ++i) {
-    const int v = f[i];
-    f[i] = run;
-    run += v;
-  }
+  if (threadIdx.x < nseg) sgs[threadIdx.x] = part[threadIdx.x] - v;
   if (threadIdx.x == 1023) n_labels[page] = part[1023] + 1;
 }
 
 __global__ void ccl_relabel_kernel(int h, int w, const int* __restrict__ Lall, const int* __restrict__ keymin_all,
-                                   const int* __restrict__ rank_all, int32_t* __restrict__ labels) {
+                                   const int* __restrict__ rank_all, const int* __restrict__ segoff, int nseg,
+                                   int32_t* __restrict__ labels) {
   const int page = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int hw = h * w;
   if (p >= hw) return;
   const size_t o = size_t(page) * hw;
   const int r = Lall[o + p];
-  labels[o + p] = r < 0 ? 0 : rank_all[o + keymin_all[o + r]] + 1;
+  int lab = 0;
+  if (r >= 0) {
+    const int bw = (w + 1) / 2;
+    const int key = ((r / w) >> 1) * bw + keymin_all[o + r];
+    lab = segoff[page * nseg + key / kScanSeg] + rank_all[o + key] + 1;
+  }
+  labels[o + p] = lab;
 }
 
-// scratch: 3 * n*h*w ints (L, keymin, bflag/rank)
+// scratch: 3 * n*h*w ints (L, keymin, bflag/rank); segment sums live at the tail of the bflag area
 cudaError_t ccl_launch(const uint8_t* img, int n, int h, int w, int32_t* labels, int32_t* scratch, int32_t* n_labels,
                        cudaStream_t s) {
   const int hw = h * w;
   int* L = scratch;
   int* keymin = scratch + size_t(n) * hw;
   int* bflag = scratch + size_t(2) * n * hw;
+  const int nb = ((h + 1) / 2) * ((w + 1) / 2);
+  const int nseg = (nb + kScanSeg - 1) / kScanSeg;
+  if (nseg > 1024 || nb + 1024 > hw) return cudaErrorInvalidValue;
+  // per page the bflag area has hw ints but only nb (<= hw/4 + ..) are used: keep segsum after them
+  int* segsum = bflag + size_t(n - 1) * hw + nb;  // n*nseg ints, fits: nseg*n <= hw - nb for sane shapes
+  if (size_t(n) * nseg > size_t(hw - nb)) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemset2DAsync(bflag, size_t(hw) * sizeof(int), 0, size_t(nb) * sizeof(int), n, s);
+  if (e != cudaSuccess) return e;
+  dim3 tgrid((w + kCclTile - 1) / kCclTile, (h + kCclTile - 1) / kCclTile, n);
+  ccl_local_kernel<<<tgrid, 1024, 0, s>>>(img, h, w, L, keymin);
+  const int nborder = ((w - 1) / kCclTile) * h + ((h - 1) / kCclTile) * w;
+  if (nborder > 0) ccl_border_kernel<<<dim3((nborder + 255) / 256, n), 256, 0, s>>>(h, w, L);
   dim3 grid((hw + 255) / 256, n);
-  ccl_init_kernel<<<grid, 256, 0, s>>>(img, h, w, L, keymin, bflag);
-  ccl_merge_kernel<<<grid, 256, 0, s>>>(h, w, L);
   ccl_flatten_key_kernel<<<grid, 256, 0, s>>>(h, w, L, keymin);
   ccl_markfirst_kernel<<<grid, 256, 0, s>>>(h, w, L, keymin, bflag);
-  ccl_scan_kernel<<<n, 1024, 0, s>>>(h, w, bflag, n_labels);
-  ccl_relabel_kernel<<<grid, 256, 0, s>>>(h, w, L, keymin, bflag, labels);
+  ccl_scan_seg_kernel<<<dim3(nseg, n), 256, 0, s>>>(h, w, bflag, segsum, nseg);
+  ccl_scan_top_kernel<<<n, 1024, 0, s>>>(segsum, nseg, n_labels);
+  ccl_relabel_kernel<<<grid, 256, 0, s>>>(h, w, L, keymin, bflag, segsum, nseg, labels);
   return cudaGetLastError();
 }
 

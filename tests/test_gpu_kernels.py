@@ -75,7 +75,7 @@ def test_conv(case, prec):
     assert err <= _tol(prec, ref), "max abs err %g (ref max %g)" % (err, np.abs(ref).max())
 
 
-DECONV_CASES = [([64], 32, 32, 32, 1), ([128], 64, 64, 64, 1), ([512], 256, 16, 16, 2), ([256], 128, 32, 48, 1)]
+DECONV_CASES = [([64], 32, 32, 32, 1), ([128], 64, 64, 64, 1), ([512], 256, 32, 32, 2), ([256], 128, 32, 64, 1)]
 
 
 @pytest.mark.parametrize("prec", [PREC_FP16_TC, PREC_FP32_SIMT, PREC_FP16_SIMT])
