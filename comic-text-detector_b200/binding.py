@@ -32,9 +32,15 @@ class CtdConfig(C.Structure):
                 ("debug_skip_postproc", C.c_int32)]
 
 
+class CtdDeviceOutputs(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("stream", "mask_u8", "det", "det_count", "bitmap", "labels", "n_labels",
+                                          "results_base")] + [("results_bytes", C.c_size_t)]
+
+
 EXPORTS = ["ctd_create", "ctd_destroy", "ctd_last_error", "ctd_forward", "ctd_get_net_outputs", "ctd_get_mask_u8",
            "ctd_get_detections", "ctd_get_db_components", "ctd_last_forward_ms", "ctd_last_launch_count",
-           "ctd_debug_read_buffer", "ctd_debug_write_buffer", "ctd_connected_components", "ctd_nms"]
+           "ctd_debug_read_buffer", "ctd_debug_write_buffer", "ctd_connected_components", "ctd_nms",
+           "ctd_timer_start", "ctd_timer_stop", "ctd_profile_forward", "ctd_get_device_outputs"]
 
 _lib = None
 
@@ -70,6 +76,10 @@ def load_library():
     lib.ctd_debug_write_buffer.argtypes = [vp, i32, vp, i32, i32, i32]
     lib.ctd_connected_components.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp]
     lib.ctd_nms.argtypes = [vp, vp, i32, C.c_float, C.c_float, vp, vp]
+    lib.ctd_timer_start.argtypes = [vp]
+    lib.ctd_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.ctd_profile_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32]
+    lib.ctd_get_device_outputs.argtypes = [vp, C.POINTER(CtdDeviceOutputs)]
     for name in EXPORTS[3:]:
         getattr(lib, name).restype = C.c_int
     _lib = lib
@@ -189,6 +199,33 @@ class Engine:
         out = np.empty((n, h // d, w // d, ch), np.float32)
         self._ck(self.lib.ctd_debug_read_buffer(self.h, tensor["buf"], _ptr(out), out.size))
         return out[..., tensor["coff"]:tensor["coff"] + tensor["c"]]
+
+    def timer_start(self):
+        self._ck(self.lib.ctd_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._ck(self.lib.ctd_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile_forward(self, pages=None, dev_ptr=None, shape=None):
+        """per-op device milliseconds of one un-graphed forward: (op_ms[n_ops], nms_ms, ccl_ms)."""
+        nops = len(self.program.ops)
+        out = np.zeros((nops + 2,), np.float32)
+        if pages is not None:
+            pages = np.ascontiguousarray(pages, dtype=np.uint8)
+            n, h, w, _ = pages.shape
+            self._ck(self.lib.ctd_profile_forward(self.h, _ptr(pages), n, h, w, 0, _ptr(out), out.size))
+        else:
+            n, h, w = shape
+            self._ck(self.lib.ctd_profile_forward(self.h, C.c_void_p(dev_ptr), n, h, w, 1, _ptr(out), out.size))
+        self.shape = (n, h, w)
+        return out[:nops], float(out[nops]), float(out[nops + 1])
+
+    def device_outputs(self):
+        o = CtdDeviceOutputs()
+        self._ck(self.lib.ctd_get_device_outputs(self.h, C.byref(o)))
+        return o
 
     def debug_write(self, tensor, arr, n, h, w):
         """fill a whole buffer (all its channels) from float32 [n][h/down][w/down][channels]."""

@@ -34,7 +34,8 @@ struct ctd_handle {
   std::vector<ctd_bufdesc> bufs;
   std::string err;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
+  std::vector<cudaEvent_t> op_events;
   PFN_encodeTiled enc = nullptr;
   char* d_blob = nullptr;
   size_t blob_bytes = 0;
@@ -43,7 +44,8 @@ struct ctd_handle {
   uint8_t* d_pages = nullptr;
   float* d_blks = nullptr;
   float* d_mask = nullptr;
-  uint8_t* d_mask_u8 = nullptr;
+  uint8_t* d_mask_u8 = nullptr;   // start of the contiguous result arena: mask_u8 | det | det_count | n_labels
+  size_t results_bytes = 0;
   float* d_lines = nullptr;
   uint8_t* d_bitmap = nullptr;
   float* d_det = nullptr;
@@ -88,10 +90,13 @@ extern "C" void ctd_destroy(ctd_handle* h) {
     if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
   for (void* p : h->d_buf) cudaFree(p);
   cudaFree(h->d_blob); cudaFree(h->d_pages); cudaFree(h->d_blks); cudaFree(h->d_mask); cudaFree(h->d_mask_u8);
-  cudaFree(h->d_lines); cudaFree(h->d_bitmap); cudaFree(h->d_det); cudaFree(h->d_det_count); cudaFree(h->d_labels);
-  cudaFree(h->d_nlabels); cudaFree(h->d_ccl_scratch); cudaFree(h->d_nms_ws);
+  cudaFree(h->d_lines); cudaFree(h->d_bitmap); cudaFree(h->d_labels);
+  cudaFree(h->d_ccl_scratch); cudaFree(h->d_nms_ws);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->tev0) cudaEventDestroy(h->tev0);
+  if (h->tev1) cudaEventDestroy(h->tev1);
+  for (auto e : h->op_events) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -127,6 +132,8 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CKC(cudaEventCreate(&h->ev0));
   CKC(cudaEventCreate(&h->ev1));
+  CKC(cudaEventCreate(&h->tev0));
+  CKC(cudaEventCreate(&h->tev1));
   {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -153,13 +160,19 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
   CKC(cudaMalloc(&h->d_pages, px * 3));
   CKC(cudaMalloc(&h->d_blks, nb * rows_per_image(mh, mw) * no * sizeof(float)));
   CKC(cudaMalloc(&h->d_mask, px * 4));
-  CKC(cudaMalloc(&h->d_mask_u8, px));
   CKC(cudaMalloc(&h->d_lines, px * 2 * 4));
   CKC(cudaMalloc(&h->d_bitmap, px));
-  CKC(cudaMalloc(&h->d_det, nb * 300 * 6 * 4));
-  CKC(cudaMalloc(&h->d_det_count, nb * 4));
   CKC(cudaMalloc(&h->d_labels, px * 4));
-  CKC(cudaMalloc(&h->d_nlabels, nb * 4));
+  {
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t o_det = al(px), o_cnt = o_det + al(nb * 300 * 6 * 4), o_nl = o_cnt + al(nb * 4);
+    h->results_bytes = o_nl + al(nb * 4);
+    CKC(cudaMalloc(&h->d_mask_u8, h->results_bytes));
+    CKC(cudaMemset(h->d_mask_u8, 0, h->results_bytes));
+    h->d_det = reinterpret_cast<float*>(h->d_mask_u8 + o_det);
+    h->d_det_count = reinterpret_cast<int*>(h->d_mask_u8 + o_cnt);
+    h->d_nlabels = reinterpret_cast<int32_t*>(h->d_mask_u8 + o_nl);
+  }
   CKC(cudaMalloc(&h->d_ccl_scratch, px * 4 * 3));
   const int cap = 4096;
   CKC(cudaMalloc(&h->d_nms_ws, nms_workspace_bytes(int(nb), cap)));
@@ -313,8 +326,10 @@ static int run_op_thin(ctd_handle* h, const ctd_op& op, int n, int ph, int pw) {
   }
 }
 
-static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* launches) {
+static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* launches, bool record = false) {
   int cnt = 0;
+  size_t evi = 0;
+  if (record) CK(cudaEventRecord(h->op_events[evi++], h->stream));
   for (size_t i = 0; i < h->ops.size(); ++i) {
     const ctd_op& op = h->ops[i];
     const bool gemm = op.kind == CTD_OP_CONV || op.kind == CTD_OP_DECONV4 || op.kind == CTD_OP_DETECT;
@@ -333,6 +348,7 @@ static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* lau
     }
     if (rc) return rc;
     ++cnt;
+    if (record) CK(cudaEventRecord(h->op_events[evi++], h->stream));
   }
   *launches = cnt;
   if (h->cfg.debug_skip_postproc) return CTD_OK;
@@ -341,8 +357,10 @@ static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* lau
   CK(nms_launch(h->d_blks, n, rows, h->cfg.nc, h->cfg.conf_thresh, h->cfg.nms_thresh, h->nms, h->d_det,
                 h->d_det_count, h->stream));
   cnt += 4;
+  if (record) CK(cudaEventRecord(h->op_events[evi++], h->stream));
   CK(ccl_launch(h->d_bitmap, n, ph, pw, h->d_labels, h->d_ccl_scratch, h->d_nlabels, h->stream));
   cnt += 8;
+  if (record) CK(cudaEventRecord(h->op_events[evi++], h->stream));
   *launches = cnt;
   return CTD_OK;
 }
@@ -450,6 +468,70 @@ extern "C" int ctd_last_launch_count(ctd_handle* h, int32_t* launches) {
   NEED_FWD();
   if (!launches) return CTD_E_INVALID;
   *launches = h->last_launches;
+  return CTD_OK;
+}
+
+extern "C" int ctd_timer_start(ctd_handle* h) {
+  if (!h) return CTD_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventRecord(h->tev0, h->stream));
+  return CTD_OK;
+}
+extern "C" int ctd_timer_stop(ctd_handle* h, float* ms) {
+  if (!h || !ms) return CTD_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventRecord(h->tev1, h->stream));
+  CK(cudaEventSynchronize(h->tev1));
+  CK(cudaEventElapsedTime(ms, h->tev0, h->tev1));
+  return CTD_OK;
+}
+
+extern "C" int ctd_profile_forward(ctd_handle* h, const uint8_t* pages, int32_t n, int32_t ph, int32_t pw,
+                                   int32_t pages_on_device, float* op_ms, int32_t cap) {
+  if (!h || !pages || !op_ms) return CTD_E_INVALID;
+  const int need = int(h->ops.size()) + 2;
+  if (cap < need) return fail(h, CTD_E_INVALID, "op_ms needs %d entries", need);
+  if (n < 1 || n > h->cfg.max_batch || ph % 64 || pw % 64 || ph > h->cfg.max_h || pw > h->cfg.max_w)
+    return fail(h, CTD_E_SHAPE, "bad shape");
+  CK(cudaSetDevice(h->cfg.device));
+  while (int(h->op_events.size()) < need + 1) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    h->op_events.push_back(e);
+  }
+  auto key = std::make_tuple(int(n), int(ph), int(pw));
+  auto it = h->plans.find(key);
+  if (it == h->plans.end()) {
+    ShapePlan sp;
+    if (int rc = build_plans(h, n, ph, pw, sp)) return rc;
+    it = h->plans.emplace(key, std::move(sp)).first;
+  }
+  CK(cudaMemcpyAsync(h->d_pages, pages, size_t(n) * ph * pw * 3,
+                     pages_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+  int launches = 0;
+  if (int rc = run_ops(h, n, ph, pw, it->second, &launches, true)) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  const int nev = h->cfg.debug_skip_postproc ? int(h->ops.size()) : need;
+  for (int i = 0; i < need; ++i) op_ms[i] = 0.f;
+  for (int i = 0; i < nev; ++i) CK(cudaEventElapsedTime(&op_ms[i], h->op_events[i], h->op_events[i + 1]));
+  h->n = n; h->ph = ph; h->pw = pw;
+  h->have_forward = true;
+  h->last_launches = launches;
+  return CTD_OK;
+}
+
+extern "C" int ctd_get_device_outputs(ctd_handle* h, ctd_device_outputs* out) {
+  NEED_FWD();
+  if (!out) return CTD_E_INVALID;
+  out->stream = h->stream;
+  out->mask_u8 = h->d_mask_u8;
+  out->det = h->d_det;
+  out->det_count = h->d_det_count;
+  out->bitmap = h->d_bitmap;
+  out->labels = h->d_labels;
+  out->n_labels = h->d_nlabels;
+  out->results_base = h->d_mask_u8;
+  out->results_bytes = h->results_bytes;
   return CTD_OK;
 }
 

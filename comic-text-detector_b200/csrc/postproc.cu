@@ -235,8 +235,10 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
 constexpr int kCclTile = 32;  // 32x32-pixel tiles, one thread per pixel
 constexpr int kScanSeg = 2048;
 
-// Pass 1: union-find inside a 32x32 tile in shared memory; every pixel then points at the GLOBAL
-// raster index of its tile-local root (the smallest index of its local component).
+// Pass 1: union-find inside a 32x32 tile in shared memory (one warp per tile row).  Every pixel
+// starts as the first pixel of its horizontal run (ballot + clz, no chains inside a row); vertical /
+// diagonal contacts with the row above are then united.  Afterwards every pixel points at the
+// GLOBAL raster index of its tile-local root (the smallest index of its local component).
 __global__ void __launch_bounds__(1024) ccl_local_kernel(const uint8_t* __restrict__ img, int h, int w,
                                                          int* __restrict__ Lall, int* __restrict__ keymin_all) {
   __shared__ int s[kCclTile * kCclTile];
@@ -247,12 +249,18 @@ __global__ void __launch_bounds__(1024) ccl_local_kernel(const uint8_t* __restri
   const size_t o = size_t(page) * h * w;
   const int l = threadIdx.x;
   const bool fg = inb && img[o + size_t(y) * w + x] != 0;
-  s[l] = fg ? l : -1;
+  const unsigned m = __ballot_sync(0xffffffffu, fg);
+  const unsigned zeros_below = ~m & ((1u << lx) - 1u);
+  const int start = zeros_below ? 32 - __clz(zeros_below) : 0;
+  s[l] = fg ? (ly << 5) + start : -1;
   __syncthreads();
-  if (fg) {
-    if (lx > 0 && s[l - 1] >= 0) uf_union(s, l, l - 1);
-    if (ly > 0) {
-      if (s[l - 32] >= 0) uf_union(s, l, l - 32);
+  if (fg && ly > 0) {
+    const bool un = s[l - 32] >= 0;
+    if (un) {
+      // N contact: only the first pixel of each (current run x upper run) overlap issues the union
+      const bool first = (lx == start) || s[l - 33] < 0;
+      if (first) uf_union(s, l, l - 32);
+    } else {
       if (lx > 0 && s[l - 33] >= 0) uf_union(s, l, l - 33);
       if (lx < 31 && s[l - 31] >= 0) uf_union(s, l, l - 31);
     }
@@ -405,7 +413,7 @@ cudaError_t ccl_launch(const uint8_t* img, int n, int h, int w, int32_t* labels,
   int* bflag = scratch + size_t(2) * n * hw;
   const int nb = ((h + 1) / 2) * ((w + 1) / 2);
   const int nseg = (nb + kScanSeg - 1) / kScanSeg;
-  if (nseg > 1024 || nb + 1024 > hw) return cudaErrorInvalidValue;
+  if (nseg > 1024) return cudaErrorInvalidValue;
   // per page the bflag area has hw ints but only nb (<= hw/4 + ..) are used: keep segsum after them
   int* segsum = bflag + size_t(n - 1) * hw + nb;  // n*nseg ints, fits: nseg*n <= hw - nb for sane shapes
   if (size_t(n) * nseg > size_t(hw - nb)) return cudaErrorInvalidValue;

@@ -160,6 +160,30 @@ CTD_API int ctd_debug_read_buffer(ctd_handle* h, int32_t buf, float* out, size_t
  * storage type) for a forward of shape (n, ph, pw); used with programs that have no STEM op.  */
 CTD_API int ctd_debug_write_buffer(ctd_handle* h, int32_t buf, const float* in, int32_t n, int32_t ph, int32_t pw);
 
+/* ---- measurement / interop ------------------------------------------------------------------
+ * CUDA-event timer on the ENGINE stream (bench.py times K forwards between start and stop).    */
+CTD_API int ctd_timer_start(ctd_handle* h);
+CTD_API int ctd_timer_stop(ctd_handle* h, float* ms); /* synchronises the engine stream          */
+/* One un-graphed forward with an event after every op: op_ms[i] = device ms of op i; the two
+ * entries after the last op are the NMS and the CCL stage.  cap >= n_ops + 2.                   */
+CTD_API int ctd_profile_forward(ctd_handle* h, const uint8_t* pages, int32_t n, int32_t ph, int32_t pw,
+                                int32_t pages_on_device, float* op_ms, int32_t cap);
+/* Device pointers of the last forward's results (valid until the next call on this handle) and
+ * the engine's cudaStream_t, so a caller can hand them to NCCL without a host round trip.       */
+typedef struct ctd_device_outputs {
+  void* stream;      /* cudaStream_t                                  */
+  void* mask_u8;     /* u8  [n][h][w]                                 */
+  void* det;         /* f32 [n][300][6]                               */
+  void* det_count;   /* i32 [n]                                       */
+  void* bitmap;      /* u8  [n][h][w]                                 */
+  void* labels;      /* i32 [n][h][w]                                 */
+  void* n_labels;    /* i32 [n]                                       */
+  void* results_base;   /* mask_u8 | det | det_count | n_labels live in ONE allocation sized for
+                           max_batch, so a single NCCL gather moves a rank's results          */
+  size_t results_bytes;
+} ctd_device_outputs;
+CTD_API int ctd_get_device_outputs(ctd_handle* h, ctd_device_outputs* out);
+
 /* ---- stand-alone array kernels (stage-isolated parity; same kernels the pipeline uses) --
  * cv2.connectedComponentsWithStats(img, connectivity=8, ltype=CV_32S) as the reference
  * effectively calls it (utils/textmask.py:93,113,138).
