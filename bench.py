@@ -62,13 +62,13 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self.reasons = set()
         self.max_mhz = None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip().split(",")
@@ -79,10 +79,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._halt.wait(0.1)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
@@ -113,7 +113,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import synth
-    cores = os.cpu_count()
+    cores = min(os.cpu_count(), args.cpu_threads)
     torch.set_num_threads(cores)
     run = cpu_pipeline_factory(1024, 1024)
     pages = [synth.structured_page(1000 + i) for i in range(max(1, args.cpu_pages))]
@@ -147,6 +147,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="pages per GPU per step")
     ap.add_argument("--cpu-pages", type=int, default=1, help="pages per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=32,
+                    help="torch intra-op threads of the CPU arm (oneDNN stops scaling long before 128 threads)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -283,12 +285,12 @@ def main():
             "stage_ms": {"conv_tc": tc_ms, "other_ops": float(op_ms.sum()) - tc_ms, "nms": nms_ms, "ccl": ccl_ms},
         }
         if not args.no_cpu_baseline and world == 1:
-            cores = os.cpu_count()
+            cores = min(os.cpu_count(), args.cpu_threads)
             torch.set_num_threads(cores)
             run = cpu_pipeline_factory(H, W)
             run(pages[0])
             t0 = time.perf_counter()
-            ncpu = 3
+            ncpu = 1
             for i in range(ncpu):
                 run(pages[i % B])
             dt = time.perf_counter() - t0

@@ -27,16 +27,20 @@
 
 namespace ctd {
 
-constexpr int kTileW = 16, kTileH = 8;  // 128 grid pixels per CTA
-constexpr int kThreads = 192;
+constexpr int kTileW = 16, kTileH = 8;  // 128 grid pixels per tile
+constexpr int kThreads = 256;           // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+constexpr int kEpiWarp0 = 4;
 
 template <int BN>
 struct TcCfg {
-  static constexpr int kStages = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);  // <=113 KB each: 2 CTAs/SM
   static constexpr int kABytes = 128 * 128;  // per stage (worst case 128-byte rows)
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static constexpr size_t kSmem = 1024 /*align slack*/ + size_t(kStages) * (kABytes + kBBytes) + 256 + BN * 4;
+  // one persistent CTA per SM: fill ~200 KB with pipeline stages
+  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kAccStages = 2;                                  // TMEM accumulator ping-pong
+  static constexpr int kTmemCols = (BN < 32 ? 32 : BN) * kAccStages;    // power of two >= 32
+  static constexpr int kBiasFloats = 512;
+  static constexpr size_t kSmem = 1024 /*align slack*/ + size_t(kStages) * (kABytes + kBBytes) + 256 + kBiasFloats * 4;
 };
 
 template <int ACT>
@@ -131,34 +135,29 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + Cfg::kStages * Cfg::kABytes;
   const uint32_t bar_base = b_base + Cfg::kStages * Cfg::kBBytes;
-  // barriers: full[s] at +8s, empty[s] at +8(S+s), tmem_full at +16S, tmem ptr at +16S+8
+  // barriers (8 B each): full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | tmem ptr
   const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * Cfg::kStages;
   const uint32_t tmem_full_bar = bar_base + 16 * Cfg::kStages;
-  const uint32_t tmem_ptr_addr = tmem_full_bar + 8;
+  const uint32_t tmem_empty_bar = tmem_full_bar + 16;
+  const uint32_t tmem_ptr_addr = tmem_empty_bar + 16;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_ptr_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::kStages * (Cfg::kABytes + Cfg::kBBytes) + 16 * Cfg::kStages + 8);
-
-  float* bias_s = reinterpret_cast<float*>(smem_gen + Cfg::kStages * (Cfg::kABytes + Cfg::kBBytes) + 256);
+  const size_t bar_off = size_t(Cfg::kStages) * (Cfg::kABytes + Cfg::kBBytes);
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 16 * Cfg::kStages + 32);
+  float* bias_s = reinterpret_cast<float*>(smem_gen + bar_off + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom& g = p.g;
-
-  // ---- tile coordinates
-  const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int img = blockIdx.x / tiles_per_img;
-  const int trem = blockIdx.x - img * tiles_per_img;
-  const int ty = trem / p.tiles_x, tx = trem - ty * p.tiles_x;
-  const int y0 = ty * kTileH, x0 = tx * kTileW;
-  const int nblk = blockIdx.y;
-  const int phase = blockIdx.z;
 
   const int kb = p.kb_elems;
   const uint32_t row_bytes = kb * 2;
   const uint32_t stage_tx = 128u * row_bytes + uint32_t(BN) * row_bytes;
   int kblocks_per_tap = 0;
   for (int s = 0; s < g.n_src; ++s) kblocks_per_tap += p.src_kblocks[s];
-  const int total_it = g.taps * kblocks_per_tap;
+  const int its_per_tile = g.taps * kblocks_per_tap;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int n_nblk = g.cout_pad / BN;
+  const int spatial_tiles = g.n_img * tiles_per_img;
+  const int total_tiles = spatial_tiles * n_nblk * g.n_phase;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < g.n_src; ++s)
@@ -168,126 +167,164 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < Cfg::kAccStages; ++s) {
+      mbar_init(tmem_full_bar + 8 * s, 1);
+      mbar_init(tmem_empty_bar + 8 * s, 128);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_addr, Cfg::kTmemCols);
-  for (int i = threadIdx.x; i < BN; i += kThreads) bias_s[i] = p.bias[nblk * BN + i];
+  if (warp == 2) tmem_alloc(tmem_ptr_addr, Cfg::kTmemCols);
+  for (int i = threadIdx.x; i < g.cout_pad && i < Cfg::kBiasFloats; i += kThreads) bias_s[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = *tmem_ptr_gen;
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  // tile index -> (phase, spatial tile, n block); n block varies fastest so that CTAs running
+  // concurrently share the A tile in L2
+  auto decode = [&](int t, int& phase, int& nblk, int& img, int& y0, int& x0) {
+    nblk = t % n_nblk;
+    const int r = t / n_nblk;
+    const int sp = r % spatial_tiles;
+    phase = r / spatial_tiles;
+    img = sp / tiles_per_img;
+    const int trem = sp - img * tiles_per_img;
+    const int ty = trem / p.tiles_x;
+    y0 = ty * kTileH;
+    x0 = (trem - ty * p.tiles_x) * kTileW;
+  };
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (elect_one()) {
       int it = 0;
-      for (int tap = 0; tap < g.taps; ++tap) {
-        const int dy = g.tap_dy[phase][tap], dx = g.tap_dx[phase][tap];
-        const int q = p.tap_map[phase][tap];
-        int kglob = tap * g.cin_total;
-        for (int s = 0; s < g.n_src; ++s) {
-          for (int cb = 0; cb < p.src_kblocks[s]; ++cb, ++it) {
-            const int stage = it % Cfg::kStages;
-            const uint32_t par = ((it / Cfg::kStages) & 1) ^ 1;
-            mbar_wait(empty_bar + 8 * stage, par);
-            mbar_arrive_expect_tx(full_bar + 8 * stage, stage_tx);
-            tma_load_4d(a_base + stage * Cfg::kABytes, &p.a_map[s][q], full_bar + 8 * stage, cb * kb, x0 + dx,
-                        y0 + dy, img);
-            tma_load_2d(b_base + stage * Cfg::kBBytes, &p.b_map, full_bar + 8 * stage, kglob + cb * kb,
-                        phase * g.cout_pad + nblk * BN);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int phase, nblk, img, y0, x0;
+        decode(t, phase, nblk, img, y0, x0);
+        for (int tap = 0; tap < g.taps; ++tap) {
+          const int dy = g.tap_dy[phase][tap], dx = g.tap_dx[phase][tap];
+          const int q = p.tap_map[phase][tap];
+          int kglob = tap * g.cin_total;
+          for (int s = 0; s < g.n_src; ++s) {
+            for (int cb = 0; cb < p.src_kblocks[s]; ++cb, ++it) {
+              const int stage = it % Cfg::kStages;
+              const uint32_t par = ((it / Cfg::kStages) & 1) ^ 1;
+              mbar_wait(empty_bar + 8 * stage, par);
+              mbar_arrive_expect_tx(full_bar + 8 * stage, stage_tx);
+              tma_load_4d(a_base + stage * Cfg::kABytes, &p.a_map[s][q], full_bar + 8 * stage, cb * kb, x0 + dx,
+                          y0 + dy, img);
+              tma_load_2d(b_base + stage * Cfg::kBBytes, &p.b_map, full_bar + 8 * stage, kglob + cb * kb,
+                          phase * g.cout_pad + nblk * BN);
+            }
+            kglob += g.src_c[s];
           }
-          kglob += g.src_c[s];
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
     const uint32_t idesc = make_idesc_f16(BN);
-    for (int it = 0; it < total_it; ++it) {
-      const int stage = it % Cfg::kStages;
-      const uint32_t par = (it / Cfg::kStages) & 1;
-      mbar_wait(full_bar + 8 * stage, par);
+    int it = 0, ti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      const int as = ti & 1;
+      mbar_wait(tmem_empty_bar + 8 * as, ((ti >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a_addr = a_base + stage * Cfg::kABytes;
-        const uint32_t b_addr = b_base + stage * Cfg::kBBytes;
-        const int ksteps = kb / 16;
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t ad = make_kmajor_desc(a_addr + k * 32, row_bytes);
-          const uint64_t bd = make_kmajor_desc(b_addr + k * 32, row_bytes);
-          umma_f16(tmem_d, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+      const uint32_t tmem_d = tmem_base + uint32_t(as * BN);
+      for (int k_it = 0; k_it < its_per_tile; ++k_it, ++it) {
+        const int stage = it % Cfg::kStages;
+        const uint32_t par = (it / Cfg::kStages) & 1;
+        mbar_wait(full_bar + 8 * stage, par);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = a_base + stage * Cfg::kABytes;
+          const uint32_t b_addr = b_base + stage * Cfg::kBBytes;
+          const int ksteps = kb / 16;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ad = make_kmajor_desc(a_addr + k * 32, row_bytes);
+            const uint64_t bd = make_kmajor_desc(b_addr + k * 32, row_bytes);
+            umma_f16(tmem_d, ad, bd, idesc, (k_it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + 8 * stage);
+          if (k_it == its_per_tile - 1) umma_commit(tmem_full_bar + 8 * as);
         }
-        umma_commit(empty_bar + 8 * stage);
-        if (it == total_it - 1) umma_commit(tmem_full_bar);
+        __syncwarp();
       }
-      __syncwarp();
     }
-  } else {
+  } else if (warp >= kEpiWarp0) {
     // =============================== epilogue ====================================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;
     const int py = row / kTileW, px = row - py * kTileW;
-    const int gy = y0 + py, gx = x0 + px;
-    const bool valid = gy < g.gh && gx < g.gw;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int ph_y = phase >> 1, ph_x = phase & 1;
-    const int oy = gy * g.out_mul + ph_y, ox = gx * g.out_mul + ph_x;
-    const uint32_t tmem_row = tmem_d + (uint32_t(quad * 32) << 16);
-    if (p.dst != nullptr) {
-      __half* out = p.dst + (size_t(img) * g.dst_h * g.dst_w + size_t(valid ? oy : 0) * g.dst_w + (valid ? ox : 0)) * g.dst_cstride +
-                    g.dst_coff + nblk * BN;
-      const int cout_left = g.cout - nblk * BN;
+    int ti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      int phase, nblk, img, y0, x0;
+      decode(t, phase, nblk, img, y0, x0);
+      const int as = ti & 1;
+      const int gy = y0 + py, gx = x0 + px;
+      const bool valid = gy < g.gh && gx < g.gw;
+      mbar_wait(tmem_full_bar + 8 * as, (ti >> 1) & 1);
+      tc_fence_after();
+      const int ph_y = phase >> 1, ph_x = phase & 1;
+      const int oy = gy * g.out_mul + ph_y, ox = gx * g.out_mul + ph_x;
+      const uint32_t tmem_row = tmem_base + uint32_t(as * BN) + (uint32_t(quad * 32) << 16);
+      const float* bias_t = bias_s + nblk * BN;
+      if (p.dst != nullptr) {
+        __half* out = p.dst + (size_t(img) * g.dst_h * g.dst_w + size_t(valid ? oy : 0) * g.dst_w + (valid ? ox : 0)) * g.dst_cstride +
+                      g.dst_coff + nblk * BN;
+        const int cout_left = g.cout - nblk * BN;
 #define CTD_EPI(ACT)                                                                              \
-  if (g.residual) epilogue_store<BN, ACT, true>(tmem_row, bias_s, out, cout_left, valid);         \
-  else epilogue_store<BN, ACT, false>(tmem_row, bias_s, out, cout_left, valid);
-      switch (g.act) {
-        case CTD_ACT_SILU: CTD_EPI(CTD_ACT_SILU) break;
-        case CTD_ACT_LEAKY: CTD_EPI(CTD_ACT_LEAKY) break;
-        case CTD_ACT_RELU: CTD_EPI(CTD_ACT_RELU) break;
-        case CTD_ACT_SIGMOID: CTD_EPI(CTD_ACT_SIGMOID) break;
-        default: CTD_EPI(CTD_ACT_NONE) break;
-      }
-#undef CTD_EPI
-    } else {
-      // Detect decode (yolo.py:36-44): columns = anchor*(5+nc) + o
-      constexpr int kChunk = BN >= 32 ? 32 : 16;
-      const int no = 5 + p.nc;
-      float* rows = p.blks + (size_t(img) * p.blks_rows_per_img + p.level_row0) * no;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += kChunk) {
-        uint32_t v[kChunk];
-        if constexpr (kChunk == 32) {
-          tmem_ld_32x32(tmem_row + uint32_t(c0), v);
-        } else {
-          tmem_ld_32x16(tmem_row + uint32_t(c0), reinterpret_cast<uint32_t(&)[16]>(v));
+  if (g.residual) epilogue_store<BN, ACT, true>(tmem_row, bias_t, out, cout_left, valid);         \
+  else epilogue_store<BN, ACT, false>(tmem_row, bias_t, out, cout_left, valid);
+        switch (g.act) {
+          case CTD_ACT_SILU: CTD_EPI(CTD_ACT_SILU) break;
+          case CTD_ACT_LEAKY: CTD_EPI(CTD_ACT_LEAKY) break;
+          case CTD_ACT_RELU: CTD_EPI(CTD_ACT_RELU) break;
+          case CTD_ACT_SIGMOID: CTD_EPI(CTD_ACT_SIGMOID) break;
+          default: CTD_EPI(CTD_ACT_NONE) break;
         }
-        tmem_ld_wait();
-        if (!valid) continue;
+#undef CTD_EPI
+      } else {
+        // Detect decode (yolo.py:36-44): columns = anchor*(5+nc) + o
+        constexpr int kChunk = BN >= 32 ? 32 : 16;
+        const int no = 5 + p.nc;
+        float* rows = p.blks + (size_t(img) * p.blks_rows_per_img + p.level_row0) * no;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += kChunk) {
+          uint32_t v[kChunk];
+          if constexpr (kChunk == 32) {
+            tmem_ld_32x32(tmem_row + uint32_t(c0), v);
+          } else {
+            tmem_ld_32x16(tmem_row + uint32_t(c0), reinterpret_cast<uint32_t(&)[16]>(v));
+          }
+          tmem_ld_wait();
+          if (!valid) continue;
 #pragma unroll
-        for (int j = 0; j < kChunk; ++j) {
-          const int col = nblk * BN + c0 + j;
-          if (col < g.cout) {
-            const int a = col / no, o = col - a * no;
-            const float s = 1.0f / (1.0f + expf(-(__uint_as_float(v[j]) + bias_s[c0 + j])));
-            float r;
-            if (o == 0) r = (s * 2.0f - 0.5f + float(gx)) * p.det_stride;
-            else if (o == 1) r = (s * 2.0f - 0.5f + float(gy)) * p.det_stride;
-            else if (o == 2) r = (s * 2.0f) * (s * 2.0f) * p.anchor_wh[2 * a];
-            else if (o == 3) r = (s * 2.0f) * (s * 2.0f) * p.anchor_wh[2 * a + 1];
-            else r = s;
-            rows[(size_t(a) * g.gh * g.gw + size_t(gy) * g.gw + gx) * no + o] = r;
+          for (int j = 0; j < kChunk; ++j) {
+            const int col = nblk * BN + c0 + j;
+            if (col < g.cout) {
+              const int a = col / no, o = col - a * no;
+              const float s = 1.0f / (1.0f + expf(-(__uint_as_float(v[j]) + bias_t[c0 + j])));
+              float r;
+              if (o == 0) r = (s * 2.0f - 0.5f + float(gx)) * p.det_stride;
+              else if (o == 1) r = (s * 2.0f - 0.5f + float(gy)) * p.det_stride;
+              else if (o == 2) r = (s * 2.0f) * (s * 2.0f) * p.anchor_wh[2 * a];
+              else if (o == 3) r = (s * 2.0f) * (s * 2.0f) * p.anchor_wh[2 * a + 1];
+              else r = s;
+              rows[(size_t(a) * g.gh * g.gw + size_t(gy) * g.gw + gx) * no + o] = r;
+            }
           }
         }
       }
+      // all of this thread's tcgen05.ld have completed (wait::ld): hand the accumulator back
+      tc_fence_before();
+      mbar_arrive(tmem_empty_bar + 8 * as);
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_d, Cfg::kTmemCols);
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -304,6 +341,8 @@ static const char* encode_map(PFN_encodeTiled enc, CUtensorMap* m, const void* b
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled failed";
 }
+
+static int g_num_sms = 148;
 
 static int pick_block_n(int cout_pad) {
   if (cout_pad >= 256 && cout_pad % 256 == 0) return 256;
@@ -374,7 +413,11 @@ const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
     cuuint32_t box[2] = {cuuint32_t(kb), cuuint32_t(bn)};
     if (const char* e = encode_map(enc, &p.b_map, w16, 2, dims, str, box, kb)) return e;
   }
-  plan.grid = dim3(unsigned(g.n_img * p.tiles_x * p.tiles_y), unsigned(g.cout_pad / bn), unsigned(g.n_phase));
+  {
+    const int total_tiles = g.n_img * p.tiles_x * p.tiles_y * (g.cout_pad / bn) * g.n_phase;
+    plan.grid = dim3(unsigned(total_tiles < g_num_sms ? total_tiles : g_num_sms), 1, 1);
+  }
+  if (g.cout_pad > 512) return "conv_tc: cout_pad > 512 not supported (bias staging)";
   switch (bn) {
     case 256: plan.smem_bytes = TcCfg<256>::kSmem; break;
     case 128: plan.smem_bytes = TcCfg<128>::kSmem; break;
@@ -387,6 +430,11 @@ const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
 
 cudaError_t conv_tc_init() {
   cudaError_t e;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) g_num_sms = n;
+  }
 #define CTD_SET(BN)                                                                                   \
   e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TcCfg<BN>::kSmem)); \
   if (e != cudaSuccess) return e;

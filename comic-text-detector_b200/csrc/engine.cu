@@ -598,7 +598,8 @@ extern "C" int ctd_connected_components(ctd_handle* h, const uint8_t* img, int32
   CK(cudaMemcpyAsync(n_labels, h->d_nlabels, 4, cudaMemcpyDeviceToHost, h->stream));
   if (stats && stats_cap > 0) {
     int32_t* d_stats = reinterpret_cast<int32_t*>(h->d_ccl_scratch);  // scratch is free again after ccl_launch
-    if (size_t(stats_cap) * 5 > px * 3) return fail(h, CTD_E_CAPACITY, "stats_cap too large");
+    if (size_t(stats_cap) * 5 > size_t(h->cfg.max_batch) * h->cfg.max_h * h->cfg.max_w * 3)
+      return fail(h, CTD_E_CAPACITY, "stats_cap too large");
     CK(ccl_stats_launch(h->d_labels, ih, iw, d_stats, stats_cap, h->stream));
     CK(cudaMemcpyAsync(stats, d_stats, size_t(stats_cap) * 5 * 4, cudaMemcpyDeviceToHost, h->stream));
   }

@@ -1,0 +1,123 @@
+"""TEST INFRASTRUCTURE: a slow CPU interpreter of the engine program (op list + weight blob) in
+torch fp32.  It executes exactly what comic-text-detector_b200/compiler.py emitted -- packed
+weights, K-concatenated sources, channel-offset destinations, in-place residuals, deconv phases --
+so the compiler / weight packing can be pinned against the oracle WITHOUT a GPU.  It shares no
+code with the CUDA kernels."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from ctd_b200 import compiler as cc
+
+
+def _act(x, a):
+    if a == cc.ACT_SILU:
+        return F.silu(x)
+    if a == cc.ACT_LEAKY:
+        return F.leaky_relu(x, 0.1)
+    if a == cc.ACT_RELU:
+        return F.relu(x)
+    if a == cc.ACT_SIGMOID:
+        return torch.sigmoid(x)
+    return x
+
+
+def _blob(prog, off, count, dtype):
+    return torch.from_numpy(np.frombuffer(prog.blob, dtype=dtype, count=count, offset=off).copy())
+
+
+def run_program(prog, pages, use_fp16_weights=False):
+    """pages u8 [n][h][w][3] -> (blks, mask, lines) like the engine's net outputs."""
+    n, h, w, _ = pages.shape
+    bufs = [torch.zeros(n, c, h // d, w // d) for c, d in prog.bufs]  # NCHW here
+    nc = prog.nc
+    no = 5 + nc
+    rows = 3 * ((h // 8) * (w // 8) + (h // 16) * (w // 16) + (h // 32) * (w // 32))
+    blks = torch.zeros(n, rows, no)
+    mask = lines = None
+    for op in prog.ops:
+        k = op["kind"]
+        srcs = [bufs[op["src_buf"][i]][:, op["src_coff"][i]:op["src_coff"][i] + op["src_c"][i]] for i in range(op["n_src"])]
+        cin = sum(op["src_c"][:op["n_src"]])
+        if k == cc.OP_STEM:
+            x = torch.from_numpy(np.ascontiguousarray(pages.transpose(0, 3, 1, 2)).astype(np.float32) / 255)
+            wt = _blob(prog, op["w32_off"], op["cout"] * 108, np.float32).view(op["cout"], 6, 6, 3).permute(0, 3, 1, 2)
+            b = _blob(prog, op["b_off"], op["cout"], np.float32)
+            y = _act(F.conv2d(x, wt, b, 2, 2), op["act"])
+            bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["cout"]] = y
+        elif k in (cc.OP_CONV, cc.OP_DETECT):
+            ks, st = op["ksize"], op["stride"]
+            K = ks * ks * cin
+            if use_fp16_weights:
+                wk = _blob(prog, op["w16_off"], op["cout_pad"] * K, np.float16).float()
+            else:
+                wk = _blob(prog, op["w32_off"], op["cout_pad"] * K, np.float32)
+            wt = wk.view(op["cout_pad"], ks, ks, cin)[:op["cout"]].permute(0, 3, 1, 2)
+            b = _blob(prog, op["b_off"], op["cout_pad"], np.float32)[:op["cout"]]
+            y = F.conv2d(torch.cat(srcs, 1), wt, b, st, ks // 2)
+            if k == cc.OP_CONV:
+                y = _act(y, op["act"])
+                dst = bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["cout"]]
+                if op["residual"]:
+                    y = y + dst
+                bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["cout"]] = y
+            else:
+                prm = _blob(prog, op["p_off"], 7, np.float32)
+                stride, anch = float(prm[0]), prm[1:].view(3, 2)
+                bs, _, ny, nx = y.shape
+                y = y.view(bs, 3, no, ny, nx).permute(0, 1, 3, 4, 2).sigmoid()
+                yv, xv = torch.meshgrid([torch.arange(ny), torch.arange(nx)], indexing="ij")
+                grid = torch.stack((xv, yv), 2).float()
+                out = y.clone()
+                out[..., 0:2] = (y[..., 0:2] * 2 - 0.5 + grid) * stride
+                out[..., 2:4] = (y[..., 2:4] * 2) ** 2 * anch.view(1, 3, 1, 1, 2)
+                r0 = sum(3 * (h // (8 << l)) * (w // (8 << l)) for l in range(op["aux"]))
+                blks[:, r0:r0 + 3 * ny * nx] = out.reshape(bs, -1, no)
+        elif k == cc.OP_DECONV4:
+            K = 4 * cin
+            wk = (_blob(prog, op["w16_off"], 4 * op["cout_pad"] * K, np.float16).float() if use_fp16_weights
+                  else _blob(prog, op["w32_off"], 4 * op["cout_pad"] * K, np.float32)).view(4, op["cout_pad"], 4, cin)
+            b = _blob(prog, op["b_off"], op["cout_pad"], np.float32)[:op["cout"]]
+            x = torch.cat(srcs, 1)
+            nb, _, ih, iw = x.shape
+            out = torch.zeros(nb, op["cout"], 2 * ih, 2 * iw)
+            d = ((0, -1), (1, 0))
+            xp = F.pad(x, (1, 1, 1, 1))
+            for ph in range(4):
+                py, px = ph >> 1, ph & 1
+                acc = torch.zeros(nb, op["cout"], ih, iw)
+                for t in range(4):
+                    dy, dx = d[py][t >> 1], d[px][t & 1]
+                    xs = xp[:, :, 1 + dy:1 + dy + ih, 1 + dx:1 + dx + iw]
+                    acc += torch.einsum("nchw,oc->nohw", xs, wk[ph, :op["cout"], t])
+                out[:, :, py::2, px::2] = acc
+            y = _act(out + b.view(1, -1, 1, 1), op["act"])
+            bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["cout"]] = y
+        elif k == cc.OP_AVGPOOL2:
+            bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["src_c"][0]] = F.avg_pool2d(srcs[0], 2, 2)
+        elif k == cc.OP_SPPF_POOL:
+            c = op["src_c"][0]
+            c0 = op["src_coff"][0]
+            y1 = F.max_pool2d(srcs[0], 5, 1, 2)
+            y2 = F.max_pool2d(y1, 5, 1, 2)
+            y3 = F.max_pool2d(y2, 5, 1, 2)
+            B = bufs[op["src_buf"][0]]
+            B[:, c0 + c:c0 + 2 * c], B[:, c0 + 2 * c:c0 + 3 * c], B[:, c0 + 3 * c:c0 + 4 * c] = y1, y2, y3
+        elif k == cc.OP_UPSAMPLE2:
+            bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["src_c"][0]] = F.interpolate(srcs[0], scale_factor=2, mode="nearest")
+        elif k == cc.OP_SEG_TAIL:
+            c = op["src_c"][0]
+            wt = _blob(prog, op["p_off"], c * 16, np.float32).view(c, 1, 4, 4)
+            mask = torch.sigmoid(F.conv_transpose2d(srcs[0], wt, None, 2, 1))
+        elif k == cc.OP_DB_TAIL:
+            prm = _blob(prog, op["p_off"], 2 * 1105, np.float32)
+            outs = []
+            for b_ in range(2):
+                q = prm[b_ * 1105:(b_ + 1) * 1105]
+                w3, b3 = q[:1024].view(16, 16, 2, 2), q[1024:1040]
+                w6, b6 = q[1040:1104].view(16, 1, 2, 2), q[1104:1105]
+                x = srcs[0][:, b_ * 16:(b_ + 1) * 16]
+                t = F.relu(F.conv_transpose2d(x, w3, b3, 2))
+                outs.append(torch.sigmoid(F.conv_transpose2d(t, w6, b6, 2)))
+            lines = torch.cat(outs, 1)
+    return blks, mask, lines
