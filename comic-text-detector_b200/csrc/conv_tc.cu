@@ -359,8 +359,9 @@ const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
   p.g = g;
   int kb = 64;
   for (int s = 0; s < g.n_src; ++s) {
-    if (g.src_c[s] % 64 != 0) kb = 32;
-    if (g.src_c[s] % 32 != 0) return "conv_tc: source channels must be a multiple of 32";
+    if (g.src_c[s] % 64 != 0 && kb > 32) kb = 32;
+    if (g.src_c[s] % 32 != 0) kb = 16;
+    if (g.src_c[s] % 16 != 0) return "conv_tc: source channels must be a multiple of 16";
     if (src_coff[s] % 8 != 0) return "conv_tc: source channel offset must be a multiple of 8";
   }
   if ((g.dst_coff % 8) != 0 || (g.dst_cstride % 8) != 0) return "conv_tc: destination slice must be 16-byte aligned";

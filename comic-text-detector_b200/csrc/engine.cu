@@ -293,7 +293,7 @@ static int run_op_simt(ctd_handle* h, const ctd_op& op, int n, int ph, int pw) {
 template <typename T>
 static int run_op_thin(ctd_handle* h, const ctd_op& op, int n, int ph, int pw) {
   cudaStream_t s = h->stream;
-  const ctd_bufdesc* sb = op.kind == CTD_OP_STEM ? nullptr : &h->bufs[op.src_buf[0]];
+  const ctd_bufdesc* sb = (op.kind == CTD_OP_STEM || op.kind == CTD_OP_S2D) ? nullptr : &h->bufs[op.src_buf[0]];
   const int sh = sb ? ph / sb->down : ph, sw = sb ? pw / sb->down : pw;
   const T* src = sb ? static_cast<const T*>(h->d_buf[op.src_buf[0]]) + op.src_coff[0] : nullptr;
   switch (op.kind) {
@@ -301,6 +301,10 @@ static int run_op_thin(ctd_handle* h, const ctd_op& op, int n, int ph, int pw) {
       CK(stem_launch<T>(h->d_pages, n, ph, pw, reinterpret_cast<const float*>(h->d_blob + op.w32_off),
                         reinterpret_cast<const float*>(h->d_blob + op.b_off), static_cast<T*>(h->d_buf[op.dst_buf]),
                         h->bufs[op.dst_buf].channels, op.dst_coff, op.cout, op.act, s));
+      return CTD_OK;
+    case CTD_OP_S2D:
+      CK(s2d_launch<T>(h->d_pages, n, ph, pw, static_cast<T*>(h->d_buf[op.dst_buf]), h->bufs[op.dst_buf].channels,
+                       op.dst_coff, s));
       return CTD_OK;
     case CTD_OP_AVGPOOL2:
       CK(avgpool2_launch<T>(src, n, sh, sw, op.src_c[0], sb->channels,

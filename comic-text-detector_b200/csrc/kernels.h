@@ -96,6 +96,9 @@ cudaError_t conv_simt_launch(const ConvSimtParams& p, cudaStream_t s);
 template <typename T>
 cudaError_t stem_launch(const uint8_t* pages, int n, int h, int w, const float* wgt /*[32][108] (ky,kx,c)*/,
                         const float* bias, T* dst, int dst_cstride, int dst_coff, int cout, int act, cudaStream_t s);
+// u8 BGR HWC page -> /255 -> space-to-depth(2): dst[n][h/2][w/2][16], channel = (dy*2+dx)*3 + c, 12..15 = 0
+template <typename T>
+cudaError_t s2d_launch(const uint8_t* pages, int n, int h, int w, T* dst, int dst_cstride, int dst_coff, cudaStream_t s);
 template <typename T>
 cudaError_t avgpool2_launch(const T* src, int n, int h, int w, int c, int src_cstride, T* dst, int dst_cstride,
                             cudaStream_t s);

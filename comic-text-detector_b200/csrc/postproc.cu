@@ -153,16 +153,30 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
   mask[(size_t(img) * cap + i) * (cap / 64) + cb] = bits;
 }
 
-// greedy scan (one warp per page), keeps at most max_det rows
+// greedy scan (one warp per page), keeps at most max_det rows.  The live part of the suppression
+// matrix (m rows x ceil(m/64) words) is staged in shared memory when it fits, so the serial loop never
+// waits on global memory.
 __global__ void __launch_bounds__(32) nms_scan_kernel(const float* __restrict__ sorted, const int* __restrict__ cand_count,
                                                       const unsigned long long* __restrict__ mask, int cap,
-                                                      float* __restrict__ det, int* __restrict__ det_count) {
-  extern __shared__ unsigned long long remv[];  // cap/64 words
+                                                      float* __restrict__ det, int* __restrict__ det_count,
+                                                      int smem_words) {
+  extern __shared__ unsigned long long sm64[];  // remv[cap/64] | staged matrix
   const int img = blockIdx.x, lane = threadIdx.x;
   int m = cand_count[img];
   if (m > cap) m = cap;
   const int words = cap / 64;
+  unsigned long long* remv = sm64;
+  unsigned long long* stage = sm64 + words;
   for (int w = lane; w < words; w += 32) remv[w] = 0ull;
+  const int wlast = (m + 63) >> 6;
+  const unsigned long long* mbase = mask + size_t(img) * cap * words;
+  const bool staged = size_t(m) * wlast <= size_t(smem_words);
+  if (staged) {
+    for (int i = lane; i < m * wlast; i += 32) {
+      const int r = i / wlast, w = i - r * wlast;
+      stage[i] = (w >= (r >> 6)) ? mbase[size_t(r) * words + w] : 0ull;
+    }
+  }
   __syncwarp();
   const float* s = sorted + size_t(img) * cap * kCandStride;
   float* o = det + size_t(img) * kMaxDet * 6;
@@ -172,9 +186,13 @@ __global__ void __launch_bounds__(32) nms_scan_kernel(const float* __restrict__ 
     if ((rw >> (i & 63)) & 1ull) continue;
     if (lane < 6) o[kept * 6 + lane] = s[i * kCandStride + lane];
     ++kept;
-    const unsigned long long* mrow = mask + (size_t(img) * cap + i) * words;
-    const int wlast = (m + 63) >> 6;
-    for (int w = (i >> 6) + lane; w < wlast; w += 32) remv[w] |= mrow[w];
+    if (staged) {
+      const unsigned long long* mrow = stage + size_t(i) * wlast;
+      for (int w = (i >> 6) + lane; w < wlast; w += 32) remv[w] |= mrow[w];
+    } else {
+      const unsigned long long* mrow = mbase + size_t(i) * words;
+      for (int w = (i >> 6) + lane; w < wlast; w += 32) remv[w] |= mrow[w];
+    }
     __syncwarp();
   }
   if (lane == 0) det_count[img] = kept;
@@ -191,7 +209,16 @@ cudaError_t nms_launch(const float* blks, int n, int rows, int nc, float conf, f
   else return cudaErrorInvalidValue;
   const int blocks = ws.cap / 64;
   nms_mask_kernel<<<dim3(blocks, blocks, n), 64, 0, s>>>(ws.sorted, ws.cand_count, ws.mask, ws.cap, iou);
-  nms_scan_kernel<<<n, 32, (ws.cap / 64) * 8, s>>>(ws.sorted, ws.cand_count, ws.mask, ws.cap, det, det_count);
+  {
+    const int stage_words = 8192;  // 64 KB: up to ~720 candidates fully staged
+    static bool attr_set = false;
+    const size_t smem = size_t(ws.cap / 64 + stage_words) * 8;
+    if (!attr_set) {
+      cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      attr_set = true;
+    }
+    nms_scan_kernel<<<n, 32, smem, s>>>(ws.sorted, ws.cand_count, ws.mask, ws.cap, det, det_count, stage_words);
+  }
   return cudaGetLastError();
 }
 

@@ -263,43 +263,113 @@ cudaError_t avgpool2_launch(const T* src, int n, int h, int w, int c, int scs, T
 template cudaError_t avgpool2_launch<float>(const float*, int, int, int, int, int, float*, int, cudaStream_t);
 template cudaError_t avgpool2_launch<__half>(const __half*, int, int, int, int, int, __half*, int, cudaStream_t);
 
+// space-to-depth stem pre-pass (one thread per output pixel: reads 2x2x3 bytes, writes 16 channels)
+template <typename T>
+__global__ void s2d_kernel(const uint8_t* __restrict__ pages, int n, int h, int w, T* __restrict__ dst, int dcs, int dco) {
+  const int oh = h / 2, ow = w / 2;
+  const long long total = (long long)n * oh * ow;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ox = int(i % ow), oy = int((i / ow) % oh), img = int(i / ((long long)ow * oh));
+  const uint8_t* p0 = pages + ((size_t(img) * h + 2 * oy) * w + 2 * ox) * 3;
+  const uint8_t* p1 = p0 + size_t(w) * 3;
+  float v[16];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    v[k] = float(p0[k]) / 255.0f;       // (dy=0,dx=0,c), (dy=0,dx=1,c)
+    v[6 + k] = float(p1[k]) / 255.0f;   // (dy=1,dx=0,c), (dy=1,dx=1,c)
+  }
+  v[12] = v[13] = v[14] = v[15] = 0.f;
+  T* o = dst + size_t(i) * dcs + dco;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) stf(o + k, v[k]);
+}
+template <typename T>
+cudaError_t s2d_launch(const uint8_t* pages, int n, int h, int w, T* dst, int dcs, int dco, cudaStream_t s) {
+  const long long total = (long long)n * (h / 2) * (w / 2);
+  s2d_kernel<T><<<unsigned((total + 255) / 256), 256, 0, s>>>(pages, n, h, w, dst, dcs, dco);
+  return cudaGetLastError();
+}
+template cudaError_t s2d_launch<float>(const uint8_t*, int, int, int, float*, int, int, cudaStream_t);
+template cudaError_t s2d_launch<__half>(const uint8_t*, int, int, int, __half*, int, int, cudaStream_t);
+
+// 8-channel vectors (16 bytes of fp16 / 32 bytes of fp32)
+struct Vec8 { float v[8]; };
+__device__ __forceinline__ Vec8 ldv8(const __half* p) {
+  Vec8 r;
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  const __half2* hh = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 t = __half22float2(hh[e]);
+    r.v[2 * e] = t.x;
+    r.v[2 * e + 1] = t.y;
+  }
+  return r;
+}
+__device__ __forceinline__ Vec8 ldv8(const float* p) {
+  Vec8 r;
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ void stv8(__half* p, const Vec8& r) {
+  uint4 q;
+  __half2* hh = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) hh[e] = __floats2half2_rn(r.v[2 * e], r.v[2 * e + 1]);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+__device__ __forceinline__ void stv8(float* p, const Vec8& r) {
+  *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
 // SPPF pools: buf[..., 0:c] = x (already written); writes y1=mp5(x), y2=mp5(y1)=mp9(x), y3=mp13(x)
-// into channel slots [c,2c), [2c,3c), [3c,4c).  Chained 5x5 s1 p2 max pools equal 9x9 / 13x13 windows.
+// into channel slots [c,2c), [2c,3c), [3c,4c).  Chained 5x5 s1 p2 max pools equal 9x9 / 13x13 windows
+// clipped at the border (-inf padding).  One thread = one pixel x 8 channels.
 template <typename T>
 __global__ void sppf_pool_kernel(T* __restrict__ buf, int n, int h, int w, int c, int cs) {
-  const long long total = (long long)n * h * w * c;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ch = int(i % c);
-    long long r = i / c;
-    const int x = int(r % w);
-    r /= w;
-    const int y = int(r % h);
-    const int img = int(r / h);
-    const T* base = buf + size_t(img) * h * w * cs + ch;
-    float m5 = -INFINITY, m9 = -INFINITY, m13 = -INFINITY;
-    for (int dy = -6; dy <= 6; ++dy) {
-      const int yy = y + dy;
-      if (yy < 0 || yy >= h) continue;
-      for (int dx = -6; dx <= 6; ++dx) {
-        const int xx = x + dx;
-        if (xx < 0 || xx >= w) continue;
-        const float v = ldf(base + (size_t(yy) * w + xx) * cs);
-        const int ad = max(abs(dy), abs(dx));
-        m13 = fmaxf(m13, v);
-        if (ad <= 4) m9 = fmaxf(m9, v);
-        if (ad <= 2) m5 = fmaxf(m5, v);
+  const int c8 = c / 8;
+  const long long total = (long long)n * h * w * c8;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ch = int(i % c8) * 8;
+  long long r = i / c8;
+  const int x = int(r % w);
+  r /= w;
+  const int y = int(r % h);
+  const int img = int(r / h);
+  const T* base = buf + size_t(img) * h * w * cs + ch;
+  Vec8 m5, m9, m13;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) m5.v[e] = m9.v[e] = m13.v[e] = -INFINITY;
+  for (int dy = -6; dy <= 6; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= h) continue;
+    for (int dx = -6; dx <= 6; ++dx) {
+      const int xx = x + dx;
+      if (xx < 0 || xx >= w) continue;
+      const Vec8 v = ldv8(base + (size_t(yy) * w + xx) * cs);
+      const int ad = max(abs(dy), abs(dx));
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        m13.v[e] = fmaxf(m13.v[e], v.v[e]);
+        if (ad <= 4) m9.v[e] = fmaxf(m9.v[e], v.v[e]);
+        if (ad <= 2) m5.v[e] = fmaxf(m5.v[e], v.v[e]);
       }
     }
-    T* o = buf + ((size_t(img) * h + y) * w + x) * cs + ch;
-    stf(o + c, m5);
-    stf(o + 2 * c, m9);
-    stf(o + 3 * c, m13);
   }
+  T* o = buf + ((size_t(img) * h + y) * w + x) * cs + ch;
+  stv8(o + c, m5);
+  stv8(o + 2 * c, m9);
+  stv8(o + 3 * c, m13);
 }
 template <typename T>
 cudaError_t sppf_pool_launch(T* buf, int n, int h, int w, int c, int cs, cudaStream_t s) {
-  const long long total = (long long)n * h * w * c;
-  sppf_pool_kernel<T><<<unsigned((total + 255) / 256), 256, 0, s>>>(buf, n, h, w, c, cs);
+  if (c % 8 || cs % 8) return cudaErrorInvalidValue;
+  const long long total = (long long)n * h * w * (c / 8);
+  sppf_pool_kernel<T><<<unsigned((total + 127) / 128), 128, 0, s>>>(buf, n, h, w, c, cs);
   return cudaGetLastError();
 }
 template cudaError_t sppf_pool_launch<float>(float*, int, int, int, int, int, cudaStream_t);
@@ -308,21 +378,22 @@ template cudaError_t sppf_pool_launch<__half>(__half*, int, int, int, int, int, 
 template <typename T>
 __global__ void upsample2_kernel(const T* __restrict__ src, int n, int h, int w, int c, int scs, T* __restrict__ dst,
                                  int dcs) {
-  const int oh = 2 * h, ow = 2 * w;
-  const long long total = (long long)n * oh * ow * c;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ch = int(i % c);
-    long long r = i / c;
-    const int ox = int(r % ow);
-    r /= ow;
-    const int oy = int(r % oh);
-    const int img = int(r / oh);
-    dst[((size_t(img) * oh + oy) * ow + ox) * dcs + ch] = src[((size_t(img) * h + oy / 2) * w + ox / 2) * scs + ch];
-  }
+  const int oh = 2 * h, ow = 2 * w, c8 = c / 8;
+  const long long total = (long long)n * oh * ow * c8;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ch = int(i % c8) * 8;
+  long long r = i / c8;
+  const int ox = int(r % ow);
+  r /= ow;
+  const int oy = int(r % oh);
+  const int img = int(r / oh);
+  stv8(dst + ((size_t(img) * oh + oy) * ow + ox) * dcs + ch, ldv8(src + ((size_t(img) * h + oy / 2) * w + ox / 2) * scs + ch));
 }
 template <typename T>
 cudaError_t upsample2_launch(const T* src, int n, int h, int w, int c, int scs, T* dst, int dcs, cudaStream_t s) {
-  const long long total = (long long)n * 4 * h * w * c;
+  if (c % 8 || scs % 8 || dcs % 8) return cudaErrorInvalidValue;
+  const long long total = (long long)n * 4 * h * w * (c / 8);
   upsample2_kernel<T><<<unsigned((total + 255) / 256), 256, 0, s>>>(src, n, h, w, c, scs, dst, dcs);
   return cudaGetLastError();
 }

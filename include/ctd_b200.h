@@ -55,8 +55,10 @@ enum ctd_op_kind {
   CTD_OP_UPSAMPLE2 = 5, /* nn.Upsample(x2, nearest)      (cfg layers 11,15)                 */
   CTD_OP_DETECT = 6,    /* Detect 1x1 conv + sigmoid + box decode (yolo.py:23-44)           */
   CTD_OP_SEG_TAIL = 7,  /* ConvT4x4s2 64->1 + sigmoid    (basemodel.py:57-60)               */
-  CTD_OP_DB_TAIL = 8    /* ConvT2x2s2+BN+ReLU -> ConvT2x2s2 -> sigmoid, both branches
+  CTD_OP_DB_TAIL = 8,   /* ConvT2x2s2+BN+ReLU -> ConvT2x2s2 -> sigmoid, both branches
                            (basemodel.py:99-103,138-142)                                    */
+  CTD_OP_S2D = 9        /* u8 BGR page -> /255 -> 2x2 space-to-depth, 12(+4 zero) channels at 1/2 resolution:
+                           turns the 6x6 s2 p2 stem conv into a 3x3 s1 p1 conv for the tensor cores       */
 };
 
 enum ctd_act { CTD_ACT_NONE = 0, CTD_ACT_SILU = 1, CTD_ACT_LEAKY = 2, CTD_ACT_RELU = 3, CTD_ACT_SIGMOID = 4 };

@@ -45,6 +45,13 @@ def run_program(prog, pages, use_fp16_weights=False):
             b = _blob(prog, op["b_off"], op["cout"], np.float32)
             y = _act(F.conv2d(x, wt, b, 2, 2), op["act"])
             bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["cout"]] = y
+        elif k == cc.OP_S2D:
+            x = torch.from_numpy(np.ascontiguousarray(pages.transpose(0, 3, 1, 2)).astype(np.float32) / 255)
+            y = torch.zeros(n, 16, h // 2, w // 2)
+            for dy in range(2):
+                for dx in range(2):
+                    y[:, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3] = x[:, :, dy::2, dx::2]
+            bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + 16] = y
         elif k in (cc.OP_CONV, cc.OP_DETECT):
             ks, st = op["ksize"], op["stride"]
             K = ks * ks * cin

@@ -39,6 +39,8 @@ CONV_CASES = [
     ([64], 32, 3, 1, cc.ACT_RELU, False, 64, 64, 1),
     ([64], 16, 3, 1, cc.ACT_RELU, False, 64, 64, 1),
     ([128], 64, 1, 1, cc.ACT_RELU, False, 192, 64, 1),
+    ([16], 32, 3, 1, cc.ACT_SILU, False, 64, 128, 2),   # 16-channel K blocks (32-byte swizzle): the s2d stem
+    ([16], 16, 1, 1, cc.ACT_NONE, False, 64, 64, 1),
 ]
 
 
