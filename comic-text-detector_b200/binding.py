@@ -34,13 +34,15 @@ class CtdConfig(C.Structure):
 
 class CtdDeviceOutputs(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("stream", "mask_u8", "det", "det_count", "bitmap", "labels", "n_labels",
-                                          "results_base")] + [("results_bytes", C.c_size_t)]
+                                          "line_boxes", "line_scores", "line_count", "results_base")] + \
+               [("results_bytes", C.c_size_t)]
 
 
 EXPORTS = ["ctd_create", "ctd_destroy", "ctd_last_error", "ctd_forward", "ctd_get_net_outputs", "ctd_get_mask_u8",
            "ctd_get_detections", "ctd_get_db_components", "ctd_last_forward_ms", "ctd_last_launch_count",
            "ctd_debug_read_buffer", "ctd_debug_write_buffer", "ctd_connected_components", "ctd_nms",
-           "ctd_timer_start", "ctd_timer_stop", "ctd_profile_forward", "ctd_get_device_outputs"]
+           "ctd_timer_start", "ctd_timer_stop", "ctd_profile_forward", "ctd_get_device_outputs",
+           "ctd_get_text_lines", "ctd_seg_represent"]
 
 _lib = None
 
@@ -76,6 +78,8 @@ def load_library():
     lib.ctd_debug_write_buffer.argtypes = [vp, i32, vp, i32, i32, i32]
     lib.ctd_connected_components.argtypes = [vp, vp, i32, i32, vp, vp, i32, vp]
     lib.ctd_nms.argtypes = [vp, vp, i32, C.c_float, C.c_float, vp, vp]
+    lib.ctd_get_text_lines.argtypes = [vp, vp, vp, vp]
+    lib.ctd_seg_represent.argtypes = [vp, vp, i32, i32, C.c_float, vp, vp, vp]
     lib.ctd_timer_start.argtypes = [vp]
     lib.ctd_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     lib.ctd_profile_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32]
@@ -180,6 +184,25 @@ class Engine:
         nl = np.empty((n,), np.int32)
         self._ck(self.lib.ctd_get_db_components(self.h, _ptr(bm), _ptr(lab), _ptr(nl)))
         return bm, lab, nl
+
+    def text_lines(self):
+        """per page (boxes int16 [k,4,2], scores f32 [k]) exactly as SegDetectorRepresenter returns them."""
+        n = self.shape[0]
+        boxes = np.empty((n, 1000, 4, 2), np.int16)
+        scores = np.empty((n, 1000), np.float32)
+        cnt = np.empty((n,), np.int32)
+        self._ck(self.lib.ctd_get_text_lines(self.h, _ptr(boxes), _ptr(scores), _ptr(cnt)))
+        return [boxes[i, :cnt[i]].copy() for i in range(n)], [scores[i, :cnt[i]].copy() for i in range(n)]
+
+    def seg_represent(self, pred, thresh=0.3):
+        pred = np.ascontiguousarray(pred, np.float32)
+        h, w = pred.shape
+        boxes = np.empty((1000, 4, 2), np.int16)
+        scores = np.empty((1000,), np.float32)
+        cnt = np.zeros((1,), np.int32)
+        self._ck(self.lib.ctd_seg_represent(self.h, _ptr(pred), h, w, thresh, _ptr(boxes), _ptr(scores), _ptr(cnt)))
+        k = int(cnt[0])
+        return boxes[:k].copy(), scores[:k].copy()
 
     def last_forward_ms(self):
         ms = C.c_float()

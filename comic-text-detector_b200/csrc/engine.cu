@@ -53,6 +53,10 @@ struct ctd_handle {
   int32_t* d_labels = nullptr;
   int32_t* d_nlabels = nullptr;
   int32_t* d_ccl_scratch = nullptr;
+  void* d_segrep_scratch = nullptr;
+  int16_t* d_line_boxes = nullptr;
+  float* d_line_scores = nullptr;
+  int32_t* d_line_count = nullptr;
   void* d_nms_ws = nullptr;
   NmsWorkspace nms{};
   std::map<std::tuple<int, int, int>, ShapePlan> plans;
@@ -91,7 +95,7 @@ extern "C" void ctd_destroy(ctd_handle* h) {
   for (void* p : h->d_buf) cudaFree(p);
   cudaFree(h->d_blob); cudaFree(h->d_pages); cudaFree(h->d_blks); cudaFree(h->d_mask); cudaFree(h->d_mask_u8);
   cudaFree(h->d_lines); cudaFree(h->d_bitmap); cudaFree(h->d_labels);
-  cudaFree(h->d_ccl_scratch); cudaFree(h->d_nms_ws);
+  cudaFree(h->d_ccl_scratch); cudaFree(h->d_nms_ws); cudaFree(h->d_segrep_scratch);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->tev0) cudaEventDestroy(h->tev0);
@@ -166,14 +170,19 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
   {
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
     const size_t o_det = al(px), o_cnt = o_det + al(nb * 300 * 6 * 4), o_nl = o_cnt + al(nb * 4);
-    h->results_bytes = o_nl + al(nb * 4);
+    const size_t o_lb = o_nl + al(nb * 4), o_ls = o_lb + al(nb * 1000 * 8 * 2), o_lc = o_ls + al(nb * 1000 * 4);
+    h->results_bytes = o_lc + al(nb * 4);
     CKC(cudaMalloc(&h->d_mask_u8, h->results_bytes));
     CKC(cudaMemset(h->d_mask_u8, 0, h->results_bytes));
     h->d_det = reinterpret_cast<float*>(h->d_mask_u8 + o_det);
     h->d_det_count = reinterpret_cast<int*>(h->d_mask_u8 + o_cnt);
     h->d_nlabels = reinterpret_cast<int32_t*>(h->d_mask_u8 + o_nl);
+    h->d_line_boxes = reinterpret_cast<int16_t*>(h->d_mask_u8 + o_lb);
+    h->d_line_scores = reinterpret_cast<float*>(h->d_mask_u8 + o_ls);
+    h->d_line_count = reinterpret_cast<int32_t*>(h->d_mask_u8 + o_lc);
   }
   CKC(cudaMalloc(&h->d_ccl_scratch, px * 4 * 3));
+  CKC(cudaMalloc(&h->d_segrep_scratch, segrep_scratch_bytes(int(nb), int(mh), int(mw), 1000)));
   const int cap = 4096;
   CKC(cudaMalloc(&h->d_nms_ws, nms_workspace_bytes(int(nb), cap)));
   nms_workspace_bind(h->nms, h->d_nms_ws, int(nb), cap);
@@ -364,6 +373,9 @@ static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* lau
   if (record) CK(cudaEventRecord(h->op_events[evi++], h->stream));
   CK(ccl_launch(h->d_bitmap, n, ph, pw, h->d_labels, h->d_ccl_scratch, h->d_nlabels, h->stream));
   cnt += 8;
+  CK(segrep_launch(h->d_bitmap, h->d_lines, size_t(2) * ph * pw, h->d_ccl_scratch, n, ph, pw, 1000, 1.5f,
+                   h->d_segrep_scratch, h->d_line_boxes, h->d_line_scores, h->d_line_count, h->stream));
+  cnt += 13;
   if (record) CK(cudaEventRecord(h->op_events[evi++], h->stream));
   *launches = cnt;
   return CTD_OK;
@@ -460,6 +472,36 @@ extern "C" int ctd_get_db_components(ctd_handle* h, uint8_t* bitmap, int32_t* la
   return CTD_OK;
 }
 
+extern "C" int ctd_get_text_lines(ctd_handle* h, int16_t* boxes, float* scores, int32_t* counts) {
+  NEED_FWD();
+  if (!boxes || !scores || !counts) return CTD_E_INVALID;
+  CK(cudaMemcpyAsync(boxes, h->d_line_boxes, size_t(h->n) * 1000 * 8 * 2, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(scores, h->d_line_scores, size_t(h->n) * 1000 * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(counts, h->d_line_count, size_t(h->n) * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return CTD_OK;
+}
+
+extern "C" int ctd_seg_represent(ctd_handle* h, const float* pred, int32_t ih, int32_t iw, float thresh, int16_t* boxes,
+                                 float* scores, int32_t* count) {
+  if (!h || !pred || !boxes || !scores || !count) return CTD_E_INVALID;
+  if (ih < 1 || iw < 1 || size_t(ih) * iw > size_t(h->cfg.max_h) * h->cfg.max_w || ih > 2048 || iw > 2048)
+    return fail(h, CTD_E_CAPACITY, "map larger than the workspace");
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t px = size_t(ih) * iw;
+  CK(cudaMemcpyAsync(h->d_lines, pred, px * 4, cudaMemcpyHostToDevice, h->stream));
+  CK(binarize_launch(h->d_lines, px, thresh, h->d_bitmap, h->stream));
+  CK(ccl_launch(h->d_bitmap, 1, ih, iw, h->d_labels, h->d_ccl_scratch, h->d_nlabels, h->stream));
+  CK(segrep_launch(h->d_bitmap, h->d_lines, px, h->d_ccl_scratch, 1, ih, iw, 1000, 1.5f, h->d_segrep_scratch,
+                   h->d_line_boxes, h->d_line_scores, h->d_line_count, h->stream));
+  CK(cudaMemcpyAsync(boxes, h->d_line_boxes, 1000 * 8 * 2, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(scores, h->d_line_scores, 1000 * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(count, h->d_line_count, 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  h->have_forward = false;
+  return CTD_OK;
+}
+
 extern "C" int ctd_last_forward_ms(ctd_handle* h, float* ms) {
   NEED_FWD();
   if (!ms) return CTD_E_INVALID;
@@ -534,6 +576,9 @@ extern "C" int ctd_get_device_outputs(ctd_handle* h, ctd_device_outputs* out) {
   out->bitmap = h->d_bitmap;
   out->labels = h->d_labels;
   out->n_labels = h->d_nlabels;
+  out->line_boxes = h->d_line_boxes;
+  out->line_scores = h->d_line_scores;
+  out->line_count = h->d_line_count;
   out->results_base = h->d_mask_u8;
   out->results_bytes = h->results_bytes;
   return CTD_OK;

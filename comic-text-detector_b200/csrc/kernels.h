@@ -136,4 +136,12 @@ cudaError_t ccl_launch(const uint8_t* img, int n, int h, int w, int32_t* labels,
                        int32_t* n_labels, cudaStream_t s);
 cudaError_t ccl_stats_launch(const int32_t* labels, int h, int w, int32_t* stats, int cap, cudaStream_t s);
 
+// SegDetectorRepresenter.boxes_from_bitmap (segrep.cu).  Lf = foreground union-find roots left in the CCL
+// scratch by ccl_launch (first n*h*w ints).  boxes i16 [n][max_cand][4][2], scores f32 [n][max_cand].
+size_t segrep_scratch_bytes(int n, int h, int w, int max_cand);
+cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_page_stride, const int* Lf, int n, int h,
+                          int w, int max_cand, float unclip_ratio, void* scratch, int16_t* boxes, float* scores,
+                          int* n_contours, cudaStream_t s);
+cudaError_t binarize_launch(const float* pred, size_t count, float thresh, uint8_t* bitmap, cudaStream_t s);
+
 }  // namespace ctd

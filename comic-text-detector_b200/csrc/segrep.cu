@@ -1,0 +1,471 @@
+// SegDetectorRepresenter.boxes_from_bitmap on the GPU (reference utils/db_utils.py:123-166):
+//   cv2.findContours(bitmap, RETR_LIST, CHAIN_APPROX_SIMPLE)  -> contour set + OpenCV order + 1000 cap
+//   get_mini_boxes / box_score_fast / unclip / get_mini_boxes -> (4,2) int16 box + f32 score per contour
+//
+// No border following: everything downstream of findContours only needs, per contour, (a) its position
+// in OpenCV's list, (b) the convex hull of its points, (c) the set of pixels inside it (for the score).
+//  * outer border of an 8-connected foreground component C: discovered at C's first raster pixel;
+//    hull = hull(C); inside = C + everything C encloses.
+//  * hole border of a 4-connected background component Q that does not touch the image frame:
+//    discovered at Q's first raster pixel (the scan meets the fg->bg transition there); its points
+//    are the foreground pixels 4-adjacent to Q (the "ring"); inside = ring + Q + everything Q encloses.
+//  * OpenCV returns the list in REVERSE discovery order; the reference keeps the first 1000.
+// "Everything enclosed" is the subtree in the component adjacency tree (parent of a fg component = the
+// bg component left of its first pixel; parent of a hole = the fg component left of its first pixel).
+#include <cuda_runtime.h>
+#include <limits.h>
+
+#include "geom.h"
+#include "kernels.h"
+
+namespace ctd {
+
+using ctdgeom::IPt;
+
+__device__ __forceinline__ int uf_find_g(const int* L, int a) {
+  int p = L[a];
+  while (p != a) {
+    a = p;
+    p = L[a];
+  }
+  return a;
+}
+__device__ __forceinline__ void uf_union_g(int* L, int a, int b) {
+  bool done;
+  do {
+    a = uf_find_g(L, a);
+    b = uf_find_g(L, b);
+    if (a < b) {
+      const int old = atomicMin(&L[b], a);
+      done = old == b;
+      b = old;
+    } else if (b < a) {
+      const int old = atomicMin(&L[a], b);
+      done = old == a;
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+
+// ---- 4-connectivity labelling of the BACKGROUND (bitmap == 0), same tile-local + border scheme as ccl_*
+__global__ void __launch_bounds__(1024) bg_local_kernel(const uint8_t* __restrict__ img, int h, int w, int* __restrict__ Lall) {
+  __shared__ int s[32 * 32];
+  const int page = blockIdx.z;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int x = blockIdx.x * 32 + lx, y = blockIdx.y * 32 + ly;
+  const bool inb = x < w && y < h;
+  const size_t o = size_t(page) * h * w;
+  const int l = threadIdx.x;
+  const bool bg = inb && img[o + size_t(y) * w + x] == 0;
+  const unsigned m = __ballot_sync(0xffffffffu, bg);
+  const unsigned zeros_below = ~m & ((1u << lx) - 1u);
+  const int start = zeros_below ? 32 - __clz(zeros_below) : 0;
+  s[l] = bg ? (ly << 5) + start : -1;
+  __syncthreads();
+  if (bg && ly > 0 && s[l - 32] >= 0) {
+    const bool first = (lx == start) || s[l - 33] < 0;
+    if (first) uf_union_g(s, l, l - 32);
+  }
+  __syncthreads();
+  if (inb) {
+    int g = -1;
+    if (bg) {
+      const int r = uf_find_g(s, l);
+      g = (blockIdx.y * 32 + (r >> 5)) * w + blockIdx.x * 32 + (r & 31);
+    }
+    Lall[o + size_t(y) * w + x] = g;
+  }
+}
+__global__ void bg_border_kernel(int h, int w, int* __restrict__ Lall) {
+  const int page = blockIdx.y;
+  int* L = Lall + size_t(page) * h * w;
+  const int nvl = (w - 1) / 32, nhl = (h - 1) / 32;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nvl * h) {
+    const int x = (i / h + 1) * 32, y = i % h;
+    const int p = y * w + x;
+    if (L[p] >= 0 && L[p - 1] >= 0) uf_union_g(L, p, p - 1);
+  } else if (i < nvl * h + nhl * w) {
+    const int j = i - nvl * h;
+    const int y = (j / w + 1) * 32, x = j % w;
+    const int p = y * w + x;
+    if (L[p] >= 0 && L[p - w] >= 0) uf_union_g(L, p, p - w);
+  }
+}
+__global__ void bg_flatten_kernel(int h, int w, int* __restrict__ Lall) {
+  const int page = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= h * w) return;
+  int* L = Lall + size_t(page) * h * w;
+  if (L[p] < 0) return;
+  L[p] = uf_find_g(L, p);
+}
+
+// ---- component tree ---------------------------------------------------------------------------
+// parent[root]: >= 0 parent root pixel, kFrame = the image frame / an outside background component
+constexpr int kFrame = -2;
+
+// bg components touching the frame are "outside": mark their roots
+__global__ void mark_outside_kernel(int h, int w, const int* __restrict__ Lb_all, int* __restrict__ parent_all) {
+  const int page = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = 2 * w + 2 * h;
+  if (i >= per) return;
+  int x, y;
+  if (i < w) { x = i; y = 0; }
+  else if (i < 2 * w) { x = i - w; y = h - 1; }
+  else if (i < 2 * w + h) { x = 0; y = i - 2 * w; }
+  else { x = w - 1; y = i - 2 * w - h; }
+  const size_t o = size_t(page) * h * w;
+  const int r = Lb_all[o + size_t(y) * w + x];
+  if (r >= 0) parent_all[o + r] = kFrame;
+}
+
+// per pixel: roots get their parent, zeroed accumulators and a discovery flag
+__global__ void roots_kernel(int h, int w, const int* __restrict__ Lf_all, const int* __restrict__ Lb_all,
+                             int* __restrict__ parent_all, int* __restrict__ flag_all, double* __restrict__ own_sum,
+                             int* __restrict__ own_cnt, double* __restrict__ tot_sum, int* __restrict__ tot_cnt,
+                             double* __restrict__ ring_sum, int* __restrict__ ring_cnt) {
+  const int page = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hw = h * w;
+  if (p >= hw) return;
+  const size_t o = size_t(page) * hw;
+  const int lf = Lf_all[o + p], lb = Lb_all[o + p];
+  int flag = 0;
+  if (lf == p) {
+    const int x = p % w;
+    int par = kFrame;
+    if (x > 0) {
+      const int q = Lb_all[o + p - 1];  // bg (p is the component's first raster pixel)
+      par = (q >= 0 && parent_all[o + q] != kFrame) ? q : kFrame;
+    }
+    parent_all[o + p] = par;
+    flag = 1;
+  } else if (lb == p) {
+    if (parent_all[o + p] != kFrame) {  // a hole: its left neighbour is foreground
+      parent_all[o + p] = Lf_all[o + p - 1];
+      flag = 1;
+    }
+  }
+  if (lf == p || lb == p) {
+    own_sum[o + p] = 0.0; own_cnt[o + p] = 0;
+    tot_sum[o + p] = 0.0; tot_cnt[o + p] = 0;
+    ring_sum[o + p] = 0.0; ring_cnt[o + p] = 0;
+  }
+  flag_all[o + p] = flag;
+}
+
+// ---- discovery order -> contour ids (OpenCV returns the reverse discovery order) ----------------
+constexpr int kSeg = 2048;
+__global__ void __launch_bounds__(256) flag_scan_seg_kernel(int hw, int* __restrict__ flag_all, int* __restrict__ segsum, int nseg) {
+  __shared__ int wsum[8];
+  const int page = blockIdx.y, seg = blockIdx.x;
+  int* f = flag_all + size_t(page) * hw + size_t(seg) * kSeg;
+  const int base = seg * kSeg;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int v[8], t = 0;
+  const int i0 = threadIdx.x * 8;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    v[e] = (base + i0 + e < hw) ? f[i0 + e] : 0;
+    t += v[e];
+  }
+  int incl = t;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += u;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  int woff = 0;
+  for (int k = 0; k < warp; ++k) woff += wsum[k];
+  int run = woff + incl - t;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    // keep the flag in bit 30 so that the next kernel still knows which pixels are discovery points
+    if (base + i0 + e < hw) f[i0 + e] = run | (v[e] << 30);
+    run += v[e];
+  }
+  if (threadIdx.x == 255) segsum[page * nseg + seg] = woff + incl;
+}
+__global__ void __launch_bounds__(1024) flag_scan_top_kernel(int* __restrict__ segsum, int nseg, int* __restrict__ total) {
+  __shared__ int part[1024];
+  const int page = blockIdx.x;
+  int* sgs = segsum + page * nseg;
+  const int v = threadIdx.x < nseg ? sgs[threadIdx.x] : 0;
+  part[threadIdx.x] = v;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    int u = 0;
+    if (threadIdx.x >= off) u = part[threadIdx.x - off];
+    __syncthreads();
+    part[threadIdx.x] += u;
+    __syncthreads();
+  }
+  if (threadIdx.x < nseg) sgs[threadIdx.x] = part[threadIdx.x] - v;
+  if (threadIdx.x == 1023) total[page] = part[1023];
+}
+// cid[root pixel] = position in OpenCV's list if < max_candidates else -1; contour table
+__global__ void assign_cid_kernel(int h, int w, const int* __restrict__ Lf_all, int* __restrict__ flag_all,
+                                  const int* __restrict__ segoff, int nseg, const int* __restrict__ total, int max_cand,
+                                  int* __restrict__ c_root, int* __restrict__ rowmin, int* __restrict__ rowmax) {
+  const int page = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hw = h * w;
+  if (p >= hw) return;
+  const size_t o = size_t(page) * hw;
+  const int f = flag_all[o + p];
+  int cid = -1;
+  if (f & (1 << 30)) {
+    const int rank = segoff[page * nseg + p / kSeg] + (f & ((1 << 30) - 1));
+    const int c = total[page] - 1 - rank;
+    if (c < max_cand) {
+      cid = c;
+      // bit 31 of the table entry: 1 = hole contour
+      c_root[page * max_cand + c] = (Lf_all[o + p] == p) ? p : (p | int(0x80000000u));
+    }
+  }
+  flag_all[o + p] = cid;  // the flag array now holds contour ids at root pixels
+  (void)rowmin; (void)rowmax;
+}
+__global__ void rows_init_kernel(int* __restrict__ rowmin, int* __restrict__ rowmax, size_t n) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i < n) {
+    rowmin[i] = INT_MAX;
+    rowmax[i] = -1;
+  }
+}
+
+// ---- per-pixel accumulation ----------------------------------------------------------------------
+__global__ void accumulate_kernel(int h, int w, const float* __restrict__ pred_all, size_t pred_page_stride,
+                                  const int* __restrict__ Lf_all, const int* __restrict__ Lb_all,
+                                  const int* __restrict__ parent_all, const int* __restrict__ cid_all,
+                                  double* __restrict__ own_sum, int* __restrict__ own_cnt, double* __restrict__ ring_sum,
+                                  int* __restrict__ ring_cnt, int* __restrict__ rowmin, int* __restrict__ rowmax, int max_cand) {
+  const int page = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hw = h * w;
+  if (p >= hw) return;
+  const size_t o = size_t(page) * hw;
+  const float v = pred_all[size_t(page) * pred_page_stride + p];
+  const int y = p / w, x = p - y * w;
+  const int lf = Lf_all[o + p];
+  if (lf >= 0) {
+    atomicAdd(&own_sum[o + lf], (double)v);
+    atomicAdd(&own_cnt[o + lf], 1);
+    const int c = cid_all[o + lf];
+    if (c >= 0) {
+      const size_t ro = (size_t(page) * max_cand + c) * h + y;
+      atomicMin(&rowmin[ro], x);
+      atomicMax(&rowmax[ro], x);
+    }
+    // ring membership: distinct holes among the 4-neighbours
+    int hs[4];
+    int nh = 0;
+    const int nb[4] = {x > 0 ? p - 1 : -1, x + 1 < w ? p + 1 : -1, y > 0 ? p - w : -1, y + 1 < h ? p + w : -1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (nb[k] < 0) continue;
+      const int q = Lb_all[o + nb[k]];
+      if (q < 0 || parent_all[o + q] == kFrame) continue;
+      bool dup = false;
+      for (int e = 0; e < nh; ++e) dup |= hs[e] == q;
+      if (!dup) hs[nh++] = q;
+    }
+    for (int e = 0; e < nh; ++e) {
+      const int q = hs[e];
+      atomicAdd(&ring_sum[o + q], (double)v);
+      atomicAdd(&ring_cnt[o + q], 1);
+      const int c2 = cid_all[o + q];
+      if (c2 >= 0) {
+        const size_t ro = (size_t(page) * max_cand + c2) * h + y;
+        atomicMin(&rowmin[ro], x);
+        atomicMax(&rowmax[ro], x);
+      }
+    }
+  } else {
+    const int lb = Lb_all[o + p];
+    if (parent_all[o + lb] != kFrame) {
+      atomicAdd(&own_sum[o + lb], (double)v);
+      atomicAdd(&own_cnt[o + lb], 1);
+    }
+  }
+}
+
+// every node adds its own sums to itself and to all its ancestors
+__global__ void tree_kernel(int h, int w, const int* __restrict__ Lf_all, const int* __restrict__ Lb_all,
+                            const int* __restrict__ parent_all, const double* __restrict__ own_sum,
+                            const int* __restrict__ own_cnt, double* __restrict__ tot_sum, int* __restrict__ tot_cnt) {
+  const int page = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hw = h * w;
+  if (p >= hw) return;
+  const size_t o = size_t(page) * hw;
+  const bool root = Lf_all[o + p] == p || (Lb_all[o + p] == p && parent_all[o + p] != kFrame);
+  if (!root) return;
+  const double s = own_sum[o + p];
+  const int c = own_cnt[o + p];
+  int a = p;
+  int guard = 0;
+  while (a >= 0 && guard++ < 4096) {
+    atomicAdd(&tot_sum[o + a], s);
+    atomicAdd(&tot_cnt[o + a], c);
+    a = parent_all[o + a];
+  }
+}
+
+// ---- per-contour geometry: one thread per candidate -------------------------------------------------
+struct ContourScratch {
+  IPt hull[ctdgeom::kMaxHull];
+  IPt tmp[ctdgeom::kMaxHull];
+  IPt off[ctdgeom::kMaxOffsetPts];
+  float f0[ctdgeom::kMaxHull], f1[ctdgeom::kMaxHull], f2[ctdgeom::kMaxHull];
+};
+
+__global__ void __launch_bounds__(64) contour_kernel(int h, int w, int max_cand, const int* __restrict__ total,
+                                                     const int* __restrict__ c_root, const int* __restrict__ rowmin,
+                                                     const int* __restrict__ rowmax, const double* __restrict__ tot_sum,
+                                                     const int* __restrict__ tot_cnt, const double* __restrict__ ring_sum,
+                                                     const int* __restrict__ ring_cnt, ContourScratch* __restrict__ scratch,
+                                                     int16_t* __restrict__ boxes, float* __restrict__ scores,
+                                                     int* __restrict__ n_out, int dst_w, int dst_h, float unclip_ratio) {
+  const int page = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int ncont = total[page];
+  if (ncont > max_cand) ncont = max_cand;
+  if (c == 0) n_out[page] = ncont;
+  if (c >= max_cand) return;
+  int16_t* bo = boxes + (size_t(page) * max_cand + c) * 8;
+  float* so = scores + size_t(page) * max_cand + c;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) bo[k] = 0;
+  *so = 0.f;
+  if (c >= ncont) return;
+  ContourScratch& S = scratch[size_t(page) * max_cand + c];
+  const int entry = c_root[page * max_cand + c];
+  const bool is_hole = entry < 0;
+  const int root = entry & 0x7fffffff;
+  const size_t o = size_t(page) * h * w;
+  const int* rmin = rowmin + (size_t(page) * max_cand + c) * h;
+  const int* rmax = rowmax + (size_t(page) * max_cand + c) * h;
+  // monotone chain over the row extremes; rows are sorted by y, so the chain runs in the transposed
+  // plane (x' = y, y' = x) and the result is transposed back (which mirrors the orientation -> reversed)
+  int k = 0;
+  bool overflow = false;
+  for (int y = 0; y < h && !overflow; ++y) {
+    const int a = rmin[y], b = rmax[y];
+    if (b < 0) continue;
+    for (int e = 0; e < (a == b ? 1 : 2); ++e) {
+      const IPt pt{y, e == 0 ? a : b};
+      while (k >= 2 && ctdgeom::cross3(S.hull[k - 2], S.hull[k - 1], pt) <= 0) --k;
+      if (k >= ctdgeom::kMaxHull) { overflow = true; break; }
+      S.hull[k++] = pt;
+    }
+  }
+  const int lower = k + 1;
+  bool first = true;
+  for (int y = h - 1; y >= 0 && !overflow; --y) {
+    const int a = rmin[y], b = rmax[y];
+    if (b < 0) continue;
+    for (int e = 0; e < (a == b ? 1 : 2); ++e) {
+      const IPt pt{y, e == 0 ? b : a};
+      if (first) { first = false; continue; }  // the very last point of the forward pass
+      while (k >= lower && ctdgeom::cross3(S.hull[k - 2], S.hull[k - 1], pt) <= 0) --k;
+      if (k >= ctdgeom::kMaxHull) { overflow = true; break; }
+      S.hull[k++] = pt;
+    }
+  }
+  if (overflow) return;
+  if (k > 1) --k;
+  // transpose back + reverse
+  for (int i = 0; i < k; ++i) S.tmp[i] = IPt{S.hull[k - 1 - i].y, S.hull[k - 1 - i].x};
+  for (int i = 0; i < k; ++i) S.hull[i] = S.tmp[i];
+  int16_t box[8];
+  if (!ctdgeom::contour_to_box(S.hull, k, S.tmp, S.off, S.f0, S.f1, S.f2, w, h, dst_w, dst_h, (double)unclip_ratio, box)) return;
+  // box_score_fast (db_utils.py:197-211): mean of pred over the filled contour polygon
+  double sum = tot_sum[o + root];
+  long long cnt = tot_cnt[o + root];
+  if (is_hole) {
+    sum += ring_sum[o + root];
+    cnt += ring_cnt[o + root];
+  }
+  *so = cnt > 0 ? (float)(sum / (double)cnt) : 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) bo[e] = box[e];
+}
+
+__global__ void binarize_kernel(const float* __restrict__ pred, size_t count, float thresh, uint8_t* __restrict__ bitmap) {
+  const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+  if (i < count) bitmap[i] = pred[i] > thresh ? 1 : 0;  // db_utils.py:71-72
+}
+cudaError_t binarize_launch(const float* pred, size_t count, float thresh, uint8_t* bitmap, cudaStream_t s) {
+  binarize_kernel<<<unsigned((count + 255) / 256), 256, 0, s>>>(pred, count, thresh, bitmap);
+  return cudaGetLastError();
+}
+
+size_t segrep_scratch_bytes(int n, int h, int w, int max_cand) {
+  const size_t hw = size_t(n) * h * w;
+  return hw * 4 * 4            // Lb, parent, flag/cid, own_cnt
+         + hw * 4 * 2          // tot_cnt, ring_cnt
+         + hw * 8 * 3          // own_sum, tot_sum, ring_sum
+         + size_t(n) * max_cand * h * 4 * 2   // rowmin, rowmax
+         + size_t(n) * max_cand * 4           // c_root
+         + size_t(n) * 2048 * 4               // segsum + totals
+         + size_t(n) * max_cand * sizeof(ContourScratch) + 4096;
+}
+
+cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_page_stride, const int* Lf, int n, int h,
+                          int w, int max_cand, float unclip_ratio, void* scratch, int16_t* boxes, float* scores,
+                          int* n_contours, cudaStream_t s) {
+  const size_t hw = size_t(h) * w, nhw = size_t(n) * hw;
+  char* p = static_cast<char*>(scratch);
+  auto take = [&](size_t bytes) { char* r = p; p += (bytes + 255) / 256 * 256; return r; };
+  int* Lb = reinterpret_cast<int*>(take(nhw * 4));
+  int* parent = reinterpret_cast<int*>(take(nhw * 4));
+  int* flag = reinterpret_cast<int*>(take(nhw * 4));
+  int* own_cnt = reinterpret_cast<int*>(take(nhw * 4));
+  int* tot_cnt = reinterpret_cast<int*>(take(nhw * 4));
+  int* ring_cnt = reinterpret_cast<int*>(take(nhw * 4));
+  double* own_sum = reinterpret_cast<double*>(take(nhw * 8));
+  double* tot_sum = reinterpret_cast<double*>(take(nhw * 8));
+  double* ring_sum = reinterpret_cast<double*>(take(nhw * 8));
+  int* rowmin = reinterpret_cast<int*>(take(size_t(n) * max_cand * h * 4));
+  int* rowmax = reinterpret_cast<int*>(take(size_t(n) * max_cand * h * 4));
+  int* c_root = reinterpret_cast<int*>(take(size_t(n) * max_cand * 4));
+  int* segsum = reinterpret_cast<int*>(take(size_t(n) * 1024 * 4));
+  int* total = reinterpret_cast<int*>(take(size_t(n) * 4));
+  ContourScratch* cs = reinterpret_cast<ContourScratch*>(take(size_t(n) * max_cand * sizeof(ContourScratch)));
+  const int nseg = int((hw + kSeg - 1) / kSeg);
+  if (nseg > 1024) return cudaErrorInvalidValue;
+
+  dim3 tgrid((w + 31) / 32, (h + 31) / 32, n);
+  dim3 grid(unsigned((hw + 255) / 256), n);
+  cudaError_t e = cudaMemsetAsync(parent, 0xff, nhw * 4, s);  // -1 = "not decided"
+  if (e != cudaSuccess) return e;
+  bg_local_kernel<<<tgrid, 1024, 0, s>>>(bitmap, h, w, Lb);
+  const int nborder = ((w - 1) / 32) * h + ((h - 1) / 32) * w;
+  if (nborder > 0) bg_border_kernel<<<dim3((nborder + 255) / 256, n), 256, 0, s>>>(h, w, Lb);
+  bg_flatten_kernel<<<grid, 256, 0, s>>>(h, w, Lb);
+  mark_outside_kernel<<<dim3((2 * w + 2 * h + 255) / 256, n), 256, 0, s>>>(h, w, Lb, parent);
+  roots_kernel<<<grid, 256, 0, s>>>(h, w, Lf, Lb, parent, flag, own_sum, own_cnt, tot_sum, tot_cnt, ring_sum, ring_cnt);
+  flag_scan_seg_kernel<<<dim3(nseg, n), 256, 0, s>>>(int(hw), flag, segsum, nseg);
+  flag_scan_top_kernel<<<n, 1024, 0, s>>>(segsum, nseg, total);
+  {
+    const size_t nr = size_t(n) * max_cand * h;
+    rows_init_kernel<<<unsigned((nr + 255) / 256), 256, 0, s>>>(rowmin, rowmax, nr);
+  }
+  assign_cid_kernel<<<grid, 256, 0, s>>>(h, w, Lf, flag, segsum, nseg, total, max_cand, c_root, rowmin, rowmax);
+  accumulate_kernel<<<grid, 256, 0, s>>>(h, w, pred, pred_page_stride, Lf, Lb, parent, flag, own_sum, own_cnt, ring_sum,
+                                         ring_cnt, rowmin, rowmax, max_cand);
+  tree_kernel<<<grid, 256, 0, s>>>(h, w, Lf, Lb, parent, own_sum, own_cnt, tot_sum, tot_cnt);
+  contour_kernel<<<dim3((max_cand + 63) / 64, n), 64, 0, s>>>(h, w, max_cand, total, c_root, rowmin, rowmax, tot_sum, tot_cnt,
+                                                              ring_sum, ring_cnt, cs, boxes, scores, n_contours, w, h,
+                                                              unclip_ratio);
+  return cudaGetLastError();
+}
+
+}  // namespace ctd

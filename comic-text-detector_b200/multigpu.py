@@ -19,7 +19,11 @@ def arena_layout(max_batch, h, w):
     o_det = al(max_batch * h * w)
     o_cnt = o_det + al(max_batch * 300 * 6 * 4)
     o_nl = o_cnt + al(max_batch * 4)
-    return dict(mask=0, det=o_det, det_count=o_cnt, n_labels=o_nl, total=o_nl + al(max_batch * 4))
+    o_lb = o_nl + al(max_batch * 4)
+    o_ls = o_lb + al(max_batch * 1000 * 8 * 2)
+    o_lc = o_ls + al(max_batch * 1000 * 4)
+    return dict(mask=0, det=o_det, det_count=o_cnt, n_labels=o_nl, line_boxes=o_lb, line_scores=o_ls, line_count=o_lc,
+                total=o_lc + al(max_batch * 4))
 
 
 def gather_arenas(local_arena, dist, rank, world, dst=0):
@@ -38,4 +42,8 @@ def unpack_arena(arena_u8, max_batch, n, h, w):
     det = a[lay["det"]:lay["det"] + n * 300 * 6 * 4].view(np.float32).reshape(n, 300, 6)
     cnt = a[lay["det_count"]:lay["det_count"] + n * 4].view(np.int32)
     nl = a[lay["n_labels"]:lay["n_labels"] + n * 4].view(np.int32)
-    return dict(mask=mask, det=[det[i, :cnt[i]] for i in range(n)], n_labels=nl)
+    lb = a[lay["line_boxes"]:lay["line_boxes"] + n * 1000 * 16].view(np.int16).reshape(n, 1000, 4, 2)
+    ls = a[lay["line_scores"]:lay["line_scores"] + n * 1000 * 4].view(np.float32).reshape(n, 1000)
+    lc = a[lay["line_count"]:lay["line_count"] + n * 4].view(np.int32)
+    return dict(mask=mask, det=[det[i, :cnt[i]] for i in range(n)], n_labels=nl,
+                line_boxes=[lb[i, :lc[i]] for i in range(n)], line_scores=[ls[i, :lc[i]] for i in range(n)])

@@ -152,6 +152,14 @@ CTD_API int ctd_get_detections(ctd_handle* h, float* det, int32_t* det_count);
  * Any pointer may be NULL.                                                                 */
 CTD_API int ctd_get_db_components(ctd_handle* h, uint8_t* bitmap, int32_t* labels, int32_t* n_labels);
 
+/* `SegDetectorRepresenter.__call__` -> `boxes_from_bitmap` (db_utils.py:40-69,123-166) on the shrink map of
+ * the last forward: per page the contours in OpenCV's findContours(RETR_LIST) order, capped at 1000
+ * (max_candidates); rows of skipped contours (short side < 2) are zero with score 0 exactly like the
+ * reference.  boxes: HOST i16 [n][1000][4][2] (x,y; order TL,TR,BR,BL), scores: HOST f32 [n][1000],
+ * counts: HOST i32 [n] = min(#contours, 1000).  The box_thresh (0.6) filter of inference.py:159-161 is
+ * left to the caller, as in the reference.                                                        */
+CTD_API int ctd_get_text_lines(ctd_handle* h, int16_t* boxes, float* scores, int32_t* counts);
+
 /* Device-side timing of the last ctd_forward (CUDA events on the engine stream), ms.       */
 CTD_API int ctd_last_forward_ms(ctd_handle* h, float* ms);
 /* Number of kernels the last ctd_forward launched (graph nodes when captured).             */
@@ -180,7 +188,10 @@ typedef struct ctd_device_outputs {
   void* bitmap;      /* u8  [n][h][w]                                 */
   void* labels;      /* i32 [n][h][w]                                 */
   void* n_labels;    /* i32 [n]                                       */
-  void* results_base;   /* mask_u8 | det | det_count | n_labels live in ONE allocation sized for
+  void* line_boxes;  /* i16 [n][1000][4][2]                           */
+  void* line_scores; /* f32 [n][1000]                                 */
+  void* line_count;  /* i32 [n]                                       */
+  void* results_base;   /* mask_u8 | det | det_count | n_labels | line_* live in ONE allocation sized for
                            max_batch, so a single NCCL gather moves a rank's results          */
   size_t results_bytes;
 } ctd_device_outputs;
@@ -194,6 +205,12 @@ CTD_API int ctd_get_device_outputs(ctd_handle* h, ctd_device_outputs* out);
  * `stats_cap` = rows available in `stats`.                                                 */
 CTD_API int ctd_connected_components(ctd_handle* h, const uint8_t* img, int32_t ih, int32_t iw, int32_t* labels,
                              int32_t* stats, int32_t stats_cap, int32_t* n_labels);
+
+/* Stage-isolated form of the above on a caller-supplied probability map (HOST f32 [ih][iw]):
+ * binarize(pred > thresh) -> contours -> boxes/scores, as `SegDetectorRepresenter(thresh).__call__`
+ * would return for one image.  boxes i16 [1000][4][2], scores f32 [1000], *count = rows used.       */
+CTD_API int ctd_seg_represent(ctd_handle* h, const float* pred, int32_t ih, int32_t iw, float thresh, int16_t* boxes,
+                              float* scores, int32_t* count);
 
 /* utils/yolov5_utils.py:124-218 on a caller-supplied prediction tensor (HOST f32
  * [rows][5+nc]); output as ctd_get_detections for one page.                                */

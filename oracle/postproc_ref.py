@@ -52,3 +52,75 @@ def connected_components_cv2(img_u8):
     import cv2
     n, labels, stats, centroids = cv2.connectedComponentsWithStats(img_u8)
     return n, labels, stats, centroids
+
+
+# ---------------------------------------------------------------------------------------------------
+# SegDetectorRepresenter (utils/db_utils.py:32-211), non-polygon path used by inference.py:158
+
+
+def _get_mini_boxes(contour):
+    """db_utils.py:176-195"""
+    import cv2
+    bounding_box = cv2.minAreaRect(contour)
+    points = sorted(list(cv2.boxPoints(bounding_box)), key=lambda x: x[0])
+    if points[1][1] > points[0][1]:
+        i1, i4 = 0, 1
+    else:
+        i1, i4 = 1, 0
+    if points[3][1] > points[2][1]:
+        i2, i3 = 2, 3
+    else:
+        i2, i3 = 3, 2
+    return [points[i1], points[i2], points[i3], points[i4]], min(bounding_box[1])
+
+
+def _box_score_fast(bitmap, _box):
+    """db_utils.py:197-211"""
+    import cv2
+    h, w = bitmap.shape[:2]
+    box = _box.copy()
+    xmin = np.clip(np.floor(box[:, 0].min()).astype(np.int64), 0, w - 1)
+    xmax = np.clip(np.ceil(box[:, 0].max()).astype(np.int64), 0, w - 1)
+    ymin = np.clip(np.floor(box[:, 1].min()).astype(np.int64), 0, h - 1)
+    ymax = np.clip(np.ceil(box[:, 1].max()).astype(np.int64), 0, h - 1)
+    mask = np.zeros((ymax - ymin + 1, xmax - xmin + 1), dtype=np.uint8)
+    box[:, 0] = box[:, 0] - xmin
+    box[:, 1] = box[:, 1] - ymin
+    cv2.fillPoly(mask, box.reshape(1, -1, 2).astype(np.int32), 1)
+    return cv2.mean(bitmap[ymin:ymax + 1, xmin:xmax + 1], mask)[0]
+
+
+def _unclip(box, unclip_ratio=1.5):
+    """db_utils.py:168-174 with the third-party calls restated in oracle/geom_ref.py (parity unpinned)."""
+    from oracle import geom_ref
+    distance = geom_ref.geos_ring_area(box) * unclip_ratio / geom_ref.geos_ring_length(box)
+    pts = geom_ref.clipper_offset_closed_polygon(np.asarray(box).tolist(), distance)
+    return np.array([pts])
+
+
+def seg_represent(pred, thresh=0.3, max_candidates=1000, unclip_ratio=1.5):
+    """SegDetectorRepresenter(thresh)(batch, pred[None,None]) for ONE map: (boxes int16 [k,4,2], scores f32 [k])
+    -- db_utils.py:40-72 (binarize) and 123-166 (boxes_from_bitmap)."""
+    import cv2
+    pred = np.asarray(pred, np.float32)
+    bitmap = pred > thresh
+    height, width = bitmap.shape
+    contours, _ = cv2.findContours((bitmap * 255).astype(np.uint8), cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+    n = min(len(contours), max_candidates)
+    boxes = np.zeros((n, 4, 2), dtype=np.int16)
+    scores = np.zeros((n,), dtype=np.float32)
+    for index in range(n):
+        contour = contours[index].squeeze(1)
+        points, sside = _get_mini_boxes(contour)
+        if sside < 2:
+            continue
+        points = np.array(points)
+        score = _box_score_fast(pred, contour)
+        box = _unclip(points, unclip_ratio).reshape(-1, 1, 2)
+        box, sside = _get_mini_boxes(box)
+        box = np.array(box)
+        box[:, 0] = np.clip(np.round(box[:, 0] / width * width), 0, width)
+        box[:, 1] = np.clip(np.round(box[:, 1] / height * height), 0, height)
+        boxes[index, :, :] = box.astype(np.int16)
+        scores[index] = score
+    return boxes, scores
