@@ -42,7 +42,7 @@ EXPORTS = ["ctd_create", "ctd_destroy", "ctd_last_error", "ctd_forward", "ctd_ge
            "ctd_get_detections", "ctd_get_db_components", "ctd_last_forward_ms", "ctd_last_launch_count",
            "ctd_debug_read_buffer", "ctd_debug_write_buffer", "ctd_connected_components", "ctd_nms",
            "ctd_timer_start", "ctd_timer_stop", "ctd_profile_forward", "ctd_get_device_outputs",
-           "ctd_get_text_lines", "ctd_seg_represent"]
+           "ctd_get_text_lines", "ctd_seg_represent", "ctd_refine_mask"]
 
 _lib = None
 
@@ -80,6 +80,7 @@ def load_library():
     lib.ctd_nms.argtypes = [vp, vp, i32, C.c_float, C.c_float, vp, vp]
     lib.ctd_get_text_lines.argtypes = [vp, vp, vp, vp]
     lib.ctd_seg_represent.argtypes = [vp, vp, i32, i32, C.c_float, vp, vp, vp]
+    lib.ctd_refine_mask.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp]
     lib.ctd_timer_start.argtypes = [vp]
     lib.ctd_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     lib.ctd_profile_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32]
@@ -203,6 +204,16 @@ class Engine:
         self._ck(self.lib.ctd_seg_represent(self.h, _ptr(pred), h, w, thresh, _ptr(boxes), _ptr(scores), _ptr(cnt)))
         k = int(cnt[0])
         return boxes[:k].copy(), scores[:k].copy()
+
+    def refine_mask(self, img, mask, windows, refine_mode=0):
+        """windows: int32 [k,4] already-expanded xyxy windows (expand_textwindow of every block)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        mask = np.ascontiguousarray(mask, np.uint8)
+        win = np.ascontiguousarray(np.asarray(windows, np.int32).reshape(-1, 4))
+        out = np.empty(mask.shape, np.uint8)
+        self._ck(self.lib.ctd_refine_mask(self.h, _ptr(img), _ptr(mask), mask.shape[0], mask.shape[1], _ptr(win), len(win),
+                                          int(refine_mode), _ptr(out)))
+        return out
 
     def last_forward_ms(self):
         ms = C.c_float()

@@ -54,6 +54,8 @@ struct ctd_handle {
   int32_t* d_nlabels = nullptr;
   int32_t* d_ccl_scratch = nullptr;
   void* d_segrep_scratch = nullptr;
+  void* d_refine_scratch = nullptr;
+  size_t refine_scratch_cap = 0;
   int16_t* d_line_boxes = nullptr;
   float* d_line_scores = nullptr;
   int32_t* d_line_count = nullptr;
@@ -95,7 +97,7 @@ extern "C" void ctd_destroy(ctd_handle* h) {
   for (void* p : h->d_buf) cudaFree(p);
   cudaFree(h->d_blob); cudaFree(h->d_pages); cudaFree(h->d_blks); cudaFree(h->d_mask); cudaFree(h->d_mask_u8);
   cudaFree(h->d_lines); cudaFree(h->d_bitmap); cudaFree(h->d_labels);
-  cudaFree(h->d_ccl_scratch); cudaFree(h->d_nms_ws); cudaFree(h->d_segrep_scratch);
+  cudaFree(h->d_ccl_scratch); cudaFree(h->d_nms_ws); cudaFree(h->d_segrep_scratch); cudaFree(h->d_refine_scratch);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->tev0) cudaEventDestroy(h->tev0);
@@ -654,6 +656,49 @@ extern "C" int ctd_connected_components(ctd_handle* h, const uint8_t* img, int32
   }
   CK(cudaStreamSynchronize(h->stream));
   h->have_forward = false;  // the page outputs were clobbered
+  return CTD_OK;
+}
+
+extern "C" int ctd_refine_mask(ctd_handle* h, const uint8_t* img, const uint8_t* mask, int32_t ih, int32_t iw,
+                               const int32_t* windows, int32_t n_win, int32_t refine_mode, uint8_t* out) {
+  if (!h || !img || !mask || !out || (n_win > 0 && !windows)) return CTD_E_INVALID;
+  if (ih < 1 || iw < 1 || (size_t(ih) * iw) % 4) return fail(h, CTD_E_SHAPE, "ih*iw must be a multiple of 4");
+  CK(cudaSetDevice(h->cfg.device));
+  struct Win { int x1, y1, x2, y2; long long off; };
+  std::vector<Win> wins;
+  size_t total = 0;
+  for (int i = 0; i < n_win; ++i) {
+    Win w{windows[4 * i], windows[4 * i + 1], windows[4 * i + 2], windows[4 * i + 3], (long long)total};
+    if (w.x1 < 0 || w.y1 < 0 || w.x2 > iw || w.y2 > ih) return fail(h, CTD_E_INVALID, "window %d outside the image", i);
+    if (w.x2 > w.x1 && w.y2 > w.y1) total += size_t(w.x2 - w.x1) * (w.y2 - w.y1);
+    total = (total + 3) / 4 * 4;
+    wins.push_back(w);
+  }
+  const size_t px = size_t(ih) * iw;
+  const size_t need = refine_scratch_bytes(total) + px * 5 + wins.size() * sizeof(Win) + 1024;
+  if (need > h->refine_scratch_cap) {
+    cudaFree(h->d_refine_scratch);
+    h->d_refine_scratch = nullptr;
+    h->refine_scratch_cap = 0;
+    CK(cudaMalloc(&h->d_refine_scratch, need + need / 4));
+    h->refine_scratch_cap = need + need / 4;
+  }
+  char* base = static_cast<char*>(h->d_refine_scratch);
+  uint8_t* d_img = reinterpret_cast<uint8_t*>(base);
+  uint8_t* d_mask = d_img + px * 3;
+  uint8_t* d_out = d_mask + px;
+  char* d_wins = reinterpret_cast<char*>(d_out + px);
+  d_wins = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(d_wins) + 255) / 256 * 256);
+  char* d_scr = d_wins + (wins.size() * sizeof(Win) + 255) / 256 * 256;
+  CK(cudaMemcpyAsync(d_img, img, px * 3, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(d_mask, mask, px, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(d_out, 0, px, h->stream));
+  if (!wins.empty()) {
+    CK(cudaMemcpyAsync(d_wins, wins.data(), wins.size() * sizeof(Win), cudaMemcpyHostToDevice, h->stream));
+    CK(refine_launch(d_img, d_mask, ih, iw, d_wins, int(wins.size()), total, d_scr, refine_mode, d_out, h->stream));
+  }
+  CK(cudaMemcpyAsync(out, d_out, px, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return CTD_OK;
 }
 

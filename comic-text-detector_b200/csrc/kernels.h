@@ -144,4 +144,9 @@ cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_
                           int* n_contours, cudaStream_t s);
 cudaError_t binarize_launch(const float* pred, size_t count, float thresh, uint8_t* bitmap, cudaStream_t s);
 
+// refine_mask (refine.cu): one CTA per block window.  d_wins: n_wins x {x1,y1,x2,y2,(int64)pixel offset}
+size_t refine_scratch_bytes(size_t total_px);
+cudaError_t refine_launch(const uint8_t* d_img, const uint8_t* d_mask, int H, int W, const void* d_wins, int n_wins,
+                          size_t total_px, void* scratch, int refine_mode, uint8_t* d_out, cudaStream_t s);
+
 }  // namespace ctd

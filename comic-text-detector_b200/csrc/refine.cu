@@ -1,0 +1,466 @@
+// refine_mask on the GPU (reference utils/textmask.py:159-169 and callees 16-132):
+// per text block window: grey conversion, eroded-mask histogram -> top-3 colours -> inRange candidates,
+// per-channel Otsu candidate, polarity by min xor-sum, candidate-by-candidate connected-component merge
+// against the eroded/thresholded mask, 3x3 dilation (inpaint mode), hole filling, OR into the page mask.
+//
+// One CTA per block window; phases are separated by __syncthreads(); all per-window planes live in a
+// scratch arena (L2 resident).  Integer arithmetic throughout except the float64 numpy/OpenCV formulas that
+// are replicated literally (np.histogram bin mapping, np.linspace edges, cv2 Otsu, cvRound of inRange bounds).
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <math.h>
+
+#include "kernels.h"
+
+namespace ctd {
+
+constexpr int kRefThreads = 512;
+
+struct RefineWin {
+  int x1, y1, x2, y2;     // window (python slice semantics: rows y1..y2-1, cols x1..x2-1)
+  long long off;          // pixel offset of this window's planes inside each scratch plane
+};
+
+struct RefinePlanes {
+  uint8_t* grey;          // [total]
+  uint8_t* cand;          // [total] current candidate (0/255)
+  uint8_t* predm;         // [total] erode(cross)+thr 60 of the mask crop (0/255)
+  uint8_t* merged;        // [total]
+  uint8_t* tmp;           // [total] dilation target / inverse
+  int* L;                 // [total] union-find
+  int* acc;               // [4*total] per-root: area, gain, loss, maxidx
+};
+
+__device__ __forceinline__ int rf_find(const int* L, int a) {
+  int p = L[a];
+  while (p != a) {
+    a = p;
+    p = L[a];
+  }
+  return a;
+}
+__device__ __forceinline__ void rf_union(int* L, int a, int b) {
+  bool done;
+  do {
+    a = rf_find(L, a);
+    b = rf_find(L, b);
+    if (a < b) {
+      const int old = atomicMin(&L[b], a);
+      done = old == b;
+      b = old;
+    } else if (b < a) {
+      const int old = atomicMin(&L[a], b);
+      done = old == a;
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+
+// 8-connectivity labelling of plane `src` (non-zero = foreground) inside one window by the whole CTA.
+// Afterwards L[i] = root (smallest index of the component) or -1.
+__device__ void cta_ccl(const uint8_t* __restrict__ src, int rw, int rh, int* __restrict__ L) {
+  // rows: run starts (one thread per row, sequential inside the row)
+  for (int y = threadIdx.x; y < rh; y += blockDim.x) {
+    int start = -1;
+    const int base = y * rw;
+    for (int x = 0; x < rw; ++x) {
+      if (src[base + x]) {
+        if (start < 0) start = base + x;
+        L[base + x] = start;
+      } else {
+        start = -1;
+        L[base + x] = -1;
+      }
+    }
+  }
+  __syncthreads();
+  const int n = rw * rh;
+  // contacts with the row above; all predicates read `src` (L is being rewritten by the unions)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (!src[i] || i < rw) continue;
+    const int x = i % rw;
+    const int up = i - rw;
+    if (src[up]) {
+      // only the first pixel of each (current run x upper run) overlap issues the union
+      const bool first = x == 0 || !src[i - 1] || !src[up - 1];
+      if (first) rf_union(L, i, up);
+    } else {
+      if (x > 0 && src[up - 1]) rf_union(L, i, up - 1);
+      if (x + 1 < rw && src[up + 1]) rf_union(L, i, up + 1);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (L[i] >= 0) L[i] = rf_find(L, i);
+  __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* sm) {
+  // sm: one shared slot, zeroed by the caller before a __syncthreads
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(sm, v);
+  return 0;
+}
+
+// merge step shared by the candidate loop and the hole filling (textmask.py:92-108 / 118-131):
+// a label is OR-ed into `merged` iff that lowers xor(merged, pred) inside the label's bounding box, i.e.
+// iff among the label's pixels not yet in `merged` more have pred == 255 than pred == 0.
+__device__ void cta_merge_labels(const int* __restrict__ L, const uint8_t* __restrict__ predm, uint8_t* __restrict__ merged,
+                                 int* __restrict__ acc, int n, int rw, bool small_bbox_rule, int area_thresh) {
+  int* area = acc;
+  int* gain = acc + n;
+  int* loss = acc + 2 * n;
+  int* maxi = acc + 3 * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (L[i] == i) { area[i] = 0; gain[i] = 0; loss[i] = 0; maxi[i] = -1; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = L[i];
+    if (r < 0) continue;
+    atomicAdd(&area[r], 1);
+    atomicMax(&maxi[r], i);
+    if (merged[i] == 0) atomicAdd(predm[i] ? &gain[r] : &loss[r], 1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = L[i];
+    if (r < 0) continue;
+    bool ok;
+    if (small_bbox_rule) {
+      // `if w * h < 3: continue` (textmask.py:97): bounding boxes 1x1, 1x2, 2x1
+      const int a = area[r];
+      const bool tiny = a == 1 || (a == 2 && (maxi[r] == r + 1 || maxi[r] == r + rw));
+      ok = !tiny;
+    } else {
+      ok = area[r] < area_thresh;  // textmask.py:120
+    }
+    if (ok && gain[r] > loss[r]) merged[i] = 255;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask,
+                                                             int H, int W, const RefineWin* __restrict__ wins, RefinePlanes P,
+                                                             int refine_mode, uint32_t* __restrict__ out_words) {
+  const RefineWin win = wins[blockIdx.x];
+  const int rw = win.x2 - win.x1, rh = win.y2 - win.y1;
+  if (rw <= 0 || rh <= 0) return;
+  const int n = rw * rh;
+  uint8_t* grey = P.grey + win.off;
+  uint8_t* cand = P.cand + win.off;
+  uint8_t* predm = P.predm + win.off;
+  uint8_t* merged = P.merged + win.off;
+  uint8_t* tmp = P.tmp + win.off;
+  int* L = P.L + win.off;
+  int* acc = P.acc + 4 * win.off;
+
+  __shared__ int hist_g[256];          // grey histogram of the eroded-mask pixels
+  __shared__ int hist_c[3][256];       // per-channel histograms of the whole window (Otsu)
+  __shared__ int cnt255[256];          // np.histogram(bins=255) counts
+  __shared__ int order[256];
+  __shared__ double edges[256];
+  __shared__ int s_first, s_last, s_ncol, s_total;
+  __shared__ int lo[3], hi[3], otsu_t[3];
+  __shared__ unsigned long long xs[12];  // xor sums: [k][pos/neg] for 3 colours, then 3 channels
+  __shared__ int proc_kind[4], proc_neg[4], s_nproc;
+  __shared__ int top2[2], s_area0;
+
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    hist_g[i] = 0; hist_c[0][i] = 0; hist_c[1][i] = 0; hist_c[2][i] = 0; cnt255[i] = 0;
+  }
+  if (threadIdx.x < 12) xs[threadIdx.x] = 0ull;
+  __syncthreads();
+
+  // ---- phase 0: grey, eroded candidates, pred mask, histograms ---------------------------------
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int y = i / rw, x = i - y * rw;
+    const size_t gp = size_t(win.y1 + y) * W + win.x1 + x;
+    const int b = img[gp * 3], g = img[gp * 3 + 1], r = img[gp * 3 + 2];
+    const int gr = (b * 1868 + g * 9617 + r * 4899 + 8192) >> 14;  // cv2.COLOR_BGR2GRAY, 8u fixed point
+    grey[i] = (uint8_t)gr;
+    atomicAdd(&hist_c[0][b], 1);
+    atomicAdd(&hist_c[1][g], 1);
+    atomicAdd(&hist_c[2][r], 1);
+    // erosions of the mask CROP (window borders ignore the outside: BORDER_CONSTANT with +inf)
+    int m3 = 255, mc = 255;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= rh) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= rw) continue;
+        const int mv = mask[size_t(win.y1 + yy) * W + win.x1 + xx];
+        m3 = min(m3, mv);
+        if (dx == 0 || dy == 0) mc = min(mc, mv);
+      }
+    }
+    if (m3 > 127) atomicAdd(&hist_g[gr], 1);       // textmask.py:60
+    predm[i] = mc > 60 ? 255 : 0;                  // textmask.py:86-89
+    merged[i] = 0;
+  }
+  __syncthreads();
+
+  // ---- phase 1: np.histogram(bins=255) of the candidate grey values, top-k colours, Otsu ---------
+  if (threadIdx.x == 0) {
+    int first = -1, last = -1, total = 0;
+    for (int v = 0; v < 256; ++v)
+      if (hist_g[v]) { if (first < 0) first = v; last = v; total += hist_g[v]; }
+    s_first = first; s_last = last; s_total = total;
+  }
+  __syncthreads();
+  {
+    // outer edges (numpy _get_outer_edges): empty -> (0,1); equal -> (v-0.5, v+0.5)
+    double fe, le;
+    if (s_total == 0) { fe = 0.0; le = 1.0; }
+    else if (s_first == s_last) { fe = s_first - 0.5; le = s_last + 0.5; }
+    else { fe = s_first; le = s_last; }
+    const double step = (le - fe) / 255.0;  // np.linspace(fe, le, 256): arange * step + start, last = stop
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) edges[i] = (i == 255) ? le : __dadd_rn(__dmul_rn((double)i, step), fe);
+    __syncthreads();
+    for (int v = threadIdx.x; v < 256; v += blockDim.x) {
+      if (!hist_g[v]) continue;
+      const double a = (double)v;
+      const double f = ((a - fe) / (le - fe)) * 255.0;  // numpy fast path: (tmp_a - first_edge) / norm_denom * n_bins
+      int idx = (int)f;
+      if (idx == 255) idx = 254;
+      if (a < edges[idx]) --idx;
+      if (a >= edges[idx + 1] && idx != 254) ++idx;
+      atomicAdd(&cnt255[idx], hist_g[v]);
+    }
+  }
+  __syncthreads();
+  // stable descending order of the 255 bins (documented normalisation of np.argsort's tie order)
+  for (int b = threadIdx.x; b < 255; b += blockDim.x) {
+    int rank = 0;
+    const int cb = cnt255[b];
+    for (int c = 0; c < 255; ++c) rank += (cnt255[c] > cb) || (cnt255[c] == cb && c < b);
+    order[rank] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // get_topk_color (textmask.py:16-27): colour = LEFT EDGE of the bin (textmask.py:61-62 swaps the names)
+    double top[3];
+    int nt = 1;
+    top[0] = edges[order[0]];
+    const double tol = (double)s_total * 0.001;
+    for (int j = 1; j < 255; ++j) {
+      const double col = edges[order[j]];
+      double dmin = 1e300;
+      for (int t = 0; t < nt; ++t) dmin = fmin(dmin, fabs(top[t] - col));
+      if (dmin > 10.0) top[nt++] = col;
+      if (nt >= 3 || (double)cnt255[order[j]] < tol) break;
+    }
+    s_ncol = nt;
+    for (int t = 0; t < nt; ++t) {
+      const double c_top = fmin(top[t] + 30.0, 255.0);
+      const double c_bot = c_top - 60.0;
+      // cv2.inRange with float bounds on 8u data: cvRound (half to even) + saturate
+      lo[t] = (int)fmin(fmax(rint(c_bot), 0.0), 255.0);
+      hi[t] = (int)fmin(fmax(rint(c_top), 0.0), 255.0);
+    }
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 35) {
+    // cv2.threshold(..., THRESH_OTSU): getThreshVal_Otsu_8u
+    const int* hh = hist_c[threadIdx.x - 32];
+    const double scale = 1.0 / (double)n;
+    double mu = 0;
+    for (int i = 0; i < 256; ++i) mu = __dadd_rn(mu, __dmul_rn((double)i, (double)hh[i]));
+    mu = __dmul_rn(mu, scale);
+    double mu1 = 0, q1 = 0, max_sigma = 0;
+    int max_val = 0;
+    for (int i = 0; i < 256; ++i) {
+      const double p_i = __dmul_rn((double)hh[i], scale);
+      mu1 = __dmul_rn(mu1, q1);
+      q1 = __dadd_rn(q1, p_i);
+      const double q2 = 1.0 - q1;
+      if (fmin(q1, q2) < 1.1920929e-07 || fmax(q1, q2) > 1.0 - 1.1920929e-07) continue;
+      // explicit roundings: the x86 build of OpenCV has no FMA contraction here
+      mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
+      const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
+      const double dm = __dsub_rn(mu1, mu2);
+      const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), dm), dm);
+      if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+    }
+    otsu_t[threadIdx.x - 32] = max_val;
+  }
+  __syncthreads();
+
+  // ---- phase 2: xor sums of every candidate and of its negative against the mask crop -------------
+  {
+    unsigned long long loc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) loc[k] = 0ull;
+    const int ncol = s_ncol;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int y = i / rw, x = i - y * rw;
+      const size_t gp = size_t(win.y1 + y) * W + win.x1 + x;
+      const int mk = mask[gp];
+      const int gr = grey[i];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (k < ncol) {
+          const int t = (gr >= lo[k] && gr <= hi[k]) ? 255 : 0;
+          loc[2 * k] += (unsigned)(t ^ mk);
+          loc[2 * k + 1] += (unsigned)((255 - t) ^ mk);
+        }
+        const int ch = img[gp * 3 + k];
+        const int t2 = ch > otsu_t[k] ? 255 : 0;
+        loc[6 + 2 * k] += (unsigned)(t2 ^ mk);
+        loc[6 + 2 * k + 1] += (unsigned)((255 - t2) ^ mk);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 12; ++k) block_sum_u64(loc[k], &xs[k]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // minxor_thresh (textmask.py:29-41): negative wins only if strictly smaller
+    unsigned long long best[4];
+    int kind[4], neg[4], np_ = 0;
+    for (int k = 0; k < s_ncol; ++k) {
+      const bool ng = xs[2 * k + 1] < xs[2 * k];
+      best[np_] = ng ? xs[2 * k + 1] : xs[2 * k];
+      kind[np_] = k; neg[np_] = ng; ++np_;
+    }
+    // Otsu: best channel (stable sort by xor sum -> first minimum in B,G,R order)  (textmask.py:43-54)
+    int bc = 0, bneg = 0;
+    unsigned long long bv = ~0ull;
+    for (int c = 0; c < 3; ++c) {
+      const bool ng = xs[6 + 2 * c + 1] < xs[6 + 2 * c];
+      const unsigned long long v = ng ? xs[6 + 2 * c + 1] : xs[6 + 2 * c];
+      if (v < bv) { bv = v; bc = c; bneg = ng; }
+    }
+    best[np_] = bv; kind[np_] = 3 + bc; neg[np_] = bneg; ++np_;
+    // mask_list.sort(key=xor_sum) (textmask.py:74): stable insertion sort
+    for (int i = 1; i < np_; ++i) {
+      const unsigned long long v = best[i];
+      const int kk = kind[i], nn = neg[i];
+      int j = i - 1;
+      while (j >= 0 && best[j] > v) { best[j + 1] = best[j]; kind[j + 1] = kind[j]; neg[j + 1] = neg[j]; --j; }
+      best[j + 1] = v; kind[j + 1] = kk; neg[j + 1] = nn;
+    }
+    for (int i = 0; i < np_; ++i) { proc_kind[i] = kind[i]; proc_neg[i] = neg[i]; }
+    s_nproc = np_;
+  }
+  __syncthreads();
+
+  // ---- phase 3: candidates in order: label, test every label, merge -------------------------------
+  for (int c = 0; c < s_nproc; ++c) {
+    const int kind = proc_kind[c], neg = proc_neg[c];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      int t;
+      if (kind < 3) {
+        const int gr = grey[i];
+        t = (gr >= lo[kind] && gr <= hi[kind]) ? 255 : 0;
+      } else {
+        const int y = i / rw, x = i - y * rw;
+        const size_t gp = size_t(win.y1 + y) * W + win.x1 + x;
+        t = img[gp * 3 + (kind - 3)] > otsu_t[kind - 3] ? 255 : 0;
+      }
+      cand[i] = (uint8_t)(neg ? 255 - t : t);
+    }
+    __syncthreads();
+    cta_ccl(cand, rw, rh, L);
+    cta_merge_labels(L, predm, merged, acc, n, rw, true, 0);
+  }
+
+  // ---- phase 4: dilate 3x3 (inpaint mode) ------------------------------------------------------------
+  if (refine_mode == 0) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int y = i / rw, x = i - y * rw;
+      int m = 0;
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= rh) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int xx = x + dx;
+          if (xx < 0 || xx >= rw) continue;
+          m = max(m, (int)merged[yy * rw + xx]);
+        }
+      }
+      tmp[i] = (uint8_t)m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) merged[i] = tmp[i];
+    __syncthreads();
+  }
+
+  // ---- phase 5: fill holes: components of the inverse smaller than the 2nd largest area -------------
+  if (threadIdx.x == 0) { top2[0] = -1; top2[1] = -1; s_area0 = 0; }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) tmp[i] = merged[i] ? 0 : 255;
+  __syncthreads();
+  cta_ccl(tmp, rw, rh, L);
+  {
+    int* area = acc;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      if (L[i] == i) area[i] = 0;
+    __syncthreads();
+    int a0 = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      if (L[i] >= 0) atomicAdd(&area[L[i]], 1);
+      else ++a0;
+    }
+    if (a0) atomicAdd(&s_area0, a0);
+    __syncthreads();
+    // two largest areas over all labels INCLUDING label 0 (the pixels where the inverse is 0), as a multiset
+    int m1 = -1, m2 = -1;
+    auto push = [&](int a) { if (a > m1) { m2 = m1; m1 = a; } else if (a > m2) m2 = a; };
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      if (L[i] == i) push(area[i]);
+    if (threadIdx.x == 0) push(s_area0);
+    for (int o = 16; o > 0; o >>= 1) {
+      const int a1 = __shfl_down_sync(0xffffffffu, m1, o), a2 = __shfl_down_sync(0xffffffffu, m2, o);
+      push(a1);
+      push(a2);
+    }
+    __shared__ int wtop[kRefThreads / 32][2];
+    if ((threadIdx.x & 31) == 0) { wtop[threadIdx.x >> 5][0] = m1; wtop[threadIdx.x >> 5][1] = m2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t1 = -1, t2 = -1;
+      for (int wv = 0; wv < kRefThreads / 32; ++wv)
+        for (int e = 0; e < 2; ++e) {
+          const int a = wtop[wv][e];
+          if (a > t1) { t2 = t1; t1 = a; } else if (a > t2) t2 = a;
+        }
+      top2[0] = t1; top2[1] = t2;
+    }
+    __syncthreads();
+  }
+  {
+    // sorted_area[-2] if more than one label else sorted_area[-1] (textmask.py:114-118); label 0 always exists
+    const int thresh = top2[1] >= 0 ? top2[1] : top2[0];
+    cta_merge_labels(L, predm, merged, acc, n, rw, false, thresh);
+  }
+
+  // ---- phase 6: mask_refined[window] |= merged (textmask.py:168); windows may overlap -> atomic OR ----
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (!merged[i]) continue;
+    const int y = i / rw, x = i - y * rw;
+    const size_t gp = size_t(win.y1 + y) * W + win.x1 + x;
+    atomicOr(&out_words[gp >> 2], 0xffu << (8 * (gp & 3)));
+  }
+}
+
+size_t refine_scratch_bytes(size_t total_px) { return total_px * (5 + 4 + 16) + 4096; }
+
+cudaError_t refine_launch(const uint8_t* d_img, const uint8_t* d_mask, int H, int W, const void* d_wins, int n_wins,
+                          size_t total_px, void* scratch, int refine_mode, uint8_t* d_out, cudaStream_t s) {
+  if (n_wins <= 0) return cudaSuccess;
+  char* p = static_cast<char*>(scratch);
+  RefinePlanes P;
+  P.L = reinterpret_cast<int*>(p); p += total_px * 4;
+  P.acc = reinterpret_cast<int*>(p); p += total_px * 16;
+  P.grey = reinterpret_cast<uint8_t*>(p); p += total_px;
+  P.cand = reinterpret_cast<uint8_t*>(p); p += total_px;
+  P.predm = reinterpret_cast<uint8_t*>(p); p += total_px;
+  P.merged = reinterpret_cast<uint8_t*>(p); p += total_px;
+  P.tmp = reinterpret_cast<uint8_t*>(p);
+  refine_kernel<<<n_wins, kRefThreads, 0, s>>>(d_img, d_mask, H, W, static_cast<const RefineWin*>(d_wins), P, refine_mode,
+                                               reinterpret_cast<uint32_t*>(d_out));
+  return cudaGetLastError();
+}
+
+}  // namespace ctd

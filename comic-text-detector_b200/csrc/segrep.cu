@@ -232,38 +232,77 @@ __global__ void assign_cid_kernel(int h, int w, const int* __restrict__ Lf_all, 
   flag_all[o + p] = cid;  // the flag array now holds contour ids at root pixels
   (void)rowmin; (void)rowmax;
 }
-__global__ void rows_init_kernel(int* __restrict__ rowmin, int* __restrict__ rowmax, size_t n) {
+__global__ void rows_init_kernel(int* __restrict__ rowmin, int* __restrict__ rowmax, size_t n, int* __restrict__ c_yrange,
+                                 size_t ncont) {
   const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
   if (i < n) {
     rowmin[i] = INT_MAX;
     rowmax[i] = -1;
   }
+  if (i < ncont) {
+    c_yrange[2 * i] = INT_MAX;
+    c_yrange[2 * i + 1] = -1;
+  }
 }
 
 // ---- per-pixel accumulation ----------------------------------------------------------------------
+// Warp-aggregated: the 32 lanes of a warp are 32 consecutive pixels of one row, which mostly share their
+// component, so lanes with the same (component, row) key elect a leader that issues ONE set of atomics.
 __global__ void accumulate_kernel(int h, int w, const float* __restrict__ pred_all, size_t pred_page_stride,
                                   const int* __restrict__ Lf_all, const int* __restrict__ Lb_all,
                                   const int* __restrict__ parent_all, const int* __restrict__ cid_all,
                                   double* __restrict__ own_sum, int* __restrict__ own_cnt, double* __restrict__ ring_sum,
-                                  int* __restrict__ ring_cnt, int* __restrict__ rowmin, int* __restrict__ rowmax, int max_cand) {
+                                  int* __restrict__ ring_cnt, int* __restrict__ rowmin, int* __restrict__ rowmax,
+                                  int* __restrict__ c_yrange, int max_cand) {
   const int page = blockIdx.y;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int hw = h * w;
-  if (p >= hw) return;
+  const bool live = p < hw;
   const size_t o = size_t(page) * hw;
-  const float v = pred_all[size_t(page) * pred_page_stride + p];
-  const int y = p / w, x = p - y * w;
-  const int lf = Lf_all[o + p];
-  if (lf >= 0) {
-    atomicAdd(&own_sum[o + lf], (double)v);
-    atomicAdd(&own_cnt[o + lf], 1);
-    const int c = cid_all[o + lf];
-    if (c >= 0) {
-      const size_t ro = (size_t(page) * max_cand + c) * h + y;
-      atomicMin(&rowmin[ro], x);
-      atomicMax(&rowmax[ro], x);
+  const int lane = threadIdx.x & 31;
+  float v = 0.f;
+  int y = 0, x = 0, lf = -1, key = -1;
+  if (live) {
+    v = pred_all[size_t(page) * pred_page_stride + p];
+    y = p / w;
+    x = p - y * w;
+    lf = Lf_all[o + p];
+    if (lf >= 0) key = lf;
+    else {
+      const int lb = Lb_all[o + p];
+      if (parent_all[o + lb] != kFrame) key = lb;
     }
-    // ring membership: distinct holes among the 4-neighbours
+  }
+  const unsigned long long k64 = (unsigned long long)(unsigned)key | ((unsigned long long)(unsigned)y << 32);
+  const unsigned peers = __match_any_sync(0xffffffffu, k64);
+  const int leader = __ffs(peers) - 1;
+  double s = 0.0;
+  int c = 0;
+#pragma unroll 4
+  for (int l = 0; l < 32; ++l) {
+    const float ov = __shfl_sync(0xffffffffu, v, l);
+    if ((peers >> l) & 1u) {
+      s += (double)ov;
+      ++c;
+    }
+  }
+  if (live && key >= 0 && lane == leader) {
+    atomicAdd(&own_sum[o + key], s);
+    atomicAdd(&own_cnt[o + key], c);
+    if (lf >= 0) {
+      const int cid = cid_all[o + lf];
+      if (cid >= 0) {
+        const int last = 31 - __clz(peers);
+        const size_t ro = (size_t(page) * max_cand + cid) * h + y;
+        atomicMin(&rowmin[ro], x);                  // the leader is the left-most peer
+        atomicMax(&rowmax[ro], x + (last - lane));
+        atomicMin(&c_yrange[(page * max_cand + cid) * 2], y);
+        atomicMax(&c_yrange[(page * max_cand + cid) * 2 + 1], y);
+      }
+    }
+  }
+  if (live && lf >= 0) {
+    // ring membership: distinct holes among the 4-neighbours (boundary pixels only -> plain atomics)
     int hs[4];
     int nh = 0;
     const int nb[4] = {x > 0 ? p - 1 : -1, x + 1 < w ? p + 1 : -1, y > 0 ? p - w : -1, y + 1 < h ? p + w : -1};
@@ -271,7 +310,9 @@ __global__ void accumulate_kernel(int h, int w, const float* __restrict__ pred_a
     for (int k = 0; k < 4; ++k) {
       if (nb[k] < 0) continue;
       const int q = Lb_all[o + nb[k]];
-      if (q < 0 || parent_all[o + q] == kFrame) continue;
+      // the hole border runs over pixels of the component that SURROUNDS the hole (its tree parent); islands
+      // inside the hole touch it too but belong to its interior
+      if (q < 0 || parent_all[o + q] != lf) continue;
       bool dup = false;
       for (int e = 0; e < nh; ++e) dup |= hs[e] == q;
       if (!dup) hs[nh++] = q;
@@ -285,13 +326,9 @@ __global__ void accumulate_kernel(int h, int w, const float* __restrict__ pred_a
         const size_t ro = (size_t(page) * max_cand + c2) * h + y;
         atomicMin(&rowmin[ro], x);
         atomicMax(&rowmax[ro], x);
+        atomicMin(&c_yrange[(page * max_cand + c2) * 2], y);
+        atomicMax(&c_yrange[(page * max_cand + c2) * 2 + 1], y);
       }
-    }
-  } else {
-    const int lb = Lb_all[o + p];
-    if (parent_all[o + lb] != kFrame) {
-      atomicAdd(&own_sum[o + lb], (double)v);
-      atomicAdd(&own_cnt[o + lb], 1);
     }
   }
 }
@@ -328,7 +365,8 @@ struct ContourScratch {
 
 __global__ void __launch_bounds__(64) contour_kernel(int h, int w, int max_cand, const int* __restrict__ total,
                                                      const int* __restrict__ c_root, const int* __restrict__ rowmin,
-                                                     const int* __restrict__ rowmax, const double* __restrict__ tot_sum,
+                                                     const int* __restrict__ rowmax, const int* __restrict__ c_yrange,
+                                                     const double* __restrict__ tot_sum,
                                                      const int* __restrict__ tot_cnt, const double* __restrict__ ring_sum,
                                                      const int* __restrict__ ring_cnt, ContourScratch* __restrict__ scratch,
                                                      int16_t* __restrict__ boxes, float* __restrict__ scores,
@@ -354,9 +392,10 @@ __global__ void __launch_bounds__(64) contour_kernel(int h, int w, int max_cand,
   const int* rmax = rowmax + (size_t(page) * max_cand + c) * h;
   // monotone chain over the row extremes; rows are sorted by y, so the chain runs in the transposed
   // plane (x' = y, y' = x) and the result is transposed back (which mirrors the orientation -> reversed)
+  const int y_lo = max(0, c_yrange[(page * max_cand + c) * 2]), y_hi = min(h - 1, c_yrange[(page * max_cand + c) * 2 + 1]);
   int k = 0;
   bool overflow = false;
-  for (int y = 0; y < h && !overflow; ++y) {
+  for (int y = y_lo; y <= y_hi && !overflow; ++y) {
     const int a = rmin[y], b = rmax[y];
     if (b < 0) continue;
     for (int e = 0; e < (a == b ? 1 : 2); ++e) {
@@ -368,7 +407,7 @@ __global__ void __launch_bounds__(64) contour_kernel(int h, int w, int max_cand,
   }
   const int lower = k + 1;
   bool first = true;
-  for (int y = h - 1; y >= 0 && !overflow; --y) {
+  for (int y = y_hi; y >= y_lo && !overflow; --y) {
     const int a = rmin[y], b = rmax[y];
     if (b < 0) continue;
     for (int e = 0; e < (a == b ? 1 : 2); ++e) {
@@ -413,7 +452,7 @@ size_t segrep_scratch_bytes(int n, int h, int w, int max_cand) {
          + hw * 4 * 2          // tot_cnt, ring_cnt
          + hw * 8 * 3          // own_sum, tot_sum, ring_sum
          + size_t(n) * max_cand * h * 4 * 2   // rowmin, rowmax
-         + size_t(n) * max_cand * 4           // c_root
+         + size_t(n) * max_cand * 12          // c_root, c_yrange
          + size_t(n) * 2048 * 4               // segsum + totals
          + size_t(n) * max_cand * sizeof(ContourScratch) + 4096;
 }
@@ -436,6 +475,7 @@ cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_
   int* rowmin = reinterpret_cast<int*>(take(size_t(n) * max_cand * h * 4));
   int* rowmax = reinterpret_cast<int*>(take(size_t(n) * max_cand * h * 4));
   int* c_root = reinterpret_cast<int*>(take(size_t(n) * max_cand * 4));
+  int* c_yrange = reinterpret_cast<int*>(take(size_t(n) * max_cand * 8));
   int* segsum = reinterpret_cast<int*>(take(size_t(n) * 1024 * 4));
   int* total = reinterpret_cast<int*>(take(size_t(n) * 4));
   ContourScratch* cs = reinterpret_cast<ContourScratch*>(take(size_t(n) * max_cand * sizeof(ContourScratch)));
@@ -456,13 +496,13 @@ cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_
   flag_scan_top_kernel<<<n, 1024, 0, s>>>(segsum, nseg, total);
   {
     const size_t nr = size_t(n) * max_cand * h;
-    rows_init_kernel<<<unsigned((nr + 255) / 256), 256, 0, s>>>(rowmin, rowmax, nr);
+    rows_init_kernel<<<unsigned((nr + 255) / 256), 256, 0, s>>>(rowmin, rowmax, nr, c_yrange, size_t(n) * max_cand);
   }
   assign_cid_kernel<<<grid, 256, 0, s>>>(h, w, Lf, flag, segsum, nseg, total, max_cand, c_root, rowmin, rowmax);
   accumulate_kernel<<<grid, 256, 0, s>>>(h, w, pred, pred_page_stride, Lf, Lb, parent, flag, own_sum, own_cnt, ring_sum,
-                                         ring_cnt, rowmin, rowmax, max_cand);
+                                         ring_cnt, rowmin, rowmax, c_yrange, max_cand);
   tree_kernel<<<grid, 256, 0, s>>>(h, w, Lf, Lb, parent, own_sum, own_cnt, tot_sum, tot_cnt);
-  contour_kernel<<<dim3((max_cand + 63) / 64, n), 64, 0, s>>>(h, w, max_cand, total, c_root, rowmin, rowmax, tot_sum, tot_cnt,
+  contour_kernel<<<dim3((max_cand + 63) / 64, n), 64, 0, s>>>(h, w, max_cand, total, c_root, rowmin, rowmax, c_yrange, tot_sum, tot_cnt,
                                                               ring_sum, ring_cnt, cs, boxes, scores, n_contours, w, h,
                                                               unclip_ratio);
   return cudaGetLastError();

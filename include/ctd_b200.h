@@ -212,6 +212,13 @@ CTD_API int ctd_connected_components(ctd_handle* h, const uint8_t* img, int32_t 
 CTD_API int ctd_seg_represent(ctd_handle* h, const float* pred, int32_t ih, int32_t iw, float thresh, int16_t* boxes,
                               float* scores, int32_t* count);
 
+/* `refine_mask(img, pred_mask, blk_list, refine_mode)` (utils/textmask.py:159-169): img HOST u8 [ih][iw][3]
+ * BGR, mask HOST u8 [ih][iw], windows HOST i32 [n_win][4] = `expand_textwindow(img.shape, blk.xyxy, 16)` of
+ * every block (python slice semantics), refine_mode 0 = REFINEMASK_INPAINT, 1 = REFINEMASK_ANNOTATION.
+ * out HOST u8 [ih][iw] = mask_refined.  ih*iw must be a multiple of 4.                                */
+CTD_API int ctd_refine_mask(ctd_handle* h, const uint8_t* img, const uint8_t* mask, int32_t ih, int32_t iw,
+                            const int32_t* windows, int32_t n_win, int32_t refine_mode, uint8_t* out);
+
 /* utils/yolov5_utils.py:124-218 on a caller-supplied prediction tensor (HOST f32
  * [rows][5+nc]); output as ctd_get_detections for one page.                                */
 CTD_API int ctd_nms(ctd_handle* h, const float* pred, int32_t rows, float conf_thresh, float iou_thresh, float* det,

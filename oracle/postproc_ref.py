@@ -124,3 +124,118 @@ def seg_represent(pred, thresh=0.3, max_candidates=1000, unclip_ratio=1.5):
         boxes[index, :, :] = box.astype(np.int16)
         scores[index] = score
     return boxes, scores
+
+
+# ---------------------------------------------------------------------------------------------------
+# refine_mask (utils/textmask.py:159-169) and callees, restated with the same cv2/numpy calls.
+# ONE deliberate normalisation: `np.argsort(bins * -1)` in get_topk_color (textmask.py:17) is an unstable
+# sort whose tie order depends on numpy's SIMD sort build (SURVEY 8c "known non-determinism"); here and in
+# the CUDA path ties are broken by ascending bin index (kind="stable").
+REFINEMASK_INPAINT, REFINEMASK_ANNOTATION = 0, 1
+
+
+def expand_textwindow(img_size, xyxy, expand_r=8):
+    """utils/imgproc_utils.py:151-161"""
+    im_h, im_w = img_size[:2]
+    x1, y1, x2, y2 = xyxy
+    w, h = x2 - x1, y2 - y1
+    paddings = int(round((max(h, w) * 0.25 + min(h, w) * 0.75) / expand_r))
+    x1, y1 = max(0, x1 - paddings), max(0, y1 - paddings)
+    x2, y2 = min(im_w - 1, x2 + paddings), min(im_h - 1, y2 + paddings)
+    return [x1, y1, x2, y2]
+
+
+def _topk_color(color_list, bins, k=3, color_var=10, bin_tol=0.001):
+    """textmask.py:16-27 (stable tie order, see header)."""
+    idx = np.argsort(bins * -1, kind="stable")
+    color_list, bins = color_list[idx], bins[idx]
+    top = [color_list[0]]
+    tol = np.sum(bins) * bin_tol
+    if len(color_list) > 1:
+        for color, b in zip(color_list[1:], bins[1:]):
+            if np.abs(np.array(top) - color).min() > color_var:
+                top.append(color)
+            if len(top) >= k or b < tol:
+                break
+    return top
+
+
+def _minxor(threshed, mask):
+    """textmask.py:29-41 (dilate=False)"""
+    import cv2
+    neg = 255 - threshed
+    neg_sum = cv2.bitwise_xor(neg, mask).sum()
+    pos_sum = cv2.bitwise_xor(threshed, mask).sum()
+    return (neg, neg_sum) if neg_sum < pos_sum else (threshed, pos_sum)
+
+
+def candidate_masks(im, msk):
+    """get_topk_masklist + get_otsuthresh_masklist (textmask.py:43-71) -> list of [mask, xor_sum]"""
+    import cv2
+    grey = cv2.cvtColor(im, cv2.COLOR_BGR2GRAY)
+    msk = np.ascontiguousarray(msk)
+    px = grey[np.where(cv2.erode(msk, np.ones((3, 3), np.uint8), iterations=1) > 127)]
+    counts, edges = np.histogram(px, bins=255)
+    out = []
+    for color in _topk_color(edges, counts, color_var=10, k=3):
+        c_top = min(color + 30, 255)
+        c_bottom = c_top - 60
+        t, s = _minxor(cv2.inRange(grey, c_bottom, c_top), msk)
+        out.append([t, s])
+    per_ch = []
+    for c in (im[..., 0], im[..., 1], im[..., 2]):
+        _, t = cv2.threshold(c, 1, 255, cv2.THRESH_OTSU + cv2.THRESH_BINARY)
+        t, s = _minxor(t, msk)
+        per_ch.append([t, s])
+    per_ch.sort(key=lambda x: x[1])
+    return out + [per_ch[0]]
+
+
+def merge_masks(mask_list, pred_mask, refine_mode=REFINEMASK_INPAINT):
+    """merge_mask_list (textmask.py:73-132) with the defaults refine_mask uses (no line filter)."""
+    import cv2
+    mask_list.sort(key=lambda x: x[1])
+    element = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (3, 3), (1, 1))
+    pred = cv2.erode(pred_mask, element, iterations=1)
+    _, pred = cv2.threshold(pred, 60, 255, cv2.THRESH_BINARY)
+    merged = np.zeros_like(pred)
+
+    def try_labels(labels, stats, n, skip_bg, area_thresh=None):
+        for li in range(n):
+            if skip_bg and li == 0:
+                continue
+            x, y, w, h, area = stats[li]
+            if area_thresh is None:
+                if w * h < 3:
+                    continue
+            elif not area < area_thresh:
+                continue
+            sl = (slice(y, y + h), slice(x, x + w))
+            tmp = np.zeros((h, w), np.uint8)
+            tmp[labels[sl] == li] = 255
+            tmp = cv2.bitwise_or(merged[sl], tmp)
+            if cv2.bitwise_xor(tmp, pred[sl]).sum() < cv2.bitwise_xor(merged[sl], pred[sl]).sum():
+                merged[sl] = tmp
+
+    for cand, _ in mask_list:
+        n, labels, stats, _c = cv2.connectedComponentsWithStats(cand, 8, cv2.CV_16U)  # effectively (cand): 8-conn, CV_32S
+        try_labels(labels, stats, n, True)
+    if refine_mode == REFINEMASK_INPAINT:
+        merged[...] = cv2.dilate(merged, np.ones((3, 3), np.uint8), iterations=1)
+    n, labels, stats, _c = cv2.connectedComponentsWithStats(255 - merged, 8, cv2.CV_16U)
+    areas = np.sort(stats[:, -1])
+    try_labels(labels, stats, n, False, areas[-2] if len(areas) > 1 else areas[-1])
+    return merged
+
+
+def refine_mask(img, pred_mask, windows_xyxy, refine_mode=REFINEMASK_INPAINT):
+    """refine_mask (textmask.py:159-169); `windows_xyxy` = [blk.xyxy for blk in blk_list]."""
+    import cv2
+    out = np.zeros_like(pred_mask)
+    for xyxy in windows_xyxy:
+        bx1, by1, bx2, by2 = expand_textwindow(img.shape, xyxy, expand_r=16)
+        im = np.ascontiguousarray(img[by1:by2, bx1:bx2])
+        msk = np.ascontiguousarray(pred_mask[by1:by2, bx1:bx2])
+        merged = merge_masks(candidate_masks(im, msk), msk, refine_mode)
+        out[by1:by2, bx1:bx2] = cv2.bitwise_or(out[by1:by2, bx1:bx2], merged)
+    return out
