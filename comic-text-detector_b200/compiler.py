@@ -100,7 +100,7 @@ class Program:
         op = dict(kind=kind, n_src=len(srcs), src_buf=[0] * MAX_SRC, src_coff=[0] * MAX_SRC, src_c=[0] * MAX_SRC,
                   dst_buf=-1, dst_coff=0, cout=0, cout_pad=0, ksize=1, stride=1, act=ACT_NONE, residual=0, aux=0,
                   w16_off=0, w32_off=0, b_off=0, p_off=0)
-        assert 1 <= len(srcs) <= MAX_SRC or kind in (OP_STEM, OP_S2D)
+        assert 1 <= len(srcs) <= MAX_SRC or kind in (OP_S2D,)
         for i, s in enumerate(srcs):
             op["src_buf"][i], op["src_coff"][i], op["src_c"][i] = s["buf"], s["coff"], s["c"]
         if dst is not None:
@@ -221,24 +221,26 @@ def compile_checkpoint(ckpt, head_act="leaky", stem_mode="s2d"):
             if i == 0:
                 assert L["k"] == 6 and L["s"] == 2 and w.shape[1] == 3 and w.shape[0] <= 32, "stem must be Conv(3,<=32,6,2,2)"
                 co = w.shape[0]
-                if stem_mode == "simt":
-                    dst = P.tensor(P.newbuf(co, 2), 0, co)
-                    w32 = w.transpose(0, 2, 3, 1).reshape(co, 108).astype(np.float32)
-                    bp = b.astype(np.float32)
-                    P._op(OP_STEM, [], dst, ksize=6, stride=2, act=ACT_SILU, cout=co, cout_pad=co,
-                          w32_off=P.add_blob(w32), b_off=P.add_blob(bp))
-                    x = [dst]
-                else:
-                    # 6x6 s2 p2 over 3 channels == 3x3 s1 p1 over the 2x2 space-to-depth image (12 channels,
-                    # padded to 16): ky = 2a+dy, kx = 2b+dx, s2d channel = (dy*2+dx)*3 + c
-                    s2d = P.tensor(P.newbuf(16, 2), 0, 16)
-                    P._op(OP_S2D, [], s2d)
-                    w3 = np.zeros((co, 16, 3, 3), np.float64)
-                    for dy in range(2):
-                        for dx in range(2):
-                            for c in range(3):
-                                w3[:, (dy * 2 + dx) * 3 + c] = w[:, c, dy::2, dx::2]
-                    x = [P.conv([s2d], w3, b, 1, ACT_SILU)]
+                dst = P.tensor(P.newbuf(co, 2), 0, co)
+                w32 = w.transpose(0, 2, 3, 1).reshape(co, 108).astype(np.float32)
+                bp = np.zeros((32,), np.float32)
+                bp[:co] = b
+                # tensor-core form: 6x6 s2 p2 over 3 channels == 3x3 s1 p1 over the 2x2 space-to-depth page
+                # (ky = 2a+dy, kx = 2b+dx, s2d channel = (dy*2+dx)*3 + c, 12 -> 16 channels).  One K block per
+                # filter ROW a: the 4-pixel window (x-1 .. x+2) x 16 channels = 64 contiguous fp16 of the padded
+                # s2d buffer (the 4th pixel has zero weights), so K = 3 x 64.
+                w3 = np.zeros((co, 16, 3, 3), np.float64)
+                for dy in range(2):
+                    for dx in range(2):
+                        for c in range(3):
+                            w3[:, (dy * 2 + dx) * 3 + c] = w[:, c, dy::2, dx::2]
+                wwin = np.zeros((32, 3, 4, 16), np.float32)
+                wwin[:co, :, :3, :] = w3.transpose(0, 2, 3, 1)  # [co][a][b][ch]
+                s2d = P.tensor(P.newbuf(16, 2), 0, 16)
+                P._op(OP_STEM, [s2d], dst, ksize=6, stride=2, act=ACT_SILU, cout=co, cout_pad=32,
+                      w32_off=P.add_blob(w32), w16_off=P.add_blob(wwin.reshape(32, 192).astype(np.float16)),
+                      b_off=P.add_blob(bp))
+                x = [dst]
             else:
                 x = [P.conv(inp, w, b, L["s"], ACT_SILU)]
         elif t == "C3":

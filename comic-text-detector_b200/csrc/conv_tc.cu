@@ -429,6 +429,45 @@ const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
   return nullptr;
 }
 
+const char* conv_tc_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void* s2d, int n, int ph, int pw,
+                              const void* w16, const float* bias, __half* dst, int dst_cstride, int dst_coff, int cout,
+                              int act) {
+  ConvTcParams& p = plan.p;
+  memset(&p, 0, sizeof(p));
+  ConvGeom& g = p.g;
+  const int oh = ph / 2, ow = pw / 2, pitch = ow + 4;
+  g.n_img = n; g.gh = oh; g.gw = ow; g.dst_h = oh; g.dst_w = ow; g.out_mul = 1; g.n_phase = 1;
+  g.taps = 3; g.cin_total = 64; g.k_total = 192; g.n_src = 1; g.src_c[0] = 64; g.src_cstride[0] = 16;
+  g.src_h = oh; g.src_w = ow; g.in_stride = 1;
+  for (int t = 0; t < 3; ++t) { g.tap_dy[0][t] = int8_t(t - 1); g.tap_dx[0][t] = 0; }
+  g.cout = cout; g.cout_pad = 32; g.dst_cstride = dst_cstride; g.dst_coff = dst_coff; g.act = act; g.residual = 0;
+  p.kb_elems = 64;
+  p.src_kblocks[0] = 1;
+  p.tiles_x = (ow + kTileW - 1) / kTileW;
+  p.tiles_y = (oh + kTileH - 1) / kTileH;
+  p.dst = dst;
+  p.bias = bias;
+  {
+    // overlapping windows: element stride of dim 1 is ONE s2d pixel (16 channels = 32 B) while the box takes
+    // 64 contiguous channels (4 pixels); window x starts at padded pixel x = original pixel x-1
+    cuuint64_t dims[4] = {64, cuuint64_t(ow), cuuint64_t(oh), cuuint64_t(n)};
+    cuuint64_t str[3] = {32, cuuint64_t(pitch) * 32, cuuint64_t(pitch) * 32 * oh};
+    cuuint32_t box[4] = {64, kTileW, kTileH, 1};
+    if (const char* e = encode_map(enc, &p.a_map[0][0], s2d, 4, dims, str, box, 64)) return e;
+  }
+  plan.block_n = 32;
+  {
+    cuuint64_t dims[2] = {192, 32};
+    cuuint64_t str[1] = {192 * 2};
+    cuuint32_t box[2] = {64, 32};
+    if (const char* e = encode_map(enc, &p.b_map, w16, 2, dims, str, box, 64)) return e;
+  }
+  const int total_tiles = n * p.tiles_x * p.tiles_y;
+  plan.grid = dim3(unsigned(total_tiles < g_num_sms ? total_tiles : g_num_sms), 1, 1);
+  plan.smem_bytes = TcCfg<32>::kSmem;
+  return nullptr;
+}
+
 cudaError_t conv_tc_init() {
   cudaError_t e;
   int dev = 0;

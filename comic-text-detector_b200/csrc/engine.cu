@@ -157,7 +157,7 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
   const size_t nb = size_t(cfg->max_batch), mh = cfg->max_h, mw = cfg->max_w;
   h->d_buf.assign(n_bufs, nullptr);
   for (int i = 0; i < n_bufs; ++i) {
-    const size_t bytes = nb * (mh / bufs[i].down) * (mw / bufs[i].down) * bufs[i].channels * h->elem;
+    const size_t bytes = nb * (mh / bufs[i].down) * (mw / bufs[i].down + 4) * bufs[i].channels * h->elem;
     CKC(cudaMalloc(&h->d_buf[i], bytes));
     CKC(cudaMemset(h->d_buf[i], 0, bytes));
   }
@@ -233,6 +233,15 @@ static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
   if (h->cfg.precision != CTD_PREC_FP16_TC) return CTD_OK;
   for (size_t i = 0; i < h->ops.size(); ++i) {
     const ctd_op& op = h->ops[i];
+    if (op.kind == CTD_OP_STEM) {
+      const char* e = conv_tc_plan_stem(sp.tc[i], h->enc, h->d_buf[op.src_buf[0]], n, ph, pw, h->d_blob + op.w16_off,
+                                        reinterpret_cast<const float*>(h->d_blob + op.b_off),
+                                        static_cast<__half*>(h->d_buf[op.dst_buf]), h->bufs[op.dst_buf].channels,
+                                        op.dst_coff, op.cout, op.act);
+      if (e) return fail(h, CTD_E_INVALID, "stem: %s", e);
+      sp.has_tc[i] = 1;
+      continue;
+    }
     if (op.kind != CTD_OP_CONV && op.kind != CTD_OP_DECONV4 && op.kind != CTD_OP_DETECT) continue;
     ConvGeom g;
     if (int rc = op_geom(h, op, n, ph, pw, g)) return rc;
@@ -305,6 +314,7 @@ template <typename T>
 static int run_op_thin(ctd_handle* h, const ctd_op& op, int n, int ph, int pw) {
   cudaStream_t s = h->stream;
   const ctd_bufdesc* sb = (op.kind == CTD_OP_STEM || op.kind == CTD_OP_S2D) ? nullptr : &h->bufs[op.src_buf[0]];
+  (void)sb;
   const int sh = sb ? ph / sb->down : ph, sw = sb ? pw / sb->down : pw;
   const T* src = sb ? static_cast<const T*>(h->d_buf[op.src_buf[0]]) + op.src_coff[0] : nullptr;
   switch (op.kind) {
@@ -315,7 +325,7 @@ static int run_op_thin(ctd_handle* h, const ctd_op& op, int n, int ph, int pw) {
       return CTD_OK;
     case CTD_OP_S2D:
       CK(s2d_launch<T>(h->d_pages, n, ph, pw, static_cast<T*>(h->d_buf[op.dst_buf]), h->bufs[op.dst_buf].channels,
-                       op.dst_coff, s));
+                       op.dst_coff, pw / 2, 0, s));
       return CTD_OK;
     case CTD_OP_AVGPOOL2:
       CK(avgpool2_launch<T>(src, n, sh, sw, op.src_c[0], sb->channels,
@@ -348,8 +358,15 @@ static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* lau
   for (size_t i = 0; i < h->ops.size(); ++i) {
     const ctd_op& op = h->ops[i];
     const bool gemm = op.kind == CTD_OP_CONV || op.kind == CTD_OP_DECONV4 || op.kind == CTD_OP_DETECT;
-    int rc;
-    if (gemm) {
+    int rc = CTD_OK;
+    if (op.kind == CTD_OP_STEM && h->cfg.precision == CTD_PREC_FP16_TC) {
+      // tensor-core stem: space-to-depth pre-pass into the padded window buffer, then the implicit GEMM
+      cudaError_t e = s2d_launch<__half>(h->d_pages, n, ph, pw, static_cast<__half*>(h->d_buf[op.src_buf[0]]), 16, 0,
+                                         pw / 2 + 4, 1, h->stream);
+      if (e == cudaSuccess) e = conv_tc_launch(sp.tc[i], h->stream);
+      rc = e == cudaSuccess ? CTD_OK : fail(h, CTD_E_CUDA, "stem op %zu: %s", i, cudaGetErrorString(e));
+      ++cnt;
+    } else if (gemm) {
       if (h->cfg.precision == CTD_PREC_FP16_TC) {
         cudaError_t e = conv_tc_launch(sp.tc[i], h->stream);
         rc = e == cudaSuccess ? CTD_OK : fail(h, CTD_E_CUDA, "conv_tc op %zu: %s", i, cudaGetErrorString(e));

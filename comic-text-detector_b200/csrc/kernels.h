@@ -74,6 +74,11 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 // Builds tensor maps + launch shape.  Returns nullptr on success, else an error string.
 const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
                          const int src_coff[], const void* w16, const float* bias, __half* dst);
+// Stem in tensor-core form: 3 filter rows x (4-pixel window x 16 channels) over the padded space-to-depth page
+// (`s2d`: [n][ph/2][pw/2 + 4][16] fp16), output [n][ph/2][pw/2][cstride] at channel offset `dst_coff`.
+const char* conv_tc_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void* s2d, int n, int ph, int pw,
+                              const void* w16, const float* bias, __half* dst, int dst_cstride, int dst_coff, int cout,
+                              int act);
 cudaError_t conv_tc_launch(const ConvTcPlan& plan, cudaStream_t s);
 cudaError_t conv_tc_init();  // sets max dynamic smem attributes once
 
@@ -98,7 +103,8 @@ cudaError_t stem_launch(const uint8_t* pages, int n, int h, int w, const float* 
                         const float* bias, T* dst, int dst_cstride, int dst_coff, int cout, int act, cudaStream_t s);
 // u8 BGR HWC page -> /255 -> space-to-depth(2): dst[n][h/2][w/2][16], channel = (dy*2+dx)*3 + c, 12..15 = 0
 template <typename T>
-cudaError_t s2d_launch(const uint8_t* pages, int n, int h, int w, T* dst, int dst_cstride, int dst_coff, cudaStream_t s);
+cudaError_t s2d_launch(const uint8_t* pages, int n, int h, int w, T* dst, int dst_cstride, int dst_coff, int pitch_px,
+                       int xoff, cudaStream_t s);
 template <typename T>
 cudaError_t avgpool2_launch(const T* src, int n, int h, int w, int c, int src_cstride, T* dst, int dst_cstride,
                             cudaStream_t s);

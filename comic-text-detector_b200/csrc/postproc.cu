@@ -153,49 +153,70 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(const float* __restrict__ 
   mask[(size_t(img) * cap + i) * (cap / 64) + cb] = bits;
 }
 
-// greedy scan (one warp per page), keeps at most max_det rows.  The live part of the suppression
-// matrix (m rows x ceil(m/64) words) is staged in shared memory when it fits, so the serial loop never
-// waits on global memory.
-__global__ void __launch_bounds__(32) nms_scan_kernel(const float* __restrict__ sorted, const int* __restrict__ cand_count,
+// greedy scan, one CTA per page, candidates in chunks of 64: the 64x64 diagonal block of a chunk is
+// resolved serially by one thread from registers/shared memory, then every thread ORs the rows of the
+// chunk's kept candidates into its own word of the suppression vector (coalesced row reads).  Stops at
+// max_det kept rows like yolov5_utils.py:201-202.
+__global__ void __launch_bounds__(64) nms_scan_kernel(const float* __restrict__ sorted, const int* __restrict__ cand_count,
                                                       const unsigned long long* __restrict__ mask, int cap,
-                                                      float* __restrict__ det, int* __restrict__ det_count,
-                                                      int smem_words) {
-  extern __shared__ unsigned long long sm64[];  // remv[cap/64] | staged matrix
-  const int img = blockIdx.x, lane = threadIdx.x;
+                                                      float* __restrict__ det, int* __restrict__ det_count) {
+  __shared__ unsigned long long remv[64];      // cap <= 4096 -> <= 64 words
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long s_keepbits;
+  __shared__ int s_kept;
+  const int img = blockIdx.x, t = threadIdx.x;
   int m = cand_count[img];
   if (m > cap) m = cap;
   const int words = cap / 64;
-  unsigned long long* remv = sm64;
-  unsigned long long* stage = sm64 + words;
-  for (int w = lane; w < words; w += 32) remv[w] = 0ull;
   const int wlast = (m + 63) >> 6;
+  remv[t] = 0ull;
+  if (t == 0) s_kept = 0;
+  __syncthreads();
   const unsigned long long* mbase = mask + size_t(img) * cap * words;
-  const bool staged = size_t(m) * wlast <= size_t(smem_words);
-  if (staged) {
-    for (int i = lane; i < m * wlast; i += 32) {
-      const int r = i / wlast, w = i - r * wlast;
-      stage[i] = (w >= (r >> 6)) ? mbase[size_t(r) * words + w] : 0ull;
-    }
-  }
-  __syncwarp();
   const float* s = sorted + size_t(img) * cap * kCandStride;
   float* o = det + size_t(img) * kMaxDet * 6;
-  int kept = 0;
-  for (int i = 0; i < m && kept < kMaxDet; ++i) {
-    const unsigned long long rw = remv[i >> 6];
-    if ((rw >> (i & 63)) & 1ull) continue;
-    if (lane < 6) o[kept * 6 + lane] = s[i * kCandStride + lane];
-    ++kept;
-    if (staged) {
-      const unsigned long long* mrow = stage + size_t(i) * wlast;
-      for (int w = (i >> 6) + lane; w < wlast; w += 32) remv[w] |= mrow[w];
-    } else {
-      const unsigned long long* mrow = mbase + size_t(i) * words;
-      for (int w = (i >> 6) + lane; w < wlast; w += 32) remv[w] |= mrow[w];
+  for (int c = 0; c < wlast; ++c) {
+    const int i = c * 64 + t;
+    diag[t] = (i < m) ? mbase[size_t(i) * words + c] : 0ull;
+    __syncthreads();
+    if (t == 0) {
+      unsigned long long rw = remv[c], keep = 0ull;
+      int kept = s_kept;
+      const int lim = min(64, m - c * 64);
+      for (int j = 0; j < lim && kept < kMaxDet; ++j) {
+        if ((rw >> j) & 1ull) continue;
+        keep |= 1ull << j;
+        rw |= diag[j];
+        ++kept;
+      }
+      s_keepbits = keep;
     }
-    __syncwarp();
+    __syncthreads();
+    const unsigned long long keep = s_keepbits;
+    const int base_kept = s_kept;
+    // write the kept rows (thread j writes its own row if kept)
+    if ((keep >> t) & 1ull) {
+      const int pos = base_kept + __popcll(keep & ((1ull << t) - 1ull));
+      const float* r = s + size_t(c * 64 + t) * kCandStride;
+#pragma unroll
+      for (int e = 0; e < 6; ++e) o[pos * 6 + e] = r[e];
+    }
+    // OR the kept rows into the later words: thread t owns word t
+    if (t > c && t < wlast) {
+      unsigned long long acc = remv[t], kb = keep;
+      while (kb) {
+        const int j = __ffsll((long long)kb) - 1;
+        kb &= kb - 1;
+        acc |= mbase[size_t(c * 64 + j) * words + t];
+      }
+      remv[t] = acc;
+    }
+    __syncthreads();
+    if (t == 0) s_kept = base_kept + __popcll(keep);
+    __syncthreads();
+    if (s_kept >= kMaxDet) break;
   }
-  if (lane == 0) det_count[img] = kept;
+  if (t == 0) det_count[img] = s_kept;
 }
 
 cudaError_t nms_launch(const float* blks, int n, int rows, int nc, float conf, float iou, NmsWorkspace& ws, float* det,
@@ -209,16 +230,8 @@ cudaError_t nms_launch(const float* blks, int n, int rows, int nc, float conf, f
   else return cudaErrorInvalidValue;
   const int blocks = ws.cap / 64;
   nms_mask_kernel<<<dim3(blocks, blocks, n), 64, 0, s>>>(ws.sorted, ws.cand_count, ws.mask, ws.cap, iou);
-  {
-    const int stage_words = 8192;  // 64 KB: up to ~720 candidates fully staged
-    static bool attr_set = false;
-    const size_t smem = size_t(ws.cap / 64 + stage_words) * 8;
-    if (!attr_set) {
-      cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-      attr_set = true;
-    }
-    nms_scan_kernel<<<n, 32, smem, s>>>(ws.sorted, ws.cand_count, ws.mask, ws.cap, det, det_count, stage_words);
-  }
+  if (ws.cap > 4096) return cudaErrorInvalidValue;
+  nms_scan_kernel<<<n, 64, 0, s>>>(ws.sorted, ws.cand_count, ws.mask, ws.cap, det, det_count);
   return cudaGetLastError();
 }
 

@@ -363,7 +363,10 @@ struct ContourScratch {
   float f0[ctdgeom::kMaxHull], f1[ctdgeom::kMaxHull], f2[ctdgeom::kMaxHull];
 };
 
-__global__ void __launch_bounds__(64) contour_kernel(int h, int w, int max_cand, const int* __restrict__ total,
+// One WARP per candidate (lane 0 runs the serial geometry; the working set lives in shared memory instead
+// of per-thread local memory), 4 candidates per CTA.
+constexpr int kContourWarps = 4;
+__global__ void __launch_bounds__(32 * kContourWarps) contour_kernel(int h, int w, int max_cand, const int* __restrict__ total,
                                                      const int* __restrict__ c_root, const int* __restrict__ rowmin,
                                                      const int* __restrict__ rowmax, const int* __restrict__ c_yrange,
                                                      const double* __restrict__ tot_sum,
@@ -371,19 +374,21 @@ __global__ void __launch_bounds__(64) contour_kernel(int h, int w, int max_cand,
                                                      const int* __restrict__ ring_cnt, ContourScratch* __restrict__ scratch,
                                                      int16_t* __restrict__ boxes, float* __restrict__ scores,
                                                      int* __restrict__ n_out, int dst_w, int dst_h, float unclip_ratio) {
+  extern __shared__ __align__(16) unsigned char csm[];
+  ContourScratch& S = reinterpret_cast<ContourScratch*>(csm)[threadIdx.x >> 5];
+  (void)scratch;
   const int page = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * kContourWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   int ncont = total[page];
   if (ncont > max_cand) ncont = max_cand;
-  if (c == 0) n_out[page] = ncont;
+  if (c == 0 && lane == 0) n_out[page] = ncont;
   if (c >= max_cand) return;
   int16_t* bo = boxes + (size_t(page) * max_cand + c) * 8;
   float* so = scores + size_t(page) * max_cand + c;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) bo[k] = 0;
-  *so = 0.f;
-  if (c >= ncont) return;
-  ContourScratch& S = scratch[size_t(page) * max_cand + c];
+  if (lane < 8) bo[lane] = 0;
+  if (lane == 0) *so = 0.f;
+  if (c >= ncont || lane != 0) return;
   const int entry = c_root[page * max_cand + c];
   const bool is_hole = entry < 0;
   const int root = entry & 0x7fffffff;
@@ -454,7 +459,7 @@ size_t segrep_scratch_bytes(int n, int h, int w, int max_cand) {
          + size_t(n) * max_cand * h * 4 * 2   // rowmin, rowmax
          + size_t(n) * max_cand * 12          // c_root, c_yrange
          + size_t(n) * 2048 * 4               // segsum + totals
-         + size_t(n) * max_cand * sizeof(ContourScratch) + 4096;
+         + 4096;
 }
 
 cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_page_stride, const int* Lf, int n, int h,
@@ -478,7 +483,7 @@ cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_
   int* c_yrange = reinterpret_cast<int*>(take(size_t(n) * max_cand * 8));
   int* segsum = reinterpret_cast<int*>(take(size_t(n) * 1024 * 4));
   int* total = reinterpret_cast<int*>(take(size_t(n) * 4));
-  ContourScratch* cs = reinterpret_cast<ContourScratch*>(take(size_t(n) * max_cand * sizeof(ContourScratch)));
+  ContourScratch* cs = nullptr;
   const int nseg = int((hw + kSeg - 1) / kSeg);
   if (nseg > 1024) return cudaErrorInvalidValue;
 
@@ -502,7 +507,13 @@ cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_
   accumulate_kernel<<<grid, 256, 0, s>>>(h, w, pred, pred_page_stride, Lf, Lb, parent, flag, own_sum, own_cnt, ring_sum,
                                          ring_cnt, rowmin, rowmax, c_yrange, max_cand);
   tree_kernel<<<grid, 256, 0, s>>>(h, w, Lf, Lb, parent, own_sum, own_cnt, tot_sum, tot_cnt);
-  contour_kernel<<<dim3((max_cand + 63) / 64, n), 64, 0, s>>>(h, w, max_cand, total, c_root, rowmin, rowmax, c_yrange, tot_sum, tot_cnt,
+  static bool attr_set = false;
+  const size_t csmem = sizeof(ContourScratch) * kContourWarps;
+  if (!attr_set) {
+    cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(csmem));
+    attr_set = true;
+  }
+  contour_kernel<<<dim3((max_cand + kContourWarps - 1) / kContourWarps, n), 32 * kContourWarps, csmem, s>>>(h, w, max_cand, total, c_root, rowmin, rowmax, c_yrange, tot_sum, tot_cnt,
                                                               ring_sum, ring_cnt, cs, boxes, scores, n_contours, w, h,
                                                               unclip_ratio);
   return cudaGetLastError();

@@ -263,36 +263,6 @@ cudaError_t avgpool2_launch(const T* src, int n, int h, int w, int c, int scs, T
 template cudaError_t avgpool2_launch<float>(const float*, int, int, int, int, int, float*, int, cudaStream_t);
 template cudaError_t avgpool2_launch<__half>(const __half*, int, int, int, int, int, __half*, int, cudaStream_t);
 
-// space-to-depth stem pre-pass (one thread per output pixel: reads 2x2x3 bytes, writes 16 channels)
-template <typename T>
-__global__ void s2d_kernel(const uint8_t* __restrict__ pages, int n, int h, int w, T* __restrict__ dst, int dcs, int dco) {
-  const int oh = h / 2, ow = w / 2;
-  const long long total = (long long)n * oh * ow;
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int ox = int(i % ow), oy = int((i / ow) % oh), img = int(i / ((long long)ow * oh));
-  const uint8_t* p0 = pages + ((size_t(img) * h + 2 * oy) * w + 2 * ox) * 3;
-  const uint8_t* p1 = p0 + size_t(w) * 3;
-  float v[16];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    v[k] = float(p0[k]) / 255.0f;       // (dy=0,dx=0,c), (dy=0,dx=1,c)
-    v[6 + k] = float(p1[k]) / 255.0f;   // (dy=1,dx=0,c), (dy=1,dx=1,c)
-  }
-  v[12] = v[13] = v[14] = v[15] = 0.f;
-  T* o = dst + size_t(i) * dcs + dco;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) stf(o + k, v[k]);
-}
-template <typename T>
-cudaError_t s2d_launch(const uint8_t* pages, int n, int h, int w, T* dst, int dcs, int dco, cudaStream_t s) {
-  const long long total = (long long)n * (h / 2) * (w / 2);
-  s2d_kernel<T><<<unsigned((total + 255) / 256), 256, 0, s>>>(pages, n, h, w, dst, dcs, dco);
-  return cudaGetLastError();
-}
-template cudaError_t s2d_launch<float>(const uint8_t*, int, int, int, float*, int, int, cudaStream_t);
-template cudaError_t s2d_launch<__half>(const uint8_t*, int, int, int, __half*, int, int, cudaStream_t);
-
 // 8-channel vectors (16 bytes of fp16 / 32 bytes of fp32)
 struct Vec8 { float v[8]; };
 __device__ __forceinline__ Vec8 ldv8(const __half* p) {
@@ -324,6 +294,53 @@ __device__ __forceinline__ void stv8(float* p, const Vec8& r) {
   *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
+
+// space-to-depth stem pre-pass (one thread per output pixel: reads 2x2x3 bytes, writes 16 channels)
+// `pitch_px` = pixels per destination row (>= w/2), `xoff` = first destination column written: the tensor-core
+// stem reads 4-pixel windows from a buffer padded by one zero pixel on the left and three on the right.
+template <typename T>
+__global__ void s2d_kernel(const uint8_t* __restrict__ pages, int n, int h, int w, T* __restrict__ dst, int dcs, int dco,
+                           int pitch_px, int xoff) {
+  const int oh = h / 2, ow = w / 2;
+  const long long total = (long long)n * oh * ow;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ox = int(i % ow), oy = int((i / ow) % oh), img = int(i / ((long long)ow * oh));
+  const uint8_t* p0 = pages + ((size_t(img) * h + 2 * oy) * w + 2 * ox) * 3;
+  const uint8_t* p1 = p0 + size_t(w) * 3;
+  float v[16];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    v[k] = float(p0[k]) / 255.0f;       // (dy=0,dx=0,c), (dy=0,dx=1,c)
+    v[6 + k] = float(p1[k]) / 255.0f;   // (dy=1,dx=0,c), (dy=1,dx=1,c)
+  }
+  v[12] = v[13] = v[14] = v[15] = 0.f;
+  T* o = dst + ((size_t(img) * oh + oy) * pitch_px + ox + xoff) * dcs + dco;
+  Vec8 a, b;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { a.v[k] = v[k]; b.v[k] = v[8 + k]; }
+  stv8(o, a);
+  stv8(o + 8, b);
+  if (xoff > 0) {
+    // keep the window padding (1 pixel left, 3 right) zero whatever this buffer held before
+    Vec8 z;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) z.v[k] = 0.f;
+    if (ox == 0)
+      for (int q = 0; q < xoff; ++q) { stv8(o - (q + 1) * dcs, z); stv8(o - (q + 1) * dcs + 8, z); }
+    if (ox == ow - 1)
+      for (int q = 1; q <= pitch_px - ow - xoff; ++q) { stv8(o + q * dcs, z); stv8(o + q * dcs + 8, z); }
+  }
+}
+template <typename T>
+cudaError_t s2d_launch(const uint8_t* pages, int n, int h, int w, T* dst, int dcs, int dco, int pitch_px, int xoff,
+                       cudaStream_t s) {
+  const long long total = (long long)n * (h / 2) * (w / 2);
+  s2d_kernel<T><<<unsigned((total + 255) / 256), 256, 0, s>>>(pages, n, h, w, dst, dcs, dco, pitch_px, xoff);
+  return cudaGetLastError();
+}
+template cudaError_t s2d_launch<float>(const uint8_t*, int, int, int, float*, int, int, int, int, cudaStream_t);
+template cudaError_t s2d_launch<__half>(const uint8_t*, int, int, int, __half*, int, int, int, int, cudaStream_t);
 
 // SPPF pools: buf[..., 0:c] = x (already written); writes y1=mp5(x), y2=mp5(y1)=mp9(x), y3=mp13(x)
 // into channel slots [c,2c), [2c,3c), [3c,4c).  Chained 5x5 s1 p2 max pools equal 9x9 / 13x13 windows

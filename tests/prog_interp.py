@@ -38,6 +38,19 @@ def run_program(prog, pages, use_fp16_weights=False):
     for op in prog.ops:
         k = op["kind"]
         srcs = [bufs[op["src_buf"][i]][:, op["src_coff"][i]:op["src_coff"][i] + op["src_c"][i]] for i in range(op["n_src"])]
+        if k == cc.OP_STEM and use_fp16_weights:
+            # tensor-core form of the stem: window-layout fp16 weights over the space-to-depth page
+            x = torch.from_numpy(np.ascontiguousarray(pages.transpose(0, 3, 1, 2)).astype(np.float32) / 255).half().float()
+            s2d = torch.zeros(n, 16, h // 2, w // 2)
+            for dy in range(2):
+                for dx in range(2):
+                    s2d[:, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3] = x[:, :, dy::2, dx::2]
+            ww = _blob(prog, op["w16_off"], 32 * 192, np.float16).float().view(32, 3, 4, 16)[:op["cout"], :, :3]
+            wt = ww.permute(0, 3, 1, 2)  # [co][ch][a][b]
+            b = _blob(prog, op["b_off"], op["cout"], np.float32)
+            y = _act(F.conv2d(s2d, wt, b, 1, 1), op["act"])
+            bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["cout"]] = y
+            continue
         cin = sum(op["src_c"][:op["n_src"]])
         if k == cc.OP_STEM:
             x = torch.from_numpy(np.ascontiguousarray(pages.transpose(0, 3, 1, 2)).astype(np.float32) / 255)
