@@ -367,25 +367,30 @@ CTD_HD int16_t quantise(float v, int src_dim, int dst_dim) {
   return (int16_t)r;
 }
 
-// The whole per-contour chain after the first hull: returns false when the contour is skipped
-// (sside < 2, degenerate offset).  hull/tmp: >= kMaxHull entries, off: >= kMaxOffsetPts, f*: >= kMaxHull.
-CTD_HD bool contour_to_box(IPt* hull, int nh, IPt* tmp, IPt* off, float* f0, float* f1, float* f2, int map_w, int map_h,
-                           int dst_w, int dst_h, double unclip_ratio, int16_t* box_out /*[8]*/) {
-  if (nh < 3) return false;  // minAreaRect of 1-2 points / collinear sets has a zero side -> sside < 2
+// The per-contour chain after the first hull, in two stages so that the CUDA kernel can sort the offset
+// points cooperatively in between.  Stage 1: get_mini_boxes + unclip -> number of offset points (0 = the
+// contour is skipped: sside < 2 or a degenerate offset).  Stage 2 (points sorted by (x, y)): hull ->
+// get_mini_boxes -> quantised int16 box.  hull/tmp: >= kMaxHull entries, off: >= kMaxOffsetPts, f*: >= kMaxHull.
+CTD_HD int contour_stage1(IPt* hull, int nh, IPt* tmp, IPt* off, float* f0, float* f1, float* f2, double unclip_ratio) {
+  if (nh < 3) return 0;  // minAreaRect of 1-2 points / collinear sets has a zero side -> sside < 2
   hull_start_maxx(hull, nh, tmp);
   const RRect r1 = min_area_rect(hull, nh, f0, f1, f2);
   const float sside = r1.w < r1.h ? r1.w : r1.h;
-  if (sside < 2.f) return false;
+  if (sside < 2.f) return 0;
   float px[4], py[4], ox[4], oy[4];
   box_points(r1, px, py);
   order_mini_box(px, py, ox, oy);
-  int m = unclip_offset(ox, oy, unclip_ratio, off, kMaxOffsetPts);
-  if (m < 3) return false;
-  sort_xy(off, m);
+  const int m = unclip_offset(ox, oy, unclip_ratio, off, kMaxOffsetPts);
+  return m < 3 ? 0 : m;
+}
+
+CTD_HD bool contour_stage2(IPt* off, int m, IPt* hull, IPt* tmp, float* f0, float* f1, float* f2, int map_w, int map_h,
+                           int dst_w, int dst_h, int16_t* box_out /*[8]*/) {
   const int nh2 = hull_sorted(off, m, hull, kMaxHull);
   if (nh2 < 3) return false;
   hull_start_maxx(hull, nh2, tmp);
   const RRect r2 = min_area_rect(hull, nh2, f0, f1, f2);
+  float px[4], py[4], ox[4], oy[4];
   box_points(r2, px, py);
   order_mini_box(px, py, ox, oy);
   for (int k = 0; k < 4; ++k) {
@@ -393,6 +398,14 @@ CTD_HD bool contour_to_box(IPt* hull, int nh, IPt* tmp, IPt* off, float* f0, flo
     box_out[2 * k + 1] = quantise(oy[k], map_h, dst_h);
   }
   return true;
+}
+
+CTD_HD bool contour_to_box(IPt* hull, int nh, IPt* tmp, IPt* off, float* f0, float* f1, float* f2, int map_w, int map_h,
+                           int dst_w, int dst_h, double unclip_ratio, int16_t* box_out /*[8]*/) {
+  const int m = contour_stage1(hull, nh, tmp, off, f0, f1, f2, unclip_ratio);
+  if (m == 0) return false;
+  sort_xy(off, m);
+  return contour_stage2(off, m, hull, tmp, f0, f1, f2, map_w, map_h, dst_w, dst_h, box_out);
 }
 
 }  // namespace ctdgeom

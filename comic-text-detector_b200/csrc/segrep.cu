@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(32 * kContourWarps) contour_kernel(int h, int 
   float* so = scores + size_t(page) * max_cand + c;
   if (lane < 8) bo[lane] = 0;
   if (lane == 0) *so = 0.f;
-  if (c >= ncont || lane != 0) return;
+  if (c >= ncont) return;   // warp-uniform
   const int entry = c_root[page * max_cand + c];
   const bool is_hole = entry < 0;
   const int root = entry & 0x7fffffff;
@@ -396,40 +396,83 @@ __global__ void __launch_bounds__(32 * kContourWarps) contour_kernel(int h, int 
   const int* rmin = rowmin + (size_t(page) * max_cand + c) * h;
   const int* rmax = rowmax + (size_t(page) * max_cand + c) * h;
   // monotone chain over the row extremes; rows are sorted by y, so the chain runs in the transposed
-  // plane (x' = y, y' = x) and the result is transposed back (which mirrors the orientation -> reversed)
+  // plane (x' = y, y' = x) and the result is transposed back (which mirrors the orientation -> reversed).
+  // The rows are prefetched 64 at a time by the whole warp (coalesced) and consumed by lane 0.
   const int y_lo = max(0, c_yrange[(page * max_cand + c) * 2]), y_hi = min(h - 1, c_yrange[(page * max_cand + c) * 2 + 1]);
+  int* rbuf = reinterpret_cast<int*>(S.f0);  // 128 ints; f0 is free until the calipers run
   int k = 0;
   bool overflow = false;
-  for (int y = y_lo; y <= y_hi && !overflow; ++y) {
-    const int a = rmin[y], b = rmax[y];
-    if (b < 0) continue;
-    for (int e = 0; e < (a == b ? 1 : 2); ++e) {
-      const IPt pt{y, e == 0 ? a : b};
-      while (k >= 2 && ctdgeom::cross3(S.hull[k - 2], S.hull[k - 1], pt) <= 0) --k;
-      if (k >= ctdgeom::kMaxHull) { overflow = true; break; }
-      S.hull[k++] = pt;
+  for (int y0 = y_lo; y0 <= y_hi; y0 += 64) {
+    for (int e = lane; e < 64; e += 32) {
+      const int y = y0 + e;
+      rbuf[e] = y <= y_hi ? rmin[y] : INT_MAX;
+      rbuf[64 + e] = y <= y_hi ? rmax[y] : -1;
     }
+    __syncwarp();
+    if (lane == 0 && !overflow) {
+      for (int e = 0; e < 64 && y0 + e <= y_hi && !overflow; ++e) {
+        const int a = rbuf[e], b = rbuf[64 + e];
+        if (b < 0) continue;
+        for (int q = 0; q < (a == b ? 1 : 2); ++q) {
+          const IPt pt{y0 + e, q == 0 ? a : b};
+          while (k >= 2 && ctdgeom::cross3(S.hull[k - 2], S.hull[k - 1], pt) <= 0) --k;
+          if (k >= ctdgeom::kMaxHull) { overflow = true; break; }
+          S.hull[k++] = pt;
+        }
+      }
+    }
+    __syncwarp();
   }
   const int lower = k + 1;
   bool first = true;
-  for (int y = y_hi; y >= y_lo && !overflow; --y) {
-    const int a = rmin[y], b = rmax[y];
-    if (b < 0) continue;
-    for (int e = 0; e < (a == b ? 1 : 2); ++e) {
-      const IPt pt{y, e == 0 ? b : a};
-      if (first) { first = false; continue; }  // the very last point of the forward pass
-      while (k >= lower && ctdgeom::cross3(S.hull[k - 2], S.hull[k - 1], pt) <= 0) --k;
-      if (k >= ctdgeom::kMaxHull) { overflow = true; break; }
-      S.hull[k++] = pt;
+  for (int y1 = y_hi; y1 >= y_lo; y1 -= 64) {
+    for (int e = lane; e < 64; e += 32) {
+      const int y = y1 - e;
+      rbuf[e] = y >= y_lo ? rmin[y] : INT_MAX;
+      rbuf[64 + e] = y >= y_lo ? rmax[y] : -1;
     }
+    __syncwarp();
+    if (lane == 0 && !overflow) {
+      for (int e = 0; e < 64 && y1 - e >= y_lo && !overflow; ++e) {
+        const int a = rbuf[e], b = rbuf[64 + e];
+        if (b < 0) continue;
+        for (int q = 0; q < (a == b ? 1 : 2); ++q) {
+          const IPt pt{y1 - e, q == 0 ? b : a};
+          if (first) { first = false; continue; }  // the very last point of the forward pass
+          while (k >= lower && ctdgeom::cross3(S.hull[k - 2], S.hull[k - 1], pt) <= 0) --k;
+          if (k >= ctdgeom::kMaxHull) { overflow = true; break; }
+          S.hull[k++] = pt;
+        }
+      }
+    }
+    __syncwarp();
   }
-  if (overflow) return;
-  if (k > 1) --k;
-  // transpose back + reverse
-  for (int i = 0; i < k; ++i) S.tmp[i] = IPt{S.hull[k - 1 - i].y, S.hull[k - 1 - i].x};
-  for (int i = 0; i < k; ++i) S.hull[i] = S.tmp[i];
+  int m = 0;
+  if (lane == 0 && !overflow) {
+    if (k > 1) --k;
+    // transpose back + reverse
+    for (int i = 0; i < k; ++i) S.tmp[i] = IPt{S.hull[k - 1 - i].y, S.hull[k - 1 - i].x};
+    for (int i = 0; i < k; ++i) S.hull[i] = S.tmp[i];
+    m = ctdgeom::contour_stage1(S.hull, k, S.tmp, S.off, S.f0, S.f1, S.f2, (double)unclip_ratio);
+  }
+  m = __shfl_sync(0xffffffffu, m, 0);
+  if (m == 0) return;
+  // cooperative rank sort of the offset points by (x, y) into S.tmp, then back
+  for (int i = lane; i < m; i += 32) {
+    const IPt p = S.off[i];
+    int rank = 0;
+    for (int j = 0; j < m; ++j) {
+      const IPt q = S.off[j];
+      rank += (q.x < p.x) || (q.x == p.x && (q.y < p.y || (q.y == p.y && j < i)));
+    }
+    S.tmp[rank] = p;
+  }
+  __syncwarp();
+  for (int i = lane; i < m; i += 32) S.off[i] = S.tmp[i];
+  __syncwarp();
+  if (lane != 0) return;
   int16_t box[8];
-  if (!ctdgeom::contour_to_box(S.hull, k, S.tmp, S.off, S.f0, S.f1, S.f2, w, h, dst_w, dst_h, (double)unclip_ratio, box)) return;
+  if (!ctdgeom::contour_stage2(S.off, m, S.hull, S.tmp, S.f0, S.f1, S.f2, w, h, dst_w, dst_h, box)) return;
   // box_score_fast (db_utils.py:197-211): mean of pred over the filled contour polygon
   double sum = tot_sum[o + root];
   long long cnt = tot_cnt[o + root];
