@@ -4,13 +4,13 @@
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--batch B]
 
 A "step" = one pass of the hot path (backbone + seg head + DB head + Detect decode + NMS +
-mask u8 + DB threshold + connected components) over one batch of B synthetic 1024x1024 pages
+mask u8 + DB threshold + connected components + text-line boxes/scores) over one batch of B synthetic 1024x1024 pages
 per GPU (BASELINE.json configs[2]/[3]: batch 16 per GPU, fp16 tcgen05 path).
 
 * value      : whole-job pages/s with the pages already resident in HBM (device timed, CUDA events
                on the engine stream, max over ranks).
 * e2e        : same metric through the C-ABI with HOST (pinned) page buffers: H2D of the pages and
-               D2H of the results (mask u8 + detections + component count) inside the timed region.
+               D2H of the results (mask u8 + detections + text-line boxes/scores + counts) inside the timed region.
 * roofline   : tensor roofline of the dominant kernel (conv_tc_kernel): algorithmic conv FLOPs
                of the tensor-core layers / their summed device time (per-op CUDA events, measured
                live here), against MEASURED_PEAKS.json's sustained bf16 GEMM rate.
@@ -39,6 +39,9 @@ def conv_flops(prog, n, h, w):
     out = []
     for o in prog.ops:
         kind = o["kind"]
+        if kind == 0:  # stem: 6x6 s2 conv 3 -> cout (algorithmic FLOPs, not the zero-padded tensor-core K)
+            out.append(2.0 * (h // 2) * (w // 2) * n * 108 * o["cout"])
+            continue
         if kind not in (1, 2, 6):
             out.append(0.0)
             continue
@@ -103,7 +106,8 @@ def cpu_pipeline_factory(h, w):
         m8 = (mask[0, 0].numpy() * 255).astype(np.uint8)
         bitmap = (lines[0, 0].numpy() > 0.3).astype(np.uint8)
         n, labels, stats, _ = postproc_ref.connected_components_cv2(bitmap)
-        return det, m8, n
+        boxes, scores = postproc_ref.seg_represent(lines[0, 0].numpy(), 0.3)
+        return det, m8, n, boxes, scores
     return run
 
 
@@ -130,7 +134,7 @@ def run_reference(args):
         "impl": "reference", "metric": "pages/sec @1024x1024 synthetic", "value": val, "unit": "pages/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "reference CPU path (oracle port: torch CPU fp32 forward + torchvision NMS + cv2 CC), "
+        "config": {"workload": "reference CPU path (oracle port: torch CPU fp32 forward + torchvision NMS + cv2 CC + SegDetectorRepresenter), "
                                "%d page(s) of 1024x1024 per step, all host threads" % len(pages)},
         "cpu_baseline": {"value": val, "unit": "pages/s", "cores": cores, "kind": "port",
                          "sample": "%d steps x %d structured synthetic 1024x1024 page(s)" % (args.steps, len(pages))},
@@ -180,6 +184,9 @@ def main():
     out_det = torch.empty((B, 300, 6), dtype=torch.float32).pin_memory()
     out_cnt = torch.empty((B,), dtype=torch.int32).pin_memory()
     out_nl = torch.empty((B,), dtype=torch.int32).pin_memory()
+    out_lb = torch.empty((B, 1000, 4, 2), dtype=torch.int16).pin_memory()
+    out_ls = torch.empty((B, 1000), dtype=torch.float32).pin_memory()
+    out_lc = torch.empty((B,), dtype=torch.int32).pin_memory()
     lib, hnd = eng.lib, eng.h
     import ctypes as C
 
@@ -192,6 +199,8 @@ def main():
         eng._ck(lib.ctd_get_mask_u8(hnd, C.c_void_p(out_mask.data_ptr())))
         eng._ck(lib.ctd_get_detections(hnd, C.c_void_p(out_det.data_ptr()), C.c_void_p(out_cnt.data_ptr())))
         eng._ck(lib.ctd_get_db_components(hnd, None, None, C.c_void_p(out_nl.data_ptr())))
+        eng._ck(lib.ctd_get_text_lines(hnd, C.c_void_p(out_lb.data_ptr()), C.c_void_p(out_ls.data_ptr()),
+                                       C.c_void_p(out_lc.data_ptr())))
 
     step_main = step_resident
     if world > 1:
@@ -246,7 +255,7 @@ def main():
     op_ms2, _, _ = eng.profile_forward(dev_ptr=dev_pages.data_ptr(), shape=(B, H, W))
     op_ms = np.minimum(op_ms, op_ms2)
     fl = conv_flops(prog, B, H, W)
-    tc_idx = [i for i, o in enumerate(prog.ops) if o["kind"] in (1, 2, 6)]
+    tc_idx = [i for i, o in enumerate(prog.ops) if o["kind"] in (0, 1, 2, 6)]
     tc_ms = float(sum(op_ms[i] for i in tc_idx))
     tc_flops = float(sum(fl[i] for i in tc_idx))
     peaks = {}
@@ -268,7 +277,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
             "data": "synthetic",
             "config": {"workload": "BASELINE configs[2]: 1024x1024 pages, batch %d per GPU, fp16 tcgen05 path, full device "
-                                   "pipeline (backbone + seg head + DB head + Detect/NMS + mask u8 + DB threshold + CCL)" % B,
+                                   "pipeline (backbone + seg head + DB head + Detect/NMS + mask u8 + DB threshold + CCL + contour boxes/scores)" % B,
                        "pages_per_gpu_per_step": B, "page": [H, W], "checkpoint": "synthetic seed 0 (oracle/synth.py)",
                        "l2": "activations per step (~%.1f GB) exceed the 126 MB L2; no explicit flush" % (
                            sum(c * (H // d) * (W // d) for c, d in prog.bufs) * 2 * B / 1e9),
@@ -278,12 +287,12 @@ def main():
             "clocks": clocks,
             "conv_roofline_frac_of_nominal": value / world * GFLOP_PER_PAGE_1024 * 1e9 / 2.25e15,
             "e2e": {"value": e2e_val, "unit": "pages/s", "h2d_bytes_per_step": int(B * H * W * 3),
-                    "d2h_bytes_per_step": int(B * H * W + B * 300 * 6 * 4 + B * 8)},
-            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (92 launches per step)", "achieved": achieved,
+                    "d2h_bytes_per_step": int(B * H * W + B * 300 * 6 * 4 + B * 12 + B * 1000 * 20)},
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (%d launches per step)" % len(tc_idx), "achieved": achieved,
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
                          "peak_source": peak_src, "flops_per_step": tc_flops, "ms_per_step": tc_ms,
                          "share_of_step": tc_ms / float(op_ms.sum() + nms_ms + ccl_ms)},
-            "stage_ms": {"conv_tc": tc_ms, "other_ops": float(op_ms.sum()) - tc_ms, "nms": nms_ms, "ccl": ccl_ms},
+            "stage_ms": {"conv_tc": tc_ms, "other_ops": float(op_ms.sum()) - tc_ms, "nms": nms_ms, "ccl_and_line_boxes": ccl_ms},
         }
         if not args.no_cpu_baseline and world == 1:
             cores = min(os.cpu_count(), args.cpu_threads)
@@ -297,7 +306,7 @@ def main():
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": ncpu / dt, "unit": "pages/s", "cores": cores, "kind": "port",
                                     "sample": "%d structured synthetic 1024x1024 pages, same stages, oracle port of the "
-                                              "reference CPU path (torch fp32 + torchvision NMS + cv2 CC)" % ncpu}
+                                              "reference CPU path (torch fp32 + torchvision NMS + cv2 CC + SegDetectorRepresenter)" % ncpu}
         print(json.dumps(line))
     eng.close()
     if dist is not None:

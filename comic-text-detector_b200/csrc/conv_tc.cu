@@ -28,7 +28,8 @@
 namespace ctd {
 
 constexpr int kTileW = 16, kTileH = 8;  // 128 grid pixels per tile
-constexpr int kThreads = 256;           // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-7 epilogue
+constexpr int kThreads = 384;           // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue
+constexpr int kEpiWarps = 8;            // two warps per TMEM lane quadrant, each takes half of the columns
 constexpr int kEpiWarp0 = 4;
 
 template <int BN>
@@ -94,36 +95,32 @@ __device__ __forceinline__ void epilogue_chunk32(const uint32_t (&v)[32], const 
   }
 }
 
+// Columns [c_begin, c_end) of the accumulator row owned by this thread, 32 at a time.
 template <int BN, int ACT, bool RES>
 __device__ __forceinline__ void epilogue_store(uint32_t tmem_row, const float* __restrict__ bias_s,
-                                               __half* __restrict__ out, int cout_left, bool valid) {
+                                               __half* __restrict__ out, int cout_left, bool valid, int c_begin,
+                                               int c_end) {
   if constexpr (BN >= 64) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 64) {
-      uint32_t v0[32], v1[32];
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+      uint32_t v0[32];
       tmem_ld_32x32(tmem_row + uint32_t(c0), v0);
-      tmem_ld_32x32(tmem_row + uint32_t(c0 + 32), v1);
       tmem_ld_wait();
-      if (valid) {
-        epilogue_chunk32<ACT, RES>(v0, bias_s + c0, out + c0, cout_left - c0);
-        epilogue_chunk32<ACT, RES>(v1, bias_s + c0 + 32, out + c0 + 32, cout_left - c0 - 32);
-      }
+      if (valid) epilogue_chunk32<ACT, RES>(v0, bias_s + c0, out + c0, cout_left - c0);
     }
-  } else if constexpr (BN == 32) {
-    uint32_t v0[32];
-    tmem_ld_32x32(tmem_row, v0);
-    tmem_ld_wait();
-    if (valid) epilogue_chunk32<ACT, RES>(v0, bias_s, out, cout_left);
   } else {
+    // BN 32 / 16: 16 columns per call (second half-warpgroup idles for BN == 16)
+    if (c_begin >= BN) return;
     uint32_t v0[32];
     uint32_t t16[16];
-    tmem_ld_32x16(tmem_row, t16);
+    tmem_ld_32x16(tmem_row + uint32_t(c_begin), t16);
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 16; ++j) v0[j] = t16[j];
 #pragma unroll
     for (int j = 16; j < 32; ++j) v0[j] = 0u;
-    if (valid) epilogue_chunk32<ACT, RES>(v0, bias_s, out, cout_left < 16 ? cout_left : 16);
+    const int left = cout_left - c_begin;
+    if (valid) epilogue_chunk32<ACT, RES>(v0, bias_s + c_begin, out + c_begin, left < 16 ? left : 16);
   }
 }
 
@@ -169,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int s = 0; s < Cfg::kAccStages; ++s) {
       mbar_init(tmem_full_bar + 8 * s, 1);
-      mbar_init(tmem_empty_bar + 8 * s, 128);
+      mbar_init(tmem_empty_bar + 8 * s, 32 * kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -253,6 +250,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   } else if (warp >= kEpiWarp0) {
     // =============================== epilogue ====================================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+    const int half = (warp - kEpiWarp0) >> 2;
+    constexpr int kHalfCols = BN >= 64 ? BN / 2 : 16;
+    const int c_begin = half * kHalfCols, c_end = c_begin + kHalfCols;
     const int row = quad * 32 + lane;
     const int py = row / kTileW, px = row - py * kTileW;
     int ti = 0;
@@ -273,8 +273,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                       g.dst_coff + nblk * BN;
         const int cout_left = g.cout - nblk * BN;
 #define CTD_EPI(ACT)                                                                              \
-  if (g.residual) epilogue_store<BN, ACT, true>(tmem_row, bias_t, out, cout_left, valid);         \
-  else epilogue_store<BN, ACT, false>(tmem_row, bias_t, out, cout_left, valid);
+  if (g.residual) epilogue_store<BN, ACT, true>(tmem_row, bias_t, out, cout_left, valid, c_begin, c_end);         \
+  else epilogue_store<BN, ACT, false>(tmem_row, bias_t, out, cout_left, valid, c_begin, c_end);
         switch (g.act) {
           case CTD_ACT_SILU: CTD_EPI(CTD_ACT_SILU) break;
           case CTD_ACT_LEAKY: CTD_EPI(CTD_ACT_LEAKY) break;
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int no = 5 + p.nc;
         float* rows = p.blks + (size_t(img) * p.blks_rows_per_img + p.level_row0) * no;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += kChunk) {
+        for (int c0 = half * kChunk; c0 < BN; c0 += 2 * kChunk) {
           uint32_t v[kChunk];
           if constexpr (kChunk == 32) {
             tmem_ld_32x32(tmem_row + uint32_t(c0), v);

@@ -454,31 +454,45 @@ __global__ void __launch_bounds__(256) seg_tail_kernel(const T* __restrict__ src
   const int tr = blockIdx.x % (tiles_x * tiles_y);
   const int q0y = (tr / tiles_x) * 14, q0x = (tr % tiles_x) * 14;  // first q block of this CTA
   const int lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
-  const int iy = q0y - 1 + ly, ix = q0x - 1 + lx;
-  float acc[16];
+  // phase 1: threads 0..127 each form the partials of TWO input pixels (rows ly and ly+8 of the tile), so
+  // every weight vector read from shared memory feeds 8 FMAs instead of 4
+  if (threadIdx.x < 128) {
+    const int ix = q0x - 1 + lx;
+    const int iy0 = q0y - 1 + ly, iy1 = iy0 + 8;
+    const bool v0 = iy0 >= 0 && iy0 < h && ix >= 0 && ix < w;
+    const bool v1 = iy1 >= 0 && iy1 < h && ix >= 0 && ix < w;
+    float a0[16], a1[16];
 #pragma unroll
-  for (int t = 0; t < 16; ++t) acc[t] = 0.f;
-  if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
-    const T* sp = src + ((size_t(img) * h + iy) * w + ix) * cs;
+    for (int t = 0; t < 16; ++t) { a0[t] = 0.f; a1[t] = 0.f; }
+    const T* sp0 = src + ((size_t(img) * h + (v0 ? iy0 : 0)) * w + (v0 ? ix : 0)) * cs;
+    const T* sp1 = src + ((size_t(img) * h + (v1 ? iy1 : 0)) * w + (v1 ? ix : 0)) * cs;
     for (int c0 = 0; c0 < c; c0 += 8) {
-      float x[8];
-      load8(sp + c0, x);
+      float x0[8], x1[8];
+      load8(sp0 + c0, x0);
+      load8(sp1 + c0, x1);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float4* wr = reinterpret_cast<const float4*>(wsm + (c0 + e) * 16);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float4 ww = wr[q];
-          acc[4 * q + 0] = fmaf(x[e], ww.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(x[e], ww.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(x[e], ww.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(x[e], ww.w, acc[4 * q + 3]);
+          a0[4 * q + 0] = fmaf(x0[e], ww.x, a0[4 * q + 0]);
+          a0[4 * q + 1] = fmaf(x0[e], ww.y, a0[4 * q + 1]);
+          a0[4 * q + 2] = fmaf(x0[e], ww.z, a0[4 * q + 2]);
+          a0[4 * q + 3] = fmaf(x0[e], ww.w, a0[4 * q + 3]);
+          a1[4 * q + 0] = fmaf(x1[e], ww.x, a1[4 * q + 0]);
+          a1[4 * q + 1] = fmaf(x1[e], ww.y, a1[4 * q + 1]);
+          a1[4 * q + 2] = fmaf(x1[e], ww.z, a1[4 * q + 2]);
+          a1[4 * q + 3] = fmaf(x1[e], ww.w, a1[4 * q + 3]);
         }
       }
     }
-  }
 #pragma unroll
-  for (int t = 0; t < 16; ++t) part[threadIdx.x * 17 + t] = acc[t];
+    for (int t = 0; t < 16; ++t) {
+      part[(ly * 16 + lx) * 17 + t] = v0 ? a0[t] : 0.f;
+      part[((ly + 8) * 16 + lx) * 17 + t] = v1 ? a1[t] : 0.f;
+    }
+  }
   __syncthreads();
   if (lx >= 14 || ly >= 14) return;
   const int qy = q0y + ly, qx = q0x + lx;
@@ -493,7 +507,6 @@ __global__ void __launch_bounds__(256) seg_tail_kernel(const T* __restrict__ src
       // oy = 2*qy + py: taps (dy,ky): py=0 -> (0,1),(-1,3); py=1 -> (0,2),(+1,0)
       const int dyA = 0, kyA = py ? 2 : 1, dyB = py ? 1 : -1, kyB = py ? 0 : 3;
       const int dxA = 0, kxA = px ? 2 : 1, dxB = px ? 1 : -1, kxB = px ? 0 : 3;
-      // fixed summation order (ky,kx ascending like a direct loop over the kernel would visit inputs)
       o[py][px] = P(dyA, dxA, kyA, kxA) + P(dyA, dxB, kyA, kxB) + P(dyB, dxA, kyB, kxA) + P(dyB, dxB, kyB, kxB);
     }
   const int H = 2 * h, W = 2 * w;
@@ -530,8 +543,25 @@ template <typename T>
 __global__ void __launch_bounds__(128) db_tail_kernel(const T* __restrict__ src, int n, int h, int w, int cs,
                                                       const float* __restrict__ params, float* __restrict__ lines,
                                                       uint8_t* __restrict__ bitmap, float db_thresh) {
-  __shared__ float prm[2 * 1105];
-  for (int i = threadIdx.x; i < 2 * 1105; i += blockDim.x) prm[i] = params[i];
+  // shared layout per branch: w3s[d1][ci][co] (1024), b3 (16), w6s[d2][co] (64), b6 (1) -> float4 reads over co
+  __shared__ __align__(16) float prm[2 * 1108];
+  for (int i = threadIdx.x; i < 2 * 1105; i += blockDim.x) {
+    const int b = i / 1105, r = i - b * 1105;
+    float v = params[i];
+    int dstp;
+    if (r < 1024) {
+      const int d1 = r & 3, co = (r >> 2) & 15, ci = r >> 6;
+      dstp = d1 * 256 + ci * 16 + co;
+    } else if (r < 1040) {
+      dstp = r;
+    } else if (r < 1104) {
+      const int q = r - 1040, d2 = q & 3, co = q >> 2;
+      dstp = 1040 + d2 * 16 + co;
+    } else {
+      dstp = 1104;
+    }
+    prm[b * 1108 + dstp] = v;
+  }
   __syncthreads();
   const long long total = (long long)n * h * w;
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -539,34 +569,62 @@ __global__ void __launch_bounds__(128) db_tail_kernel(const T* __restrict__ src,
   const int x = int(i % w), y = int((i / w) % h), img = int(i / ((long long)w * h));
   const T* sp = src + i * cs;
   const int H = 4 * h, W = 4 * w;
+  float xin[32];
+  load8(sp, xin);
+  load8(sp + 8, xin + 8);
+  load8(sp + 16, xin + 16);
+  load8(sp + 24, xin + 24);
+#pragma unroll 1
   for (int b = 0; b < 2; ++b) {
-    const float* w3 = prm + b * 1105;
-    const float* b3 = w3 + 1024;
-    const float* w6 = b3 + 16;
-    const float b6 = w6[64];
-    float xin[16];
-#pragma unroll
-    for (int ci = 0; ci < 16; ++ci) xin[ci] = ldf(sp + b * 16 + ci);
-    float* outp = lines + ((size_t(img) * 2 + b) * H + 4 * y) * W + 4 * x;
+    const float* w3s = prm + b * 1108;
+    const float* b3 = w3s + 1024;
+    const float* w6s = b3 + 16;
+    const float b6 = w6s[64];
+    float res[16];
 #pragma unroll
     for (int d1 = 0; d1 < 4; ++d1) {  // first deconv position (dy1,dx1)
       float t[16];
 #pragma unroll
-      for (int co = 0; co < 16; ++co) {
-        float a = b3[co];
+      for (int co = 0; co < 16; ++co) t[co] = b3[co];
 #pragma unroll
-        for (int ci = 0; ci < 16; ++ci) a = fmaf(xin[ci], w3[(ci * 16 + co) * 4 + d1], a);
-        t[co] = fmaxf(a, 0.f);
+      for (int ci = 0; ci < 16; ++ci) {
+        const float xv = xin[b * 16 + ci];
+        const float4* wr = reinterpret_cast<const float4*>(w3s + d1 * 256 + ci * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 ww = wr[q];
+          t[4 * q + 0] = fmaf(xv, ww.x, t[4 * q + 0]);
+          t[4 * q + 1] = fmaf(xv, ww.y, t[4 * q + 1]);
+          t[4 * q + 2] = fmaf(xv, ww.z, t[4 * q + 2]);
+          t[4 * q + 3] = fmaf(xv, ww.w, t[4 * q + 3]);
+        }
       }
+#pragma unroll
+      for (int co = 0; co < 16; ++co) t[co] = fmaxf(t[co], 0.f);
 #pragma unroll
       for (int d2 = 0; d2 < 4; ++d2) {
         float a = b6;
+        const float4* wr = reinterpret_cast<const float4*>(w6s + d2 * 16);
 #pragma unroll
-        for (int co = 0; co < 16; ++co) a = fmaf(t[co], w6[co * 4 + d2], a);
-        const float s = 1.0f / (1.0f + expf(-a));
+        for (int q = 0; q < 4; ++q) {
+          const float4 ww = wr[q];
+          a = fmaf(t[4 * q + 0], ww.x, a);
+          a = fmaf(t[4 * q + 1], ww.y, a);
+          a = fmaf(t[4 * q + 2], ww.z, a);
+          a = fmaf(t[4 * q + 3], ww.w, a);
+        }
         const int oy = (d1 >> 1) * 2 + (d2 >> 1), ox = (d1 & 1) * 2 + (d2 & 1);
-        outp[size_t(oy) * W + ox] = s;
-        if (b == 0) bitmap[(size_t(img) * H + 4 * y + oy) * W + 4 * x + ox] = s > db_thresh ? 1 : 0;
+        res[oy * 4 + ox] = 1.0f / (1.0f + expf(-a));
+      }
+    }
+    float* outp = lines + ((size_t(img) * 2 + b) * H + 4 * y) * W + 4 * x;
+#pragma unroll
+    for (int oy = 0; oy < 4; ++oy) {
+      *reinterpret_cast<float4*>(outp + size_t(oy) * W) = make_float4(res[oy * 4], res[oy * 4 + 1], res[oy * 4 + 2], res[oy * 4 + 3]);
+      if (b == 0) {
+        uchar4 bm = make_uchar4(res[oy * 4] > db_thresh, res[oy * 4 + 1] > db_thresh, res[oy * 4 + 2] > db_thresh,
+                                res[oy * 4 + 3] > db_thresh);
+        *reinterpret_cast<uchar4*>(bitmap + (size_t(img) * H + 4 * y + oy) * W + 4 * x) = bm;
       }
     }
   }
