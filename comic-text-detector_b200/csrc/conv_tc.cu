@@ -29,7 +29,7 @@ namespace ctd {
 
 constexpr int kTileW = 16, kTileH = 8;  // 128 grid pixels per tile
 constexpr int kThreads = 384;           // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue
-constexpr int kEpiWarps = 8;            // two warps per TMEM lane quadrant, each takes half of the columns
+constexpr int kEpiWarps = 8;            // two warpgroups of 4 (one warp per TMEM lane quadrant) on alternate tiles
 constexpr int kEpiWarp0 = 4;
 
 template <int BN>
@@ -38,10 +38,12 @@ struct TcCfg {
   static constexpr int kBBytes = BN * 128;
   // one persistent CTA per SM: fill ~200 KB with pipeline stages
   static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
-  static constexpr int kAccStages = 2;                                  // TMEM accumulator ping-pong
-  static constexpr int kTmemCols = (BN < 32 ? 32 : BN) * kAccStages;    // power of two >= 32
+  // TMEM accumulator stages (512 columns per SM): small tiles get a deep ring so that two epilogue warpgroups
+  // can drain two tiles at once while the MMA warp runs ahead
+  static constexpr int kAccStages = BN >= 256 ? 2 : (BN >= 128 ? 4 : 8);
+  static constexpr int kTmemCols = BN * kAccStages < 32 ? 32 : BN * kAccStages;   // power of two >= 32
   static constexpr int kBiasFloats = 512;
-  static constexpr size_t kSmem = 1024 /*align slack*/ + size_t(kStages) * (kABytes + kBBytes) + 256 + kBiasFloats * 4;
+  static constexpr size_t kSmem = 1024 /*align slack*/ + size_t(kStages) * (kABytes + kBBytes) + 512 + kBiasFloats * 4;
 };
 
 template <int ACT>
@@ -95,32 +97,28 @@ __device__ __forceinline__ void epilogue_chunk32(const uint32_t (&v)[32], const 
   }
 }
 
-// Columns [c_begin, c_end) of the accumulator row owned by this thread, 32 at a time.
+// The whole accumulator row owned by this thread, 32 columns at a time.
 template <int BN, int ACT, bool RES>
 __device__ __forceinline__ void epilogue_store(uint32_t tmem_row, const float* __restrict__ bias_s,
-                                               __half* __restrict__ out, int cout_left, bool valid, int c_begin,
-                                               int c_end) {
-  if constexpr (BN >= 64) {
+                                               __half* __restrict__ out, int cout_left, bool valid) {
+  if constexpr (BN >= 32) {
 #pragma unroll 1
-    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v0[32];
       tmem_ld_32x32(tmem_row + uint32_t(c0), v0);
       tmem_ld_wait();
       if (valid) epilogue_chunk32<ACT, RES>(v0, bias_s + c0, out + c0, cout_left - c0);
     }
   } else {
-    // BN 32 / 16: 16 columns per call (second half-warpgroup idles for BN == 16)
-    if (c_begin >= BN) return;
     uint32_t v0[32];
     uint32_t t16[16];
-    tmem_ld_32x16(tmem_row + uint32_t(c_begin), t16);
+    tmem_ld_32x16(tmem_row, t16);
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 16; ++j) v0[j] = t16[j];
 #pragma unroll
     for (int j = 16; j < 32; ++j) v0[j] = 0u;
-    const int left = cout_left - c_begin;
-    if (valid) epilogue_chunk32<ACT, RES>(v0, bias_s + c_begin, out + c_begin, left < 16 ? left : 16);
+    if (valid) epilogue_chunk32<ACT, RES>(v0, bias_s, out, cout_left < 16 ? cout_left : 16);
   }
 }
 
@@ -132,15 +130,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + Cfg::kStages * Cfg::kABytes;
   const uint32_t bar_base = b_base + Cfg::kStages * Cfg::kBBytes;
-  // barriers (8 B each): full[S] | empty[S] | tmem_full[2] | tmem_empty[2] | tmem ptr
+  // barriers (8 B each): full[S] | empty[S] | tmem_full[A] | tmem_empty[A] | tmem ptr   (<= 512 bytes)
   const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * Cfg::kStages;
   const uint32_t tmem_full_bar = bar_base + 16 * Cfg::kStages;
-  const uint32_t tmem_empty_bar = tmem_full_bar + 16;
-  const uint32_t tmem_ptr_addr = tmem_empty_bar + 16;
+  const uint32_t tmem_empty_bar = tmem_full_bar + 8 * Cfg::kAccStages;
+  const uint32_t tmem_ptr_addr = tmem_empty_bar + 8 * Cfg::kAccStages;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const size_t bar_off = size_t(Cfg::kStages) * (Cfg::kABytes + Cfg::kBBytes);
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 16 * Cfg::kStages + 32);
-  float* bias_s = reinterpret_cast<float*>(smem_gen + bar_off + 256);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 16 * Cfg::kStages + 16 * Cfg::kAccStages);
+  float* bias_s = reinterpret_cast<float*>(smem_gen + bar_off + 512);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom& g = p.g;
@@ -166,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int s = 0; s < Cfg::kAccStages; ++s) {
       mbar_init(tmem_full_bar + 8 * s, 1);
-      mbar_init(tmem_empty_bar + 8 * s, 32 * kEpiWarps);
+      mbar_init(tmem_empty_bar + 8 * s, 128);
     }
     fence_barrier_init();
   }
@@ -223,8 +222,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t idesc = make_idesc_f16(BN);
     int it = 0, ti = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-      const int as = ti & 1;
-      mbar_wait(tmem_empty_bar + 8 * as, ((ti >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+      const int as = ti % Cfg::kAccStages;
+      mbar_wait(tmem_empty_bar + 8 * as, ((ti / Cfg::kAccStages) & 1) ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + uint32_t(as * BN);
       for (int k_it = 0; k_it < its_per_tile; ++k_it, ++it) {
@@ -250,19 +249,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   } else if (warp >= kEpiWarp0) {
     // =============================== epilogue ====================================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may read
-    const int half = (warp - kEpiWarp0) >> 2;
-    constexpr int kHalfCols = BN >= 64 ? BN / 2 : 16;
-    const int c_begin = half * kHalfCols, c_end = c_begin + kHalfCols;
+    const int group = (warp - kEpiWarp0) >> 2;  // two warpgroups take alternate tiles
     const int row = quad * 32 + lane;
     const int py = row / kTileW, px = row - py * kTileW;
     int ti = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      if ((ti & 1) != group) continue;
       int phase, nblk, img, y0, x0;
       decode(t, phase, nblk, img, y0, x0);
-      const int as = ti & 1;
+      const int as = ti % Cfg::kAccStages;
       const int gy = y0 + py, gx = x0 + px;
       const bool valid = gy < g.gh && gx < g.gw;
-      mbar_wait(tmem_full_bar + 8 * as, (ti >> 1) & 1);
+      mbar_wait(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
       tc_fence_after();
       const int ph_y = phase >> 1, ph_x = phase & 1;
       const int oy = gy * g.out_mul + ph_y, ox = gx * g.out_mul + ph_x;
@@ -273,8 +271,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                       g.dst_coff + nblk * BN;
         const int cout_left = g.cout - nblk * BN;
 #define CTD_EPI(ACT)                                                                              \
-  if (g.residual) epilogue_store<BN, ACT, true>(tmem_row, bias_t, out, cout_left, valid, c_begin, c_end);         \
-  else epilogue_store<BN, ACT, false>(tmem_row, bias_t, out, cout_left, valid, c_begin, c_end);
+  if (g.residual) epilogue_store<BN, ACT, true>(tmem_row, bias_t, out, cout_left, valid);         \
+  else epilogue_store<BN, ACT, false>(tmem_row, bias_t, out, cout_left, valid);
         switch (g.act) {
           case CTD_ACT_SILU: CTD_EPI(CTD_ACT_SILU) break;
           case CTD_ACT_LEAKY: CTD_EPI(CTD_ACT_LEAKY) break;
@@ -289,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int no = 5 + p.nc;
         float* rows = p.blks + (size_t(img) * p.blks_rows_per_img + p.level_row0) * no;
 #pragma unroll 1
-        for (int c0 = half * kChunk; c0 < BN; c0 += 2 * kChunk) {
+        for (int c0 = 0; c0 < BN; c0 += kChunk) {
           uint32_t v[kChunk];
           if constexpr (kChunk == 32) {
             tmem_ld_32x32(tmem_row + uint32_t(c0), v);
