@@ -37,13 +37,14 @@ struct TcCfg {
   static constexpr int kABytes = 128 * 128;  // per stage (worst case 128-byte rows)
   static constexpr int kBBytes = BN * 128;
   // one persistent CTA per SM: fill ~200 KB with pipeline stages
-  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kStages = BN >= 256 ? 3 : (BN >= 128 ? 5 : 7);
+  static constexpr int kStoreBytes = BN >= 64 ? 2 * 128 * 128 : 0;      // one 128x64 fp16 staging tile per epilogue warpgroup
   // TMEM accumulator stages (512 columns per SM): small tiles get a deep ring so that two epilogue warpgroups
   // can drain two tiles at once while the MMA warp runs ahead
   static constexpr int kAccStages = BN >= 256 ? 2 : (BN >= 128 ? 4 : 8);
   static constexpr int kTmemCols = BN * kAccStages < 32 ? 32 : BN * kAccStages;   // power of two >= 32
   static constexpr int kBiasFloats = 512;
-  static constexpr size_t kSmem = 1024 /*align slack*/ + size_t(kStages) * (kABytes + kBBytes) + 512 + kBiasFloats * 4;
+  static constexpr size_t kSmem = 1024 /*align slack*/ + size_t(kStages) * (kABytes + kBBytes) + 512 + kBiasFloats * 4 + kStoreBytes + 1024;
 };
 
 template <int ACT>
@@ -97,6 +98,47 @@ __device__ __forceinline__ void epilogue_chunk32(const uint32_t (&v)[32], const 
   }
 }
 
+// 32 columns -> bias + activation (+ residual read from global) -> fp16 -> the 128-byte-swizzled staging row of
+// this thread (16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) * 16)); `half` selects chunks 0-3 / 4-7.
+template <int ACT, bool RES>
+__device__ __forceinline__ void epilogue_chunk32_smem(const uint32_t (&v)[32], const float* __restrict__ bias_s,
+                                                      const __half* __restrict__ res, uint32_t stage_row, int row, int half) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float f[8];
+    const float4 b0 = *reinterpret_cast<const float4*>(bias_s + q * 8);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias_s + q * 8 + 4);
+    f[0] = apply_act<ACT>(__uint_as_float(v[q * 8 + 0]) + b0.x);
+    f[1] = apply_act<ACT>(__uint_as_float(v[q * 8 + 1]) + b0.y);
+    f[2] = apply_act<ACT>(__uint_as_float(v[q * 8 + 2]) + b0.z);
+    f[3] = apply_act<ACT>(__uint_as_float(v[q * 8 + 3]) + b0.w);
+    f[4] = apply_act<ACT>(__uint_as_float(v[q * 8 + 4]) + b1.x);
+    f[5] = apply_act<ACT>(__uint_as_float(v[q * 8 + 5]) + b1.y);
+    f[6] = apply_act<ACT>(__uint_as_float(v[q * 8 + 6]) + b1.z);
+    f[7] = apply_act<ACT>(__uint_as_float(v[q * 8 + 7]) + b1.w);
+    if constexpr (RES) {
+      const uint4 r = *reinterpret_cast<const uint4*>(res + q * 8);
+      const __half2* rh = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 rf = __half22float2(rh[e]);
+        f[2 * e] += rf.x;
+        f[2 * e + 1] += rf.y;
+      }
+    }
+    uint32_t w0, w1, w2, w3;
+    {
+      __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+      __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+      w0 = *reinterpret_cast<uint32_t*>(&h0); w1 = *reinterpret_cast<uint32_t*>(&h1);
+      w2 = *reinterpret_cast<uint32_t*>(&h2); w3 = *reinterpret_cast<uint32_t*>(&h3);
+    }
+    const int j = half * 4 + q;
+    const uint32_t addr = stage_row + uint32_t(((j ^ (row & 7)) << 4));
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+  }
+}
+
 // The whole accumulator row owned by this thread, 32 columns at a time.
 template <int BN, int ACT, bool RES>
 __device__ __forceinline__ void epilogue_store(uint32_t tmem_row, const float* __restrict__ bias_s,
@@ -122,6 +164,35 @@ __device__ __forceinline__ void epilogue_store(uint32_t tmem_row, const float* _
   }
 }
 
+// TMA-store epilogue for BN >= 64: 64 output channels at a time are staged in the warpgroup's swizzled
+// 128x128-byte buffer and written by ONE bulk tensor store (coalesced 128-byte rows, image-edge clipping by
+// the TMA unit) instead of 128 threads x 8 strided 16-byte stores.
+template <int BN, int ACT, bool RES>
+__device__ __forceinline__ void epilogue_store_tma(uint32_t tmem_row, const float* __restrict__ bias_s,
+                                                   const __half* __restrict__ res, uint32_t stage_base, int row,
+                                                   const CUtensorMap* omap, int n0, int ox0, int oy0, int img,
+                                                   uint32_t bar_id, bool leader) {
+  const uint32_t stage_row = stage_base + uint32_t(row) * 128u;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 64) {
+    uint32_t v0[32], v1[32];
+    tmem_ld_32x32(tmem_row + uint32_t(c0), v0);
+    tmem_ld_32x32(tmem_row + uint32_t(c0 + 32), v1);
+    tmem_ld_wait();
+    // the previous chunk's store must have finished reading the staging buffer
+    if (leader) tma_store_wait_read();
+    named_barrier_sync(bar_id, 128);
+    epilogue_chunk32_smem<ACT, RES>(v0, bias_s + c0, res + c0, stage_row, row, 0);
+    epilogue_chunk32_smem<ACT, RES>(v1, bias_s + c0 + 32, res + c0 + 32, stage_row, row, 1);
+    fence_proxy_async();
+    named_barrier_sync(bar_id, 128);
+    if (leader) {
+      tma_store_4d(omap, stage_base, n0 + c0, ox0, oy0, img);
+      tma_store_commit();
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   using Cfg = TcCfg<BN>;
@@ -140,6 +211,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 16 * Cfg::kStages + 16 * Cfg::kAccStages);
   float* bias_s = reinterpret_cast<float*>(smem_gen + bar_off + 512);
+  // staging tiles of the TMA-store epilogue: 1024-byte aligned, one per epilogue warpgroup
+  const uint32_t store_base = (bar_base + 512u + uint32_t(Cfg::kBiasFloats) * 4u + 1023u) & ~1023u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom& g = p.g;
@@ -159,6 +232,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (int s = 0; s < g.n_src; ++s)
       for (int q = 0; q < (g.in_stride == 2 ? 4 : 1); ++q) prefetch_tensormap(&p.a_map[s][q]);
     prefetch_tensormap(&p.b_map);
+    if (p.use_tma_store)
+      for (int q = 0; q < g.n_phase; ++q) prefetch_tensormap(&p.o_map[q]);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
@@ -270,6 +345,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         __half* out = p.dst + (size_t(img) * g.dst_h * g.dst_w + size_t(valid ? oy : 0) * g.dst_w + (valid ? ox : 0)) * g.dst_cstride +
                       g.dst_coff + nblk * BN;
         const int cout_left = g.cout - nblk * BN;
+        bool done_tma = false;
+        if constexpr (BN >= 64) {
+          if (p.use_tma_store) {
+            const uint32_t stage_base = store_base + uint32_t(group) * (128u * 128u);
+            const bool leader = (threadIdx.x & 127) == 0;
+            const CUtensorMap* om = &p.o_map[phase];
+#define CTD_EPT(ACT)                                                                                              \
+  if (g.residual) epilogue_store_tma<BN, ACT, true>(tmem_row, bias_t, out, stage_base, row, om, nblk * BN, x0, y0, img, 1 + group, leader); \
+  else epilogue_store_tma<BN, ACT, false>(tmem_row, bias_t, out, stage_base, row, om, nblk * BN, x0, y0, img, 1 + group, leader);
+            switch (g.act) {
+              case CTD_ACT_SILU: CTD_EPT(CTD_ACT_SILU) break;
+              case CTD_ACT_LEAKY: CTD_EPT(CTD_ACT_LEAKY) break;
+              case CTD_ACT_RELU: CTD_EPT(CTD_ACT_RELU) break;
+              case CTD_ACT_SIGMOID: CTD_EPT(CTD_ACT_SIGMOID) break;
+              default: CTD_EPT(CTD_ACT_NONE) break;
+            }
+#undef CTD_EPT
+            done_tma = true;
+          }
+        }
+        if (!done_tma) {
 #define CTD_EPI(ACT)                                                                              \
   if (g.residual) epilogue_store<BN, ACT, true>(tmem_row, bias_t, out, cout_left, valid);         \
   else epilogue_store<BN, ACT, false>(tmem_row, bias_t, out, cout_left, valid);
@@ -281,6 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           default: CTD_EPI(CTD_ACT_NONE) break;
         }
 #undef CTD_EPI
+        }
       } else {
         // Detect decode (yolo.py:36-44): columns = anchor*(5+nc) + o
         constexpr int kChunk = BN >= 32 ? 32 : 16;
@@ -317,6 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       tc_fence_before();
       mbar_arrive(tmem_empty_bar + 8 * as);
     }
+    if (p.use_tma_store && (threadIdx.x & 127) == 0) tma_store_wait_all();  // smem must outlive the bulk stores
   }
   tc_fence_before();
   __syncthreads();
@@ -406,6 +504,20 @@ const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
     }
   const int bn = pick_block_n(g.cout_pad);
   plan.block_n = bn;
+  p.use_tma_store = 0;
+  if (bn >= 64 && dst != nullptr && g.cout % 64 == 0) {
+    // destination slice as a 4-D tensor (channels of this op, x, y, image); deconv phases are parity views
+    const size_t cs = size_t(g.dst_cstride);
+    for (int ph = 0; ph < g.n_phase; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      cuuint64_t dims[4] = {cuuint64_t(g.cout), cuuint64_t(g.gw), cuuint64_t(g.gh), cuuint64_t(g.n_img)};
+      cuuint64_t str[3] = {cs * 2 * g.out_mul, cs * 2 * g.dst_w * g.out_mul, cs * 2 * size_t(g.dst_w) * g.dst_h};
+      cuuint32_t box[4] = {64, kTileW, kTileH, 1};
+      const char* base = reinterpret_cast<const char*>(dst) + (size_t(g.dst_coff) + (size_t(py) * g.dst_w + px) * cs) * 2;
+      if (const char* e = encode_map(enc, &p.o_map[ph], base, 4, dims, str, box, 64)) return e;
+    }
+    p.use_tma_store = 1;
+  }
   {
     cuuint64_t dims[2] = {cuuint64_t(g.k_total), cuuint64_t(g.n_phase) * cuuint64_t(g.cout_pad)};
     cuuint64_t str[1] = {cuuint64_t(g.k_total) * 2};

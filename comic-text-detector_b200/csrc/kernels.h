@@ -44,6 +44,8 @@ void fill_conv_geom_taps(ConvGeom& g, int kind, int ksize, int stride);
 struct alignas(64) ConvTcParams {
   CUtensorMap a_map[CTD_MAX_SRC][4];  // [source][parity]: parity maps only for stride-2 convs
   CUtensorMap b_map;                  // packed weights [n_phase*cout_pad][k_total], K-major
+  CUtensorMap o_map[4];               // destination slice, one map per deconv phase (TMA-store epilogue)
+  int use_tma_store;                  // 1: epilogue stages 64-channel chunks in smem and stores them by TMA
   ConvGeom g;
   int kb_elems;                       // channels per K block: 64 / 32 / 16 (swizzle 128/64/32 B)
   int src_kblocks[CTD_MAX_SRC];
