@@ -151,6 +151,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="pages per GPU per step")
     ap.add_argument("--cpu-pages", type=int, default=1, help="pages per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--api-pages", type=int, default=8, help="pages timed through the TextDetector Python API (0 = skip)")
     ap.add_argument("--cpu-threads", type=int, default=16,
                     help="torch intra-op threads of the CPU arm (measured on the B200 host: 16 threads 0.25 s/forward, "
                          "64 threads 0.48 s, 128 threads 33 s -- more threads only hurt)")
@@ -294,6 +295,21 @@ def main():
                          "share_of_step": tc_ms / float(op_ms.sum() + nms_ms + ccl_ms)},
             "stage_ms": {"conv_tc": tc_ms, "other_ops": float(op_ms.sum()) - tc_ms, "nms": nms_ms, "ccl_and_line_boxes": ccl_ms},
         }
+        if world == 1 and args.api_pages > 0:
+            # the drop-in Python API, one page per call (TextDetector.__call__: H2D, all GPU stages, host
+            # group_output, GPU refine_mask, D2H of masks): what a caller of the reference's interface sees
+            det = ctd_b200.TextDetector(ck, input_size=1024, act="leaky")
+            det(pages[0].copy())
+            t0 = time.perf_counter()
+            nblk = 0
+            for i in range(args.api_pages):
+                _m, _mr, _bl = det(pages[i % B].copy())
+                nblk += len(_bl)
+            dt = time.perf_counter() - t0
+            det.close()
+            line["api_e2e"] = {"value": args.api_pages / dt, "unit": "pages/s", "pages": args.api_pages,
+                               "blocks_per_page": nblk / args.api_pages,
+                               "what": "TextDetector.__call__ per page, single stream, incl. host group_output"}
         if not args.no_cpu_baseline and world == 1:
             cores = min(os.cpu_count(), args.cpu_threads)
             torch.set_num_threads(cores)

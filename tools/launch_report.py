@@ -38,7 +38,7 @@ def main():
         print("%-52s n=%3d %10.1f us %5.1f%%" % (k[:52], c, t, 100 * t / tot))
     if len(sys.argv) > 2:
         ops = [l.split() for l in open(sys.argv[2]) if l.startswith("op ")]
-        gemm = [o for o in ops if o[3] in ("1", "2", "6")]
+        gemm = [o for o in ops if o[3] in ("0", "1", "2", "6")]
         tc = [(k, t, g) for (k, t, g) in second if "conv_tc" in k]
         bs = 16
         print()
@@ -46,7 +46,10 @@ def main():
         for o, (k, t, g) in zip(gemm, tc):
             kind, kk, s, cin, cout, down = int(o[3]), int(o[5]), int(o[7]), int(o[9]), int(o[11]), int(o[13])
             hw = (1024 // down) ** 2 * bs
-            fl = 2 * hw * 16 * cin * cout if kind == 2 else 2 * (hw // (s * s)) * kk * kk * cin * cout
+            if kind == 0:
+                fl = 2 * (1024 // 2) ** 2 * bs * 108 * cout
+            else:
+                fl = 2 * hw * 16 * cin * cout if kind == 2 else 2 * (hw // (s * s)) * kk * kk * cin * cout
             tflop += fl
             bn = re.search(r"conv_tc_kernel<\(int\)(\d+)>|conv_tc_kernel<(\d+)>", k)
             print("op%-3s kind %d k%d s%d cin %4d cout %4d /%-2d BN=%-3s grid=%-16s %8.1f us %7.1f TF/s" % (
