@@ -42,7 +42,8 @@ EXPORTS = ["ctd_create", "ctd_destroy", "ctd_last_error", "ctd_forward", "ctd_ge
            "ctd_get_detections", "ctd_get_db_components", "ctd_last_forward_ms", "ctd_last_launch_count",
            "ctd_debug_read_buffer", "ctd_debug_write_buffer", "ctd_connected_components", "ctd_nms",
            "ctd_timer_start", "ctd_timer_stop", "ctd_profile_forward", "ctd_get_device_outputs",
-           "ctd_get_text_lines", "ctd_seg_represent", "ctd_refine_mask"]
+           "ctd_get_text_lines", "ctd_seg_represent", "ctd_refine_mask", "ctd_submit", "ctd_collect",
+           "ctd_results_bytes"]
 
 _lib = None
 
@@ -85,6 +86,9 @@ def load_library():
     lib.ctd_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
     lib.ctd_profile_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32]
     lib.ctd_get_device_outputs.argtypes = [vp, C.POINTER(CtdDeviceOutputs)]
+    lib.ctd_submit.argtypes = [vp, i32, vp, i32, i32, i32, vp]
+    lib.ctd_collect.argtypes = [vp, i32]
+    lib.ctd_results_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
     for name in EXPORTS[3:]:
         getattr(lib, name).restype = C.c_int
     _lib = lib
@@ -255,6 +259,21 @@ class Engine:
             self._ck(self.lib.ctd_profile_forward(self.h, C.c_void_p(dev_ptr), n, h, w, 1, _ptr(out), out.size))
         self.shape = (n, h, w)
         return out[:nops], float(out[nops]), float(out[nops + 1])
+
+    # ---- pipelined host path: two batches in flight, copies under compute -----------------------
+    def results_bytes(self):
+        n = C.c_size_t()
+        self._ck(self.lib.ctd_results_bytes(self.h, C.byref(n)))
+        return int(n.value)
+
+    def submit(self, slot, pages_ptr, n, h, w, results_ptr):
+        """asynchronous forward of HOST pages (raw pointers, ideally pinned) into HOST `results`
+        (results_bytes() bytes; unpack with multigpu.unpack_arena)."""
+        self._ck(self.lib.ctd_submit(self.h, slot, C.c_void_p(pages_ptr), n, h, w, C.c_void_p(results_ptr)))
+        self.shape = (n, h, w)
+
+    def collect(self, slot):
+        self._ck(self.lib.ctd_collect(self.h, slot))
 
     def device_outputs(self):
         o = CtdDeviceOutputs()

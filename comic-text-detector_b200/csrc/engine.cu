@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <tuple>
@@ -62,6 +63,19 @@ struct ctd_handle {
   void* d_nms_ws = nullptr;
   NmsWorkspace nms{};
   std::map<std::tuple<int, int, int>, ShapePlan> plans;
+  // pipelined host path (ctd_submit / ctd_collect): two staging slots, copy streams either side of compute
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  uint8_t* d_stage_in[2] = {nullptr, nullptr};
+  uint8_t* d_stage_out[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in_done[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
+  cudaEvent_t ev_out_ready[2] = {nullptr, nullptr}, ev_out_done[2] = {nullptr, nullptr};
+  bool slot_busy[2] = {false, false};
+  // overlapped schedule: post-processing of the DB maps / the Detect rows runs on side streams under the
+  // remaining network ops (see run_ops)
+  bool overlap = false;
+  cudaStream_t side = nullptr, side2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+  std::vector<char> db_ancestor;   // op feeds the DB tail (computed once in ctd_create)
   // last forward
   int n = 0, ph = 0, pw = 0;
   int last_launches = 0;
@@ -103,6 +117,21 @@ extern "C" void ctd_destroy(ctd_handle* h) {
   if (h->tev0) cudaEventDestroy(h->tev0);
   if (h->tev1) cudaEventDestroy(h->tev1);
   for (auto e : h->op_events) cudaEventDestroy(e);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->d_stage_in[i]); cudaFree(h->d_stage_out[i]);
+    if (h->ev_in_done[i]) cudaEventDestroy(h->ev_in_done[i]);
+    if (h->ev_in_free[i]) cudaEventDestroy(h->ev_in_free[i]);
+    if (h->ev_out_ready[i]) cudaEventDestroy(h->ev_out_ready[i]);
+    if (h->ev_out_done[i]) cudaEventDestroy(h->ev_out_done[i]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_fork2) cudaEventDestroy(h->ev_fork2);
+  if (h->ev_join2) cudaEventDestroy(h->ev_join2);
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->side2) cudaStreamDestroy(h->side2);
+  if (h->copy_in) cudaStreamDestroy(h->copy_in);
+  if (h->copy_out) cudaStreamDestroy(h->copy_out);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -124,6 +153,27 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
   h->cfg = *cfg;
   h->ops.assign(ops, ops + n_ops);
   h->bufs.assign(bufs, bufs + n_bufs);
+  {
+    // ancestors of the DB tail at buffer granularity (a buffer, once needed, stays needed: several ops may
+    // write disjoint channel ranges of it); one backward pass is enough because producers precede consumers
+    h->db_ancestor.assign(size_t(n_ops), 0);
+    std::vector<char> needed(size_t(n_bufs), 0);
+    bool have_db = false;
+    for (int i = n_ops - 1; i >= 0; --i) {
+      const ctd_op& op = ops[i];
+      bool anc = false;
+      if (op.kind == CTD_OP_DB_TAIL && !have_db) { anc = true; have_db = true; }
+      else if (have_db && op.dst_buf >= 0 && op.dst_buf < n_bufs && needed[op.dst_buf] &&
+               op.kind != CTD_OP_DETECT && op.kind != CTD_OP_SEG_TAIL && op.kind != CTD_OP_DB_TAIL) anc = true;
+      if (!anc) continue;
+      h->db_ancestor[size_t(i)] = 1;
+      for (int k = 0; k < op.n_src && k < 3; ++k)
+        if (op.src_buf[k] >= 0 && op.src_buf[k] < n_bufs) needed[op.src_buf[k]] = 1;
+      if (op.residual && op.dst_buf >= 0 && op.dst_buf < n_bufs) needed[op.dst_buf] = 1;
+    }
+    const char* ov = getenv("CTD_OVERLAP");
+    h->overlap = have_db && !(ov && ov[0] == '0');
+  }
   h->elem = cfg->precision == CTD_PREC_FP32_SIMT ? 4 : 2;
   auto bail = [&](int code) { std::string e = h->err; ctd_destroy(h); g_create_error = e; return code; };
 #define CKC(expr)                                                                                        \
@@ -135,7 +185,18 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
     }                                                                                                    \
   } while (0)
   CKC(cudaSetDevice(cfg->device));
-  CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    CKC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CKC(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, lo));
+    // side streams get the HIGHER priority: their small blocks slot in whenever a persistent conv CTA retires
+    CKC(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, hi));
+    CKC(cudaStreamCreateWithPriority(&h->side2, cudaStreamNonBlocking, hi));
+  }
+  CKC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
   CKC(cudaEventCreate(&h->ev0));
   CKC(cudaEventCreate(&h->ev1));
   CKC(cudaEventCreate(&h->tev0));
@@ -351,41 +412,91 @@ static int run_op_thin(ctd_handle* h, const ctd_op& op, int n, int ph, int pw) {
   }
 }
 
+static int run_one_op(ctd_handle* h, size_t i, int n, int ph, int pw, ShapePlan& sp, int* cnt) {
+  const ctd_op& op = h->ops[i];
+  const bool gemm = op.kind == CTD_OP_CONV || op.kind == CTD_OP_DECONV4 || op.kind == CTD_OP_DETECT;
+  int rc = CTD_OK;
+  if (op.kind == CTD_OP_STEM && h->cfg.precision == CTD_PREC_FP16_TC) {
+    // tensor-core stem: space-to-depth pre-pass into the padded window buffer, then the implicit GEMM
+    cudaError_t e = s2d_launch<__half>(h->d_pages, n, ph, pw, static_cast<__half*>(h->d_buf[op.src_buf[0]]), 16, 0,
+                                       pw / 2 + 4, 1, h->stream);
+    if (e == cudaSuccess) e = conv_tc_launch(sp.tc[i], h->stream);
+    rc = e == cudaSuccess ? CTD_OK : fail(h, CTD_E_CUDA, "stem op %zu: %s", i, cudaGetErrorString(e));
+    ++*cnt;
+  } else if (gemm) {
+    if (h->cfg.precision == CTD_PREC_FP16_TC) {
+      cudaError_t e = conv_tc_launch(sp.tc[i], h->stream);
+      rc = e == cudaSuccess ? CTD_OK : fail(h, CTD_E_CUDA, "conv_tc op %zu: %s", i, cudaGetErrorString(e));
+    } else if (h->cfg.precision == CTD_PREC_FP32_SIMT) {
+      rc = run_op_simt<float>(h, op, n, ph, pw);
+    } else {
+      rc = run_op_simt<__half>(h, op, n, ph, pw);
+    }
+  } else {
+    rc = h->elem == 4 ? run_op_thin<float>(h, op, n, ph, pw) : run_op_thin<__half>(h, op, n, ph, pw);
+  }
+  ++*cnt;
+  return rc;
+}
+
 static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* launches, bool record = false) {
   int cnt = 0;
   size_t evi = 0;
+  const int rows = rows_per_image(ph, pw);
+  if (h->overlap && !record && !h->cfg.debug_skip_postproc) {
+    // Two-phase order.  Phase 1: every op the DB maps depend on (program order).  Then the DB post-processing
+    // (CCL + contour boxes: latency-bound kernels that leave most SMs idle) forks to a side stream and runs
+    // UNDER phase 2 = the rest of the network (Detect heads, the seg-head tail); NMS forks the same way once
+    // the Detect rows exist.  No buffer is shared between the branches (the compiler never reuses buffers).
+    for (size_t i = 0; i < h->ops.size(); ++i)
+      if (h->db_ancestor[i])
+        if (int rc = run_one_op(h, i, n, ph, pw, sp, &cnt)) return rc;
+    CK(cudaEventRecord(h->ev_fork, h->stream));
+    CK(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    CK(ccl_launch(h->d_bitmap, n, ph, pw, h->d_labels, h->d_ccl_scratch, h->d_nlabels, h->side));
+    CK(segrep_launch(h->d_bitmap, h->d_lines, size_t(2) * ph * pw, h->d_ccl_scratch, n, ph, pw, 1000, 1.5f,
+                     h->d_segrep_scratch, h->d_line_boxes, h->d_line_scores, h->d_line_count, h->side));
+    CK(cudaEventRecord(h->ev_join, h->side));
+    cnt += 21;
+    size_t last_detect = h->ops.size();
+    for (size_t i = 0; i < h->ops.size(); ++i)
+      if (!h->db_ancestor[i] && h->ops[i].kind == CTD_OP_DETECT) last_detect = i;
+    bool nms_forked = false;
+    for (int pass = 0; pass < 2; ++pass)   // Detect heads first so NMS can start early
+      for (size_t i = 0; i < h->ops.size(); ++i) {
+        if (h->db_ancestor[i]) continue;
+        const bool early = last_detect != h->ops.size() && i <= last_detect && h->ops[i].kind == CTD_OP_DETECT;
+        if ((pass == 0) != early) continue;
+        if (int rc = run_one_op(h, i, n, ph, pw, sp, &cnt)) return rc;
+        if (i == last_detect) {
+          CK(cudaEventRecord(h->ev_fork2, h->stream));
+          CK(cudaStreamWaitEvent(h->side2, h->ev_fork2, 0));
+          CK(nms_launch(h->d_blks, n, rows, h->cfg.nc, h->cfg.conf_thresh, h->cfg.nms_thresh, h->nms, h->d_det,
+                        h->d_det_count, h->side2));
+          CK(cudaEventRecord(h->ev_join2, h->side2));
+          nms_forked = true;
+          cnt += 4;
+        }
+      }
+    if (!nms_forked) {
+      CK(nms_launch(h->d_blks, n, rows, h->cfg.nc, h->cfg.conf_thresh, h->cfg.nms_thresh, h->nms, h->d_det,
+                    h->d_det_count, h->stream));
+      cnt += 4;
+    } else {
+      CK(cudaStreamWaitEvent(h->stream, h->ev_join2, 0));
+    }
+    CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    *launches = cnt;
+    return CTD_OK;
+  }
   if (record) CK(cudaEventRecord(h->op_events[evi++], h->stream));
   for (size_t i = 0; i < h->ops.size(); ++i) {
-    const ctd_op& op = h->ops[i];
-    const bool gemm = op.kind == CTD_OP_CONV || op.kind == CTD_OP_DECONV4 || op.kind == CTD_OP_DETECT;
-    int rc = CTD_OK;
-    if (op.kind == CTD_OP_STEM && h->cfg.precision == CTD_PREC_FP16_TC) {
-      // tensor-core stem: space-to-depth pre-pass into the padded window buffer, then the implicit GEMM
-      cudaError_t e = s2d_launch<__half>(h->d_pages, n, ph, pw, static_cast<__half*>(h->d_buf[op.src_buf[0]]), 16, 0,
-                                         pw / 2 + 4, 1, h->stream);
-      if (e == cudaSuccess) e = conv_tc_launch(sp.tc[i], h->stream);
-      rc = e == cudaSuccess ? CTD_OK : fail(h, CTD_E_CUDA, "stem op %zu: %s", i, cudaGetErrorString(e));
-      ++cnt;
-    } else if (gemm) {
-      if (h->cfg.precision == CTD_PREC_FP16_TC) {
-        cudaError_t e = conv_tc_launch(sp.tc[i], h->stream);
-        rc = e == cudaSuccess ? CTD_OK : fail(h, CTD_E_CUDA, "conv_tc op %zu: %s", i, cudaGetErrorString(e));
-      } else if (h->cfg.precision == CTD_PREC_FP32_SIMT) {
-        rc = run_op_simt<float>(h, op, n, ph, pw);
-      } else {
-        rc = run_op_simt<__half>(h, op, n, ph, pw);
-      }
-    } else {
-      rc = h->elem == 4 ? run_op_thin<float>(h, op, n, ph, pw) : run_op_thin<__half>(h, op, n, ph, pw);
-    }
-    if (rc) return rc;
-    ++cnt;
+    if (int rc = run_one_op(h, i, n, ph, pw, sp, &cnt)) return rc;
     if (record) CK(cudaEventRecord(h->op_events[evi++], h->stream));
   }
   *launches = cnt;
   if (h->cfg.debug_skip_postproc) return CTD_OK;
   // post-processing on the same stream
-  const int rows = rows_per_image(ph, pw);
   CK(nms_launch(h->d_blks, n, rows, h->cfg.nc, h->cfg.conf_thresh, h->cfg.nms_thresh, h->nms, h->d_det,
                 h->d_det_count, h->stream));
   cnt += 4;
@@ -400,9 +511,8 @@ static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* lau
   return CTD_OK;
 }
 
-extern "C" int ctd_forward(ctd_handle* h, const uint8_t* pages, int32_t n, int32_t ph, int32_t pw,
-                           int32_t pages_on_device) {
-  if (!h || !pages) return CTD_E_INVALID;
+// shape checks + plan lookup + (first time) graph capture; the forward itself is enqueue_forward()
+static int prepare_forward(ctd_handle* h, int32_t n, int32_t ph, int32_t pw, ShapePlan** out) {
   if (n < 1 || n > h->cfg.max_batch) return fail(h, CTD_E_CAPACITY, "batch %d exceeds max_batch %d", n, h->cfg.max_batch);
   if (ph % 64 || pw % 64 || ph > h->cfg.max_h || pw > h->cfg.max_w || ph < 64 || pw < 64)
     return fail(h, CTD_E_SHAPE, "page %dx%d must be a multiple of 64 and <= %dx%d", ph, pw, h->cfg.max_h, h->cfg.max_w);
@@ -415,26 +525,23 @@ extern "C" int ctd_forward(ctd_handle* h, const uint8_t* pages, int32_t n, int32
     it = h->plans.emplace(key, std::move(sp)).first;
   }
   ShapePlan& sp = it->second;
-  const size_t bytes = size_t(n) * ph * pw * 3;
-  CK(cudaEventRecord(h->ev0, h->stream));
-  CK(cudaMemcpyAsync(h->d_pages, pages, bytes, pages_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                     h->stream));
-  if (h->cfg.use_graph) {
-    if (!sp.graph) {
-      // DETECT params are fetched with a blocking memcpy in the SIMT path: plans are already built, so
-      // capture only sees kernel launches (TC path).  SIMT paths run un-captured.
-      if (h->cfg.precision == CTD_PREC_FP16_TC) {
-        cudaGraph_t graph;
-        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = run_ops(h, n, ph, pw, sp, &sp.launches);
-        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
-        if (rc) return rc;
-        CK(e);
-        CK(cudaGraphInstantiate(&sp.graph, graph, 0));
-        cudaGraphDestroy(graph);
-      }
-    }
+  if (h->cfg.use_graph && !sp.graph && h->cfg.precision == CTD_PREC_FP16_TC) {
+    // DETECT params are fetched with a blocking memcpy in the SIMT path: plans are already built, so
+    // capture only sees kernel launches (TC path).  SIMT paths run un-captured.
+    cudaGraph_t graph;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = run_ops(h, n, ph, pw, sp, &sp.launches);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    if (rc) return rc;
+    CK(e);
+    CK(cudaGraphInstantiate(&sp.graph, graph, 0));
+    cudaGraphDestroy(graph);
   }
+  *out = &sp;
+  return CTD_OK;
+}
+
+static int enqueue_forward(ctd_handle* h, int32_t n, int32_t ph, int32_t pw, ShapePlan& sp) {
   if (sp.graph) {
     CK(cudaGraphLaunch(sp.graph, h->stream));
   } else {
@@ -444,6 +551,81 @@ extern "C" int ctd_forward(ctd_handle* h, const uint8_t* pages, int32_t n, int32
   h->last_launches = sp.launches;
   h->n = n; h->ph = ph; h->pw = pw;
   h->have_forward = true;
+  return CTD_OK;
+}
+
+extern "C" int ctd_forward(ctd_handle* h, const uint8_t* pages, int32_t n, int32_t ph, int32_t pw,
+                           int32_t pages_on_device) {
+  if (!h || !pages) return CTD_E_INVALID;
+  ShapePlan* sp = nullptr;
+  if (int rc = prepare_forward(h, n, ph, pw, &sp)) return rc;
+  const size_t bytes = size_t(n) * ph * pw * 3;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  CK(cudaMemcpyAsync(h->d_pages, pages, bytes, pages_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                     h->stream));
+  return enqueue_forward(h, n, ph, pw, *sp);
+}
+
+// ---- pipelined host path ---------------------------------------------------------------------------
+// submit(slot): copy_in: [wait slot's staging free] H2D pages -> stage_in[slot]
+//               compute: [wait H2D] stage_in -> d_pages (D2D), forward, arena -> stage_out[slot] (D2D)
+//               copy_out: [wait arena copy] D2H stage_out[slot] -> results_host
+// so the H2D of batch i+1 and the D2H of batch i-1 run under the forward of batch i.
+static int ensure_pipeline(ctd_handle* h) {
+  if (h->copy_in) return CTD_OK;
+  CK(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+  const size_t in_bytes = size_t(h->cfg.max_batch) * h->cfg.max_h * h->cfg.max_w * 3;
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaMalloc(&h->d_stage_in[i], in_bytes));
+    CK(cudaMalloc(&h->d_stage_out[i], h->results_bytes));
+    CK(cudaEventCreateWithFlags(&h->ev_in_done[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_in_free[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_out_ready[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_out_done[i], cudaEventDisableTiming));
+  }
+  return CTD_OK;
+}
+
+extern "C" int ctd_submit(ctd_handle* h, int32_t slot, const uint8_t* pages_host, int32_t n, int32_t ph, int32_t pw,
+                          void* results_host) {
+  if (!h || !pages_host || !results_host || slot < 0 || slot > 1) return CTD_E_INVALID;
+  if (h->cfg.debug_skip_postproc) return fail(h, CTD_E_INVALID, "ctd_submit needs the full pipeline");
+  if (h->slot_busy[slot]) return fail(h, CTD_E_INVALID, "slot %d has an uncollected submission", slot);
+  ShapePlan* sp = nullptr;
+  if (int rc = prepare_forward(h, n, ph, pw, &sp)) return rc;
+  if (int rc = ensure_pipeline(h)) return rc;
+  const size_t bytes = size_t(n) * ph * pw * 3;
+  CK(cudaStreamWaitEvent(h->copy_in, h->ev_in_free[slot], 0));   // no-op before the slot's first use
+  CK(cudaMemcpyAsync(h->d_stage_in[slot], pages_host, bytes, cudaMemcpyHostToDevice, h->copy_in));
+  CK(cudaEventRecord(h->ev_in_done[slot], h->copy_in));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_in_done[slot], 0));
+  CK(cudaMemcpyAsync(h->d_pages, h->d_stage_in[slot], bytes, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaEventRecord(h->ev_in_free[slot], h->stream));
+  if (int rc = enqueue_forward(h, n, ph, pw, *sp)) return rc;
+  CK(cudaStreamWaitEvent(h->stream, h->ev_out_done[slot], 0));  // previous D2H of this slot has drained
+  CK(cudaMemcpyAsync(h->d_stage_out[slot], h->d_mask_u8, h->results_bytes, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaEventRecord(h->ev_out_ready[slot], h->stream));
+  CK(cudaStreamWaitEvent(h->copy_out, h->ev_out_ready[slot], 0));
+  CK(cudaMemcpyAsync(results_host, h->d_stage_out[slot], h->results_bytes, cudaMemcpyDeviceToHost, h->copy_out));
+  CK(cudaEventRecord(h->ev_out_done[slot], h->copy_out));
+  h->slot_busy[slot] = true;
+  return CTD_OK;
+}
+
+extern "C" int ctd_collect(ctd_handle* h, int32_t slot) {
+  if (!h || slot < 0 || slot > 1) return CTD_E_INVALID;
+  if (!h->slot_busy[slot]) return fail(h, CTD_E_INVALID, "slot %d has nothing in flight", slot);
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventSynchronize(h->ev_out_done[slot]));
+  h->slot_busy[slot] = false;
+  return CTD_OK;
+}
+
+extern "C" int ctd_results_bytes(ctd_handle* h, size_t* bytes) {
+  if (!h || !bytes) return CTD_E_INVALID;
+  *bytes = h->results_bytes;
   return CTD_OK;
 }
 

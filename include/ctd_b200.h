@@ -160,6 +160,22 @@ CTD_API int ctd_get_db_components(ctd_handle* h, uint8_t* bitmap, int32_t* label
  * left to the caller, as in the reference.                                                        */
 CTD_API int ctd_get_text_lines(ctd_handle* h, int16_t* boxes, float* scores, int32_t* counts);
 
+/* ---- pipelined host-buffer path (throughput mode of ctd_forward + ctd_get_*) -----------------
+ * The reference serves pages one call at a time (inference.py:141-178: H2D, net, D2H, numpy post-
+ * processing, all serial).  A caller that streams batches keeps two in flight instead:
+ *   ctd_submit(h, slot, pages, n, ph, pw, results)   asynchronous: H2D of the HOST pages on a copy
+ *       stream, the whole forward + post-processing on the engine stream, D2H of the result arena
+ *       (mask_u8 | det | det_count | n_labels | line_boxes | line_scores | line_count, layout of
+ *       ctd_device_outputs / ctd_results_bytes) into HOST `results` on a second copy stream;
+ *   ctd_collect(h, slot)                              blocks until that slot's `results` are complete.
+ * slot is 0 or 1; a slot must be collected before it is submitted again.  `pages` and `results`
+ * should be pinned (cudaHostAlloc / torch pin_memory) or the copies serialise.  Submissions execute
+ * in order; ctd_get_* after a submit refer to the most recently submitted batch.               */
+CTD_API int ctd_submit(ctd_handle* h, int32_t slot, const uint8_t* pages_host, int32_t n, int32_t ph, int32_t pw,
+                       void* results_host);
+CTD_API int ctd_collect(ctd_handle* h, int32_t slot);
+CTD_API int ctd_results_bytes(ctd_handle* h, size_t* bytes);
+
 /* Device-side timing of the last ctd_forward (CUDA events on the engine stream), ms.       */
 CTD_API int ctd_last_forward_ms(ctd_handle* h, float* ms);
 /* Number of kernels the last ctd_forward launched (graph nodes when captured).             */

@@ -45,3 +45,44 @@ def test_text_detector_matches_oracle_chain(mode, keep_undetected):
             assert len(blk_list) > 3
     finally:
         det.close()
+
+
+def test_submit_collect_matches_blocking_forward():
+    """ctd_submit/ctd_collect (two batches in flight, copies on side streams) must deliver byte-identical result
+    arenas to the blocking ctd_forward + ctd_get_* path, in submission order, for different pages per batch."""
+    import torch
+    from ctd_b200 import multigpu
+    ck = get_checkpoint(0, True)
+    prog = ctd_b200.compiler.compile_checkpoint(ck)
+    B, H, W = 2, 256, 256
+    eng = ctd_b200.Engine(prog, max_batch=B, max_h=H, max_w=W, use_graph=True)
+    try:
+        batches = [np.stack([synth.structured_page(3000 + 10 * k + i, H, W) for i in range(B)]) for k in range(5)]
+        want = []
+        for pg in batches:
+            eng.forward(pg)
+            boxes, scores = eng.text_lines()
+            want.append((eng.mask_u8().copy(), eng.detections(), boxes, scores))
+        nbytes = eng.results_bytes()
+        assert nbytes == multigpu.arena_layout(B, H, W)["total"]
+        host_in = [torch.from_numpy(pg).pin_memory() for pg in batches]
+        host_out = [torch.zeros((nbytes,), dtype=torch.uint8).pin_memory() for _ in batches]
+        pending = []
+        for k in range(len(batches)):
+            if len(pending) == 2:
+                eng.collect(pending.pop(0))
+            eng.submit(k & 1, host_in[k].data_ptr(), B, H, W, host_out[k].data_ptr())
+            pending.append(k & 1)
+        with pytest.raises(ctd_b200.binding.CtdError):
+            eng.submit(pending[0], host_in[0].data_ptr(), B, H, W, host_out[0].data_ptr())  # slot still in flight
+        while pending:
+            eng.collect(pending.pop(0))
+        for k, (mask, dets, boxes, scores) in enumerate(want):
+            got = multigpu.unpack_arena(host_out[k].numpy(), B, B, H, W)
+            assert np.array_equal(got["mask"], mask)
+            for i in range(B):
+                assert np.array_equal(got["det"][i], dets[i])
+                assert np.array_equal(got["line_boxes"][i], boxes[i]) and np.array_equal(got["line_scores"][i], scores[i])
+                assert len(boxes[i]) > 0
+    finally:
+        eng.close()
