@@ -424,6 +424,228 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
 }
 
+
+// =========================================================================================
+// Halo variant.  For 3x3 stride-1 convolutions (and the 2x2-tap deconvolution phases) with few channels the
+// tap-per-box scheme above is bound by the TMA unit, not by the tensor cores: every tap re-fetches the same
+// 128 pixels (9 boxes of 128 rows per tile, plus 9 weight boxes).  Here
+//   * the weights of the CTA's phase are loaded ONCE and stay resident in shared memory;
+//   * a tile is 8 wide x 16 high, and ONE box per K block brings the (8+2hx) x (16+2hy) halo block;
+//   * filter tap (dy,dx) is the same smem block viewed through a matrix descriptor that starts
+//     (dy+hy)*(8+2hx) + (dx+hx) rows in and steps (8+2hx) rows between 8-row groups (SBO): the 8 pixels of a
+//     tile row are 8 consecutive halo rows, so every 8-row core group stays contiguous.  The 128B/64B swizzle
+//     is a function of the absolute shared-memory address for both TMA (writer) and the MMA (reader), so a
+//     view that starts off the 1024-byte pattern boundary is read consistently with the descriptor's
+//     base_offset left at 0 (measured on B200: setting base_offset = (addr >> 7) & 7 gives wrong results).
+// The CTA -> phase mapping is static (blockIdx.x % n_phase), tiles of that phase are strided over its CTAs.
+constexpr int kHaloTileW = 8, kHaloTileH = 16;
+constexpr int kHaloMaxStages = 8;
+
+template <int BN>
+struct HaloCfg {
+  static constexpr int kAccStages = 8;                      // BN <= 64 -> <= 512 TMEM columns
+  static constexpr int kTmemCols = BN * kAccStages;
+  static constexpr int kStoreBytes = BN >= 64 ? 2 * 128 * 128 : 0;
+  static constexpr int kBiasFloats = 64;
+  static constexpr size_t smem_bytes(int w_bytes, int stages, int stage_bytes) {
+    return 1024 + size_t((w_bytes + 1023) / 1024 * 1024) + size_t(stages) * stage_bytes + 512 + kBiasFloats * 4 + 1024 +
+           kStoreBytes;
+  }
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_constant__ ConvTcParams p) {
+  using Cfg = HaloCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t w_base = smem_base;
+  const uint32_t w_region = (uint32_t(p.halo_w_bytes) + 1023u) & ~1023u;
+  const uint32_t a_base = w_base + w_region;
+  const int S = p.halo_stages;
+  const uint32_t stage_bytes = uint32_t(p.halo_stage_bytes);
+  const uint32_t bar_base = a_base + uint32_t(S) * stage_bytes;
+  // barriers: full[8] | empty[8] | tmem_full[8] | tmem_empty[8] | weights | tmem ptr
+  const uint32_t full_bar = bar_base, empty_bar = bar_base + 64, tmem_full_bar = bar_base + 128;
+  const uint32_t tmem_empty_bar = bar_base + 192, w_bar = bar_base + 256, tmem_ptr_addr = bar_base + 264;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const size_t bar_off = size_t(w_region) + size_t(S) * stage_bytes;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 264);
+  float* bias_s = reinterpret_cast<float*>(smem_gen + bar_off + 512);
+  const uint32_t store_base = (bar_base + 512u + uint32_t(Cfg::kBiasFloats) * 4u + 1023u) & ~1023u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvGeom& g = p.g;
+  const int kb = p.kb_elems;
+  const uint32_t row_bytes = kb * 2;
+  const int hx = p.halo_hx, hy = p.halo_hy;
+  const int halo_w = kHaloTileW + 2 * hx, halo_h = kHaloTileH + 2 * hy;
+  const uint32_t stage_tx = uint32_t(halo_w * halo_h) * row_bytes;
+  int kblocks = 0;
+  for (int s = 0; s < g.n_src; ++s) kblocks += p.src_kblocks[s];
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int spatial_tiles = g.n_img * tiles_per_img;
+  const int phase = int(blockIdx.x) % g.n_phase;
+  const int rank = int(blockIdx.x) / g.n_phase, nrank = int(gridDim.x) / g.n_phase;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < g.n_src; ++s) prefetch_tensormap(&p.a_map[s][0]);
+    prefetch_tensormap(&p.b_map);
+    if (p.use_tma_store) prefetch_tensormap(&p.o_map[phase]);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int s = 0; s < Cfg::kAccStages; ++s) {
+      mbar_init(tmem_full_bar + 8 * s, 1);
+      mbar_init(tmem_empty_bar + 8 * s, 128);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_addr, Cfg::kTmemCols);
+  for (int i = threadIdx.x; i < BN; i += kThreads) bias_s[i] = i < g.cout_pad ? p.bias[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  auto decode = [&](int t, int& img, int& y0, int& x0) {
+    img = t / tiles_per_img;
+    const int trem = t - img * tiles_per_img;
+    const int ty = trem / p.tiles_x;
+    y0 = ty * kHaloTileH;
+    x0 = (trem - ty * p.tiles_x) * kHaloTileW;
+  };
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(w_bar, uint32_t(p.halo_w_bytes));
+      for (int tap = 0; tap < g.taps; ++tap) {
+        int kglob = tap * g.cin_total, kbi = 0;
+        for (int s = 0; s < g.n_src; ++s) {
+          for (int cb = 0; cb < p.src_kblocks[s]; ++cb, ++kbi)
+            tma_load_2d(w_base + uint32_t(tap * kblocks + kbi) * uint32_t(BN) * row_bytes, &p.b_map, w_bar,
+                        kglob + cb * kb, phase * g.cout_pad);
+          kglob += g.src_c[s];
+        }
+      }
+      int it = 0;
+      for (int t = rank; t < spatial_tiles; t += nrank) {
+        int img, y0, x0;
+        decode(t, img, y0, x0);
+        for (int s = 0; s < g.n_src; ++s)
+          for (int cb = 0; cb < p.src_kblocks[s]; ++cb, ++it) {
+            const int stage = it % S;
+            const uint32_t par = ((it / S) & 1) ^ 1;
+            mbar_wait(empty_bar + 8 * stage, par);
+            mbar_arrive_expect_tx(full_bar + 8 * stage, stage_tx);
+            tma_load_4d(a_base + uint32_t(stage) * stage_bytes, &p.a_map[s][0], full_bar + 8 * stage, cb * kb, x0 - hx,
+                        y0 - hy, img);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    const uint32_t idesc = make_idesc_f16(BN);
+    const uint32_t sbo = uint32_t(halo_w) * row_bytes;
+    mbar_wait(w_bar, 0);
+    int it = 0, ti = 0;
+    for (int t = rank; t < spatial_tiles; t += nrank, ++ti) {
+      const int as = ti % Cfg::kAccStages;
+      mbar_wait(tmem_empty_bar + 8 * as, ((ti / Cfg::kAccStages) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + uint32_t(as * BN);
+      for (int kbi = 0; kbi < kblocks; ++kbi, ++it) {
+        const int stage = it % S;
+        mbar_wait(full_bar + 8 * stage, (it / S) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_stage = a_base + uint32_t(stage) * stage_bytes;
+          const int ksteps = kb / 16;
+          for (int tap = 0; tap < g.taps; ++tap) {
+            const int dy = g.tap_dy[phase][tap], dx = g.tap_dx[phase][tap];
+            const uint32_t a_tap = a_stage + uint32_t((dy + hy) * halo_w + (dx + hx)) * row_bytes;
+            const uint32_t b_tap = w_base + uint32_t(tap * kblocks + kbi) * uint32_t(BN) * row_bytes;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t ad = make_kmajor_desc_ex(a_tap + k * 32, row_bytes, sbo, 0u);
+              const uint64_t bd = make_kmajor_desc(b_tap + k * 32, row_bytes);
+              umma_f16(tmem_d, ad, bd, idesc, (kbi > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(empty_bar + 8 * stage);
+          if (kbi == kblocks - 1) umma_commit(tmem_full_bar + 8 * as);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // =============================== epilogue ====================================
+    const int quad = warp & 3;
+    const int group = (warp - kEpiWarp0) >> 2;
+    const int row = quad * 32 + lane;
+    const int py = row / kHaloTileW, px = row - py * kHaloTileW;
+    int ti = 0;
+    for (int t = rank; t < spatial_tiles; t += nrank, ++ti) {
+      if ((ti & 1) != group) continue;
+      int img, y0, x0;
+      decode(t, img, y0, x0);
+      const int as = ti % Cfg::kAccStages;
+      const int gy = y0 + py, gx = x0 + px;
+      const bool valid = gy < g.gh && gx < g.gw;
+      mbar_wait(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
+      tc_fence_after();
+      const int ph_y = phase >> 1, ph_x = phase & 1;
+      const int oy = gy * g.out_mul + ph_y, ox = gx * g.out_mul + ph_x;
+      const uint32_t tmem_row = tmem_base + uint32_t(as * BN) + (uint32_t(quad * 32) << 16);
+      __half* out = p.dst + (size_t(img) * g.dst_h * g.dst_w + size_t(valid ? oy : 0) * g.dst_w + (valid ? ox : 0)) * g.dst_cstride +
+                    g.dst_coff;
+      bool done_tma = false;
+      if constexpr (BN >= 64) {
+        if (p.use_tma_store) {
+          const uint32_t stage_base = store_base + uint32_t(group) * (128u * 128u);
+          const bool leader = (threadIdx.x & 127) == 0;
+          const CUtensorMap* om = &p.o_map[phase];
+#define CTD_EPT(ACT)                                                                                              \
+  if (g.residual) epilogue_store_tma<BN, ACT, true>(tmem_row, bias_s, out, stage_base, row, om, 0, x0, y0, img, 1 + group, leader); \
+  else epilogue_store_tma<BN, ACT, false>(tmem_row, bias_s, out, stage_base, row, om, 0, x0, y0, img, 1 + group, leader);
+          switch (g.act) {
+            case CTD_ACT_SILU: CTD_EPT(CTD_ACT_SILU) break;
+            case CTD_ACT_LEAKY: CTD_EPT(CTD_ACT_LEAKY) break;
+            case CTD_ACT_RELU: CTD_EPT(CTD_ACT_RELU) break;
+            case CTD_ACT_SIGMOID: CTD_EPT(CTD_ACT_SIGMOID) break;
+            default: CTD_EPT(CTD_ACT_NONE) break;
+          }
+#undef CTD_EPT
+          done_tma = true;
+        }
+      }
+      if (!done_tma) {
+#define CTD_EPI(ACT)                                                                              \
+  if (g.residual) epilogue_store<BN, ACT, true>(tmem_row, bias_s, out, g.cout, valid);            \
+  else epilogue_store<BN, ACT, false>(tmem_row, bias_s, out, g.cout, valid);
+        switch (g.act) {
+          case CTD_ACT_SILU: CTD_EPI(CTD_ACT_SILU) break;
+          case CTD_ACT_LEAKY: CTD_EPI(CTD_ACT_LEAKY) break;
+          case CTD_ACT_RELU: CTD_EPI(CTD_ACT_RELU) break;
+          case CTD_ACT_SIGMOID: CTD_EPI(CTD_ACT_SIGMOID) break;
+          default: CTD_EPI(CTD_ACT_NONE) break;
+        }
+#undef CTD_EPI
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty_bar + 8 * as);
+    }
+    if (p.use_tma_store && (threadIdx.x & 127) == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 // =========================================================================================
 // host side
 
@@ -539,6 +761,85 @@ const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
   return nullptr;
 }
 
+const char* conv_halo_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
+                           const int src_coff[], const void* w16, const float* bias, __half* dst) {
+  plan.halo = 0;
+  if (dst == nullptr || g.in_stride != 1) return nullptr;
+  if (!((g.n_phase == 1 && g.taps == 9) || (g.n_phase == 4 && g.taps == 4))) return nullptr;
+  if (g.cout_pad != 32 && g.cout_pad != 64) return nullptr;   // one N block per CTA, TMEM ring of 8
+  int kb = 64;
+  for (int s = 0; s < g.n_src; ++s) {
+    if (g.src_c[s] % 64 != 0) kb = 32;
+    if (g.src_c[s] % 32 != 0) return nullptr;
+    if (src_coff[s] % 8 != 0) return nullptr;
+  }
+  if ((g.dst_coff % 8) != 0 || (g.dst_cstride % 8) != 0) return nullptr;
+  for (int ph = 0; ph < g.n_phase; ++ph)
+    for (int t = 0; t < g.taps; ++t)
+      if (g.tap_dy[ph][t] < -1 || g.tap_dy[ph][t] > 1 || g.tap_dx[ph][t] < -1 || g.tap_dx[ph][t] > 1) return nullptr;
+  const int bn = g.cout_pad;
+  const int row_bytes = kb * 2;
+  int kblocks = 0;
+  for (int s = 0; s < g.n_src; ++s) kblocks += g.src_c[s] / kb;
+  const int w_bytes = g.taps * kblocks * bn * row_bytes;
+  const int hx = 1, hy = 1;
+  const int halo_rows = (kHaloTileW + 2 * hx) * (kHaloTileH + 2 * hy);
+  const int stage_bytes = (halo_rows * row_bytes + 1023) / 1024 * 1024;
+  const size_t fixed = bn == 64 ? HaloCfg<64>::smem_bytes(w_bytes, 0, 0) : HaloCfg<32>::smem_bytes(w_bytes, 0, 0);
+  const size_t budget = 227 * 1024;
+  if (fixed + 3 * size_t(stage_bytes) > budget) return nullptr;   // weights too large to keep resident
+  int stages = int((budget - fixed) / stage_bytes);
+  if (stages > kHaloMaxStages) stages = kHaloMaxStages;
+
+  ConvTcParams& p = plan.p;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  p.kb_elems = kb;
+  for (int s = 0; s < g.n_src; ++s) p.src_kblocks[s] = g.src_c[s] / kb;
+  p.tiles_x = (g.gw + kHaloTileW - 1) / kHaloTileW;
+  p.tiles_y = (g.gh + kHaloTileH - 1) / kHaloTileH;
+  p.dst = dst;
+  p.bias = bias;
+  p.halo_hx = hx; p.halo_hy = hy;
+  p.halo_stages = stages; p.halo_stage_bytes = stage_bytes; p.halo_w_bytes = w_bytes;
+  for (int s = 0; s < g.n_src; ++s) {
+    const size_t cs = size_t(g.src_cstride[s]);
+    const char* base = static_cast<const char*>(src_ptr[s]) + size_t(src_coff[s]) * 2;
+    cuuint64_t dims[4] = {cuuint64_t(g.src_c[s]), cuuint64_t(g.src_w), cuuint64_t(g.src_h), cuuint64_t(g.n_img)};
+    cuuint64_t str[3] = {cs * 2, cs * 2 * g.src_w, cs * 2 * g.src_w * g.src_h};
+    cuuint32_t box[4] = {cuuint32_t(kb), cuuint32_t(kHaloTileW + 2 * hx), cuuint32_t(kHaloTileH + 2 * hy), 1};
+    if (const char* e = encode_map(enc, &p.a_map[s][0], base, 4, dims, str, box, kb)) return e;
+  }
+  p.use_tma_store = 0;
+  if (bn >= 64 && g.cout % 64 == 0) {
+    const size_t cs = size_t(g.dst_cstride);
+    for (int ph = 0; ph < g.n_phase; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      cuuint64_t dims[4] = {cuuint64_t(g.cout), cuuint64_t(g.gw), cuuint64_t(g.gh), cuuint64_t(g.n_img)};
+      cuuint64_t str[3] = {cs * 2 * g.out_mul, cs * 2 * g.dst_w * g.out_mul, cs * 2 * size_t(g.dst_w) * g.dst_h};
+      cuuint32_t box[4] = {64, kHaloTileW, kHaloTileH, 1};
+      const char* base = reinterpret_cast<const char*>(dst) + (size_t(g.dst_coff) + (size_t(py) * g.dst_w + px) * cs) * 2;
+      if (const char* e = encode_map(enc, &p.o_map[ph], base, 4, dims, str, box, 64)) return e;
+    }
+    p.use_tma_store = 1;
+  }
+  {
+    cuuint64_t dims[2] = {cuuint64_t(g.k_total), cuuint64_t(g.n_phase) * cuuint64_t(g.cout_pad)};
+    cuuint64_t str[1] = {cuuint64_t(g.k_total) * 2};
+    cuuint32_t box[2] = {cuuint32_t(kb), cuuint32_t(bn)};
+    if (const char* e = encode_map(enc, &p.b_map, w16, 2, dims, str, box, kb)) return e;
+  }
+  const int spatial_tiles = g.n_img * p.tiles_x * p.tiles_y;
+  int per_phase = g_num_sms / g.n_phase;
+  if (per_phase > spatial_tiles) per_phase = spatial_tiles;
+  if (per_phase < 1) per_phase = 1;
+  plan.grid = dim3(unsigned(per_phase * g.n_phase), 1, 1);
+  plan.block_n = bn;
+  plan.smem_bytes = bn == 64 ? HaloCfg<64>::smem_bytes(w_bytes, stages, stage_bytes) : HaloCfg<32>::smem_bytes(w_bytes, stages, stage_bytes);
+  plan.halo = 1;
+  return nullptr;
+}
+
 const char* conv_tc_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void* s2d, int n, int ph, int pw,
                               const void* w16, const float* bias, __half* dst, int dst_cstride, int dst_coff, int cout,
                               int act) {
@@ -590,10 +891,19 @@ cudaError_t conv_tc_init() {
   if (e != cudaSuccess) return e;
   CTD_SET(256) CTD_SET(128) CTD_SET(64) CTD_SET(32) CTD_SET(16)
 #undef CTD_SET
+  e = cudaFuncSetAttribute(conv_halo_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 cudaError_t conv_tc_launch(const ConvTcPlan& plan, cudaStream_t s) {
+  if (plan.halo) {
+    if (plan.block_n == 64) conv_halo_kernel<64><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p);
+    else conv_halo_kernel<32><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p);
+    return cudaGetLastError();
+  }
   switch (plan.block_n) {
     case 256: conv_tc_kernel<256><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p); break;
     case 128: conv_tc_kernel<128><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p); break;

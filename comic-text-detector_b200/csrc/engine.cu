@@ -72,6 +72,7 @@ struct ctd_handle {
   bool slot_busy[2] = {false, false};
   // overlapped schedule: post-processing of the DB maps / the Detect rows runs on side streams under the
   // remaining network ops (see run_ops)
+  int halo_mode = 1;   // CTD_HALO=0 routes every conv through conv_tc_kernel (A/B measurements)
   bool overlap = false;
   cudaStream_t side = nullptr, side2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
@@ -163,14 +164,19 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
       const ctd_op& op = ops[i];
       bool anc = false;
       if (op.kind == CTD_OP_DB_TAIL && !have_db) { anc = true; have_db = true; }
-      else if (have_db && op.dst_buf >= 0 && op.dst_buf < n_bufs && needed[op.dst_buf] &&
-               op.kind != CTD_OP_DETECT && op.kind != CTD_OP_SEG_TAIL && op.kind != CTD_OP_DB_TAIL) anc = true;
+      else if (have_db && op.kind != CTD_OP_DETECT && op.kind != CTD_OP_SEG_TAIL && op.kind != CTD_OP_DB_TAIL) {
+        // SPPF_POOL appends its pooled channels to its own source buffer (no dst_buf)
+        const int wbuf = op.kind == CTD_OP_SPPF_POOL ? op.src_buf[0] : op.dst_buf;
+        anc = wbuf >= 0 && wbuf < n_bufs && needed[wbuf];
+      }
       if (!anc) continue;
       h->db_ancestor[size_t(i)] = 1;
       for (int k = 0; k < op.n_src && k < 3; ++k)
         if (op.src_buf[k] >= 0 && op.src_buf[k] < n_bufs) needed[op.src_buf[k]] = 1;
       if (op.residual && op.dst_buf >= 0 && op.dst_buf < n_bufs) needed[op.dst_buf] = 1;
     }
+    const char* hm = getenv("CTD_HALO");
+    h->halo_mode = hm ? atoi(hm) : 1;
     const char* ov = getenv("CTD_OVERLAP");
     h->overlap = have_db && !(ov && ov[0] == '0');
   }
@@ -313,8 +319,14 @@ static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
       coff[s] = op.src_coff[s];
     }
     __half* dst = op.kind == CTD_OP_DETECT ? nullptr : static_cast<__half*>(h->d_buf[op.dst_buf]);
-    const char* e = conv_tc_plan(sp.tc[i], h->enc, g, src, coff, h->d_blob + op.w16_off,
-                                 reinterpret_cast<const float*>(h->d_blob + op.b_off), dst);
+    const char* e = nullptr;
+    sp.tc[i].halo = 0;
+    if (h->halo_mode > 0 && op.kind != CTD_OP_DETECT)
+      e = conv_halo_plan(sp.tc[i], h->enc, g, src, coff, h->d_blob + op.w16_off,
+                         reinterpret_cast<const float*>(h->d_blob + op.b_off), dst);
+    if (!e && !sp.tc[i].halo)
+      e = conv_tc_plan(sp.tc[i], h->enc, g, src, coff, h->d_blob + op.w16_off,
+                       reinterpret_cast<const float*>(h->d_blob + op.b_off), dst);
     if (e) return fail(h, CTD_E_INVALID, "op %zu: %s", i, e);
     if (op.kind == CTD_OP_DETECT) {
       ConvTcParams& p = sp.tc[i].p;
@@ -446,7 +458,7 @@ static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* lau
   if (h->overlap && !record && !h->cfg.debug_skip_postproc) {
     // Two-phase order.  Phase 1: every op the DB maps depend on (program order).  Then the DB post-processing
     // (CCL + contour boxes: latency-bound kernels that leave most SMs idle) forks to a side stream and runs
-    // UNDER phase 2 = the rest of the network (Detect heads, the seg-head tail); NMS forks the same way once
+    // UNDER phase 2 = the rest of the network (PAN, Detect heads, the seg-head tail); NMS forks the same way once
     // the Detect rows exist.  No buffer is shared between the branches (the compiler never reuses buffers).
     for (size_t i = 0; i < h->ops.size(); ++i)
       if (h->db_ancestor[i])
@@ -462,22 +474,19 @@ static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* lau
     for (size_t i = 0; i < h->ops.size(); ++i)
       if (!h->db_ancestor[i] && h->ops[i].kind == CTD_OP_DETECT) last_detect = i;
     bool nms_forked = false;
-    for (int pass = 0; pass < 2; ++pass)   // Detect heads first so NMS can start early
-      for (size_t i = 0; i < h->ops.size(); ++i) {
-        if (h->db_ancestor[i]) continue;
-        const bool early = last_detect != h->ops.size() && i <= last_detect && h->ops[i].kind == CTD_OP_DETECT;
-        if ((pass == 0) != early) continue;
-        if (int rc = run_one_op(h, i, n, ph, pw, sp, &cnt)) return rc;
-        if (i == last_detect) {
-          CK(cudaEventRecord(h->ev_fork2, h->stream));
-          CK(cudaStreamWaitEvent(h->side2, h->ev_fork2, 0));
-          CK(nms_launch(h->d_blks, n, rows, h->cfg.nc, h->cfg.conf_thresh, h->cfg.nms_thresh, h->nms, h->d_det,
-                        h->d_det_count, h->side2));
-          CK(cudaEventRecord(h->ev_join2, h->side2));
-          nms_forked = true;
-          cnt += 4;
-        }
+    for (size_t i = 0; i < h->ops.size(); ++i) {   // program order: PAN -> Detect heads -> seg-head tail
+      if (h->db_ancestor[i]) continue;
+      if (int rc = run_one_op(h, i, n, ph, pw, sp, &cnt)) return rc;
+      if (i == last_detect) {
+        CK(cudaEventRecord(h->ev_fork2, h->stream));
+        CK(cudaStreamWaitEvent(h->side2, h->ev_fork2, 0));
+        CK(nms_launch(h->d_blks, n, rows, h->cfg.nc, h->cfg.conf_thresh, h->cfg.nms_thresh, h->nms, h->d_det,
+                      h->d_det_count, h->side2));
+        CK(cudaEventRecord(h->ev_join2, h->side2));
+        nms_forked = true;
+        cnt += 4;
       }
+    }
     if (!nms_forked) {
       CK(nms_launch(h->d_blks, n, rows, h->cfg.nc, h->cfg.conf_thresh, h->cfg.nms_thresh, h->nms, h->d_det,
                     h->d_det_count, h->stream));

@@ -60,10 +60,16 @@ struct alignas(64) ConvTcParams {
   float det_stride;
   float anchor_wh[6];     // pixels
   int nc;
+  // halo variant (conv_halo_kernel): weights resident in smem, ONE activation box per K block holds the tile
+  // plus its halo and every filter tap is an MMA operand view into it
+  int halo_hx, halo_hy;               // halo pixels either side in x / y (0 or 1)
+  int halo_stages, halo_stage_bytes;  // activation ring
+  int halo_w_bytes;                   // resident weights of one phase: taps * kblocks * BN * kb * 2
 };
 
 struct ConvTcPlan {
   ConvTcParams p;
+  int halo = 0;                       // 1: launch conv_halo_kernel
   int block_n;
   dim3 grid;
   size_t smem_bytes;
@@ -81,6 +87,10 @@ const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
 const char* conv_tc_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void* s2d, int n, int ph, int pw,
                               const void* w16, const float* bias, __half* dst, int dst_cstride, int dst_coff, int cout,
                               int act);
+// Halo variant for stride-1 3x3 convolutions and the 2x2-tap deconvolution phases whose weights fit in shared
+// memory.  Sets plan.halo = 1 when the op is eligible, leaves it 0 (and returns nullptr) when not.
+const char* conv_halo_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
+                           const int src_coff[], const void* w16, const float* bias, __half* dst);
 cudaError_t conv_tc_launch(const ConvTcPlan& plan, cudaStream_t s);
 cudaError_t conv_tc_init();  // sets max dynamic smem attributes once
 

@@ -163,6 +163,19 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
   d |= layout << 61;
   return d;
 }
+// Same, with an explicit stride between 8-row groups and the 3-bit base_offset field [49,52) (needed when the
+// operand view does not start on the swizzle pattern's 1024-byte repeat).
+__device__ __forceinline__ uint64_t make_kmajor_desc_ex(uint32_t smem_addr, uint32_t swizzle_bytes, uint32_t sbo_bytes,
+                                                        uint32_t base_offset) {
+  const uint64_t layout = swizzle_bytes == 128 ? 2ull : (swizzle_bytes == 64 ? 4ull : 6ull);
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= 1ull << 46;
+  d |= static_cast<uint64_t>(base_offset & 7u) << 49;
+  d |= layout << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16: fp16 A/B (K-major both), fp32 D, M=128, N=n.
 //   [4,6) D fmt (1=f32) | [7,10) A fmt (0=f16) | [10,13) B fmt | bit15/16 A/B major (0=K)
 //   [17,23) N>>3 | [24,29) M>>4

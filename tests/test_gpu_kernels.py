@@ -41,6 +41,9 @@ CONV_CASES = [
     ([128], 64, 1, 1, cc.ACT_RELU, False, 192, 64, 1),
     ([16], 32, 3, 1, cc.ACT_SILU, False, 64, 128, 2),   # 16-channel K blocks (32-byte swizzle): the s2d stem
     ([16], 16, 1, 1, cc.ACT_NONE, False, 64, 64, 1),
+    ([64, 64], 64, 3, 1, cc.ACT_LEAKY, False, 64, 128, 2),   # halo kernel: two K blocks from two sources
+    ([32, 64], 64, 3, 1, cc.ACT_RELU, True, 128, 64, 1),     # halo kernel: 32-channel K blocks (64-byte swizzle)
+    ([128], 32, 3, 1, cc.ACT_SILU, False, 64, 192, 1),
 ]
 
 
@@ -77,7 +80,8 @@ def test_conv(case, prec):
     assert err <= _tol(prec, ref), "max abs err %g (ref max %g)" % (err, np.abs(ref).max())
 
 
-DECONV_CASES = [([64], 32, 32, 32, 1), ([128], 64, 64, 64, 1), ([512], 256, 32, 32, 2), ([256], 128, 32, 64, 1)]
+DECONV_CASES = [([64], 32, 32, 32, 1), ([128], 64, 64, 64, 1), ([512], 256, 32, 32, 2), ([256], 128, 32, 64, 1),
+                ([96], 64, 96, 32, 2)]
 
 
 @pytest.mark.parametrize("prec", [PREC_FP16_TC, PREC_FP32_SIMT, PREC_FP16_SIMT])
