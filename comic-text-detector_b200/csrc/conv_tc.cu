@@ -102,7 +102,7 @@ __device__ __forceinline__ void epilogue_chunk32(const uint32_t (&v)[32], const 
 // this thread (16-byte chunk j of row r lives at r*128 + ((j ^ (r & 7)) * 16)); `half` selects chunks 0-3 / 4-7.
 template <int ACT, bool RES>
 __device__ __forceinline__ void epilogue_chunk32_smem(const uint32_t (&v)[32], const float* __restrict__ bias_s,
-                                                      const __half* __restrict__ res, uint32_t stage_row, int row, int half) {
+                                                      const uint4 (&res)[4], uint32_t stage_row, int row, int half) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float f[8];
@@ -117,8 +117,7 @@ __device__ __forceinline__ void epilogue_chunk32_smem(const uint32_t (&v)[32], c
     f[6] = apply_act<ACT>(__uint_as_float(v[q * 8 + 6]) + b1.z);
     f[7] = apply_act<ACT>(__uint_as_float(v[q * 8 + 7]) + b1.w);
     if constexpr (RES) {
-      const uint4 r = *reinterpret_cast<const uint4*>(res + q * 8);
-      const __half2* rh = reinterpret_cast<const __half2*>(&r);
+      const __half2* rh = reinterpret_cast<const __half2*>(&res[q]);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 rf = __half22float2(rh[e]);
@@ -175,21 +174,45 @@ __device__ __forceinline__ void epilogue_store_tma(uint32_t tmem_row, const floa
   const uint32_t stage_row = stage_base + uint32_t(row) * 128u;
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 64) {
-    uint32_t v0[32], v1[32];
-    tmem_ld_32x32(tmem_row + uint32_t(c0), v0);
-    tmem_ld_32x32(tmem_row + uint32_t(c0 + 32), v1);
+    // residual first: eight independent 16-byte loads in flight under the TMEM read and the barrier below
+    uint4 r0[4], r1[4];
+    if constexpr (RES) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        r0[q] = *reinterpret_cast<const uint4*>(res + c0 + q * 8);
+        r1[q] = *reinterpret_cast<const uint4*>(res + c0 + 32 + q * 8);
+      }
+    }
+    // one 32-column half at a time keeps the accumulator registers at 32 (no spills next to the residual)
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_row + uint32_t(c0), v);
     tmem_ld_wait();
     // the previous chunk's store must have finished reading the staging buffer
     if (leader) tma_store_wait_read();
     named_barrier_sync(bar_id, 128);
-    epilogue_chunk32_smem<ACT, RES>(v0, bias_s + c0, res + c0, stage_row, row, 0);
-    epilogue_chunk32_smem<ACT, RES>(v1, bias_s + c0 + 32, res + c0 + 32, stage_row, row, 1);
+    epilogue_chunk32_smem<ACT, RES>(v, bias_s + c0, r0, stage_row, row, 0);
+    tmem_ld_32x32(tmem_row + uint32_t(c0 + 32), v);
+    tmem_ld_wait();
+    epilogue_chunk32_smem<ACT, RES>(v, bias_s + c0 + 32, r1, stage_row, row, 1);
     fence_proxy_async();
     named_barrier_sync(bar_id, 128);
     if (leader) {
       tma_store_4d(omap, stage_base, n0 + c0, ox0, oy0, img);
       tma_store_commit();
     }
+  }
+}
+
+// Issue the MMAs of one K block: `ksteps` x (M128 x BN x K16), descriptors advanced by 32 bytes (>>4 = 2) per
+// step.  Straight-line code: the issuing warp's instruction stream is the bottleneck for small tiles, so
+// nothing but the adds and the tcgen05.mma themselves is left in here.
+__device__ __forceinline__ void issue_kblock(uint32_t tmem_d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc0,
+                                             int ksteps) {
+  umma_f16(tmem_d, ad, bd, idesc, acc0);
+  if (ksteps >= 2) umma_f16(tmem_d, ad + 2, bd + 2, idesc, 1u);
+  if (ksteps >= 4) {
+    umma_f16(tmem_d, ad + 4, bd + 4, idesc, 1u);
+    umma_f16(tmem_d, ad + 6, bd + 6, idesc, 1u);
   }
 }
 
@@ -295,30 +318,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
     const uint32_t idesc = make_idesc_f16(BN);
-    int it = 0, ti = 0;
+    const bool leader = elect_one();   // one fixed thread issues every MMA and commit of this CTA
+    const uint64_t a_desc0 = make_kmajor_desc(a_base, row_bytes), b_desc0 = make_kmajor_desc(b_base, row_bytes);
+    const int ksteps = kb / 16;
+    int stage = 0, ti = 0;
+    uint32_t full_par = 0;
+    uint64_t ad = a_desc0, bd = b_desc0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
       const int as = ti % Cfg::kAccStages;
       mbar_wait(tmem_empty_bar + 8 * as, ((ti / Cfg::kAccStages) & 1) ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + uint32_t(as * BN);
-      for (int k_it = 0; k_it < its_per_tile; ++k_it, ++it) {
-        const int stage = it % Cfg::kStages;
-        const uint32_t par = (it / Cfg::kStages) & 1;
-        mbar_wait(full_bar + 8 * stage, par);
+      for (int k_it = 0; k_it < its_per_tile; ++k_it) {
+        mbar_wait(full_bar + 8 * stage, full_par);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_addr = a_base + stage * Cfg::kABytes;
-          const uint32_t b_addr = b_base + stage * Cfg::kBBytes;
-          const int ksteps = kb / 16;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = make_kmajor_desc(a_addr + k * 32, row_bytes);
-            const uint64_t bd = make_kmajor_desc(b_addr + k * 32, row_bytes);
-            umma_f16(tmem_d, ad, bd, idesc, (k_it > 0 || k > 0) ? 1u : 0u);
-          }
+        if (leader) {
+          issue_kblock(tmem_d, ad, bd, idesc, k_it > 0 ? 1u : 0u, ksteps);
           umma_commit(empty_bar + 8 * stage);
           if (k_it == its_per_tile - 1) umma_commit(tmem_full_bar + 8 * as);
         }
-        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0; full_par ^= 1u; ad = a_desc0; bd = b_desc0;
+        } else {
+          ad += uint64_t(Cfg::kABytes >> 4); bd += uint64_t(Cfg::kBBytes >> 4);
+        }
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -430,9 +453,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 // tap-per-box scheme above is bound by the TMA unit, not by the tensor cores: every tap re-fetches the same
 // 128 pixels (9 boxes of 128 rows per tile, plus 9 weight boxes).  Here
 //   * the weights of the CTA's phase are loaded ONCE and stay resident in shared memory;
-//   * a tile is 8 wide x 16 high, and ONE box per K block brings the (8+2hx) x (16+2hy) halo block;
+//   * a tile is 8 wide x 16 high, and ONE box per K block brings the tile plus its halo (W x H pixels, lox/loy
+//     of them before the tile); stride-2 convolutions take one such box per parity view of the source;
 //   * filter tap (dy,dx) is the same smem block viewed through a matrix descriptor that starts
-//     (dy+hy)*(8+2hx) + (dx+hx) rows in and steps (8+2hx) rows between 8-row groups (SBO): the 8 pixels of a
+//     (dy+loy)*W + (dx+lox) rows in and steps W rows between 8-row groups (SBO): the 8 pixels of a
 //     tile row are 8 consecutive halo rows, so every 8-row core group stays contiguous.  The 128B/64B swizzle
 //     is a function of the absolute shared-memory address for both TMA (writer) and the MMA (reader), so a
 //     view that starts off the 1024-byte pattern boundary is read consistently with the descriptor's
@@ -477,9 +501,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
   const ConvGeom& g = p.g;
   const int kb = p.kb_elems;
   const uint32_t row_bytes = kb * 2;
-  const int hx = p.halo_hx, hy = p.halo_hy;
-  const int halo_w = kHaloTileW + 2 * hx, halo_h = kHaloTileH + 2 * hy;
+  const int lox = p.halo_lox, loy = p.halo_loy;   // halo pixels before the tile (x / y)
+  const int halo_w = p.halo_w, halo_h = p.halo_h;
   const uint32_t stage_tx = uint32_t(halo_w * halo_h) * row_bytes;
+  const int n_par = g.in_stride == 2 ? 4 : 1;     // stride-2: one halo box per parity view of the source
   int kblocks = 0;
   for (int s = 0; s < g.n_src; ++s) kblocks += p.src_kblocks[s];
   const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -488,7 +513,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
   const int rank = int(blockIdx.x) / g.n_phase, nrank = int(gridDim.x) / g.n_phase;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < g.n_src; ++s) prefetch_tensormap(&p.a_map[s][0]);
+    for (int s = 0; s < g.n_src; ++s)
+      for (int q = 0; q < n_par; ++q) prefetch_tensormap(&p.a_map[s][q]);
     prefetch_tensormap(&p.b_map);
     if (p.use_tma_store) prefetch_tensormap(&p.o_map[phase]);
     for (int s = 0; s < S; ++s) {
@@ -534,49 +560,70 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
       for (int t = rank; t < spatial_tiles; t += nrank) {
         int img, y0, x0;
         decode(t, img, y0, x0);
-        for (int s = 0; s < g.n_src; ++s)
-          for (int cb = 0; cb < p.src_kblocks[s]; ++cb, ++it) {
-            const int stage = it % S;
-            const uint32_t par = ((it / S) & 1) ^ 1;
-            mbar_wait(empty_bar + 8 * stage, par);
-            mbar_arrive_expect_tx(full_bar + 8 * stage, stage_tx);
-            tma_load_4d(a_base + uint32_t(stage) * stage_bytes, &p.a_map[s][0], full_bar + 8 * stage, cb * kb, x0 - hx,
-                        y0 - hy, img);
-          }
+        for (int q = 0; q < n_par; ++q)
+          for (int s = 0; s < g.n_src; ++s)
+            for (int cb = 0; cb < p.src_kblocks[s]; ++cb, ++it) {
+              const int stage = it % S;
+              const uint32_t par = ((it / S) & 1) ^ 1;
+              mbar_wait(empty_bar + 8 * stage, par);
+              mbar_arrive_expect_tx(full_bar + 8 * stage, stage_tx);
+              tma_load_4d(a_base + uint32_t(stage) * stage_bytes, &p.a_map[s][q], full_bar + 8 * stage, cb * kb,
+                          x0 - lox, y0 - loy, img);
+            }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
     const uint32_t idesc = make_idesc_f16(BN);
     const uint32_t sbo = uint32_t(halo_w) * row_bytes;
+    const bool leader = elect_one();
+    const int ksteps = kb / 16;
+    // per-tap operand views, relative to the stage / weight base (16-byte units, added to the descriptors)
+    uint32_t tap_a[kMaxTaps], tap_b[kMaxTaps];
+    int tap_q[kMaxTaps];
+#pragma unroll
+    for (int tap = 0; tap < kMaxTaps; ++tap) {
+      const bool on = tap < g.taps;
+      const int dy = on ? g.tap_dy[phase][tap] : 0, dx = on ? g.tap_dx[phase][tap] : 0;
+      tap_a[tap] = (uint32_t((dy + loy) * halo_w + (dx + lox)) * row_bytes) >> 4;
+      tap_b[tap] = (uint32_t(tap * kblocks) * uint32_t(BN) * row_bytes) >> 4;
+      tap_q[tap] = on ? p.tap_map[phase][tap] : -1;
+    }
+    const uint64_t a_desc0 = make_kmajor_desc_ex(a_base, row_bytes, sbo, 0u);
+    const uint64_t b_desc0 = make_kmajor_desc(w_base, row_bytes);
+    const uint32_t a_step = stage_bytes >> 4, b_kb_step = (uint32_t(BN) * row_bytes) >> 4;
     mbar_wait(w_bar, 0);
-    int it = 0, ti = 0;
+    int stage = 0, ti = 0;
+    uint32_t full_par = 0;
+    uint64_t ad_stage = a_desc0;
     for (int t = rank; t < spatial_tiles; t += nrank, ++ti) {
       const int as = ti % Cfg::kAccStages;
       mbar_wait(tmem_empty_bar + 8 * as, ((ti / Cfg::kAccStages) & 1) ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + uint32_t(as * BN);
-      for (int kbi = 0; kbi < kblocks; ++kbi, ++it) {
-        const int stage = it % S;
-        mbar_wait(full_bar + 8 * stage, (it / S) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a_stage = a_base + uint32_t(stage) * stage_bytes;
-          const int ksteps = kb / 16;
-          for (int tap = 0; tap < g.taps; ++tap) {
-            const int dy = g.tap_dy[phase][tap], dx = g.tap_dx[phase][tap];
-            const uint32_t a_tap = a_stage + uint32_t((dy + hy) * halo_w + (dx + hx)) * row_bytes;
-            const uint32_t b_tap = w_base + uint32_t(tap * kblocks + kbi) * uint32_t(BN) * row_bytes;
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t ad = make_kmajor_desc_ex(a_tap + k * 32, row_bytes, sbo, 0u);
-              const uint64_t bd = make_kmajor_desc(b_tap + k * 32, row_bytes);
-              umma_f16(tmem_d, ad, bd, idesc, (kbi > 0 || tap > 0 || k > 0) ? 1u : 0u);
+      uint32_t acc = 0u;
+      for (int q = 0; q < n_par; ++q) {
+        uint64_t bd_kb = b_desc0;
+        for (int kbi = 0; kbi < kblocks; ++kbi) {
+          mbar_wait(full_bar + 8 * stage, full_par);
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int tap = 0; tap < kMaxTaps; ++tap) {
+              if (tap_q[tap] != q) continue;
+              issue_kblock(tmem_d, ad_stage + tap_a[tap], bd_kb + tap_b[tap], idesc, acc, ksteps);
+              acc = 1u;
             }
+            umma_commit(empty_bar + 8 * stage);
+            if (q == n_par - 1 && kbi == kblocks - 1) umma_commit(tmem_full_bar + 8 * as);
           }
-          umma_commit(empty_bar + 8 * stage);
-          if (kbi == kblocks - 1) umma_commit(tmem_full_bar + 8 * as);
+          bd_kb += b_kb_step;
+          if (++stage == S) {
+            stage = 0; full_par ^= 1u; ad_stage = a_desc0;
+          } else {
+            ad_stage += a_step;
+          }
         }
-        __syncwarp();
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -761,55 +808,22 @@ const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
   return nullptr;
 }
 
-const char* conv_halo_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
-                           const int src_coff[], const void* w16, const float* bias, __half* dst) {
-  plan.halo = 0;
-  if (dst == nullptr || g.in_stride != 1) return nullptr;
-  if (!((g.n_phase == 1 && g.taps == 9) || (g.n_phase == 4 && g.taps == 4))) return nullptr;
-  if (g.cout_pad != 32 && g.cout_pad != 64) return nullptr;   // one N block per CTA, TMEM ring of 8
-  int kb = 64;
-  for (int s = 0; s < g.n_src; ++s) {
-    if (g.src_c[s] % 64 != 0) kb = 32;
-    if (g.src_c[s] % 32 != 0) return nullptr;
-    if (src_coff[s] % 8 != 0) return nullptr;
-  }
-  if ((g.dst_coff % 8) != 0 || (g.dst_cstride % 8) != 0) return nullptr;
-  for (int ph = 0; ph < g.n_phase; ++ph)
-    for (int t = 0; t < g.taps; ++t)
-      if (g.tap_dy[ph][t] < -1 || g.tap_dy[ph][t] > 1 || g.tap_dx[ph][t] < -1 || g.tap_dx[ph][t] > 1) return nullptr;
+// shared tail of the halo plans: ring depth, weight map, output maps, launch shape
+static const char* halo_finish(ConvTcPlan& plan, PFN_encodeTiled enc, const void* w16, __half* dst, int kb, int kblocks) {
+  ConvTcParams& p = plan.p;
+  const ConvGeom& g = p.g;
   const int bn = g.cout_pad;
   const int row_bytes = kb * 2;
-  int kblocks = 0;
-  for (int s = 0; s < g.n_src; ++s) kblocks += g.src_c[s] / kb;
   const int w_bytes = g.taps * kblocks * bn * row_bytes;
-  const int hx = 1, hy = 1;
-  const int halo_rows = (kHaloTileW + 2 * hx) * (kHaloTileH + 2 * hy);
-  const int stage_bytes = (halo_rows * row_bytes + 1023) / 1024 * 1024;
+  const int stage_bytes = (p.halo_w * p.halo_h * row_bytes + 1023) / 1024 * 1024;
   const size_t fixed = bn == 64 ? HaloCfg<64>::smem_bytes(w_bytes, 0, 0) : HaloCfg<32>::smem_bytes(w_bytes, 0, 0);
   const size_t budget = 227 * 1024;
-  if (fixed + 3 * size_t(stage_bytes) > budget) return nullptr;   // weights too large to keep resident
+  if (fixed + 3 * size_t(stage_bytes) > budget) return "halo: weights do not fit";
   int stages = int((budget - fixed) / stage_bytes);
   if (stages > kHaloMaxStages) stages = kHaloMaxStages;
-
-  ConvTcParams& p = plan.p;
-  memset(&p, 0, sizeof(p));
-  p.g = g;
-  p.kb_elems = kb;
-  for (int s = 0; s < g.n_src; ++s) p.src_kblocks[s] = g.src_c[s] / kb;
+  p.halo_stages = stages; p.halo_stage_bytes = stage_bytes; p.halo_w_bytes = w_bytes;
   p.tiles_x = (g.gw + kHaloTileW - 1) / kHaloTileW;
   p.tiles_y = (g.gh + kHaloTileH - 1) / kHaloTileH;
-  p.dst = dst;
-  p.bias = bias;
-  p.halo_hx = hx; p.halo_hy = hy;
-  p.halo_stages = stages; p.halo_stage_bytes = stage_bytes; p.halo_w_bytes = w_bytes;
-  for (int s = 0; s < g.n_src; ++s) {
-    const size_t cs = size_t(g.src_cstride[s]);
-    const char* base = static_cast<const char*>(src_ptr[s]) + size_t(src_coff[s]) * 2;
-    cuuint64_t dims[4] = {cuuint64_t(g.src_c[s]), cuuint64_t(g.src_w), cuuint64_t(g.src_h), cuuint64_t(g.n_img)};
-    cuuint64_t str[3] = {cs * 2, cs * 2 * g.src_w, cs * 2 * g.src_w * g.src_h};
-    cuuint32_t box[4] = {cuuint32_t(kb), cuuint32_t(kHaloTileW + 2 * hx), cuuint32_t(kHaloTileH + 2 * hy), 1};
-    if (const char* e = encode_map(enc, &p.a_map[s][0], base, 4, dims, str, box, kb)) return e;
-  }
   p.use_tma_store = 0;
   if (bn >= 64 && g.cout % 64 == 0) {
     const size_t cs = size_t(g.dst_cstride);
@@ -838,6 +852,104 @@ const char* conv_halo_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom
   plan.smem_bytes = bn == 64 ? HaloCfg<64>::smem_bytes(w_bytes, stages, stage_bytes) : HaloCfg<32>::smem_bytes(w_bytes, stages, stage_bytes);
   plan.halo = 1;
   return nullptr;
+}
+
+const char* conv_halo_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
+                           const int src_coff[], const void* w16, const float* bias, __half* dst) {
+  plan.halo = 0;
+  if (dst == nullptr) return nullptr;
+  const bool s1 = g.in_stride == 1 && ((g.n_phase == 1 && g.taps == 9) || (g.n_phase == 4 && g.taps == 4));
+  const bool s2 = g.in_stride == 2 && g.n_phase == 1 && g.taps == 9 && g.src_h % 2 == 0 && g.src_w % 2 == 0;
+  if (!s1 && !s2) return nullptr;
+  if (g.cout_pad != 32 && g.cout_pad != 64) return nullptr;   // one N block per CTA, TMEM ring of 8
+  int kb = 64;
+  for (int s = 0; s < g.n_src; ++s) {
+    if (g.src_c[s] % 64 != 0) kb = 32;
+    if (g.src_c[s] % 32 != 0) return nullptr;
+    if (src_coff[s] % 8 != 0) return nullptr;
+  }
+  if ((g.dst_coff % 8) != 0 || (g.dst_cstride % 8) != 0) return nullptr;
+  for (int ph = 0; ph < g.n_phase; ++ph)
+    for (int t = 0; t < g.taps; ++t)
+      if (g.tap_dy[ph][t] < -1 || g.tap_dy[ph][t] > 1 || g.tap_dx[ph][t] < -1 || g.tap_dx[ph][t] > 1) return nullptr;
+  int kblocks = 0;
+  for (int s = 0; s < g.n_src; ++s) kblocks += g.src_c[s] / kb;
+  {
+    const size_t w_bytes = size_t(g.taps) * kblocks * g.cout_pad * kb * 2;
+    if (w_bytes > 110 * 1024) return nullptr;   // weights must stay resident next to >= 3 activation stages
+  }
+  ConvTcParams& p = plan.p;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  p.kb_elems = kb;
+  for (int s = 0; s < g.n_src; ++s) p.src_kblocks[s] = g.src_c[s] / kb;
+  p.dst = dst;
+  p.bias = bias;
+  p.halo_lox = 1; p.halo_loy = 1;
+  // stride 1: one pixel either side; stride 2: the parity views only ever reach one pixel back
+  p.halo_w = kHaloTileW + (s2 ? 1 : 2);
+  p.halo_h = kHaloTileH + (s2 ? 1 : 2);
+  for (int s = 0; s < g.n_src; ++s) {
+    const size_t cs = size_t(g.src_cstride[s]);
+    const char* base = static_cast<const char*>(src_ptr[s]) + size_t(src_coff[s]) * 2;
+    cuuint32_t box[4] = {cuuint32_t(kb), cuuint32_t(p.halo_w), cuuint32_t(p.halo_h), 1};
+    if (!s2) {
+      cuuint64_t dims[4] = {cuuint64_t(g.src_c[s]), cuuint64_t(g.src_w), cuuint64_t(g.src_h), cuuint64_t(g.n_img)};
+      cuuint64_t str[3] = {cs * 2, cs * 2 * g.src_w, cs * 2 * g.src_w * g.src_h};
+      if (const char* e = encode_map(enc, &p.a_map[s][0], base, 4, dims, str, box, kb)) return e;
+    } else {
+      for (int q = 0; q < 4; ++q) {   // parity views: pixel (2*yh+yp, 2*xh+xp)
+        const int yp = q >> 1, xp = q & 1;
+        cuuint64_t dims[4] = {cuuint64_t(g.src_c[s]), cuuint64_t(g.src_w / 2), cuuint64_t(g.src_h / 2), cuuint64_t(g.n_img)};
+        cuuint64_t str[3] = {cs * 2 * 2, cs * 2 * g.src_w * 2, cs * 2 * g.src_w * g.src_h};
+        const char* b2 = base + (size_t(yp) * g.src_w + xp) * cs * 2;
+        if (const char* e = encode_map(enc, &p.a_map[s][q], b2, 4, dims, str, box, kb)) return e;
+      }
+    }
+  }
+  for (int ph = 0; ph < g.n_phase; ++ph)
+    for (int t = 0; t < g.taps; ++t) {
+      if (s2) {
+        // source pixel = 2*o + d, d in {-1,0,1}: d=-1 -> (h=o-1, parity 1); d=0 -> (o,0); d=1 -> (o,1)
+        const int dy = g.tap_dy[ph][t], dx = g.tap_dx[ph][t];
+        p.tap_map[ph][t] = int8_t((dy != 0) * 2 + (dx != 0));
+        p.g.tap_dy[ph][t] = int8_t(dy < 0 ? -1 : 0);
+        p.g.tap_dx[ph][t] = int8_t(dx < 0 ? -1 : 0);
+      } else {
+        p.tap_map[ph][t] = 0;
+      }
+    }
+  const char* e = halo_finish(plan, enc, w16, dst, kb, kblocks);
+  if (e) { plan.halo = 0; return nullptr; }   // not eligible after all: the caller falls back to conv_tc_plan
+  return nullptr;
+}
+
+const char* conv_halo_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void* s2d, int n, int ph, int pw,
+                                const void* w16, const float* bias, __half* dst, int dst_cstride, int dst_coff, int cout,
+                                int act) {
+  ConvTcParams& p = plan.p;
+  memset(&p, 0, sizeof(p));
+  plan.halo = 0;
+  ConvGeom& g = p.g;
+  const int oh = ph / 2, ow = pw / 2, pitch = ow + 4;
+  g.n_img = n; g.gh = oh; g.gw = ow; g.dst_h = oh; g.dst_w = ow; g.out_mul = 1; g.n_phase = 1;
+  g.taps = 3; g.cin_total = 64; g.k_total = 192; g.n_src = 1; g.src_c[0] = 64; g.src_cstride[0] = 16;
+  g.src_h = oh; g.src_w = ow; g.in_stride = 1;
+  for (int t = 0; t < 3; ++t) { g.tap_dy[0][t] = int8_t(t - 1); g.tap_dx[0][t] = 0; }
+  g.cout = cout; g.cout_pad = 32; g.dst_cstride = dst_cstride; g.dst_coff = dst_coff; g.act = act; g.residual = 0;
+  p.kb_elems = 64;
+  p.src_kblocks[0] = 1;
+  p.dst = dst;
+  p.bias = bias;
+  p.halo_lox = 0; p.halo_loy = 1;   // the 4-pixel window already holds the x neighbours
+  p.halo_w = kHaloTileW; p.halo_h = kHaloTileH + 2;
+  {
+    cuuint64_t dims[4] = {64, cuuint64_t(ow), cuuint64_t(oh), cuuint64_t(n)};
+    cuuint64_t str[3] = {32, cuuint64_t(pitch) * 32, cuuint64_t(pitch) * 32 * oh};
+    cuuint32_t box[4] = {64, cuuint32_t(p.halo_w), cuuint32_t(p.halo_h), 1};
+    if (const char* e = encode_map(enc, &p.a_map[0][0], s2d, 4, dims, str, box, 64)) return e;
+  }
+  return halo_finish(plan, enc, w16, dst, 64, 1);
 }
 
 const char* conv_tc_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void* s2d, int n, int ph, int pw,

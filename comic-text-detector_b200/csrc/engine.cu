@@ -301,10 +301,10 @@ static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
   for (size_t i = 0; i < h->ops.size(); ++i) {
     const ctd_op& op = h->ops[i];
     if (op.kind == CTD_OP_STEM) {
-      const char* e = conv_tc_plan_stem(sp.tc[i], h->enc, h->d_buf[op.src_buf[0]], n, ph, pw, h->d_blob + op.w16_off,
-                                        reinterpret_cast<const float*>(h->d_blob + op.b_off),
-                                        static_cast<__half*>(h->d_buf[op.dst_buf]), h->bufs[op.dst_buf].channels,
-                                        op.dst_coff, op.cout, op.act);
+      const char* e = (h->halo_mode > 0 ? conv_halo_plan_stem : conv_tc_plan_stem)(
+          sp.tc[i], h->enc, h->d_buf[op.src_buf[0]], n, ph, pw, h->d_blob + op.w16_off,
+          reinterpret_cast<const float*>(h->d_blob + op.b_off), static_cast<__half*>(h->d_buf[op.dst_buf]),
+          h->bufs[op.dst_buf].channels, op.dst_coff, op.cout, op.act);
       if (e) return fail(h, CTD_E_INVALID, "stem: %s", e);
       sp.has_tc[i] = 1;
       continue;

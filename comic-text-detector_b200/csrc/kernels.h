@@ -62,7 +62,8 @@ struct alignas(64) ConvTcParams {
   int nc;
   // halo variant (conv_halo_kernel): weights resident in smem, ONE activation box per K block holds the tile
   // plus its halo and every filter tap is an MMA operand view into it
-  int halo_hx, halo_hy;               // halo pixels either side in x / y (0 or 1)
+  int halo_lox, halo_loy;             // halo pixels before the tile in x / y
+  int halo_w, halo_h;                 // halo block size in pixels (tile 8 x 16 + halo)
   int halo_stages, halo_stage_bytes;  // activation ring
   int halo_w_bytes;                   // resident weights of one phase: taps * kblocks * BN * kb * 2
 };
@@ -91,6 +92,10 @@ const char* conv_tc_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void*
 // memory.  Sets plan.halo = 1 when the op is eligible, leaves it 0 (and returns nullptr) when not.
 const char* conv_halo_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
                            const int src_coff[], const void* w16, const float* bias, __half* dst);
+// Stem through the halo kernel (window map of conv_tc_plan_stem, halo in y only).
+const char* conv_halo_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void* s2d, int n, int ph, int pw,
+                                const void* w16, const float* bias, __half* dst, int dst_cstride, int dst_coff, int cout,
+                                int act);
 cudaError_t conv_tc_launch(const ConvTcPlan& plan, cudaStream_t s);
 cudaError_t conv_tc_init();  // sets max dynamic smem attributes once
 

@@ -382,9 +382,61 @@ __global__ void sppf_pool_kernel(T* __restrict__ buf, int n, int h, int w, int c
   stv8(o + 2 * c, m9);
   stv8(o + 3 * c, m13);
 }
+// Same result, whole image of one 8-channel group resident in shared memory: the three chained 5x5 pools run as
+// separable row / column passes (2 x 5 reads per level instead of one 13x13 window per pixel).
+template <typename T>
+__global__ void sppf_pool_tile_kernel(T* __restrict__ buf, int h, int w, int c, int cs) {
+  extern __shared__ __align__(16) unsigned char sppf_sm[];
+  T* a = reinterpret_cast<T*>(sppf_sm);
+  T* b = a + size_t(h) * w * 8;
+  const int ch = blockIdx.x * 8, img = blockIdx.y, hw = h * w;
+  T* base = buf + size_t(img) * hw * cs + ch;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) stv8(a + size_t(i) * 8, ldv8(base + size_t(i) * cs));
+  __syncthreads();
+  for (int level = 1; level <= 3; ++level) {
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) {   // row pass a -> b
+      const int y = i / w, x = i - y * w;
+      Vec8 m = ldv8(a + size_t(i) * 8);
+#pragma unroll
+      for (int d = -2; d <= 2; ++d) {
+        if (d == 0 || x + d < 0 || x + d >= w) continue;
+        const Vec8 v = ldv8(a + size_t(i + d) * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m.v[e] = fmaxf(m.v[e], v.v[e]);
+      }
+      stv8(b + size_t(i) * 8, m);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < hw; i += blockDim.x) {   // column pass b -> a (+ output slot `level`)
+      const int y = i / w;
+      Vec8 m = ldv8(b + size_t(i) * 8);
+#pragma unroll
+      for (int d = -2; d <= 2; ++d) {
+        if (d == 0 || y + d < 0 || y + d >= h) continue;
+        const Vec8 v = ldv8(b + size_t(i + d * w) * 8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m.v[e] = fmaxf(m.v[e], v.v[e]);
+      }
+      stv8(a + size_t(i) * 8, m);
+      stv8(base + size_t(i) * cs + size_t(level) * c, m);
+    }
+    __syncthreads();
+  }
+}
+
 template <typename T>
 cudaError_t sppf_pool_launch(T* buf, int n, int h, int w, int c, int cs, cudaStream_t s) {
   if (c % 8 || cs % 8) return cudaErrorInvalidValue;
+  const size_t smem = size_t(2) * h * w * 8 * sizeof(T);
+  if (smem <= 200 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(sppf_pool_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_set = true;
+    }
+    sppf_pool_tile_kernel<T><<<dim3(c / 8, n), 256, smem, s>>>(buf, h, w, c, cs);
+    return cudaGetLastError();
+  }
   const long long total = (long long)n * h * w * (c / 8);
   sppf_pool_kernel<T><<<unsigned((total + 127) / 128), 128, 0, s>>>(buf, n, h, w, c, cs);
   return cudaGetLastError();

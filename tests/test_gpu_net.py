@@ -18,9 +18,11 @@ pytestmark = pytest.mark.gpu
 # fp16 engines: every activation/weight is stored in fp16 (fp32 accumulate).  A CPU emulation of that storage
 # through the same graph (tests/prog_interp.py with fp16 rounding) gives mean |err| 3-4e-3 and isolated maxima of
 # 0.1-0.35 where the random-weight net is locally ill-conditioned, so the stated fp16 tolerance is statistical.
+# The 99.9th percentile sits at 0.13-0.151 depending on the fp32 accumulation ORDER (tap-major vs K-block-major
+# kernels give 0.147 / 0.151 on the same page), hence 0.2.
 TOL = {PREC_FP32_SIMT: dict(maps=1e-3, maps_mean=1e-4, p999=1e-3, blks_rel=2e-3),
-       PREC_FP16_TC: dict(maps=0.5, maps_mean=1e-2, p999=0.15, blks_rel=1.0),
-       PREC_FP16_SIMT: dict(maps=0.5, maps_mean=1e-2, p999=0.15, blks_rel=1.0)}
+       PREC_FP16_TC: dict(maps=0.5, maps_mean=1e-2, p999=0.2, blks_rel=1.0),
+       PREC_FP16_SIMT: dict(maps=0.5, maps_mean=1e-2, p999=0.2, blks_rel=1.0)}
 
 
 def _pages(n, h, w, seed=1000):
@@ -81,3 +83,38 @@ def test_batch_invariance():
     finally:
         eng.close()
     assert np.array_equal(m3[1], m1[0]) and np.array_equal(l3[1], l1[0]) and np.array_equal(b3[1], b1[0])
+
+
+def test_tc_layers_track_fp32_engine():
+    """Layer-by-layer: every buffer of the tcgen05 engine (halo / tap-per-box / stem kernels, fp16 storage) against the
+    same buffer of the fp32 CUDA-core engine on the same page.  fp16 storage noise grows slowly through the net;
+    a kernel bug (a wrong tap, a bad border) shows up as an O(1) relative error in the first buffer it touches."""
+    ck = get_checkpoint(0, True)
+    n, h, w = 1, 256, 192
+    pages = _pages(n, h, w, seed=77)
+    prog = ctd_b200.compiler.compile_checkpoint(ck)
+    outs = {}
+    for prec in (PREC_FP32_SIMT, PREC_FP16_TC):
+        eng = ctd_b200.Engine(prog, precision=prec, max_batch=n, max_h=h, max_w=w)
+        try:
+            eng.forward(pages)
+            res = []
+            for i, op in enumerate(prog.ops):
+                if op["kind"] in (6, 7, 8) or op["dst_buf"] < 0:
+                    continue
+                t = dict(buf=op["dst_buf"], coff=op["dst_coff"], c=op["cout"], down=prog.bufs[op["dst_buf"]][1])
+                if t["c"] <= 0:
+                    continue
+                res.append((i, eng.debug_read(t)))
+            outs[prec] = res
+        finally:
+            eng.close()
+    worst = []
+    for (i, a), (_j, b) in zip(outs[PREC_FP32_SIMT], outs[PREC_FP16_TC]):
+        scale = float(np.abs(a).max()) + 1e-6
+        err = float(np.abs(a - b).max()) / scale
+        rms = float(np.sqrt(np.mean((a - b) ** 2))) / (float(np.sqrt(np.mean(a ** 2))) + 1e-6)
+        worst.append((err, rms, i))
+        # first layers: pure fp16 rounding; deeper: accumulated storage noise (measured rms <= ~1e-2)
+        assert rms <= (4e-3 if i < 6 else 5e-2), "op %d (kind %d): max rel err %.3g, rms rel %.3g" % (i, prog.ops[i]["kind"], err, rms)
+    print("worst layers (max rel err, rms rel, op):", sorted(worst, reverse=True)[:5])
