@@ -290,7 +290,18 @@ def compile_checkpoint(ckpt, head_act="leaky", stem_mode="s2d"):
     u256 = up_c3(ssd, [f128, u128], "upconv4")
     u512 = up_c3(ssd, [f256, u256], "upconv5")
     w6 = _np(ssd["upconv6.0.weight"])  # (C,1,4,4)
-    P._op(OP_SEG_TAIL, [u512], None, p_off=P.add_blob(w6.reshape(w6.shape[0], 16).astype(np.float32)))
+    # tensor-core form: the four sub-pixel phases of ConvT 4x4 s2 p1 (C -> 1) as ONE 3x3 convolution with
+    # 4 output channels (n = py*2+px; phase taps (d, k): parity 0 -> (0,1),(-1,3); parity 1 -> (0,2),(+1,0))
+    ci6 = w6.shape[0]
+    wc = np.zeros((16, 3, 3, ci6), np.float32)
+    TAPS = (((0, 1), (-1, 3)), ((0, 2), (1, 0)))
+    for py in range(2):
+        for px in range(2):
+            for dy, ky in TAPS[py]:
+                for dx, kx in TAPS[px]:
+                    wc[py * 2 + px, dy + 1, dx + 1, :] = w6[:, 0, ky, kx]
+    P._op(OP_SEG_TAIL, [u512], None, p_off=P.add_blob(w6.reshape(w6.shape[0], 16).astype(np.float32)),
+          w16_off=P.add_blob(wc.reshape(16, 9 * ci6).astype(np.float16)), cout=4, cout_pad=16)
 
     # ---- text_det: DBHead.forward (basemodel.py:106-125) ----------------------------------------
     du128 = up_c3(dsd, [f64, u64], "upconv3")

@@ -468,7 +468,7 @@ constexpr int kHaloMaxStages = 8;
 template <int BN>
 struct HaloCfg {
   static constexpr int kAccStages = 8;                      // BN <= 64 -> <= 512 TMEM columns
-  static constexpr int kTmemCols = BN * kAccStages;
+  static constexpr int kTmemCols = BN * kAccStages;         // 128 / 256 / 512
   static constexpr int kStoreBytes = BN >= 64 ? 2 * 128 * 128 : 0;
   static constexpr int kBiasFloats = 64;
   static constexpr size_t smem_bytes(int w_bytes, int stages, int stage_bytes) {
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr_addr, Cfg::kTmemCols);
-  for (int i = threadIdx.x; i < BN; i += kThreads) bias_s[i] = i < g.cout_pad ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < BN; i += kThreads) bias_s[i] = (p.bias != nullptr && i < g.cout_pad) ? p.bias[i] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -645,6 +645,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
       const int ph_y = phase >> 1, ph_x = phase & 1;
       const int oy = gy * g.out_mul + ph_y, ox = gx * g.out_mul + ph_x;
       const uint32_t tmem_row = tmem_base + uint32_t(as * BN) + (uint32_t(quad * 32) << 16);
+      if constexpr (BN == 16) {
+        // seg tail: 4 phase logits per grid pixel -> sigmoid -> 2x2 block of the f32 and u8 masks
+        uint32_t v[16];
+        tmem_ld_32x16(tmem_row, v);
+        tmem_ld_wait();
+        if (valid) {
+          const size_t ow2 = size_t(g.gw) * 2;
+          const size_t o0 = (size_t(img) * g.gh * 2 + size_t(gy) * 2) * ow2 + size_t(gx) * 2;
+#pragma unroll
+          for (int py2 = 0; py2 < 2; ++py2) {
+            const float s0 = 1.0f / (1.0f + expf(-__uint_as_float(v[py2 * 2])));
+            const float s1 = 1.0f / (1.0f + expf(-__uint_as_float(v[py2 * 2 + 1])));
+            *reinterpret_cast<float2*>(p.seg_f32 + o0 + py2 * ow2) = make_float2(s0, s1);
+            *reinterpret_cast<uchar2*>(p.seg_u8 + o0 + py2 * ow2) = make_uchar2((uint8_t)(s0 * 255.0f), (uint8_t)(s1 * 255.0f));
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tmem_empty_bar + 8 * as);
+        continue;
+      }
       __half* out = p.dst + (size_t(img) * g.dst_h * g.dst_w + size_t(valid ? oy : 0) * g.dst_w + (valid ? ox : 0)) * g.dst_cstride +
                     g.dst_coff;
       bool done_tma = false;
@@ -816,7 +836,7 @@ static const char* halo_finish(ConvTcPlan& plan, PFN_encodeTiled enc, const void
   const int row_bytes = kb * 2;
   const int w_bytes = g.taps * kblocks * bn * row_bytes;
   const int stage_bytes = (p.halo_w * p.halo_h * row_bytes + 1023) / 1024 * 1024;
-  const size_t fixed = bn == 64 ? HaloCfg<64>::smem_bytes(w_bytes, 0, 0) : HaloCfg<32>::smem_bytes(w_bytes, 0, 0);
+  const size_t fixed = bn == 64 ? HaloCfg<64>::smem_bytes(w_bytes, 0, 0) : HaloCfg<32>::smem_bytes(w_bytes, 0, 0);   // 32 == 16
   const size_t budget = 227 * 1024;
   if (fixed + 3 * size_t(stage_bytes) > budget) return "halo: weights do not fit";
   int stages = int((budget - fixed) / stage_bytes);
@@ -825,7 +845,7 @@ static const char* halo_finish(ConvTcPlan& plan, PFN_encodeTiled enc, const void
   p.tiles_x = (g.gw + kHaloTileW - 1) / kHaloTileW;
   p.tiles_y = (g.gh + kHaloTileH - 1) / kHaloTileH;
   p.use_tma_store = 0;
-  if (bn >= 64 && g.cout % 64 == 0) {
+  if (bn >= 64 && g.cout % 64 == 0 && dst != nullptr) {
     const size_t cs = size_t(g.dst_cstride);
     for (int ph = 0; ph < g.n_phase; ++ph) {
       const int py = ph >> 1, px = ph & 1;
@@ -855,20 +875,23 @@ static const char* halo_finish(ConvTcPlan& plan, PFN_encodeTiled enc, const void
 }
 
 const char* conv_halo_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
-                           const int src_coff[], const void* w16, const float* bias, __half* dst) {
+                           const int src_coff[], const void* w16, const float* bias, __half* dst, float* seg_f32,
+                           uint8_t* seg_u8) {
   plan.halo = 0;
-  if (dst == nullptr) return nullptr;
+  const bool seg = seg_f32 != nullptr && seg_u8 != nullptr;
+  if (dst == nullptr && !seg) return nullptr;
+  if (seg != (g.cout_pad == 16)) return nullptr;   // BN = 16 exists only with the seg-tail epilogue
   const bool s1 = g.in_stride == 1 && ((g.n_phase == 1 && g.taps == 9) || (g.n_phase == 4 && g.taps == 4));
   const bool s2 = g.in_stride == 2 && g.n_phase == 1 && g.taps == 9 && g.src_h % 2 == 0 && g.src_w % 2 == 0;
   if (!s1 && !s2) return nullptr;
-  if (g.cout_pad != 32 && g.cout_pad != 64) return nullptr;   // one N block per CTA, TMEM ring of 8
+  if (g.cout_pad != 16 && g.cout_pad != 32 && g.cout_pad != 64) return nullptr;   // one N block per CTA, TMEM ring of 8
   int kb = 64;
   for (int s = 0; s < g.n_src; ++s) {
     if (g.src_c[s] % 64 != 0) kb = 32;
     if (g.src_c[s] % 32 != 0) return nullptr;
     if (src_coff[s] % 8 != 0) return nullptr;
   }
-  if ((g.dst_coff % 8) != 0 || (g.dst_cstride % 8) != 0) return nullptr;
+  if (!seg && ((g.dst_coff % 8) != 0 || (g.dst_cstride % 8) != 0)) return nullptr;
   for (int ph = 0; ph < g.n_phase; ++ph)
     for (int t = 0; t < g.taps; ++t)
       if (g.tap_dy[ph][t] < -1 || g.tap_dy[ph][t] > 1 || g.tap_dx[ph][t] < -1 || g.tap_dx[ph][t] > 1) return nullptr;
@@ -885,6 +908,7 @@ const char* conv_halo_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom
   for (int s = 0; s < g.n_src; ++s) p.src_kblocks[s] = g.src_c[s] / kb;
   p.dst = dst;
   p.bias = bias;
+  p.seg_f32 = seg_f32; p.seg_u8 = seg_u8;
   p.halo_lox = 1; p.halo_loy = 1;
   // stride 1: one pixel either side; stride 2: the parity views only ever reach one pixel back
   p.halo_w = kHaloTileW + (s2 ? 1 : 2);
@@ -1007,13 +1031,16 @@ cudaError_t conv_tc_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_halo_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 cudaError_t conv_tc_launch(const ConvTcPlan& plan, cudaStream_t s) {
   if (plan.halo) {
     if (plan.block_n == 64) conv_halo_kernel<64><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p);
-    else conv_halo_kernel<32><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p);
+    else if (plan.block_n == 32) conv_halo_kernel<32><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p);
+    else conv_halo_kernel<16><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p);
     return cudaGetLastError();
   }
   switch (plan.block_n) {

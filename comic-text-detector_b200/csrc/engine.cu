@@ -309,6 +309,20 @@ static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
       sp.has_tc[i] = 1;
       continue;
     }
+    if (op.kind == CTD_OP_SEG_TAIL && h->halo_mode > 0 && op.w16_off > 0 && op.cout_pad == 16) {
+      // final ConvT 4x4 s2 (C -> 1) + sigmoid + u8 mask as a 3x3 / 4-output halo convolution
+      ctd_op c3 = op;
+      c3.kind = CTD_OP_CONV; c3.ksize = 3; c3.stride = 1;
+      ConvGeom g;
+      if (int rc = op_geom(h, c3, n, ph, pw, g)) return rc;
+      const void* src[CTD_MAX_SRC] = {h->d_buf[op.src_buf[0]]};
+      int coff[CTD_MAX_SRC] = {op.src_coff[0]};
+      const char* e = conv_halo_plan(sp.tc[i], h->enc, g, src, coff, h->d_blob + op.w16_off, nullptr, nullptr, h->d_mask,
+                                     h->d_mask_u8);
+      if (e) return fail(h, CTD_E_INVALID, "seg tail: %s", e);
+      sp.has_tc[i] = sp.tc[i].halo ? 1 : 0;
+      continue;
+    }
     if (op.kind != CTD_OP_CONV && op.kind != CTD_OP_DECONV4 && op.kind != CTD_OP_DETECT) continue;
     ConvGeom g;
     if (int rc = op_geom(h, op, n, ph, pw, g)) return rc;
@@ -435,6 +449,9 @@ static int run_one_op(ctd_handle* h, size_t i, int n, int ph, int pw, ShapePlan&
     if (e == cudaSuccess) e = conv_tc_launch(sp.tc[i], h->stream);
     rc = e == cudaSuccess ? CTD_OK : fail(h, CTD_E_CUDA, "stem op %zu: %s", i, cudaGetErrorString(e));
     ++*cnt;
+  } else if (op.kind == CTD_OP_SEG_TAIL && h->cfg.precision == CTD_PREC_FP16_TC && sp.has_tc[i]) {
+    cudaError_t e = conv_tc_launch(sp.tc[i], h->stream);
+    rc = e == cudaSuccess ? CTD_OK : fail(h, CTD_E_CUDA, "seg tail op %zu: %s", i, cudaGetErrorString(e));
   } else if (gemm) {
     if (h->cfg.precision == CTD_PREC_FP16_TC) {
       cudaError_t e = conv_tc_launch(sp.tc[i], h->stream);

@@ -66,6 +66,10 @@ struct alignas(64) ConvTcParams {
   int halo_w, halo_h;                 // halo block size in pixels (tile 8 x 16 + halo)
   int halo_stages, halo_stage_bytes;  // activation ring
   int halo_w_bytes;                   // resident weights of one phase: taps * kblocks * BN * kb * 2
+  // seg-tail epilogue (halo kernel, BN = 16): accumulator columns 0..3 are the sub-pixel phases of the final
+  // ConvT 4x4 s2 (C -> 1); sigmoid -> f32 mask + truncated u8 mask at (2y+py, 2x+px)
+  float* seg_f32;
+  uint8_t* seg_u8;
 };
 
 struct ConvTcPlan {
@@ -91,7 +95,8 @@ const char* conv_tc_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void*
 // Halo variant for stride-1 3x3 convolutions and the 2x2-tap deconvolution phases whose weights fit in shared
 // memory.  Sets plan.halo = 1 when the op is eligible, leaves it 0 (and returns nullptr) when not.
 const char* conv_halo_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
-                           const int src_coff[], const void* w16, const float* bias, __half* dst);
+                           const int src_coff[], const void* w16, const float* bias, __half* dst,
+                           float* seg_f32 = nullptr, uint8_t* seg_u8 = nullptr);
 // Stem through the halo kernel (window map of conv_tc_plan_stem, halo in y only).
 const char* conv_halo_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void* s2d, int n, int ph, int pw,
                                 const void* w16, const float* bias, __half* dst, int dst_cstride, int dst_coff, int cout,
