@@ -42,13 +42,15 @@ def conv_flops(prog, n, h, w):
         if kind == 0:  # stem: 6x6 s2 conv 3 -> cout (algorithmic FLOPs, not the zero-padded tensor-core K)
             out.append(2.0 * (h // 2) * (w // 2) * n * 108 * o["cout"])
             continue
-        if kind not in (1, 2, 6):
+        if kind not in (1, 2, 6, 7):
             out.append(0.0)
             continue
         down = prog.bufs[o["src_buf"][0]][1]
         px = (h // down) * (w // down) * n
         cin = sum(o["src_c"][: o["n_src"]])
-        if kind == 2:
+        if kind == 7:   # seg tail: ConvT 4x4 s2, C -> 1 (16 taps per input pixel)
+            out.append(2.0 * px * 16 * cin)
+        elif kind == 2:
             out.append(2.0 * px * 16 * cin * o["cout"])
         else:
             k, s = o["ksize"], o["stride"]
@@ -280,7 +282,7 @@ def main():
     op_ms2, _, _ = eng.profile_forward(dev_ptr=dev_pages.data_ptr(), shape=(B, H, W))
     op_ms = np.minimum(op_ms, op_ms2)
     fl = conv_flops(prog, B, H, W)
-    tc_idx = [i for i, o in enumerate(prog.ops) if o["kind"] in (0, 1, 2, 6)]
+    tc_idx = [i for i, o in enumerate(prog.ops) if o["kind"] in (0, 1, 2, 6, 7)]
     tc_ms = float(sum(op_ms[i] for i in tc_idx))
     tc_flops = float(sum(fl[i] for i in tc_idx))
     peaks = {}
@@ -291,6 +293,15 @@ def main():
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+    # DRAM bytes of the same launches from the committed ncu capture (profiles/): not measurable live
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json")))
+        if int(tj.get("batch", 0)) == B:
+            traffic = float(tj["dram_bytes"])
+            traffic_src = "profiles/r01_conv_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over the %d conv launches of one step)" % int(tj["launches"])
+    except Exception:
+        pass
 
     if rank == 0:
         total_pages = B * world * args.steps
@@ -316,8 +327,8 @@ def main():
                     "mode": "ctd_submit/ctd_collect, two batches in flight (copies under compute), pinned host buffers",
                     "sync_value": total_pages / (ms_e2e_sync * 1e-3),
                     "sync_mode": "ctd_forward + ctd_get_* blocking, nothing overlapped"},
-            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (%d launches per step)" % len(tc_idx), "achieved": achieved,
-                         "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+            "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel + conv_halo_kernel, the tcgen05 implicit-GEMM convolutions (%d launches per step)" % len(tc_idx), "achieved": achieved,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic, "traffic_unit": "bytes/step", "traffic_source": traffic_src,
                          "peak_source": peak_src, "flops_per_step": tc_flops, "ms_per_step": tc_ms,
                          "share_of_step": tc_ms / float(op_ms.sum() + nms_ms + ccl_ms)},
             "stage_ms": {"conv_tc": tc_ms, "other_ops": float(op_ms.sum()) - tc_ms, "nms": nms_ms, "ccl_and_line_boxes": ccl_ms},

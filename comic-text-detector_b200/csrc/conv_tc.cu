@@ -713,6 +713,201 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
   }
 }
 
+
+// =========================================================================================
+// Halo activations + streamed weights (BN = 128 / 256).  The wide 3x3 convolutions and deconvolution phases are
+// bound by L2 -> shared-memory operand traffic in conv_tc_kernel (every tap re-fetches its 16 KB activation box).
+// Here the activation halo block of a K block is fetched ONCE (A ring) and viewed per tap exactly as in
+// conv_halo_kernel, while the weights (too large to stay resident) stream through their own ring, one
+// BN x 64-channel box per (K block, tap).  Operand bytes per K block drop from taps*(16 KB + BN*128 B) to
+// 23 KB + taps*BN*128 B.
+template <int BN>
+struct HsCfg {
+  static constexpr int kAStages = BN >= 256 ? 2 : 3;
+  static constexpr int kBStages = BN >= 256 ? 4 : 7;
+  static constexpr int kAStageBytes = 24 * 1024;              // 10 x 18 halo rows of 128 B, 1024-aligned
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kAccStages = 512 / BN;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kStoreBytes = 2 * 128 * 128;
+  static constexpr int kBiasFloats = 512;
+  static constexpr size_t kSmem = 1024 + size_t(kAStages) * kAStageBytes + size_t(kBStages) * kBBytes + 512 + kBiasFloats * 4 +
+                                  1024 + kStoreBytes;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) conv_hs_kernel(const __grid_constant__ ConvTcParams p) {
+  using Cfg = HsCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = a_base + Cfg::kAStages * Cfg::kAStageBytes;
+  const uint32_t bar_base = b_base + Cfg::kBStages * Cfg::kBBytes;
+  // barriers: a_full[4] | a_empty[4] | b_full[8] | b_empty[8] | tmem_full[4] | tmem_empty[4] | tmem ptr
+  const uint32_t a_full = bar_base, a_empty = bar_base + 32, b_full = bar_base + 64, b_empty = bar_base + 128;
+  const uint32_t tmem_full_bar = bar_base + 192, tmem_empty_bar = bar_base + 224, tmem_ptr_addr = bar_base + 256;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const size_t bar_off = size_t(Cfg::kAStages) * Cfg::kAStageBytes + size_t(Cfg::kBStages) * Cfg::kBBytes;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 256);
+  float* bias_s = reinterpret_cast<float*>(smem_gen + bar_off + 512);
+  const uint32_t store_base = (bar_base + 512u + uint32_t(Cfg::kBiasFloats) * 4u + 1023u) & ~1023u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvGeom& g = p.g;
+  constexpr int kb = 64;
+  constexpr uint32_t row_bytes = 128;
+  const int lox = p.halo_lox, loy = p.halo_loy;
+  const int halo_w = p.halo_w, halo_h = p.halo_h;
+  const uint32_t a_tx = uint32_t(halo_w * halo_h) * row_bytes;
+  constexpr uint32_t b_tx = uint32_t(BN) * row_bytes;
+  int kblocks = 0;
+  for (int s = 0; s < g.n_src; ++s) kblocks += p.src_kblocks[s];
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int n_nblk = g.cout_pad / BN;
+  const int spatial_tiles = g.n_img * tiles_per_img;
+  const int total_tiles = spatial_tiles * n_nblk * g.n_phase;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < g.n_src; ++s) prefetch_tensormap(&p.a_map[s][0]);
+    prefetch_tensormap(&p.b_map);
+    if (p.use_tma_store)
+      for (int q = 0; q < g.n_phase; ++q) prefetch_tensormap(&p.o_map[q]);
+    for (int s = 0; s < Cfg::kAStages; ++s) { mbar_init(a_full + 8 * s, 1); mbar_init(a_empty + 8 * s, 1); }
+    for (int s = 0; s < Cfg::kBStages; ++s) { mbar_init(b_full + 8 * s, 1); mbar_init(b_empty + 8 * s, 1); }
+    for (int s = 0; s < Cfg::kAccStages; ++s) { mbar_init(tmem_full_bar + 8 * s, 1); mbar_init(tmem_empty_bar + 8 * s, 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_addr, Cfg::kTmemCols);
+  for (int i = threadIdx.x; i < g.cout_pad && i < Cfg::kBiasFloats; i += kThreads) bias_s[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  // tile index -> (phase, spatial tile, n block), n block fastest (CTAs running together share the halo in L2)
+  auto decode = [&](int t, int& phase, int& nblk, int& img, int& y0, int& x0) {
+    nblk = t % n_nblk;
+    const int r = t / n_nblk;
+    const int sp = r % spatial_tiles;
+    phase = r / spatial_tiles;
+    img = sp / tiles_per_img;
+    const int trem = sp - img * tiles_per_img;
+    const int ty = trem / p.tiles_x;
+    y0 = ty * kHaloTileH;
+    x0 = (trem - ty * p.tiles_x) * kHaloTileW;
+  };
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (elect_one()) {
+      int ia = 0, ib = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int phase, nblk, img, y0, x0;
+        decode(t, phase, nblk, img, y0, x0);
+        int kbi = 0;
+        for (int s = 0; s < g.n_src; ++s)
+          for (int cb = 0; cb < p.src_kblocks[s]; ++cb, ++kbi, ++ia) {
+            const int sa = ia % Cfg::kAStages;
+            mbar_wait(a_empty + 8 * sa, ((ia / Cfg::kAStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(a_full + 8 * sa, a_tx);
+            tma_load_4d(a_base + sa * Cfg::kAStageBytes, &p.a_map[s][0], a_full + 8 * sa, cb * kb, x0 - lox, y0 - loy, img);
+            for (int tap = 0; tap < g.taps; ++tap, ++ib) {
+              const int sb = ib % Cfg::kBStages;
+              mbar_wait(b_empty + 8 * sb, ((ib / Cfg::kBStages) & 1) ^ 1);
+              mbar_arrive_expect_tx(b_full + 8 * sb, b_tx);
+              tma_load_2d(b_base + sb * Cfg::kBBytes, &p.b_map, b_full + 8 * sb, tap * g.cin_total + kbi * kb,
+                          phase * g.cout_pad + nblk * BN);
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    const uint32_t idesc = make_idesc_f16(BN);
+    const uint32_t sbo = uint32_t(halo_w) * row_bytes;
+    const bool leader = elect_one();
+    const uint64_t a_desc0 = make_kmajor_desc_ex(a_base, row_bytes, sbo, 0u);
+    const uint64_t b_desc0 = make_kmajor_desc(b_base, row_bytes);
+    int sa = 0, sb = 0, ti = 0;
+    uint32_t a_par = 0, b_par = 0;
+    uint64_t ad_stage = a_desc0, bd = b_desc0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      const int phase = (t / n_nblk) / spatial_tiles;
+      const int as = ti % Cfg::kAccStages;
+      mbar_wait(tmem_empty_bar + 8 * as, ((ti / Cfg::kAccStages) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + uint32_t(as * BN);
+      uint32_t acc = 0u;
+      for (int kbi = 0; kbi < kblocks; ++kbi) {
+        mbar_wait(a_full + 8 * sa, a_par);
+        for (int tap = 0; tap < g.taps; ++tap) {
+          const int dy = g.tap_dy[phase][tap], dx = g.tap_dx[phase][tap];
+          const uint32_t a_off = (uint32_t((dy + loy) * halo_w + (dx + lox)) * row_bytes) >> 4;
+          mbar_wait(b_full + 8 * sb, b_par);
+          tc_fence_after();
+          if (leader) {
+            issue_kblock(tmem_d, ad_stage + a_off, bd, idesc, acc, 4);
+            umma_commit(b_empty + 8 * sb);
+            if (tap == g.taps - 1) {
+              umma_commit(a_empty + 8 * sa);
+              if (kbi == kblocks - 1) umma_commit(tmem_full_bar + 8 * as);
+            }
+          }
+          acc = 1u;
+          if (++sb == Cfg::kBStages) { sb = 0; b_par ^= 1u; bd = b_desc0; } else { bd += uint64_t(Cfg::kBBytes >> 4); }
+        }
+        if (++sa == Cfg::kAStages) { sa = 0; a_par ^= 1u; ad_stage = a_desc0; } else { ad_stage += uint64_t(Cfg::kAStageBytes >> 4); }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // =============================== epilogue ====================================
+    const int quad = warp & 3;
+    const int group = (warp - kEpiWarp0) >> 2;
+    const int row = quad * 32 + lane;
+    const int py = row / kHaloTileW, px = row - py * kHaloTileW;
+    int ti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      if ((ti & 1) != group) continue;
+      int phase, nblk, img, y0, x0;
+      decode(t, phase, nblk, img, y0, x0);
+      const int as = ti % Cfg::kAccStages;
+      const int gy = y0 + py, gx = x0 + px;
+      const bool valid = gy < g.gh && gx < g.gw;
+      mbar_wait(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
+      tc_fence_after();
+      const int ph_y = phase >> 1, ph_x = phase & 1;
+      const int oy = gy * g.out_mul + ph_y, ox = gx * g.out_mul + ph_x;
+      const uint32_t tmem_row = tmem_base + uint32_t(as * BN) + (uint32_t(quad * 32) << 16);
+      const float* bias_t = bias_s + nblk * BN;
+      __half* out = p.dst + (size_t(img) * g.dst_h * g.dst_w + size_t(valid ? oy : 0) * g.dst_w + (valid ? ox : 0)) * g.dst_cstride +
+                    g.dst_coff + nblk * BN;
+      const uint32_t stage_base = store_base + uint32_t(group) * (128u * 128u);
+      const bool lead = (threadIdx.x & 127) == 0;
+      const CUtensorMap* om = &p.o_map[phase];
+#define CTD_EPT(ACT)                                                                                              \
+  if (g.residual) epilogue_store_tma<BN, ACT, true>(tmem_row, bias_t, out, stage_base, row, om, nblk * BN, x0, y0, img, 1 + group, lead); \
+  else epilogue_store_tma<BN, ACT, false>(tmem_row, bias_t, out, stage_base, row, om, nblk * BN, x0, y0, img, 1 + group, lead);
+      switch (g.act) {
+        case CTD_ACT_SILU: CTD_EPT(CTD_ACT_SILU) break;
+        case CTD_ACT_LEAKY: CTD_EPT(CTD_ACT_LEAKY) break;
+        case CTD_ACT_RELU: CTD_EPT(CTD_ACT_RELU) break;
+        case CTD_ACT_SIGMOID: CTD_EPT(CTD_ACT_SIGMOID) break;
+        default: CTD_EPT(CTD_ACT_NONE) break;
+      }
+#undef CTD_EPT
+      tc_fence_before();
+      mbar_arrive(tmem_empty_bar + 8 * as);
+    }
+    if ((threadIdx.x & 127) == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 // =========================================================================================
 // host side
 
@@ -948,6 +1143,66 @@ const char* conv_halo_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom
   return nullptr;
 }
 
+const char* conv_hs_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
+                         const int src_coff[], const void* w16, const float* bias, __half* dst) {
+  plan.halo = 0;
+  if (dst == nullptr || g.in_stride != 1) return nullptr;
+  if (!((g.n_phase == 1 && g.taps == 9) || (g.n_phase == 4 && g.taps == 4))) return nullptr;
+  const int bn = (g.cout_pad % 256 == 0) ? 256 : ((g.cout_pad % 128 == 0) ? 128 : 0);
+  if (bn == 0 || g.cout_pad > 512 || g.cout % 64 != 0) return nullptr;   // TMA-store epilogue only
+  for (int s = 0; s < g.n_src; ++s)
+    if (g.src_c[s] % 64 != 0 || src_coff[s] % 8 != 0) return nullptr;
+  if ((g.dst_coff % 8) != 0 || (g.dst_cstride % 8) != 0) return nullptr;
+  for (int ph = 0; ph < g.n_phase; ++ph)
+    for (int t = 0; t < g.taps; ++t)
+      if (g.tap_dy[ph][t] < -1 || g.tap_dy[ph][t] > 1 || g.tap_dx[ph][t] < -1 || g.tap_dx[ph][t] > 1) return nullptr;
+  ConvTcParams& p = plan.p;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  p.kb_elems = 64;
+  for (int s = 0; s < g.n_src; ++s) p.src_kblocks[s] = g.src_c[s] / 64;
+  p.dst = dst;
+  p.bias = bias;
+  p.halo_lox = 1; p.halo_loy = 1;
+  p.halo_w = kHaloTileW + 2; p.halo_h = kHaloTileH + 2;
+  p.tiles_x = (g.gw + kHaloTileW - 1) / kHaloTileW;
+  p.tiles_y = (g.gh + kHaloTileH - 1) / kHaloTileH;
+  for (int s = 0; s < g.n_src; ++s) {
+    const size_t cs = size_t(g.src_cstride[s]);
+    const char* base = static_cast<const char*>(src_ptr[s]) + size_t(src_coff[s]) * 2;
+    cuuint64_t dims[4] = {cuuint64_t(g.src_c[s]), cuuint64_t(g.src_w), cuuint64_t(g.src_h), cuuint64_t(g.n_img)};
+    cuuint64_t str[3] = {cs * 2, cs * 2 * g.src_w, cs * 2 * g.src_w * g.src_h};
+    cuuint32_t box[4] = {64, cuuint32_t(p.halo_w), cuuint32_t(p.halo_h), 1};
+    if (const char* e = encode_map(enc, &p.a_map[s][0], base, 4, dims, str, box, 64)) return e;
+  }
+  {
+    const size_t cs = size_t(g.dst_cstride);
+    for (int ph = 0; ph < g.n_phase; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      cuuint64_t dims[4] = {cuuint64_t(g.cout), cuuint64_t(g.gw), cuuint64_t(g.gh), cuuint64_t(g.n_img)};
+      cuuint64_t str[3] = {cs * 2 * g.out_mul, cs * 2 * g.dst_w * g.out_mul, cs * 2 * size_t(g.dst_w) * g.dst_h};
+      cuuint32_t box[4] = {64, kHaloTileW, kHaloTileH, 1};
+      const char* base = reinterpret_cast<const char*>(dst) + (size_t(g.dst_coff) + (size_t(py) * g.dst_w + px) * cs) * 2;
+      if (const char* e = encode_map(enc, &p.o_map[ph], base, 4, dims, str, box, 64)) return e;
+    }
+    p.use_tma_store = 1;
+  }
+  {
+    cuuint64_t dims[2] = {cuuint64_t(g.k_total), cuuint64_t(g.n_phase) * cuuint64_t(g.cout_pad)};
+    cuuint64_t str[1] = {cuuint64_t(g.k_total) * 2};
+    cuuint32_t box[2] = {64, cuuint32_t(bn)};
+    if (const char* e = encode_map(enc, &p.b_map, w16, 2, dims, str, box, 64)) return e;
+  }
+  const int total_tiles = g.n_img * p.tiles_x * p.tiles_y * (g.cout_pad / bn) * g.n_phase;
+  plan.grid = dim3(unsigned(total_tiles < g_num_sms ? total_tiles : g_num_sms), 1, 1);
+  plan.block_n = bn;
+  plan.smem_bytes = bn == 256 ? HsCfg<256>::kSmem : HsCfg<128>::kSmem;
+  p.halo_stages = bn == 256 ? HsCfg<256>::kAStages : HsCfg<128>::kAStages;
+  p.hs_b_stages = bn == 256 ? HsCfg<256>::kBStages : HsCfg<128>::kBStages;
+  plan.halo = 2;
+  return nullptr;
+}
+
 const char* conv_halo_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void* s2d, int n, int ph, int pw,
                                 const void* w16, const float* bias, __half* dst, int dst_cstride, int dst_coff, int cout,
                                 int act) {
@@ -1033,10 +1288,19 @@ cudaError_t conv_tc_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_hs_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(HsCfg<256>::kSmem));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_hs_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(HsCfg<128>::kSmem));
+  if (e != cudaSuccess) return e;
   return cudaSuccess;
 }
 
 cudaError_t conv_tc_launch(const ConvTcPlan& plan, cudaStream_t s) {
+  if (plan.halo == 2) {
+    if (plan.block_n == 256) conv_hs_kernel<256><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p);
+    else conv_hs_kernel<128><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p);
+    return cudaGetLastError();
+  }
   if (plan.halo) {
     if (plan.block_n == 64) conv_halo_kernel<64><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p);
     else if (plan.block_n == 32) conv_halo_kernel<32><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p);

@@ -72,7 +72,7 @@ struct ctd_handle {
   bool slot_busy[2] = {false, false};
   // overlapped schedule: post-processing of the DB maps / the Detect rows runs on side streams under the
   // remaining network ops (see run_ops)
-  int halo_mode = 1;   // CTD_HALO=0 routes every conv through conv_tc_kernel (A/B measurements)
+  int halo_mode = 3;   // CTD_HALO bit mask (0 routes every conv through conv_tc_kernel, for A/B measurements)
   bool overlap = false;
   cudaStream_t side = nullptr, side2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
@@ -176,7 +176,7 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
       if (op.residual && op.dst_buf >= 0 && op.dst_buf < n_bufs) needed[op.dst_buf] = 1;
     }
     const char* hm = getenv("CTD_HALO");
-    h->halo_mode = hm ? atoi(hm) : 1;
+    h->halo_mode = hm ? atoi(hm) : 3;   // bit 0: conv_halo_kernel (resident weights), bit 1: conv_hs_kernel (streamed)
     const char* ov = getenv("CTD_OVERLAP");
     h->overlap = have_db && !(ov && ov[0] == '0');
   }
@@ -301,7 +301,7 @@ static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
   for (size_t i = 0; i < h->ops.size(); ++i) {
     const ctd_op& op = h->ops[i];
     if (op.kind == CTD_OP_STEM) {
-      const char* e = (h->halo_mode > 0 ? conv_halo_plan_stem : conv_tc_plan_stem)(
+      const char* e = ((h->halo_mode & 1) ? conv_halo_plan_stem : conv_tc_plan_stem)(
           sp.tc[i], h->enc, h->d_buf[op.src_buf[0]], n, ph, pw, h->d_blob + op.w16_off,
           reinterpret_cast<const float*>(h->d_blob + op.b_off), static_cast<__half*>(h->d_buf[op.dst_buf]),
           h->bufs[op.dst_buf].channels, op.dst_coff, op.cout, op.act);
@@ -309,7 +309,7 @@ static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
       sp.has_tc[i] = 1;
       continue;
     }
-    if (op.kind == CTD_OP_SEG_TAIL && h->halo_mode > 0 && op.w16_off > 0 && op.cout_pad == 16) {
+    if (op.kind == CTD_OP_SEG_TAIL && (h->halo_mode & 1) && op.w16_off > 0 && op.cout_pad == 16) {
       // final ConvT 4x4 s2 (C -> 1) + sigmoid + u8 mask as a 3x3 / 4-output halo convolution
       ctd_op c3 = op;
       c3.kind = CTD_OP_CONV; c3.ksize = 3; c3.stride = 1;
@@ -335,9 +335,12 @@ static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
     __half* dst = op.kind == CTD_OP_DETECT ? nullptr : static_cast<__half*>(h->d_buf[op.dst_buf]);
     const char* e = nullptr;
     sp.tc[i].halo = 0;
-    if (h->halo_mode > 0 && op.kind != CTD_OP_DETECT)
+    if ((h->halo_mode & 1) && op.kind != CTD_OP_DETECT)
       e = conv_halo_plan(sp.tc[i], h->enc, g, src, coff, h->d_blob + op.w16_off,
                          reinterpret_cast<const float*>(h->d_blob + op.b_off), dst);
+    if (!e && !sp.tc[i].halo && (h->halo_mode & 2) && op.kind != CTD_OP_DETECT)
+      e = conv_hs_plan(sp.tc[i], h->enc, g, src, coff, h->d_blob + op.w16_off,
+                       reinterpret_cast<const float*>(h->d_blob + op.b_off), dst);
     if (!e && !sp.tc[i].halo)
       e = conv_tc_plan(sp.tc[i], h->enc, g, src, coff, h->d_blob + op.w16_off,
                        reinterpret_cast<const float*>(h->d_blob + op.b_off), dst);

@@ -66,6 +66,7 @@ struct alignas(64) ConvTcParams {
   int halo_w, halo_h;                 // halo block size in pixels (tile 8 x 16 + halo)
   int halo_stages, halo_stage_bytes;  // activation ring
   int halo_w_bytes;                   // resident weights of one phase: taps * kblocks * BN * kb * 2
+  int hs_b_stages;                    // conv_hs_kernel: depth of the streamed-weight ring (halo_stages = A ring)
   // seg-tail epilogue (halo kernel, BN = 16): accumulator columns 0..3 are the sub-pixel phases of the final
   // ConvT 4x4 s2 (C -> 1); sigmoid -> f32 mask + truncated u8 mask at (2y+py, 2x+px)
   float* seg_f32;
@@ -74,7 +75,7 @@ struct alignas(64) ConvTcParams {
 
 struct ConvTcPlan {
   ConvTcParams p;
-  int halo = 0;                       // 1: launch conv_halo_kernel
+  int halo = 0;                       // 1: launch conv_halo_kernel, 2: conv_hs_kernel (halo A, streamed B)
   int block_n;
   dim3 grid;
   size_t smem_bytes;
@@ -97,6 +98,10 @@ const char* conv_tc_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void*
 const char* conv_halo_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
                            const int src_coff[], const void* w16, const float* bias, __half* dst,
                            float* seg_f32 = nullptr, uint8_t* seg_u8 = nullptr);
+// Halo activations + STREAMED weights for the wide stride-1 3x3 convolutions / deconvolution phases whose weights
+// do not fit in shared memory (BN = 128 / 256).  Sets plan.halo = 2 when eligible.
+const char* conv_hs_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
+                         const int src_coff[], const void* w16, const float* bias, __half* dst);
 // Stem through the halo kernel (window map of conv_tc_plan_stem, halo in y only).
 const char* conv_halo_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void* s2d, int n, int ph, int pw,
                                 const void* w16, const float* bias, __half* dst, int dst_cstride, int dst_coff, int cout,

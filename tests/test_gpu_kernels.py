@@ -44,6 +44,8 @@ CONV_CASES = [
     ([64, 64], 64, 3, 1, cc.ACT_LEAKY, False, 64, 128, 2),   # halo kernel: two K blocks from two sources
     ([32, 64], 64, 3, 1, cc.ACT_RELU, True, 128, 64, 1),     # halo kernel: 32-channel K blocks (64-byte swizzle)
     ([128], 32, 3, 1, cc.ACT_SILU, False, 64, 192, 1),
+    ([256], 256, 3, 1, cc.ACT_LEAKY, True, 64, 64, 1),       # halo A + streamed weights, BN=256, residual
+    ([128, 128], 512, 3, 1, cc.ACT_SILU, False, 64, 128, 1),  # same, two sources x two N blocks
 ]
 
 
