@@ -166,22 +166,29 @@ __device__ __forceinline__ void epilogue_store(uint32_t tmem_row, const float* _
 // TMA-store epilogue for BN >= 64: 64 output channels at a time are staged in the warpgroup's swizzled
 // 128x128-byte buffer and written by ONE bulk tensor store (coalesced 128-byte rows, image-edge clipping by
 // the TMA unit) instead of 128 threads x 8 strided 16-byte stores.
+// Residual rows of one 64-channel chunk (2 x 4 x 16 bytes per thread).  Loaded BEFORE the accumulator wait so the
+// global-memory latency hides under the MMA of the tile.
+struct ResChunk { uint4 lo[4], hi[4]; };
+__device__ __forceinline__ void load_res_chunk(ResChunk& r, const __half* __restrict__ res) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    r.lo[q] = *reinterpret_cast<const uint4*>(res + q * 8);
+    r.hi[q] = *reinterpret_cast<const uint4*>(res + 32 + q * 8);
+  }
+}
+
 template <int BN, int ACT, bool RES>
 __device__ __forceinline__ void epilogue_store_tma(uint32_t tmem_row, const float* __restrict__ bias_s,
                                                    const __half* __restrict__ res, uint32_t stage_base, int row,
                                                    const CUtensorMap* omap, int n0, int ox0, int oy0, int img,
-                                                   uint32_t bar_id, bool leader) {
+                                                   uint32_t bar_id, bool leader, ResChunk& r) {
   const uint32_t stage_row = stage_base + uint32_t(row) * 128u;
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 64) {
-    // residual first: eight independent 16-byte loads in flight under the TMEM read and the barrier below
-    uint4 r0[4], r1[4];
+    // chunk 0 was prefetched by the caller; later chunks load here, eight independent 16-byte loads in flight
+    // under the TMEM read and the barrier below
     if constexpr (RES) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        r0[q] = *reinterpret_cast<const uint4*>(res + c0 + q * 8);
-        r1[q] = *reinterpret_cast<const uint4*>(res + c0 + 32 + q * 8);
-      }
+      if (c0 > 0) load_res_chunk(r, res + c0);
     }
     // one 32-column half at a time keeps the accumulator registers at 32 (no spills next to the residual)
     uint32_t v[32];
@@ -190,10 +197,10 @@ __device__ __forceinline__ void epilogue_store_tma(uint32_t tmem_row, const floa
     // the previous chunk's store must have finished reading the staging buffer
     if (leader) tma_store_wait_read();
     named_barrier_sync(bar_id, 128);
-    epilogue_chunk32_smem<ACT, RES>(v, bias_s + c0, r0, stage_row, row, 0);
+    epilogue_chunk32_smem<ACT, RES>(v, bias_s + c0, r.lo, stage_row, row, 0);
     tmem_ld_32x32(tmem_row + uint32_t(c0 + 32), v);
     tmem_ld_wait();
-    epilogue_chunk32_smem<ACT, RES>(v, bias_s + c0 + 32, r1, stage_row, row, 1);
+    epilogue_chunk32_smem<ACT, RES>(v, bias_s + c0 + 32, r.hi, stage_row, row, 1);
     fence_proxy_async();
     named_barrier_sync(bar_id, 128);
     if (leader) {
@@ -358,15 +365,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int as = ti % Cfg::kAccStages;
       const int gy = y0 + py, gx = x0 + px;
       const bool valid = gy < g.gh && gx < g.gw;
-      mbar_wait(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
-      tc_fence_after();
       const int ph_y = phase >> 1, ph_x = phase & 1;
       const int oy = gy * g.out_mul + ph_y, ox = gx * g.out_mul + ph_x;
+      __half* out = p.dst == nullptr ? nullptr
+                                     : p.dst + (size_t(img) * g.dst_h * g.dst_w + size_t(valid ? oy : 0) * g.dst_w + (valid ? ox : 0)) * g.dst_cstride +
+                                           g.dst_coff + nblk * BN;
+      ResChunk rc;
+      if constexpr (BN >= 64) {
+        if (p.use_tma_store && g.residual) load_res_chunk(rc, out);
+      }
+      mbar_wait(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
+      tc_fence_after();
       const uint32_t tmem_row = tmem_base + uint32_t(as * BN) + (uint32_t(quad * 32) << 16);
       const float* bias_t = bias_s + nblk * BN;
       if (p.dst != nullptr) {
-        __half* out = p.dst + (size_t(img) * g.dst_h * g.dst_w + size_t(valid ? oy : 0) * g.dst_w + (valid ? ox : 0)) * g.dst_cstride +
-                      g.dst_coff + nblk * BN;
         const int cout_left = g.cout - nblk * BN;
         bool done_tma = false;
         if constexpr (BN >= 64) {
@@ -375,8 +387,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const bool leader = (threadIdx.x & 127) == 0;
             const CUtensorMap* om = &p.o_map[phase];
 #define CTD_EPT(ACT)                                                                                              \
-  if (g.residual) epilogue_store_tma<BN, ACT, true>(tmem_row, bias_t, out, stage_base, row, om, nblk * BN, x0, y0, img, 1 + group, leader); \
-  else epilogue_store_tma<BN, ACT, false>(tmem_row, bias_t, out, stage_base, row, om, nblk * BN, x0, y0, img, 1 + group, leader);
+  if (g.residual) epilogue_store_tma<BN, ACT, true>(tmem_row, bias_t, out, stage_base, row, om, nblk * BN, x0, y0, img, 1 + group, leader, rc); \
+  else epilogue_store_tma<BN, ACT, false>(tmem_row, bias_t, out, stage_base, row, om, nblk * BN, x0, y0, img, 1 + group, leader, rc);
             switch (g.act) {
               case CTD_ACT_SILU: CTD_EPT(CTD_ACT_SILU) break;
               case CTD_ACT_LEAKY: CTD_EPT(CTD_ACT_LEAKY) break;
@@ -640,10 +652,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
       const int as = ti % Cfg::kAccStages;
       const int gy = y0 + py, gx = x0 + px;
       const bool valid = gy < g.gh && gx < g.gw;
-      mbar_wait(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
-      tc_fence_after();
       const int ph_y = phase >> 1, ph_x = phase & 1;
       const int oy = gy * g.out_mul + ph_y, ox = gx * g.out_mul + ph_x;
+      ResChunk rc;
+      if constexpr (BN >= 64) {
+        if (p.use_tma_store && g.residual)
+          load_res_chunk(rc, p.dst + (size_t(img) * g.dst_h * g.dst_w + size_t(valid ? oy : 0) * g.dst_w + (valid ? ox : 0)) * g.dst_cstride + g.dst_coff);
+      }
+      mbar_wait(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
+      tc_fence_after();
       const uint32_t tmem_row = tmem_base + uint32_t(as * BN) + (uint32_t(quad * 32) << 16);
       if constexpr (BN == 16) {
         // seg tail: 4 phase logits per grid pixel -> sigmoid -> 2x2 block of the f32 and u8 masks
@@ -674,8 +691,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
           const bool leader = (threadIdx.x & 127) == 0;
           const CUtensorMap* om = &p.o_map[phase];
 #define CTD_EPT(ACT)                                                                                              \
-  if (g.residual) epilogue_store_tma<BN, ACT, true>(tmem_row, bias_s, out, stage_base, row, om, 0, x0, y0, img, 1 + group, leader); \
-  else epilogue_store_tma<BN, ACT, false>(tmem_row, bias_s, out, stage_base, row, om, 0, x0, y0, img, 1 + group, leader);
+  if (g.residual) epilogue_store_tma<BN, ACT, true>(tmem_row, bias_s, out, stage_base, row, om, 0, x0, y0, img, 1 + group, leader, rc); \
+  else epilogue_store_tma<BN, ACT, false>(tmem_row, bias_s, out, stage_base, row, om, 0, x0, y0, img, 1 + group, leader, rc);
           switch (g.act) {
             case CTD_ACT_SILU: CTD_EPT(CTD_ACT_SILU) break;
             case CTD_ACT_LEAKY: CTD_EPT(CTD_ACT_LEAKY) break;
@@ -873,20 +890,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_hs_kernel(const __grid_const
       const int as = ti % Cfg::kAccStages;
       const int gy = y0 + py, gx = x0 + px;
       const bool valid = gy < g.gh && gx < g.gw;
-      mbar_wait(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
-      tc_fence_after();
       const int ph_y = phase >> 1, ph_x = phase & 1;
       const int oy = gy * g.out_mul + ph_y, ox = gx * g.out_mul + ph_x;
-      const uint32_t tmem_row = tmem_base + uint32_t(as * BN) + (uint32_t(quad * 32) << 16);
-      const float* bias_t = bias_s + nblk * BN;
       __half* out = p.dst + (size_t(img) * g.dst_h * g.dst_w + size_t(valid ? oy : 0) * g.dst_w + (valid ? ox : 0)) * g.dst_cstride +
                     g.dst_coff + nblk * BN;
+      ResChunk rc;
+      if (g.residual) load_res_chunk(rc, out);
+      mbar_wait(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
+      tc_fence_after();
+      const uint32_t tmem_row = tmem_base + uint32_t(as * BN) + (uint32_t(quad * 32) << 16);
+      const float* bias_t = bias_s + nblk * BN;
       const uint32_t stage_base = store_base + uint32_t(group) * (128u * 128u);
       const bool lead = (threadIdx.x & 127) == 0;
       const CUtensorMap* om = &p.o_map[phase];
 #define CTD_EPT(ACT)                                                                                              \
-  if (g.residual) epilogue_store_tma<BN, ACT, true>(tmem_row, bias_t, out, stage_base, row, om, nblk * BN, x0, y0, img, 1 + group, lead); \
-  else epilogue_store_tma<BN, ACT, false>(tmem_row, bias_t, out, stage_base, row, om, nblk * BN, x0, y0, img, 1 + group, lead);
+  if (g.residual) epilogue_store_tma<BN, ACT, true>(tmem_row, bias_t, out, stage_base, row, om, nblk * BN, x0, y0, img, 1 + group, lead, rc); \
+  else epilogue_store_tma<BN, ACT, false>(tmem_row, bias_t, out, stage_base, row, om, nblk * BN, x0, y0, img, 1 + group, lead, rc);
       switch (g.act) {
         case CTD_ACT_SILU: CTD_EPT(CTD_ACT_SILU) break;
         case CTD_ACT_LEAKY: CTD_EPT(CTD_ACT_LEAKY) break;

@@ -363,6 +363,40 @@ struct ContourScratch {
   float f0[ctdgeom::kMaxHull], f1[ctdgeom::kMaxHull], f2[ctdgeom::kMaxHull];
 };
 
+// Longest-job-first order: the serial per-contour geometry costs roughly in proportion to the rows a contour spans,
+// and the kernel is bound by its longest contour.  One CTA per page sorts (rows desc, id asc) with a bitonic network
+// so that contour_kernel starts the tall contours first and fills the tail with the small ones.
+__global__ void __launch_bounds__(1024) contour_order_kernel(int max_cand, const int* __restrict__ total,
+                                                             const int* __restrict__ c_yrange, int* __restrict__ perm) {
+  __shared__ unsigned int key[1024];
+  const int page = blockIdx.x, i = threadIdx.x;
+  int ncont = total[page];
+  if (ncont > max_cand) ncont = max_cand;
+  unsigned int k = 0xffffffffu;   // ascending sort of (~rows, id): padding last
+  if (i < max_cand) {
+    int rows = 0;
+    if (i < ncont) {
+      const int y0 = c_yrange[(page * max_cand + i) * 2], y1 = c_yrange[(page * max_cand + i) * 2 + 1];
+      rows = y1 >= y0 ? y1 - y0 + 1 : 0;
+      if (rows > 0xfffff) rows = 0xfffff;
+    }
+    k = ((0xfffffu - (unsigned int)rows) << 12) | (unsigned int)i;   // max_cand <= 1024 < 4096
+  }
+  key[i] = k;
+  __syncthreads();
+  for (int size = 2; size <= 1024; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const int j = i ^ stride;
+      if (j > i) {
+        const unsigned int a = key[i], b = key[j];
+        const bool up = (i & size) == 0;
+        if ((a > b) == up) { key[i] = b; key[j] = a; }
+      }
+      __syncthreads();
+    }
+  if (i < max_cand) perm[page * max_cand + i] = int(key[i] & 0xfffu);
+}
+
 // One WARP per candidate (lane 0 runs the serial geometry; the working set lives in shared memory instead
 // of per-thread local memory), 4 candidates per CTA.
 constexpr int kContourWarps = 4;
@@ -373,17 +407,20 @@ __global__ void __launch_bounds__(32 * kContourWarps) contour_kernel(int h, int 
                                                      const int* __restrict__ tot_cnt, const double* __restrict__ ring_sum,
                                                      const int* __restrict__ ring_cnt, ContourScratch* __restrict__ scratch,
                                                      int16_t* __restrict__ boxes, float* __restrict__ scores,
-                                                     int* __restrict__ n_out, int dst_w, int dst_h, float unclip_ratio) {
+                                                     int* __restrict__ n_out, int dst_w, int dst_h, float unclip_ratio,
+                                                     const int* __restrict__ perm, int n_pages) {
   extern __shared__ __align__(16) unsigned char csm[];
   ContourScratch& S = reinterpret_cast<ContourScratch*>(csm)[threadIdx.x >> 5];
   (void)scratch;
-  const int page = blockIdx.y;
-  const int c = blockIdx.x * kContourWarps + (threadIdx.x >> 5);
+  // 1-D grid, page fastest: every page's tallest contours are scheduled before anybody's small ones
+  const int page = int(blockIdx.x) % n_pages;
+  const int slot = (int(blockIdx.x) / n_pages) * kContourWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   int ncont = total[page];
   if (ncont > max_cand) ncont = max_cand;
-  if (c == 0 && lane == 0) n_out[page] = ncont;
-  if (c >= max_cand) return;
+  if (slot == 0 && lane == 0) n_out[page] = ncont;
+  if (slot >= max_cand) return;
+  const int c = perm[page * max_cand + slot];
   int16_t* bo = boxes + (size_t(page) * max_cand + c) * 8;
   float* so = scores + size_t(page) * max_cand + c;
   if (lane < 8) bo[lane] = 0;
@@ -500,9 +537,9 @@ size_t segrep_scratch_bytes(int n, int h, int w, int max_cand) {
          + hw * 4 * 2          // tot_cnt, ring_cnt
          + hw * 8 * 3          // own_sum, tot_sum, ring_sum
          + size_t(n) * max_cand * h * 4 * 2   // rowmin, rowmax
-         + size_t(n) * max_cand * 12          // c_root, c_yrange
+         + size_t(n) * max_cand * 16          // c_root, c_yrange, perm
          + size_t(n) * 2048 * 4               // segsum + totals
-         + 4096;
+         + 8192;
 }
 
 cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_page_stride, const int* Lf, int n, int h,
@@ -524,6 +561,7 @@ cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_
   int* rowmax = reinterpret_cast<int*>(take(size_t(n) * max_cand * h * 4));
   int* c_root = reinterpret_cast<int*>(take(size_t(n) * max_cand * 4));
   int* c_yrange = reinterpret_cast<int*>(take(size_t(n) * max_cand * 8));
+  int* perm = reinterpret_cast<int*>(take(size_t(n) * max_cand * 4));
   int* segsum = reinterpret_cast<int*>(take(size_t(n) * 1024 * 4));
   int* total = reinterpret_cast<int*>(take(size_t(n) * 4));
   ContourScratch* cs = nullptr;
@@ -556,9 +594,11 @@ cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_
     cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(csmem));
     attr_set = true;
   }
-  contour_kernel<<<dim3((max_cand + kContourWarps - 1) / kContourWarps, n), 32 * kContourWarps, csmem, s>>>(h, w, max_cand, total, c_root, rowmin, rowmax, c_yrange, tot_sum, tot_cnt,
-                                                              ring_sum, ring_cnt, cs, boxes, scores, n_contours, w, h,
-                                                              unclip_ratio);
+  if (max_cand > 1024) return cudaErrorInvalidValue;
+  contour_order_kernel<<<n, 1024, 0, s>>>(max_cand, total, c_yrange, perm);
+  contour_kernel<<<unsigned((max_cand + kContourWarps - 1) / kContourWarps) * unsigned(n), 32 * kContourWarps, csmem, s>>>(
+      h, w, max_cand, total, c_root, rowmin, rowmax, c_yrange, tot_sum, tot_cnt, ring_sum, ring_cnt, cs, boxes, scores,
+      n_contours, w, h, unclip_ratio, perm, n);
   return cudaGetLastError();
 }
 

@@ -55,6 +55,10 @@ def _inside_or_on(p, poly):
 def quads_intersect(pa, pb) -> bool:
     pa = [(int(x), int(y)) for x, y in pa]
     pb = [(int(x), int(y)) for x, y in pb]
+    # closed sets with disjoint bounding boxes cannot touch (exact, and most line pairs on a page are far apart)
+    if (max(p[0] for p in pa) < min(p[0] for p in pb) or max(p[0] for p in pb) < min(p[0] for p in pa) or
+            max(p[1] for p in pa) < min(p[1] for p in pb) or max(p[1] for p in pb) < min(p[1] for p in pa)):
+        return False
     for i in range(len(pa)):
         for j in range(len(pb)):
             if _segments_touch(pa[i], pa[(i + 1) % len(pa)], pb[j], pb[(j + 1) % len(pb)]):
@@ -285,15 +289,26 @@ def group_output(blks, lines, im_w, im_h, mask=None, sort_blklist=True) -> List[
     loose = {"ver": [], "hor": []}
     assign_thresh, mask_thresh = 0.4, 0.1
     # 1. lines -> blocks by overlap / line area
+    bxy = np.array([b.xyxy for b in blk_list], np.int64).reshape(-1, 4)
     for line in lines:
         bx1, bx2 = line[:, 0].min(), line[:, 0].max()
         by1, by2 = line[:, 1].min(), line[:, 1].max()
         best, best_i = -1, -1
         line_area = (by2 - by1) * (bx2 - bx1)
-        for j, blk in enumerate(blk_list):
-            score = overlap_area(blk.xyxy, [bx1, by1, bx2, by2]) / line_area
-            if best < score:
-                best, best_i = score, j
+        if line_area != 0 and len(blk_list) > 0:
+            # all blocks at once; first maximum wins, like the reference's strict `best < score` scan
+            ix1, iy1 = np.maximum(bxy[:, 0], int(bx1)), np.maximum(bxy[:, 1], int(by1))
+            ix2, iy2 = np.minimum(bxy[:, 2], int(bx2)), np.minimum(bxy[:, 3], int(by2))
+            inter = np.where((iy2 < iy1) | (ix2 < ix1), -1, (iy2 - iy1) * (ix2 - ix1))
+            score = inter / float(line_area)
+            j = int(np.argmax(score))
+            if best < score[j]:
+                best, best_i = score[j], j
+        else:
+            for j, blk in enumerate(blk_list):
+                score = overlap_area(blk.xyxy, [bx1, by1, bx2, by2]) / line_area
+                if best < score:
+                    best, best_i = score, j
         if best > assign_thresh:
             blk_list[best_i].lines.append(line)
             continue

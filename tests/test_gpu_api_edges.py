@@ -1,0 +1,97 @@
+"""-m gpu: error behaviour and edge inputs of the C ABI / drop-in class (the reference raises Python exceptions at the
+same places: bad shapes, oversize batches), plus size-independent properties at the full 1024x1024 page size."""
+import numpy as np
+import pytest
+
+import ctd_b200
+from ctd_b200 import multigpu
+from oracle import synth
+from util import get_checkpoint
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def prog():
+    return ctd_b200.compiler.compile_checkpoint(get_checkpoint(0, True))
+
+
+def test_shape_and_capacity_errors(prog):
+    eng = ctd_b200.Engine(prog, max_batch=2, max_h=256, max_w=256)
+    try:
+        with pytest.raises(ctd_b200.binding.CtdError, match="multiple of 64"):
+            eng.forward(np.zeros((1, 100, 128, 3), np.uint8))
+        with pytest.raises(ctd_b200.binding.CtdError, match="multiple of 64"):
+            eng.forward(np.zeros((1, 320, 256, 3), np.uint8))       # larger than the reserved workspace
+        with pytest.raises(ctd_b200.binding.CtdError, match="max_batch"):
+            eng.forward(np.zeros((3, 256, 256, 3), np.uint8))
+        with pytest.raises(ctd_b200.binding.CtdError):
+            eng.collect(0)                                            # nothing in flight
+        eng.forward(np.zeros((2, 128, 192, 3), np.uint8))           # smaller, non-square shapes are fine
+        assert eng.mask_u8().shape == (2, 128, 192)
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("fill", [0, 255])
+def test_blank_pages_through_the_detector(fill):
+    det = ctd_b200.TextDetector(get_checkpoint(0, True), input_size=256, act="leaky")
+    try:
+        img = np.full((256, 256, 3), fill, np.uint8)
+        mask, mask_refined, blk_list = det(img, keep_undetected_mask=True)
+        assert mask.shape == (256, 256) and mask_refined.shape == (256, 256)
+        assert mask.dtype == np.uint8 and mask_refined.dtype == np.uint8
+        if len(blk_list) == 0:
+            assert not mask_refined.any() or mask.max() > 30      # only the undetected-mask pass can add pixels
+        for b in blk_list:
+            x1, y1, x2, y2 = b.xyxy
+            assert 0 <= x1 <= x2 <= 256 and 0 <= y1 <= y2 <= 256
+    finally:
+        det.close()
+
+
+def test_letterboxed_page_keeps_reference_shapes():
+    """page != net size: aspect-preserving resize + bottom/right padding (imgproc_utils.py:86-117); mask comes back at
+    the page size, boxes inside the page (inference.py:164-172)."""
+    det = ctd_b200.TextDetector(get_checkpoint(0, True), input_size=256, act="leaky")
+    try:
+        page = synth.structured_page(5, 360, 250)          # portrait, not a multiple of anything
+        mask, mask_refined, blk_list = det(page.copy())
+        assert mask.shape == (360, 250) and mask_refined.shape == (360, 250)
+        for b in blk_list:
+            x1, y1, x2, y2 = b.xyxy
+            assert 0 <= x1 <= x2 <= 250 and 0 <= y1 <= y2 <= 360
+            for ln in b.lines:
+                a = np.array(ln)
+                assert a.shape == (4, 2)
+    finally:
+        det.close()
+
+
+def test_full_size_forward_is_deterministic_and_batch_invariant(prog):
+    """1024x1024, batch 3 vs batch 1: bit-identical result arenas run to run, and page k of a batch equals the same page
+    processed alone (pages are independent, inference.py:141-178)."""
+    h = w = 1024
+    pages = np.stack([synth.structured_page(1000 + i, h, w) for i in range(3)])
+    eng = ctd_b200.Engine(prog, max_batch=3, max_h=h, max_w=w)
+    try:
+        def snapshot(pg):
+            eng.forward(pg)
+            boxes, scores = eng.text_lines()
+            return eng.mask_u8().copy(), eng.detections(), boxes, scores, eng.db_components(want_labels=False)[0].copy()
+        a = snapshot(pages)
+        b = snapshot(pages)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[4], b[4])
+        for i in range(3):
+            assert np.array_equal(a[1][i], b[1][i]) and np.array_equal(a[2][i], b[2][i]) and np.array_equal(a[3][i], b[3][i])
+        one = snapshot(pages[1:2])
+        assert np.array_equal(one[0][0], a[0][1]) and np.array_equal(one[4][0], a[4][1])
+        assert np.array_equal(one[1][0], a[1][1]) and np.array_equal(one[2][0], a[2][1]) and np.array_equal(one[3][0], a[3][1])
+        # structure of the result: counts within the reference's caps, scores in [0,1], boxes inside the page
+        for i in range(3):
+            assert len(a[1][i]) <= 300 and len(a[2][i]) <= 1000
+            assert np.all((a[3][i] >= 0) & (a[3][i] <= 1))
+            assert a[2][i].min(initial=0) >= 0 and a[2][i].max(initial=0) <= 1024
+        assert multigpu.arena_layout(3, h, w)["total"] == eng.results_bytes()
+    finally:
+        eng.close()
