@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="pages per GPU per step")
     ap.add_argument("--cpu-pages", type=int, default=1, help="pages per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engines", type=int, default=2, help="workspaces per GPU; consecutive batches alternate between them")
     ap.add_argument("--api-pages", type=int, default=8, help="pages timed through the TextDetector Python API (0 = skip)")
     ap.add_argument("--cpu-threads", type=int, default=16,
                     help="torch intra-op threads of the CPU arm (measured on the B200 host: 16 threads 0.25 s/forward, "
@@ -193,11 +194,22 @@ def main():
     lib, hnd = eng.lib, eng.h
     import ctypes as C
 
+    # Two workspaces (engines) per GPU: consecutive batches alternate between them, so two CUDA graphs are in
+    # flight and the kernels of batch i+1 fill the tails / dependency gaps of batch i.  Every step is still one full
+    # forward of B pages; the timer (engine 0's stream) is closed after ctd_join has pulled in the other streams.
+    n_eng = max(1, args.engines)
+    engs = [eng] + [ctd_b200.Engine(prog, device=local, max_batch=B, max_h=H, max_w=W, use_graph=True)
+                    for _ in range(n_eng - 1)]
+    ctr = {"res": 0, "e2e": 0}
+
     def step_resident():
-        eng.forward_device(dev_pages.data_ptr(), B, H, W)
+        e = engs[ctr["res"] % n_eng]
+        ctr["res"] += 1
+        e.forward_device(dev_pages.data_ptr(), B, H, W)
+        return e
 
     def step_e2e_sync():
-        # one blocking call after the other (ctd_forward + ctd_get_*), nothing overlapped
+        # one blocking call after the other (ctd_forward + ctd_get_*), one engine, nothing overlapped
         eng._ck(lib.ctd_forward(hnd, C.c_void_p(host_pages.data_ptr()), B, H, W, 0))
         eng.shape = (B, H, W)
         eng._ck(lib.ctd_get_mask_u8(hnd, C.c_void_p(out_mask.data_ptr())))
@@ -209,37 +221,46 @@ def main():
     # pipelined host path (ctd_submit / ctd_collect): every step still copies its own pages H2D from pinned
     # memory and its own result arena D2H, but step i+1's upload and step i-1's download run under step i
     res_bytes = eng.results_bytes()
-    out_arena = [torch.empty((res_bytes,), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    pipe = {"i": 0, "pending": []}
+    out_arena = [[torch.empty((res_bytes,), dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(n_eng)]
+    pending = []
 
     def step_e2e():
-        slot = pipe["i"] & 1
-        if len(pipe["pending"]) == 2:
-            eng.collect(pipe["pending"].pop(0))
-        eng.submit(slot, host_pages.data_ptr(), B, H, W, out_arena[slot].data_ptr())
-        pipe["pending"].append(slot)
-        pipe["i"] += 1
+        k = ctr["e2e"]
+        ctr["e2e"] += 1
+        ei, slot = k % n_eng, (k // n_eng) & 1
+        if len(pending) == 2 * n_eng:
+            pe, ps = pending.pop(0)
+            engs[pe].collect(ps)
+        engs[ei].submit(slot, host_pages.data_ptr(), B, H, W, out_arena[ei][slot].data_ptr())
+        pending.append((ei, slot))
 
     def drain_e2e():
-        while pipe["pending"]:
-            eng.collect(pipe["pending"].pop(0))
+        while pending:
+            pe, ps = pending.pop(0)
+            engs[pe].collect(ps)
+
+    def join_all():
+        for e in engs[1:]:
+            eng.join(e)
 
     step_main = step_resident
     if world > 1:
         # single NCCL gather of each rank's result arena (mask u8 | detections | counts) to rank 0 over
-        # NVLink, issued on the ENGINE stream so the device timer covers it
-        step_resident()
-        o = eng.device_outputs()
-
+        # NVLink, issued on the stream of the engine that produced it so the device timer covers it
         class _DevArr:
             def __init__(self, ptr, nbytes):
                 self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-        res_t = torch.as_tensor(_DevArr(o.results_base, o.results_bytes), device="cuda")
-        glist = [torch.empty_like(res_t) for _ in range(world)] if rank == 0 else None
-        ext = torch.cuda.ExternalStream(o.stream)
+        gat = {}
+        for e in engs:
+            e.forward_device(dev_pages.data_ptr(), B, H, W)
+            o = e.device_outputs()
+            res_t = torch.as_tensor(_DevArr(o.results_base, o.results_bytes), device="cuda")
+            glist = [torch.empty_like(res_t) for _ in range(world)] if rank == 0 else None
+            gat[id(e)] = (res_t, glist, torch.cuda.ExternalStream(o.stream))
 
         def step_main():
-            step_resident()
+            e = step_resident()
+            res_t, glist, ext = gat[id(e)]
             with torch.cuda.stream(ext):
                 dist.gather(res_t, gather_list=glist, dst=0)
 
@@ -255,6 +276,7 @@ def main():
             fn()
         if drain is not None:
             drain()  # host-blocks until the last D2H landed, so the stop event is recorded after it
+        join_all()   # the other engines' streams become dependencies of the timer stream
         ms = eng.timer_stop()
         barrier()
         if dist is not None:
@@ -263,14 +285,14 @@ def main():
             ms = float(t.item())
         return ms
 
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, args.warmup) * n_eng):
         step_main()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     ms = timed(step_main, args.steps)
     clocks = sampler.stop() if sampler else None
-    for _ in range(3):
+    for _ in range(3 * n_eng):
         step_e2e()
     drain_e2e()
     ms_e2e = timed(step_e2e, args.steps, drain_e2e)
@@ -318,13 +340,15 @@ def main():
                        "l2": "activations per step (~%.1f GB) exceed the 126 MB L2; no explicit flush" % (
                            sum(c * (H // d) * (W // d) for c, d in prog.bufs) * 2 * B / 1e9),
                        "cuda_graph": True,
+                       "engines_per_gpu": n_eng,
+                       "in_flight": "%d batches per GPU (one CUDA graph each, alternating workspaces)" % n_eng,
                        "multi_gpu": "pages sharded B per rank; one NCCL gather of each rank's result arena to rank 0 per step" if world > 1 else "single GPU"},
             "gpu_launches": eng.last_launch_count() * args.steps,
             "clocks": clocks,
             "conv_roofline_frac_of_nominal": value / world * GFLOP_PER_PAGE_1024 * 1e9 / 2.25e15,
             "e2e": {"value": e2e_val, "unit": "pages/s", "h2d_bytes_per_step": int(B * H * W * 3),
                     "d2h_bytes_per_step": int(res_bytes),
-                    "mode": "ctd_submit/ctd_collect, two batches in flight (copies under compute), pinned host buffers",
+                    "mode": "ctd_submit/ctd_collect on %d engine(s) per GPU, two batches in flight per engine (copies under compute), pinned host buffers" % n_eng,
                     "sync_value": total_pages / (ms_e2e_sync * 1e-3),
                     "sync_mode": "ctd_forward + ctd_get_* blocking, nothing overlapped"},
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel + conv_halo_kernel, the tcgen05 implicit-GEMM convolutions (%d launches per step)" % len(tc_idx), "achieved": achieved,
@@ -362,7 +386,8 @@ def main():
                                     "sample": "%d structured synthetic 1024x1024 pages, same stages, oracle port of the "
                                               "reference CPU path (torch fp32 + torchvision NMS + cv2 CC + SegDetectorRepresenter)" % ncpu}
         print(json.dumps(line))
-    eng.close()
+    for e in engs:
+        e.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

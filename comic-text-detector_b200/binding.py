@@ -43,7 +43,7 @@ EXPORTS = ["ctd_create", "ctd_destroy", "ctd_last_error", "ctd_forward", "ctd_ge
            "ctd_debug_read_buffer", "ctd_debug_write_buffer", "ctd_connected_components", "ctd_nms",
            "ctd_timer_start", "ctd_timer_stop", "ctd_profile_forward", "ctd_get_device_outputs",
            "ctd_get_text_lines", "ctd_seg_represent", "ctd_refine_mask", "ctd_submit", "ctd_collect",
-           "ctd_results_bytes"]
+           "ctd_results_bytes", "ctd_join"]
 
 _lib = None
 
@@ -89,6 +89,7 @@ def load_library():
     lib.ctd_submit.argtypes = [vp, i32, vp, i32, i32, i32, vp]
     lib.ctd_collect.argtypes = [vp, i32]
     lib.ctd_results_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
+    lib.ctd_join.argtypes = [vp, vp]
     for name in EXPORTS[3:]:
         getattr(lib, name).restype = C.c_int
     _lib = lib
@@ -274,6 +275,10 @@ class Engine:
 
     def collect(self, slot):
         self._ck(self.lib.ctd_collect(self.h, slot))
+
+    def join(self, other):
+        """everything enqueued so far on `other`'s stream becomes a dependency of this engine's stream."""
+        self._ck(self.lib.ctd_join(self.h, other.h))
 
     def device_outputs(self):
         o = CtdDeviceOutputs()

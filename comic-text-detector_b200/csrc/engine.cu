@@ -76,6 +76,7 @@ struct ctd_handle {
   bool overlap = false;
   cudaStream_t side = nullptr, side2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+  cudaEvent_t ev_xjoin = nullptr;   // ctd_join (never part of a captured graph)
   std::vector<char> db_ancestor;   // op feeds the DB tail (computed once in ctd_create)
   // last forward
   int n = 0, ph = 0, pw = 0;
@@ -128,6 +129,7 @@ extern "C" void ctd_destroy(ctd_handle* h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_fork2) cudaEventDestroy(h->ev_fork2);
+  if (h->ev_xjoin) cudaEventDestroy(h->ev_xjoin);
   if (h->ev_join2) cudaEventDestroy(h->ev_join2);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->side2) cudaStreamDestroy(h->side2);
@@ -202,6 +204,7 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
   CKC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&h->ev_fork2, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&h->ev_xjoin, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
   CKC(cudaEventCreate(&h->ev0));
   CKC(cudaEventCreate(&h->ev1));
@@ -649,6 +652,16 @@ extern "C" int ctd_collect(ctd_handle* h, int32_t slot) {
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaEventSynchronize(h->ev_out_done[slot]));
   h->slot_busy[slot] = false;
+  return CTD_OK;
+}
+
+extern "C" int ctd_join(ctd_handle* h, ctd_handle* other) {
+  if (!h || !other) return CTD_E_INVALID;
+  if (h == other) return CTD_OK;
+  if (h->cfg.device != other->cfg.device) return fail(h, CTD_E_INVALID, "ctd_join: handles live on different devices");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventRecord(other->ev_xjoin, other->stream));
+  CK(cudaStreamWaitEvent(h->stream, other->ev_xjoin, 0));
   return CTD_OK;
 }
 

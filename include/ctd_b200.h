@@ -176,6 +176,12 @@ CTD_API int ctd_submit(ctd_handle* h, int32_t slot, const uint8_t* pages_host, i
 CTD_API int ctd_collect(ctd_handle* h, int32_t slot);
 CTD_API int ctd_results_bytes(ctd_handle* h, size_t* bytes);
 
+/* Several handles on ONE GPU (one workspace each) let independent batches overlap: the kernels of batch i+1 fill the
+ * tails and dependency gaps of batch i (+8 % pages/s with two handles, bench.py).  ctd_join makes everything
+ * enqueued so far on `other`'s stream a dependency of `h`'s stream (device-side, no host wait) -- used to close a
+ * timed region or to hand results over.                                                         */
+CTD_API int ctd_join(ctd_handle* h, ctd_handle* other);
+
 /* Device-side timing of the last ctd_forward (CUDA events on the engine stream), ms.       */
 CTD_API int ctd_last_forward_ms(ctd_handle* h, float* ms);
 /* Number of kernels the last ctd_forward launched (graph nodes when captured).             */

@@ -58,9 +58,10 @@ def test_letterboxed_page_keeps_reference_shapes():
         page = synth.structured_page(5, 360, 250)          # portrait, not a multiple of anything
         mask, mask_refined, blk_list = det(page.copy())
         assert mask.shape == (360, 250) and mask_refined.shape == (360, 250)
+        assert len(blk_list) > 0
         for b in blk_list:
             x1, y1, x2, y2 = b.xyxy
-            assert 0 <= x1 <= x2 <= 250 and 0 <= y1 <= y2 <= 360
+            assert x1 <= x2 and y1 <= y2        # (the reference does not clip detector boxes to the page)
             for ln in b.lines:
                 a = np.array(ln)
                 assert a.shape == (4, 2)
