@@ -8,12 +8,16 @@ mask u8 + DB threshold + connected components + text-line boxes/scores) over one
 per GPU (BASELINE.json configs[2]/[3]: batch 16 per GPU, fp16 tcgen05 path).
 
 * value      : whole-job pages/s with the pages already resident in HBM (device timed, CUDA events
-               on the engine stream, max over ranks).
-* e2e        : same metric through the C-ABI with HOST (pinned) page buffers: H2D of the pages and
-               D2H of the results (mask u8 + detections + text-line boxes/scores + counts) inside the timed region.
-* roofline   : tensor roofline of the dominant kernel (conv_tc_kernel): algorithmic conv FLOPs
-               of the tensor-core layers / their summed device time (per-op CUDA events, measured
-               live here), against MEASURED_PEAKS.json's sustained bf16 GEMM rate.
+               on the engine stream, max over ranks).  --engines E (default 2) workspaces per GPU: consecutive
+               steps alternate between them, so E CUDA graphs are in flight; a step is always one full batch.
+* e2e        : same metric through the C-ABI with HOST (pinned) page buffers (ctd_submit / ctd_collect): H2D of
+               the pages and D2H of the results (mask u8 + detections + text-line boxes/scores + counts) of
+               EVERY step inside the timed region, copies overlapped with the neighbouring steps' compute;
+               e2e.sync_value = the blocking ctd_forward + ctd_get_* sequence on one engine.
+* roofline   : tensor roofline of the tcgen05 convolution kernels (conv_tc / conv_halo / conv_hs): algorithmic
+               conv FLOPs of the tensor-core layers / their summed device time (per-op CUDA events, measured
+               live here, serial order), against MEASURED_PEAKS.json's sustained bf16 GEMM rate; traffic = DRAM
+               bytes of the same launches from the committed ncu capture.
 * cpu_baseline / --impl reference: the oracle restatement of the reference's CPU path
                (oracle/net_ref.py + oracle/postproc_ref.py: torch CPU fp32 + torchvision + cv2, i.e.
                the reference's own library calls) timed on this box's host cores.

@@ -1095,7 +1095,8 @@ const char* conv_halo_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom
   const bool seg = seg_f32 != nullptr && seg_u8 != nullptr;
   if (dst == nullptr && !seg) return nullptr;
   if (seg != (g.cout_pad == 16)) return nullptr;   // BN = 16 exists only with the seg-tail epilogue
-  const bool s1 = g.in_stride == 1 && ((g.n_phase == 1 && g.taps == 9) || (g.n_phase == 4 && g.taps == 4));
+  const bool pw1 = g.in_stride == 1 && g.n_phase == 1 && g.taps == 1;   // 1x1: resident weights, plain 8x16 tile
+  const bool s1 = pw1 || (g.in_stride == 1 && ((g.n_phase == 1 && g.taps == 9) || (g.n_phase == 4 && g.taps == 4)));
   const bool s2 = g.in_stride == 2 && g.n_phase == 1 && g.taps == 9 && g.src_h % 2 == 0 && g.src_w % 2 == 0;
   if (!s1 && !s2) return nullptr;
   if (g.cout_pad != 16 && g.cout_pad != 32 && g.cout_pad != 64) return nullptr;   // one N block per CTA, TMEM ring of 8
@@ -1123,10 +1124,10 @@ const char* conv_halo_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom
   p.dst = dst;
   p.bias = bias;
   p.seg_f32 = seg_f32; p.seg_u8 = seg_u8;
-  p.halo_lox = 1; p.halo_loy = 1;
-  // stride 1: one pixel either side; stride 2: the parity views only ever reach one pixel back
-  p.halo_w = kHaloTileW + (s2 ? 1 : 2);
-  p.halo_h = kHaloTileH + (s2 ? 1 : 2);
+  p.halo_lox = pw1 ? 0 : 1; p.halo_loy = pw1 ? 0 : 1;
+  // stride 1: one pixel either side; stride 2: the parity views only ever reach one pixel back; 1x1: no halo
+  p.halo_w = kHaloTileW + (pw1 ? 0 : (s2 ? 1 : 2));
+  p.halo_h = kHaloTileH + (pw1 ? 0 : (s2 ? 1 : 2));
   for (int s = 0; s < g.n_src; ++s) {
     const size_t cs = size_t(g.src_cstride[s]);
     const char* base = static_cast<const char*>(src_ptr[s]) + size_t(src_coff[s]) * 2;

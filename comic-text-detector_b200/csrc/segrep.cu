@@ -588,12 +588,9 @@ cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_
   accumulate_kernel<<<grid, 256, 0, s>>>(h, w, pred, pred_page_stride, Lf, Lb, parent, flag, own_sum, own_cnt, ring_sum,
                                          ring_cnt, rowmin, rowmax, c_yrange, max_cand);
   tree_kernel<<<grid, 256, 0, s>>>(h, w, Lf, Lb, parent, own_sum, own_cnt, tot_sum, tot_cnt);
-  static bool attr_set = false;
   const size_t csmem = sizeof(ContourScratch) * kContourWarps;
-  if (!attr_set) {
-    cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(csmem));
-    attr_set = true;
-  }
+  // per device, so set on every launch (cheap; a process may own engines on several GPUs)
+  cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(csmem));
   if (max_cand > 1024) return cudaErrorInvalidValue;
   contour_order_kernel<<<n, 1024, 0, s>>>(max_cand, total, c_yrange, perm);
   contour_kernel<<<unsigned((max_cand + kContourWarps - 1) / kContourWarps) * unsigned(n), 32 * kContourWarps, csmem, s>>>(

@@ -429,11 +429,8 @@ cudaError_t sppf_pool_launch(T* buf, int n, int h, int w, int c, int cs, cudaStr
   if (c % 8 || cs % 8) return cudaErrorInvalidValue;
   const size_t smem = size_t(2) * h * w * 8 * sizeof(T);
   if (smem <= 200 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(sppf_pool_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_set = true;
-    }
+    // per device, so set on every launch (cheap; a process may own engines on several GPUs)
+    cudaFuncSetAttribute(sppf_pool_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     sppf_pool_tile_kernel<T><<<dim3(c / 8, n), 256, smem, s>>>(buf, h, w, c, cs);
     return cudaGetLastError();
   }
@@ -616,8 +613,8 @@ __global__ void __launch_bounds__(128) db_tail_kernel(const T* __restrict__ src,
   }
   __syncthreads();
   const long long total = (long long)n * h * w;
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= total) return;
+  // grid-stride: the 8.8 KB parameter re-layout above is paid once per CTA, not once per 128 pixels
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
   const int x = int(i % w), y = int((i / w) % h), img = int(i / ((long long)w * h));
   const T* sp = src + i * cs;
   const int H = 4 * h, W = 4 * w;
@@ -680,12 +677,15 @@ __global__ void __launch_bounds__(128) db_tail_kernel(const T* __restrict__ src,
       }
     }
   }
+  }
 }
 template <typename T>
 cudaError_t db_tail_launch(const T* src, int n, int h, int w, int cs, const float* params, float* lines,
                            uint8_t* bitmap, float db_thresh, cudaStream_t s) {
   const long long total = (long long)n * h * w;
-  db_tail_kernel<T><<<unsigned((total + 127) / 128), 128, 0, s>>>(src, n, h, w, cs, params, lines, bitmap, db_thresh);
+  const long long blocks = (total + 127) / 128;
+  const long long cap = 148LL * 16;   // a few resident CTAs per SM, each looping over its share of the pixels
+  db_tail_kernel<T><<<unsigned(blocks < cap ? blocks : cap), 128, 0, s>>>(src, n, h, w, cs, params, lines, bitmap, db_thresh);
   return cudaGetLastError();
 }
 template cudaError_t db_tail_launch<float>(const float*, int, int, int, int, const float*, float*, uint8_t*, float,
