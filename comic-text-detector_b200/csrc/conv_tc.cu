@@ -18,6 +18,7 @@
 //
 // Reference semantics: Conv.forward_fuse (models/yolov5/common.py:48-49), Bottleneck add
 // (common.py:104), ConvTranspose2d+BN+ReLU (basemodel.py:26-28), Detect (yolo.py:23-44).
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -280,6 +281,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  griddep_launch_dependents();   // successors may begin their prologue as our CTAs retire
+  griddep_wait();                // activations / residuals written by the predecessor are visible from here on
 
   // tile index -> (phase, spatial tile, n block); n block varies fastest so that CTAs running
   // concurrently share the A tile in L2
@@ -546,6 +549,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  griddep_launch_dependents();   // successors may begin their prologue as our CTAs retire
+  if (warp != 0) griddep_wait(); // the producer waits AFTER issuing the (constant) weight loads, see below
 
   auto decode = [&](int t, int& img, int& y0, int& x0) {
     img = t / tiles_per_img;
@@ -568,6 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
           kglob += g.src_c[s];
         }
       }
+      griddep_wait();   // weights are constant; the activations below are the predecessor's output
       int it = 0;
       for (int t = rank; t < spatial_tiles; t += nrank) {
         int img, y0, x0;
@@ -800,6 +806,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_hs_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
+  griddep_launch_dependents();   // successors may begin their prologue as our CTAs retire
+  griddep_wait();                // activations / residuals written by the predecessor are visible from here on
 
   // tile index -> (phase, spatial tile, n block), n block fastest (CTAs running together share the halo in L2)
   auto decode = [&](int t, int& phase, int& nblk, int& img, int& y0, int& x0) {
@@ -942,6 +950,8 @@ static const char* encode_map(PFN_encodeTiled enc, CUtensorMap* m, const void* b
 }
 
 static int g_num_sms = 148;
+static int g_use_pdl = 0;   // CTD_PDL=1 enables programmatic dependent launch (measured: no gain once a second
+                            // workspace fills the tails -- early dependents park on SMs the other batch could use)
 
 static int pick_block_n(int cout_pad) {
   if (cout_pad >= 256 && cout_pad % 256 == 0) return 256;
@@ -1292,6 +1302,10 @@ const char* conv_tc_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void*
 
 cudaError_t conv_tc_init() {
   cudaError_t e;
+  {
+    const char* pdl = getenv("CTD_PDL");
+    g_use_pdl = (pdl && pdl[0] == '1') ? 1 : 0;
+  }
   int dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) {
     int n = 0;
@@ -1315,24 +1329,40 @@ cudaError_t conv_tc_init() {
   return cudaSuccess;
 }
 
+// All conv kernels are launched as programmatic dependents (see griddep_wait in ptx.cuh).
+template <typename K>
+static cudaError_t launch_pdl(K kernel, dim3 grid, size_t smem, cudaStream_t s, const ConvTcParams& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 cudaError_t conv_tc_launch(const ConvTcPlan& plan, cudaStream_t s) {
   if (plan.halo == 2) {
-    if (plan.block_n == 256) conv_hs_kernel<256><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p);
-    else conv_hs_kernel<128><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p);
+    if (plan.block_n == 256) return launch_pdl(conv_hs_kernel<256>, plan.grid, plan.smem_bytes, s, plan.p);
+    else return launch_pdl(conv_hs_kernel<128>, plan.grid, plan.smem_bytes, s, plan.p);
     return cudaGetLastError();
   }
   if (plan.halo) {
-    if (plan.block_n == 64) conv_halo_kernel<64><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p);
-    else if (plan.block_n == 32) conv_halo_kernel<32><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p);
-    else conv_halo_kernel<16><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p);
+    if (plan.block_n == 64) return launch_pdl(conv_halo_kernel<64>, plan.grid, plan.smem_bytes, s, plan.p);
+    else if (plan.block_n == 32) return launch_pdl(conv_halo_kernel<32>, plan.grid, plan.smem_bytes, s, plan.p);
+    else return launch_pdl(conv_halo_kernel<16>, plan.grid, plan.smem_bytes, s, plan.p);
     return cudaGetLastError();
   }
   switch (plan.block_n) {
-    case 256: conv_tc_kernel<256><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p); break;
-    case 128: conv_tc_kernel<128><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p); break;
-    case 64: conv_tc_kernel<64><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p); break;
-    case 32: conv_tc_kernel<32><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p); break;
-    default: conv_tc_kernel<16><<<plan.grid, kThreads, plan.smem_bytes, s>>>(plan.p); break;
+    case 256: return launch_pdl(conv_tc_kernel<256>, plan.grid, plan.smem_bytes, s, plan.p); break;
+    case 128: return launch_pdl(conv_tc_kernel<128>, plan.grid, plan.smem_bytes, s, plan.p); break;
+    case 64: return launch_pdl(conv_tc_kernel<64>, plan.grid, plan.smem_bytes, s, plan.p); break;
+    case 32: return launch_pdl(conv_tc_kernel<32>, plan.grid, plan.smem_bytes, s, plan.p); break;
+    default: return launch_pdl(conv_tc_kernel<16>, plan.grid, plan.smem_bytes, s, plan.p); break;
   }
   return cudaGetLastError();
 }
