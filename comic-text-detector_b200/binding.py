@@ -43,7 +43,8 @@ EXPORTS = ["ctd_create", "ctd_destroy", "ctd_last_error", "ctd_forward", "ctd_ge
            "ctd_debug_read_buffer", "ctd_debug_write_buffer", "ctd_connected_components", "ctd_nms",
            "ctd_timer_start", "ctd_timer_stop", "ctd_profile_forward", "ctd_get_device_outputs",
            "ctd_get_text_lines", "ctd_seg_represent", "ctd_refine_mask", "ctd_submit", "ctd_collect",
-           "ctd_results_bytes", "ctd_join"]
+           "ctd_results_bytes", "ctd_join", "ctd_forward_resized", "ctd_get_mask_u8_resized",
+           "ctd_resize_linear_u8"]
 
 _lib = None
 
@@ -90,6 +91,9 @@ def load_library():
     lib.ctd_collect.argtypes = [vp, i32]
     lib.ctd_results_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
     lib.ctd_join.argtypes = [vp, vp]
+    lib.ctd_forward_resized.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32]
+    lib.ctd_get_mask_u8_resized.argtypes = [vp, i32, i32, i32, i32, vp]
+    lib.ctd_resize_linear_u8.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32]
     for name in EXPORTS[3:]:
         getattr(lib, name).restype = C.c_int
     _lib = lib
@@ -152,6 +156,30 @@ class Engine:
         assert c == 3
         self._ck(self.lib.ctd_forward(self.h, _ptr(pages), n, h, w, 0))
         self.shape = (n, h, w)
+
+    def forward_resized(self, page, unpad_h, unpad_w, net_h, net_w):
+        """letterbox on the GPU: page u8 [ih][iw][3] of any size -> cv2-exact INTER_LINEAR resize to
+        unpad_h x unpad_w, zero padding to net_h x net_w, forward (n = 1)."""
+        page = np.ascontiguousarray(page, dtype=np.uint8)
+        ih, iw, c = page.shape
+        assert c == 3
+        self._ck(self.lib.ctd_forward_resized(self.h, _ptr(page), ih, iw, unpad_h, unpad_w, net_h, net_w))
+        self.shape = (1, net_h, net_w)
+
+    def mask_u8_resized(self, crop_h, crop_w, out_h, out_w):
+        """`cv2.resize(mask[:crop_h, :crop_w], (out_w, out_h), INTER_LINEAR)` of page 0 (inference.py:164-168)."""
+        out = np.empty((out_h, out_w), np.uint8)
+        self._ck(self.lib.ctd_get_mask_u8_resized(self.h, crop_h, crop_w, out_h, out_w, _ptr(out)))
+        return out
+
+    def resize_linear_u8(self, src, dsize_wh):
+        """`cv2.resize(src, dsize_wh, interpolation=cv2.INTER_LINEAR)` for uint8 [H,W] / [H,W,3] (bit-exact)."""
+        src = np.ascontiguousarray(src, dtype=np.uint8)
+        ch = 1 if src.ndim == 2 else src.shape[2]
+        dw, dh = int(dsize_wh[0]), int(dsize_wh[1])
+        out = np.empty((dh, dw) if src.ndim == 2 else (dh, dw, ch), np.uint8)
+        self._ck(self.lib.ctd_resize_linear_u8(self.h, _ptr(src), src.shape[0], src.shape[1], ch, _ptr(out), dh, dw))
+        return out
 
     def forward_device(self, dev_ptr, n, h, w):
         """pages already resident in HBM (device pointer as int)."""

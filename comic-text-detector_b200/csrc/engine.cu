@@ -57,6 +57,8 @@ struct ctd_handle {
   void* d_segrep_scratch = nullptr;
   void* d_refine_scratch = nullptr;
   size_t refine_scratch_cap = 0;
+  uint8_t* d_io_scratch = nullptr;   // page upload / resized mask staging of the resize entry points
+  size_t io_scratch_cap = 0;
   int16_t* d_line_boxes = nullptr;
   float* d_line_scores = nullptr;
   int32_t* d_line_count = nullptr;
@@ -113,7 +115,7 @@ extern "C" void ctd_destroy(ctd_handle* h) {
   for (void* p : h->d_buf) cudaFree(p);
   cudaFree(h->d_blob); cudaFree(h->d_pages); cudaFree(h->d_blks); cudaFree(h->d_mask); cudaFree(h->d_mask_u8);
   cudaFree(h->d_lines); cudaFree(h->d_bitmap); cudaFree(h->d_labels);
-  cudaFree(h->d_ccl_scratch); cudaFree(h->d_nms_ws); cudaFree(h->d_segrep_scratch); cudaFree(h->d_refine_scratch);
+  cudaFree(h->d_ccl_scratch); cudaFree(h->d_nms_ws); cudaFree(h->d_segrep_scratch); cudaFree(h->d_refine_scratch); cudaFree(h->d_io_scratch);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->tev0) cudaEventDestroy(h->tev0);
@@ -652,6 +654,62 @@ extern "C" int ctd_collect(ctd_handle* h, int32_t slot) {
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaEventSynchronize(h->ev_out_done[slot]));
   h->slot_busy[slot] = false;
+  return CTD_OK;
+}
+
+static int ensure_io_scratch(ctd_handle* h, size_t bytes) {
+  if (bytes <= h->io_scratch_cap) return CTD_OK;
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(h->d_io_scratch);
+  h->d_io_scratch = nullptr;
+  h->io_scratch_cap = 0;
+  CK(cudaMalloc(&h->d_io_scratch, bytes + bytes / 4));
+  h->io_scratch_cap = bytes + bytes / 4;
+  return CTD_OK;
+}
+
+extern "C" int ctd_forward_resized(ctd_handle* h, const uint8_t* page, int32_t ih, int32_t iw, int32_t unpad_h,
+                                   int32_t unpad_w, int32_t net_h, int32_t net_w) {
+  if (!h || !page) return CTD_E_INVALID;
+  if (ih < 1 || iw < 1 || unpad_h < 1 || unpad_w < 1 || unpad_h > net_h || unpad_w > net_w)
+    return fail(h, CTD_E_SHAPE, "letterbox %dx%d -> %dx%d does not fit the %dx%d net input", ih, iw, unpad_h, unpad_w, net_h, net_w);
+  ShapePlan* sp = nullptr;
+  if (int rc = prepare_forward(h, 1, net_h, net_w, &sp)) return rc;
+  const size_t bytes = size_t(ih) * iw * 3;
+  if (int rc = ensure_io_scratch(h, bytes)) return rc;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  CK(cudaMemcpyAsync(h->d_io_scratch, page, bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(resize_linear_u8_launch(h->d_io_scratch, ih, iw, size_t(iw) * 3, 3, h->d_pages, unpad_h, unpad_w, net_h, net_w, h->stream));
+  return enqueue_forward(h, 1, net_h, net_w, *sp);
+}
+
+extern "C" int ctd_get_mask_u8_resized(ctd_handle* h, int32_t crop_h, int32_t crop_w, int32_t out_h, int32_t out_w,
+                                       uint8_t* mask_out) {
+  if (!h || !mask_out) return CTD_E_INVALID;
+  if (!h->have_forward) return fail(h, CTD_E_INVALID, "no forward pass has been run on this handle");
+  if (crop_h < 1 || crop_w < 1 || crop_h > h->ph || crop_w > h->pw || out_h < 1 || out_w < 1)
+    return fail(h, CTD_E_SHAPE, "bad crop %dx%d of the %dx%d mask", crop_h, crop_w, h->ph, h->pw);
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t bytes = size_t(out_h) * out_w;
+  if (int rc = ensure_io_scratch(h, bytes)) return rc;
+  CK(resize_linear_u8_launch(h->d_mask_u8, crop_h, crop_w, size_t(h->pw), 1, h->d_io_scratch, out_h, out_w, out_h, out_w, h->stream));
+  CK(cudaMemcpyAsync(mask_out, h->d_io_scratch, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return CTD_OK;
+}
+
+extern "C" int ctd_resize_linear_u8(ctd_handle* h, const uint8_t* src, int32_t sh, int32_t sw, int32_t channels, uint8_t* dst,
+                                    int32_t dh, int32_t dw) {
+  if (!h || !src || !dst) return CTD_E_INVALID;
+  if ((channels != 1 && channels != 3) || sh < 1 || sw < 1 || dh < 1 || dw < 1) return fail(h, CTD_E_SHAPE, "bad resize shape");
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t sb = size_t(sh) * sw * channels, db = size_t(dh) * dw * channels;
+  const size_t so = (sb + 255) / 256 * 256;
+  if (int rc = ensure_io_scratch(h, so + db)) return rc;
+  CK(cudaMemcpyAsync(h->d_io_scratch, src, sb, cudaMemcpyHostToDevice, h->stream));
+  CK(resize_linear_u8_launch(h->d_io_scratch, sh, sw, size_t(sw) * channels, channels, h->d_io_scratch + so, dh, dw, dh, dw, h->stream));
+  CK(cudaMemcpyAsync(dst, h->d_io_scratch + so, db, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return CTD_OK;
 }
 

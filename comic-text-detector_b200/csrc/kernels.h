@@ -178,6 +178,10 @@ cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_
 cudaError_t binarize_launch(const float* pred, size_t count, float thresh, uint8_t* bitmap, cudaStream_t s);
 
 // refine_mask (refine.cu): one CTA per block window.  d_wins: n_wins x {x1,y1,x2,y2,(int64)pixel offset}
+// cv2.resize INTER_LINEAR, uint8, 1 or 3 channels, bit-exact (resize.cu).  src rows are `src_pitch` bytes apart; the
+// dh x dw result is written at the top-left of a canvas_h x canvas_w canvas whose remaining pixels are zeroed.
+cudaError_t resize_linear_u8_launch(const uint8_t* src, int sh, int sw, size_t src_pitch, int channels, uint8_t* dst,
+                                    int dh, int dw, int canvas_h, int canvas_w, cudaStream_t s);
 size_t refine_scratch_bytes(size_t total_px);
 cudaError_t refine_launch(const uint8_t* d_img, const uint8_t* d_mask, int H, int W, const void* d_wins, int n_wins,
                           size_t total_px, void* scratch, int refine_mode, uint8_t* d_out, cudaStream_t s);

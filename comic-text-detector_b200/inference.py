@@ -22,16 +22,20 @@ REFINEMASK_INPAINT = 0
 REFINEMASK_ANNOTATION = 1
 
 
-def letterbox(im, new_shape=(1024, 1024)):
-    """`letterbox(im, new_shape, auto=False)` of the reference (utils/imgproc_utils.py:86-117): aspect-preserving
-    resize (cv2.INTER_LINEAR) + bottom/right zero padding.  Net-sized pages pass through untouched; the resize of
-    other page sizes is the reference's own host-side OpenCV call (row f1 of SURVEY 8f: next on the GPU)."""
-    shape = im.shape[:2]
-    r = min(new_shape[0] / shape[0], new_shape[1] / shape[1])
-    new_unpad = int(round(shape[1] * r)), int(round(shape[0] * r))
+def letterbox_geometry(shape_hw, new_shape=(1024, 1024)):
+    """The size arithmetic of `letterbox(im, new_shape, auto=False)` (utils/imgproc_utils.py:86-117): aspect-preserving
+    scale r, resized size (w, h) = round(size * r) (Python's round), bottom/right padding (dw, dh)."""
+    r = min(new_shape[0] / shape_hw[0], new_shape[1] / shape_hw[1])
+    new_unpad = int(round(shape_hw[1] * r)), int(round(shape_hw[0] * r))
     dw, dh = new_shape[1] - new_unpad[0], new_shape[0] - new_unpad[1]
-    dh, dw = int(dh), int(dw)
-    if shape[::-1] != new_unpad:
+    return r, new_unpad, int(dw), int(dh)
+
+
+def letterbox(im, new_shape=(1024, 1024)):
+    """Host restatement of the reference's `letterbox` (kept for tests / tools; the detector itself resizes on the
+    GPU through `Engine.forward_resized`, bit-exact with cv2.INTER_LINEAR)."""
+    r, new_unpad, dw, dh = letterbox_geometry(im.shape[:2], new_shape)
+    if im.shape[:2][::-1] != new_unpad:
         import cv2
         im = cv2.resize(im, new_unpad, interpolation=cv2.INTER_LINEAR)
     if dw or dh:
@@ -80,12 +84,15 @@ class TextDetector:
         self.net.close()
 
     def __call__(self, img, refine_mode=REFINEMASK_INPAINT, keep_undetected_mask=False):
-        import cv2
         eng = self.net
-        # preprocess_img (inference.py:72-83): the BGR<->RGB double flip cancels, the net sees BGR
-        img_in, ratio, (dw, dh) = letterbox(img, self.input_size)
+        # preprocess_img (inference.py:72-83): the BGR<->RGB double flip cancels, the net sees BGR.  The letterbox
+        # resize + padding run on the GPU (cv2-exact INTER_LINEAR); net-sized pages skip the resize kernel.
         im_h, im_w = img.shape[:2]
-        eng.forward(np.ascontiguousarray(img_in)[None])
+        _r, new_unpad, dw, dh = letterbox_geometry((im_h, im_w), self.input_size)
+        if (im_h, im_w) == tuple(self.input_size):
+            eng.forward(np.ascontiguousarray(img)[None])
+        else:
+            eng.forward_resized(img, new_unpad[1], new_unpad[0], self.input_size[0], self.input_size[1])
         resize_ratio = (im_w / (self.input_size[0] - dw), im_h / (self.input_size[1] - dh))
 
         # postprocess_yolo (inference.py:101-114) on the GPU NMS rows
@@ -94,15 +101,12 @@ class TextDetector:
         det[..., [1, 3]] = det[..., [1, 3]] * resize_ratio[1]
         blks = (det[..., 0:4].astype(np.int32), det[..., 5].astype(np.int32), np.round(det[..., 4], 3))
 
-        mask = eng.mask_u8()[0]                                   # postprocess_mask (inference.py:85-99)
         boxes, scores = eng.text_lines()                          # SegDetectorRepresenter (inference.py:158)
         keep = np.where(scores[0] > 0.6)                          # box_thresh (inference.py:159-161)
         lines = boxes[0][keep]
 
-        mask = mask[: mask.shape[0] - dh, : mask.shape[1] - dw]   # inference.py:164-165
-        if mask.shape[:2] != (im_h, im_w):
-            mask = cv2.resize(mask, (im_w, im_h), interpolation=cv2.INTER_LINEAR)
-        mask = np.ascontiguousarray(mask)
+        # postprocess_mask + crop + cv2.resize back to the page (inference.py:85-99,164-168), all on the GPU
+        mask = eng.mask_u8_resized(self.input_size[0] - dh, self.input_size[1] - dw, im_h, im_w)
         if lines.size == 0:
             lines = []
         else:
@@ -118,10 +122,18 @@ class TextDetector:
 
     # ---- textmask.py:159-169 ---------------------------------------------------------------------
     def _refine(self, img, mask, blk_list: List[TextBlock], refine_mode):
-        if (img.shape[0] * img.shape[1]) % 4:
-            raise ValueError("page area must be a multiple of 4 pixels")
-        wins = [expand_textwindow(img.shape, blk.xyxy, expand_r=16) for blk in blk_list]
-        return self.net.refine_mask(img, mask, np.array(wins, np.int32).reshape(-1, 4), refine_mode)
+        wins = np.array([expand_textwindow(img.shape, blk.xyxy, expand_r=16) for blk in blk_list], np.int32).reshape(-1, 4)
+        h, w = img.shape[:2]
+        if (h * w) % 4 == 0:
+            return self.net.refine_mask(img, mask, wins, refine_mode)
+        # the kernel wants h*w % 4 == 0: pad the columns with zeros (windows lie inside the page, so their
+        # contents and therefore the result are unchanged) and crop the padding off again
+        wp = (w + 3) // 4 * 4
+        img_p = np.zeros((h, wp, 3), np.uint8)
+        img_p[:, :w] = img
+        mask_p = np.zeros((h, wp), np.uint8)
+        mask_p[:, :w] = mask
+        return np.ascontiguousarray(self.net.refine_mask(img_p, mask_p, wins, refine_mode)[:, :w])
 
     # ---- textmask.py:135-156 ---------------------------------------------------------------------
     def _refine_undetected(self, img, mask_pred, mask_refined, blk_list, refine_mode):

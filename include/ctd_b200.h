@@ -160,6 +160,22 @@ CTD_API int ctd_get_db_components(ctd_handle* h, uint8_t* bitmap, int32_t* label
  * left to the caller, as in the reference.                                                        */
 CTD_API int ctd_get_text_lines(ctd_handle* h, int16_t* boxes, float* scores, int32_t* counts);
 
+/* ---- pages that are not net-sized -----------------------------------------
+ * `letterbox(im, new_shape, auto=False)` + `preprocess_img` (imgproc_utils.py:86-117, inference.py:72-83) on the
+ * GPU: the HOST page (u8 BGR HWC, any size ih x iw) is resized with OpenCV-exact INTER_LINEAR to
+ * unpad_h x unpad_w (the caller computes these with the reference's formula: r = min(net_h/ih, net_w/iw),
+ * unpad = round(size * r)), zero-padded bottom/right to net_h x net_w (multiples of 64) and forwarded (n = 1).   */
+CTD_API int ctd_forward_resized(ctd_handle* h, const uint8_t* page, int32_t ih, int32_t iw, int32_t unpad_h, int32_t unpad_w,
+                                int32_t net_h, int32_t net_w);
+/* Mask back-projection (inference.py:164-168): `mask[:crop_h, :crop_w]` of page 0 of the last forward,
+ * `cv2.resize(.., (out_w, out_h), INTER_LINEAR)` -> HOST u8 [out_h][out_w].                                      */
+CTD_API int ctd_get_mask_u8_resized(ctd_handle* h, int32_t crop_h, int32_t crop_w, int32_t out_h, int32_t out_w,
+                                    uint8_t* mask_out);
+/* Stand-alone `cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR)` for u8 images with 1 or 3 channels
+ * (HOST in, HOST out); bit-exact with OpenCV 4.x, see csrc/resize.cu.                                            */
+CTD_API int ctd_resize_linear_u8(ctd_handle* h, const uint8_t* src, int32_t sh, int32_t sw, int32_t channels, uint8_t* dst,
+                                 int32_t dh, int32_t dw);
+
 /* ---- pipelined host-buffer path (throughput mode of ctd_forward + ctd_get_*) -----------------
  * The reference serves pages one call at a time (inference.py:141-178: H2D, net, D2H, numpy post-
  * processing, all serial).  A caller that streams batches keeps two in flight instead:

@@ -96,3 +96,52 @@ def test_full_size_forward_is_deterministic_and_batch_invariant(prog):
         assert multigpu.arena_layout(3, h, w)["total"] == eng.results_bytes()
     finally:
         eng.close()
+
+
+RESIZE_CASES = [((360, 250), (178, 256)), ((1654, 1170), (724, 1024)), ((724, 1024), (1170, 1654)), ((100, 100), (50, 50)),
+                ((100, 100), (200, 200)), ((77, 33), (100, 211)), ((512, 512), (511, 513)), ((17, 5), (3, 9)),
+                ((2, 2), (7, 5)), ((1, 9), (4, 4)), ((9, 1), (1, 30)), ((640, 480), (320, 480)), ((64, 64), (64, 64))]
+
+
+@pytest.mark.parametrize("case", RESIZE_CASES, ids=lambda c: "%dx%d_to_%dx%d" % (c[0][0], c[0][1], c[1][1], c[1][0]))
+@pytest.mark.parametrize("channels", [1, 3])
+def test_gpu_resize_is_cv2_exact(prog, case, channels):
+    """ctd_resize_linear_u8 against the oracle (itself pinned against cv2 in tests/test_cpu_resize.py) and, where the
+    box has OpenCV, against cv2.resize directly: bit-exact."""
+    from oracle.resize_ref import resize_linear_u8
+    (sh, sw), (dw, dh) = case
+    rng = np.random.default_rng(sh * 131 + sw * 7 + dw)
+    src = rng.integers(0, 256, (sh, sw, channels), dtype=np.uint8)
+    if channels == 1:
+        src = src[:, :, 0]
+    eng = ctd_b200.Engine(prog, max_batch=1, max_h=64, max_w=64)
+    try:
+        got = eng.resize_linear_u8(src, (dw, dh))
+    finally:
+        eng.close()
+    assert np.array_equal(got, resize_linear_u8(src, (dw, dh)))
+    try:
+        import cv2
+    except ImportError:
+        return
+    assert np.array_equal(got, cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR))
+
+
+def test_gpu_letterbox_equals_host_letterbox():
+    """TextDetector on a page that is not net-sized: the GPU letterbox + mask back-projection must reproduce the
+    host path (reference `letterbox` + `cv2.resize` of the cropped mask) bit for bit."""
+    import cv2
+    from ctd_b200 import inference
+    det = ctd_b200.TextDetector(get_checkpoint(0, True), input_size=256, act="leaky")
+    try:
+        for shape in [(361, 251), (200, 300), (512, 512)]:
+            page = synth.structured_page(11, shape[0], shape[1])
+            mask, mask_refined, blk_list = det(page.copy())
+            im_in, _ratio, (dw, dh) = inference.letterbox(page, (256, 256))
+            det.net.forward(im_in[None])
+            m = det.net.mask_u8()[0][: 256 - dh, : 256 - dw]
+            want = cv2.resize(m, (shape[1], shape[0]), interpolation=cv2.INTER_LINEAR)
+            assert mask.shape == shape and np.array_equal(mask, want), shape
+            assert mask_refined.shape == shape
+    finally:
+        det.close()
