@@ -86,3 +86,39 @@ def test_submit_collect_matches_blocking_forward():
                 assert len(boxes[i]) > 0
     finally:
         eng.close()
+
+
+def test_two_workspaces_interleaved_equal_single():
+    """Two engines (workspaces) on one GPU with batches alternating between them and `ctd_join` ordering the streams
+    (what bench.py times) must give exactly the results of one engine used serially."""
+    ck = get_checkpoint(0, True)
+    prog = ctd_b200.compiler.compile_checkpoint(ck)
+    B, H, W = 2, 256, 256
+    batches = [np.stack([synth.structured_page(4000 + 10 * k + i, H, W) for i in range(B)]) for k in range(4)]
+    single = ctd_b200.Engine(prog, max_batch=B, max_h=H, max_w=W)
+    try:
+        want = []
+        for pg in batches:
+            single.forward(pg)
+            want.append((single.mask_u8().copy(), single.detections(), single.text_lines()))
+    finally:
+        single.close()
+    engs = [ctd_b200.Engine(prog, max_batch=B, max_h=H, max_w=W) for _ in range(2)]
+    try:
+        got = []
+        for rnd in range(2):                      # 2 rounds x 2 engines, both forwards in flight before any read
+            for k, e in enumerate(engs):
+                e.forward(batches[2 * rnd + k])
+            engs[0].join(engs[1])
+            for e in engs:
+                got.append((e.mask_u8().copy(), e.detections(), e.text_lines()))
+        for (m0, d0, (b0, s0)), (m1, d1, (b1, s1)) in zip(want, got):
+            assert np.array_equal(m0, m1)
+            for i in range(B):
+                assert np.array_equal(d0[i], d1[i]) and np.array_equal(b0[i], b1[i]) and np.array_equal(s0[i], s1[i])
+        with pytest.raises(ctd_b200.binding.CtdError):
+            engs[0].lib.ctd_join.restype  # noqa: B018  (attribute exists)
+            engs[0]._ck(engs[0].lib.ctd_join(engs[0].h, None))
+    finally:
+        for e in engs:
+            e.close()
