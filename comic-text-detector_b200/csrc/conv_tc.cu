@@ -331,26 +331,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const bool leader = elect_one();   // one fixed thread issues every MMA and commit of this CTA
     const uint64_t a_desc0 = make_kmajor_desc(a_base, row_bytes), b_desc0 = make_kmajor_desc(b_base, row_bytes);
     const int ksteps = kb / 16;
-    int stage = 0, ti = 0;
-    uint32_t full_par = 0;
-    uint64_t ad = a_desc0, bd = b_desc0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-      const int as = ti % Cfg::kAccStages;
-      mbar_wait(tmem_empty_bar + 8 * as, ((ti / Cfg::kAccStages) & 1) ^ 1);  // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + uint32_t(as * BN);
-      for (int k_it = 0; k_it < its_per_tile; ++k_it) {
-        mbar_wait(full_bar + 8 * stage, full_par);
+    if (leader) {   // the whole loop on the one issuing lane: no per-stage reconvergence
+      int stage = 0, ti = 0;
+      uint32_t full_par = 0;
+      uint64_t ad = a_desc0, bd = b_desc0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+        const int as = ti % Cfg::kAccStages;
+        mbar_wait(tmem_empty_bar + 8 * as, ((ti / Cfg::kAccStages) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        if (leader) {
+        const uint32_t tmem_d = tmem_base + uint32_t(as * BN);
+        for (int k_it = 0; k_it < its_per_tile; ++k_it) {
+          mbar_wait(full_bar + 8 * stage, full_par);
+          tc_fence_after();
           issue_kblock(tmem_d, ad, bd, idesc, k_it > 0 ? 1u : 0u, ksteps);
           umma_commit(empty_bar + 8 * stage);
           if (k_it == its_per_tile - 1) umma_commit(tmem_full_bar + 8 * as);
-        }
-        if (++stage == Cfg::kStages) {
-          stage = 0; full_par ^= 1u; ad = a_desc0; bd = b_desc0;
-        } else {
-          ad += uint64_t(Cfg::kABytes >> 4); bd += uint64_t(Cfg::kBBytes >> 4);
+          if (++stage == Cfg::kStages) {
+            stage = 0; full_par ^= 1u; ad = a_desc0; bd = b_desc0;
+          } else {
+            ad += uint64_t(Cfg::kABytes >> 4); bd += uint64_t(Cfg::kBBytes >> 4);
+          }
         }
       }
     }
@@ -853,35 +853,43 @@ __global__ void __launch_bounds__(kThreads, 1) conv_hs_kernel(const __grid_const
     const bool leader = elect_one();
     const uint64_t a_desc0 = make_kmajor_desc_ex(a_base, row_bytes, sbo, 0u);
     const uint64_t b_desc0 = make_kmajor_desc(b_base, row_bytes);
-    int sa = 0, sb = 0, ti = 0;
-    uint32_t a_par = 0, b_par = 0;
-    uint64_t ad_stage = a_desc0, bd = b_desc0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
-      const int phase = (t / n_nblk) / spatial_tiles;
-      const int as = ti % Cfg::kAccStages;
-      mbar_wait(tmem_empty_bar + 8 * as, ((ti / Cfg::kAccStages) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + uint32_t(as * BN);
-      uint32_t acc = 0u;
-      for (int kbi = 0; kbi < kblocks; ++kbi) {
-        mbar_wait(a_full + 8 * sa, a_par);
-        for (int tap = 0; tap < g.taps; ++tap) {
-          const int dy = g.tap_dy[phase][tap], dx = g.tap_dx[phase][tap];
-          const uint32_t a_off = (uint32_t((dy + loy) * halo_w + (dx + lox)) * row_bytes) >> 4;
-          mbar_wait(b_full + 8 * sb, b_par);
-          tc_fence_after();
-          if (leader) {
-            issue_kblock(tmem_d, ad_stage + a_off, bd, idesc, acc, 4);
-            umma_commit(b_empty + 8 * sb);
-            if (tap == g.taps - 1) {
-              umma_commit(a_empty + 8 * sa);
-              if (kbi == kblocks - 1) umma_commit(tmem_full_bar + 8 * as);
-            }
-          }
-          acc = 1u;
-          if (++sb == Cfg::kBStages) { sb = 0; b_par ^= 1u; bd = b_desc0; } else { bd += uint64_t(Cfg::kBBytes >> 4); }
+    // The whole loop runs on the ONE issuing lane (no per-tap reconvergence), with the per-tap operand views of the
+    // tile's phase precomputed into registers: the issuing thread's instruction stream, not the tensor pipe, was the
+    // limiter of this kernel (~70 SASS instructions per tap before, ncu source view).
+    if (leader) {
+      int sa = 0, sb = 0, ti = 0;
+      uint32_t a_par = 0, b_par = 0;
+      uint64_t ad_stage = a_desc0, bd = b_desc0;
+      const int ntaps = g.taps;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+        const int phase = (t / n_nblk) / spatial_tiles;
+        uint32_t tap_a[kMaxTaps];
+#pragma unroll
+        for (int tap = 0; tap < kMaxTaps; ++tap) {
+          const int dy = tap < ntaps ? g.tap_dy[phase][tap] : 0, dx = tap < ntaps ? g.tap_dx[phase][tap] : 0;
+          tap_a[tap] = (uint32_t((dy + loy) * halo_w + (dx + lox)) * row_bytes) >> 4;
         }
-        if (++sa == Cfg::kAStages) { sa = 0; a_par ^= 1u; ad_stage = a_desc0; } else { ad_stage += uint64_t(Cfg::kAStageBytes >> 4); }
+        const int as = ti % Cfg::kAccStages;
+        mbar_wait(tmem_empty_bar + 8 * as, ((ti / Cfg::kAccStages) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + uint32_t(as * BN);
+        uint32_t acc = 0u;
+        for (int kbi = 0; kbi < kblocks; ++kbi) {
+          mbar_wait(a_full + 8 * sa, a_par);
+#pragma unroll
+          for (int tap = 0; tap < kMaxTaps; ++tap) {
+            if (tap >= ntaps) break;
+            mbar_wait(b_full + 8 * sb, b_par);
+            tc_fence_after();
+            issue_kblock(tmem_d, ad_stage + tap_a[tap], bd, idesc, acc, 4);
+            acc = 1u;
+            umma_commit(b_empty + 8 * sb);
+            if (++sb == Cfg::kBStages) { sb = 0; b_par ^= 1u; bd = b_desc0; } else { bd += uint64_t(Cfg::kBBytes >> 4); }
+          }
+          umma_commit(a_empty + 8 * sa);
+          if (kbi == kblocks - 1) umma_commit(tmem_full_bar + 8 * as);
+          if (++sa == Cfg::kAStages) { sa = 0; a_par ^= 1u; ad_stage = a_desc0; } else { ad_stage += uint64_t(Cfg::kAStageBytes >> 4); }
+        }
       }
     }
   } else if (warp >= kEpiWarp0) {
