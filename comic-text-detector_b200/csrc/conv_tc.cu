@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int cb = 0; cb < p.src_kblocks[s]; ++cb, ++it) {
               const int stage = it % Cfg::kStages;
               const uint32_t par = ((it / Cfg::kStages) & 1) ^ 1;
-              mbar_wait(empty_bar + 8 * stage, par);
+              mbar_wait_relaxed(empty_bar + 8 * stage, par);
               mbar_arrive_expect_tx(full_bar + 8 * stage, stage_tx);
               tma_load_4d(a_base + stage * Cfg::kABytes, &p.a_map[s][q], full_bar + 8 * stage, cb * kb, x0 + dx,
                           y0 + dy, img);
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if constexpr (BN >= 64) {
         if (p.use_tma_store && g.residual) load_res_chunk(rc, out);
       }
-      mbar_wait(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
+      mbar_wait_relaxed(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + uint32_t(as * BN) + (uint32_t(quad * 32) << 16);
       const float* bias_t = bias_s + nblk * BN;
@@ -583,7 +583,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
             for (int cb = 0; cb < p.src_kblocks[s]; ++cb, ++it) {
               const int stage = it % S;
               const uint32_t par = ((it / S) & 1) ^ 1;
-              mbar_wait(empty_bar + 8 * stage, par);
+              mbar_wait_relaxed(empty_bar + 8 * stage, par);
               mbar_arrive_expect_tx(full_bar + 8 * stage, stage_tx);
               tma_load_4d(a_base + uint32_t(stage) * stage_bytes, &p.a_map[s][q], full_bar + 8 * stage, cb * kb,
                           x0 - lox, y0 - loy, img);
@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_halo_kernel(const __grid_con
         if (p.use_tma_store && g.residual)
           load_res_chunk(rc, p.dst + (size_t(img) * g.dst_h * g.dst_w + size_t(valid ? oy : 0) * g.dst_w + (valid ? ox : 0)) * g.dst_cstride + g.dst_coff);
       }
-      mbar_wait(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
+      mbar_wait_relaxed(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + uint32_t(as * BN) + (uint32_t(quad * 32) << 16);
       if constexpr (BN == 16) {
@@ -833,12 +833,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_hs_kernel(const __grid_const
         for (int s = 0; s < g.n_src; ++s)
           for (int cb = 0; cb < p.src_kblocks[s]; ++cb, ++kbi, ++ia) {
             const int sa = ia % Cfg::kAStages;
-            mbar_wait(a_empty + 8 * sa, ((ia / Cfg::kAStages) & 1) ^ 1);
+            mbar_wait_relaxed(a_empty + 8 * sa, ((ia / Cfg::kAStages) & 1) ^ 1);
             mbar_arrive_expect_tx(a_full + 8 * sa, a_tx);
             tma_load_4d(a_base + sa * Cfg::kAStageBytes, &p.a_map[s][0], a_full + 8 * sa, cb * kb, x0 - lox, y0 - loy, img);
             for (int tap = 0; tap < g.taps; ++tap, ++ib) {
               const int sb = ib % Cfg::kBStages;
-              mbar_wait(b_empty + 8 * sb, ((ib / Cfg::kBStages) & 1) ^ 1);
+              mbar_wait_relaxed(b_empty + 8 * sb, ((ib / Cfg::kBStages) & 1) ^ 1);
               mbar_arrive_expect_tx(b_full + 8 * sb, b_tx);
               tma_load_2d(b_base + sb * Cfg::kBBytes, &p.b_map, b_full + 8 * sb, tap * g.cin_total + kbi * kb,
                           phase * g.cout_pad + nblk * BN);
@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_hs_kernel(const __grid_const
                     g.dst_coff + nblk * BN;
       ResChunk rc;
       if (g.residual) load_res_chunk(rc, out);
-      mbar_wait(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
+      mbar_wait_relaxed(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + uint32_t(as * BN) + (uint32_t(quad * 32) << 16);
       const float* bias_t = bias_s + nblk * BN;
