@@ -38,3 +38,17 @@ def test_letterbox_geometry_matches_host_letterbox():
         r2, unpad, dw2, dh2 = inference.letterbox_geometry(shape, (1024, 1024))
         assert out.shape == (1024, 1024, 3) and (dw, dh) == (dw2, dh2) and r == r2
         assert unpad == (1024 - dw, 1024 - dh)
+
+
+def test_oracle_resize_equals_committed_cv2_goldens():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resize_cv2.npz"))
+    n = 0
+    for k in g.files:
+        if not k.startswith("src_"):
+            continue
+        want = g["dst_" + k[4:]]
+        got = resize_linear_u8(g[k], (want.shape[1], want.shape[0]))
+        assert np.array_equal(got, want), k
+        n += 1
+    assert n == 12

@@ -145,3 +145,49 @@ def test_gpu_letterbox_equals_host_letterbox():
             assert mask_refined.shape == shape
     finally:
         det.close()
+
+
+def test_model2annotations_writes_the_reference_files(tmp_path):
+    """`model2annotations` (inference.py:19-70) end to end on the GPU detector: per page <name>.txt (YOLO), line-<name>.txt,
+    <name>.json, <name>.png, mask-<name>.png; the file FORMATS are pinned byte-for-byte against the reference's writer
+    in tests/test_cpu_annotations.py."""
+    import json
+    import cv2
+    from ctd_b200 import annotations as ann
+    src, dst = tmp_path / "in", tmp_path / "out"
+    src.mkdir()
+    for i, shape in enumerate([(256, 256), (300, 212)]):
+        cv2.imwrite(str(src / ("page%d.jpg" % i)), synth.structured_page(20 + i, shape[0], shape[1]))
+    (src / "notes.txt").write_text("not an image")
+    det = ctd_b200.TextDetector(get_checkpoint(0, True), input_size=256, act="leaky")
+    try:
+        ann.model2annotations(None, str(src), str(dst), save_json=True, detector=det)
+    finally:
+        det.close()
+    names = sorted(p.name for p in dst.iterdir())
+    for i in range(2):
+        for f in ("page%d.txt", "page%d.json", "page%d.png", "mask-page%d.png"):
+            assert f % i in names, (f % i, names)
+        blks = json.loads((dst / ("page%d.json" % i)).read_text())
+        labels = (dst / ("page%d.txt" % i)).read_text()
+        assert len(blks) == (len(labels.split("\n")) if labels else 0)
+        n_lines = sum(len(b["lines"]) for b in blks)
+        if n_lines:
+            rows = (dst / ("line-page%d.txt" % i)).read_text().strip().split("\n")
+            assert len(rows) == n_lines and all(len(r.split()) == 8 for r in rows)
+        m = cv2.imread(str(dst / ("mask-page%d.png" % i)), cv2.IMREAD_GRAYSCALE)
+        assert m.shape == cv2.imread(str(dst / ("page%d.png" % i))).shape[:2]
+    assert not any(n.startswith("notes") for n in names)
+
+
+def test_gpu_resize_equals_committed_cv2_goldens(prog):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resize_cv2.npz"))
+    eng = ctd_b200.Engine(prog, max_batch=1, max_h=64, max_w=64)
+    try:
+        for k in g.files:
+            if k.startswith("src_"):
+                want = g["dst_" + k[4:]]
+                assert np.array_equal(eng.resize_linear_u8(g[k], (want.shape[1], want.shape[0])), want), k
+    finally:
+        eng.close()
