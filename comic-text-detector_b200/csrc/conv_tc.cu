@@ -943,6 +943,215 @@ __global__ void __launch_bounds__(kThreads, 1) conv_hs_kernel(const __grid_const
   }
 }
 
+
+// =========================================================================================
+// Swapped-operand variant for 128 output channels (conv_sw_kernel).  D^T[128 couts x 256 pixels]: the weight box of a
+// (K block, tap) is the M=128 operand, the activation halo block viewed per tap is the N=256 operand (tile 8 x 32
+// pixels; the same descriptor trick as conv_halo_kernel, SBO = halo width).  One tcgen05.mma therefore covers
+// 256 pixels x 128 channels instead of 128 x 128 -- the issue cost per FLOP halves for the 128-wide layers.
+// Accumulator lanes are CHANNELS, columns are pixels: each epilogue thread owns one channel, adds its bias, applies the
+// activation and writes fp16 into a [pixel][128 channels] staging block (32 pixels = 8 KB at a time, double buffered),
+// which a TMA store (no swizzle, 256-byte rows) scatters into the NHWC destination.
+constexpr int kSwTileW = 8, kSwTileH = 32;
+struct SwCfg {
+  static constexpr int kActStages = 2;
+  static constexpr int kActStageBytes = 44 * 1024;   // (8+2) x (32+2) halo rows of 128 B = 43520, 1024-aligned
+  static constexpr int kWStages = 6;
+  static constexpr int kWBytes = 128 * 128;          // 128 couts x 64 channels
+  static constexpr int kAccStages = 2;               // 2 x 256 TMEM columns
+  static constexpr int kTmemCols = 512;
+  static constexpr int kChunkBytes = 32 * 256;       // 32 pixels x 128 channels fp16
+  static constexpr int kStoreBytes = 2 * 2 * kChunkBytes;   // two epilogue warpgroups x two buffers
+  static constexpr size_t kSmem = size_t(kActStages) * kActStageBytes + size_t(kWStages) * kWBytes + kStoreBytes + 512 + 512;
+};
+
+template <int ACT>
+__device__ __forceinline__ void sw_store_chunk(const uint32_t (&v)[32], float bias, uint32_t buf, int co) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const __half hv = __float2half_rn(apply_act<ACT>(__uint_as_float(v[j]) + bias));
+    const unsigned short bits = __half_as_ushort(hv);
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(buf + uint32_t(j) * 256u + uint32_t(co) * 2u), "h"(bits) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_sw_kernel(const __grid_constant__ ConvTcParams p) {
+  using Cfg = SwCfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t act_base = smem_base;
+  const uint32_t w_base = act_base + Cfg::kActStages * Cfg::kActStageBytes;
+  const uint32_t store_base = w_base + Cfg::kWStages * Cfg::kWBytes;
+  const uint32_t bar_base = store_base + Cfg::kStoreBytes;
+  // barriers: act_full[4] | act_empty[4] | w_full[8] | w_empty[8] | tmem_full[4] | tmem_empty[4] | tmem ptr
+  const uint32_t act_full = bar_base, act_empty = bar_base + 32, w_full = bar_base + 64, w_empty = bar_base + 128;
+  const uint32_t tmem_full_bar = bar_base + 192, tmem_empty_bar = bar_base + 224, tmem_ptr_addr = bar_base + 256;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const size_t bar_off = size_t(Cfg::kActStages) * Cfg::kActStageBytes + size_t(Cfg::kWStages) * Cfg::kWBytes + Cfg::kStoreBytes;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 256);
+  float* bias_s = reinterpret_cast<float*>(smem_gen + bar_off + 512);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvGeom& g = p.g;
+  constexpr int kb = 64;
+  constexpr uint32_t row_bytes = 128;
+  const int lox = p.halo_lox, loy = p.halo_loy;
+  const int halo_w = p.halo_w, halo_h = p.halo_h;
+  const uint32_t act_tx = uint32_t(halo_w * halo_h) * row_bytes;
+  constexpr uint32_t w_tx = 128u * row_bytes;
+  int kblocks = 0;
+  for (int s = 0; s < g.n_src; ++s) kblocks += p.src_kblocks[s];
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int spatial_tiles = g.n_img * tiles_per_img;
+  const int total_tiles = spatial_tiles * g.n_phase;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < g.n_src; ++s) prefetch_tensormap(&p.a_map[s][0]);
+    prefetch_tensormap(&p.b_map);
+    for (int q = 0; q < g.n_phase; ++q) prefetch_tensormap(&p.o_map[q]);
+    for (int s = 0; s < Cfg::kActStages; ++s) { mbar_init(act_full + 8 * s, 1); mbar_init(act_empty + 8 * s, 1); }
+    for (int s = 0; s < Cfg::kWStages; ++s) { mbar_init(w_full + 8 * s, 1); mbar_init(w_empty + 8 * s, 1); }
+    for (int s = 0; s < Cfg::kAccStages; ++s) { mbar_init(tmem_full_bar + 8 * s, 1); mbar_init(tmem_empty_bar + 8 * s, 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_addr, Cfg::kTmemCols);
+  for (int i = threadIdx.x; i < 128; i += kThreads) bias_s[i] = i < g.cout_pad ? p.bias[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  griddep_launch_dependents();
+  griddep_wait();
+
+  auto decode = [&](int t, int& phase, int& img, int& y0, int& x0) {
+    const int sp = t % spatial_tiles;
+    phase = t / spatial_tiles;
+    img = sp / tiles_per_img;
+    const int trem = sp - img * tiles_per_img;
+    const int ty = trem / p.tiles_x;
+    y0 = ty * kSwTileH;
+    x0 = (trem - ty * p.tiles_x) * kSwTileW;
+  };
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (elect_one()) {
+      int ia = 0, iw = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int phase, img, y0, x0;
+        decode(t, phase, img, y0, x0);
+        int kbi = 0;
+        for (int s = 0; s < g.n_src; ++s)
+          for (int cb = 0; cb < p.src_kblocks[s]; ++cb, ++kbi, ++ia) {
+            const int sa = ia % Cfg::kActStages;
+            mbar_wait_relaxed(act_empty + 8 * sa, ((ia / Cfg::kActStages) & 1) ^ 1);
+            mbar_arrive_expect_tx(act_full + 8 * sa, act_tx);
+            tma_load_4d(act_base + sa * Cfg::kActStageBytes, &p.a_map[s][0], act_full + 8 * sa, cb * kb, x0 - lox, y0 - loy, img);
+            for (int tap = 0; tap < g.taps; ++tap, ++iw) {
+              const int sw = iw % Cfg::kWStages;
+              mbar_wait_relaxed(w_empty + 8 * sw, ((iw / Cfg::kWStages) & 1) ^ 1);
+              mbar_arrive_expect_tx(w_full + 8 * sw, w_tx);
+              tma_load_2d(w_base + sw * Cfg::kWBytes, &p.b_map, w_full + 8 * sw, tap * g.cin_total + kbi * kb, phase * g.cout_pad);
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (one lane) =======================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_f16(256);
+      const uint32_t sbo = uint32_t(halo_w) * row_bytes;
+      const uint64_t act_desc0 = make_kmajor_desc_ex(act_base, row_bytes, sbo, 0u);   // N operand: halo views
+      const uint64_t w_desc0 = make_kmajor_desc(w_base, row_bytes);                    // M operand: weight box
+      int sa = 0, sw = 0, ti = 0;
+      uint32_t a_par = 0, w_par = 0;
+      uint64_t act_stage = act_desc0, wd = w_desc0;
+      const int ntaps = g.taps;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+        const int phase = t / spatial_tiles;
+        uint32_t tap_off[kMaxTaps];
+#pragma unroll
+        for (int tap = 0; tap < kMaxTaps; ++tap) {
+          const int dy = tap < ntaps ? g.tap_dy[phase][tap] : 0, dx = tap < ntaps ? g.tap_dx[phase][tap] : 0;
+          tap_off[tap] = (uint32_t((dy + loy) * halo_w + (dx + lox)) * row_bytes) >> 4;
+        }
+        const int as = ti & 1;
+        mbar_wait(tmem_empty_bar + 8 * as, ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + uint32_t(as * 256);
+        uint32_t acc = 0u;
+        for (int kbi = 0; kbi < kblocks; ++kbi) {
+          mbar_wait(act_full + 8 * sa, a_par);
+#pragma unroll
+          for (int tap = 0; tap < kMaxTaps; ++tap) {
+            if (tap >= ntaps) break;
+            mbar_wait(w_full + 8 * sw, w_par);
+            tc_fence_after();
+            issue_kblock(tmem_d, wd, act_stage + tap_off[tap], idesc, acc, 4);   // A = weights, B = pixels
+            acc = 1u;
+            umma_commit(w_empty + 8 * sw);
+            if (++sw == Cfg::kWStages) { sw = 0; w_par ^= 1u; wd = w_desc0; } else { wd += uint64_t(Cfg::kWBytes >> 4); }
+          }
+          umma_commit(act_empty + 8 * sa);
+          if (kbi == kblocks - 1) umma_commit(tmem_full_bar + 8 * as);
+          if (++sa == Cfg::kActStages) { sa = 0; a_par ^= 1u; act_stage = act_desc0; }
+          else { act_stage += uint64_t(Cfg::kActStageBytes >> 4); }
+        }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // =============================== epilogue (channel-major accumulators) ========
+    const int quad = warp & 3;
+    const int group = (warp - kEpiWarp0) >> 2;
+    const int co = quad * 32 + lane;                   // this thread's output channel
+    const float bias = bias_s[co];
+    const bool lead = (threadIdx.x & 127) == 0;
+    const uint32_t buf0 = store_base + uint32_t(group) * (2u * Cfg::kChunkBytes);
+    int ti = 0, nchunk = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      if ((ti & 1) != group) continue;
+      int phase, img, y0, x0;
+      decode(t, phase, img, y0, x0);
+      const int as = ti & 1;
+      mbar_wait_relaxed(tmem_full_bar + 8 * as, (ti >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_row = tmem_base + uint32_t(as * 256) + (uint32_t(quad * 32) << 16);
+      const CUtensorMap* om = &p.o_map[phase];
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c, ++nchunk) {         // 32 pixels = tile rows 4c .. 4c+3
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_row + uint32_t(c * 32), v);
+        tmem_ld_wait();
+        const uint32_t buf = buf0 + uint32_t(nchunk & 1) * Cfg::kChunkBytes;
+        if (lead) tma_store_wait_read1();             // the store that used this buffer two chunks ago has drained
+        named_barrier_sync(1 + group, 128);
+        switch (g.act) {
+          case CTD_ACT_SILU: sw_store_chunk<CTD_ACT_SILU>(v, bias, buf, co); break;
+          case CTD_ACT_LEAKY: sw_store_chunk<CTD_ACT_LEAKY>(v, bias, buf, co); break;
+          case CTD_ACT_RELU: sw_store_chunk<CTD_ACT_RELU>(v, bias, buf, co); break;
+          case CTD_ACT_SIGMOID: sw_store_chunk<CTD_ACT_SIGMOID>(v, bias, buf, co); break;
+          default: sw_store_chunk<CTD_ACT_NONE>(v, bias, buf, co); break;
+        }
+        fence_proxy_async();
+        named_barrier_sync(1 + group, 128);
+        if (lead) {
+          tma_store_4d(om, buf, 0, x0, y0 + 4 * c, img);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tmem_empty_bar + 8 * as);
+    }
+    if (lead) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 // =========================================================================================
 // host side
 
@@ -955,6 +1164,15 @@ static const char* encode_map(PFN_encodeTiled enc, CUtensorMap* m, const void* b
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled failed";
+}
+
+static const char* encode_map_noswizzle(PFN_encodeTiled enc, CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims,
+                                        const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? nullptr : "cuTensorMapEncodeTiled (no swizzle) failed";
 }
 
 static int g_num_sms = 148;
@@ -1241,6 +1459,63 @@ const char* conv_hs_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
   return nullptr;
 }
 
+const char* conv_sw_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
+                         const int src_coff[], const void* w16, const float* bias, __half* dst) {
+  plan.halo = 0;
+  if (dst == nullptr || g.in_stride != 1 || g.residual) return nullptr;
+  if (!((g.n_phase == 1 && g.taps == 9) || (g.n_phase == 4 && g.taps == 4))) return nullptr;
+  if (g.cout_pad != 128 || g.cout != 128) return nullptr;
+  for (int s = 0; s < g.n_src; ++s)
+    if (g.src_c[s] % 64 != 0 || src_coff[s] % 8 != 0) return nullptr;
+  if ((g.dst_coff % 8) != 0 || (g.dst_cstride % 8) != 0) return nullptr;
+  for (int ph = 0; ph < g.n_phase; ++ph)
+    for (int t = 0; t < g.taps; ++t)
+      if (g.tap_dy[ph][t] < -1 || g.tap_dy[ph][t] > 1 || g.tap_dx[ph][t] < -1 || g.tap_dx[ph][t] > 1) return nullptr;
+  ConvTcParams& p = plan.p;
+  memset(&p, 0, sizeof(p));
+  p.g = g;
+  p.kb_elems = 64;
+  for (int s = 0; s < g.n_src; ++s) p.src_kblocks[s] = g.src_c[s] / 64;
+  p.dst = dst;
+  p.bias = bias;
+  p.halo_lox = 1; p.halo_loy = 1;
+  p.halo_w = kSwTileW + 2; p.halo_h = kSwTileH + 2;
+  p.tiles_x = (g.gw + kSwTileW - 1) / kSwTileW;
+  p.tiles_y = (g.gh + kSwTileH - 1) / kSwTileH;
+  for (int s = 0; s < g.n_src; ++s) {
+    const size_t cs = size_t(g.src_cstride[s]);
+    const char* base = static_cast<const char*>(src_ptr[s]) + size_t(src_coff[s]) * 2;
+    cuuint64_t dims[4] = {cuuint64_t(g.src_c[s]), cuuint64_t(g.src_w), cuuint64_t(g.src_h), cuuint64_t(g.n_img)};
+    cuuint64_t str[3] = {cs * 2, cs * 2 * g.src_w, cs * 2 * g.src_w * g.src_h};
+    cuuint32_t box[4] = {64, cuuint32_t(p.halo_w), cuuint32_t(p.halo_h), 1};
+    if (const char* e = encode_map(enc, &p.a_map[s][0], base, 4, dims, str, box, 64)) return e;
+  }
+  {
+    const size_t cs = size_t(g.dst_cstride);
+    for (int ph = 0; ph < g.n_phase; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      cuuint64_t dims[4] = {cuuint64_t(g.cout), cuuint64_t(g.gw), cuuint64_t(g.gh), cuuint64_t(g.n_img)};
+      cuuint64_t str[3] = {cs * 2 * g.out_mul, cs * 2 * g.dst_w * g.out_mul, cs * 2 * size_t(g.dst_w) * g.dst_h};
+      cuuint32_t box[4] = {128, kSwTileW, 4, 1};   // one staging chunk: 4 tile rows x 8 pixels x 128 channels
+      const char* base = reinterpret_cast<const char*>(dst) + (size_t(g.dst_coff) + (size_t(py) * g.dst_w + px) * cs) * 2;
+      if (const char* e = encode_map_noswizzle(enc, &p.o_map[ph], base, 4, dims, str, box)) return e;
+    }
+    p.use_tma_store = 1;
+  }
+  {
+    cuuint64_t dims[2] = {cuuint64_t(g.k_total), cuuint64_t(g.n_phase) * cuuint64_t(g.cout_pad)};
+    cuuint64_t str[1] = {cuuint64_t(g.k_total) * 2};
+    cuuint32_t box[2] = {64, 128};
+    if (const char* e = encode_map(enc, &p.b_map, w16, 2, dims, str, box, 64)) return e;
+  }
+  const int total_tiles = g.n_img * p.tiles_x * p.tiles_y * g.n_phase;
+  plan.grid = dim3(unsigned(total_tiles < g_num_sms ? total_tiles : g_num_sms), 1, 1);
+  plan.block_n = 128;
+  plan.smem_bytes = SwCfg::kSmem + 1024;
+  plan.halo = 3;
+  return nullptr;
+}
+
 const char* conv_halo_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void* s2d, int n, int ph, int pw,
                                 const void* w16, const float* bias, __half* dst, int dst_cstride, int dst_coff, int cout,
                                 int act) {
@@ -1330,6 +1605,8 @@ cudaError_t conv_tc_init() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_halo_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(conv_sw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SwCfg::kSmem + 1024));
+  if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_hs_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(HsCfg<256>::kSmem));
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(conv_hs_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(HsCfg<128>::kSmem));
@@ -1354,6 +1631,7 @@ static cudaError_t launch_pdl(K kernel, dim3 grid, size_t smem, cudaStream_t s, 
 }
 
 cudaError_t conv_tc_launch(const ConvTcPlan& plan, cudaStream_t s) {
+  if (plan.halo == 3) return launch_pdl(conv_sw_kernel, plan.grid, plan.smem_bytes, s, plan.p);
   if (plan.halo == 2) {
     if (plan.block_n == 256) return launch_pdl(conv_hs_kernel<256>, plan.grid, plan.smem_bytes, s, plan.p);
     else return launch_pdl(conv_hs_kernel<128>, plan.grid, plan.smem_bytes, s, plan.p);

@@ -74,7 +74,7 @@ struct ctd_handle {
   bool slot_busy[2] = {false, false};
   // overlapped schedule: post-processing of the DB maps / the Detect rows runs on side streams under the
   // remaining network ops (see run_ops)
-  int halo_mode = 3;   // CTD_HALO bit mask (0 routes every conv through conv_tc_kernel, for A/B measurements)
+  int halo_mode = 7;   // CTD_HALO bit mask (0 routes every conv through conv_tc_kernel, for A/B measurements)
   bool overlap = false;
   cudaStream_t side = nullptr, side2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
@@ -180,7 +180,7 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
       if (op.residual && op.dst_buf >= 0 && op.dst_buf < n_bufs) needed[op.dst_buf] = 1;
     }
     const char* hm = getenv("CTD_HALO");
-    h->halo_mode = hm ? atoi(hm) : 3;   // bit 0: conv_halo_kernel (resident weights), bit 1: conv_hs_kernel (streamed)
+    h->halo_mode = hm ? atoi(hm) : 7;   // bit 0: conv_halo_kernel (resident weights), 1: conv_hs_kernel (streamed), 2: conv_sw_kernel
     const char* ov = getenv("CTD_OVERLAP");
     h->overlap = have_db && !(ov && ov[0] == '0');
   }
@@ -343,6 +343,9 @@ static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
     if ((h->halo_mode & 1) && op.kind != CTD_OP_DETECT)
       e = conv_halo_plan(sp.tc[i], h->enc, g, src, coff, h->d_blob + op.w16_off,
                          reinterpret_cast<const float*>(h->d_blob + op.b_off), dst);
+    if (!e && !sp.tc[i].halo && (h->halo_mode & 4) && op.kind != CTD_OP_DETECT)
+      e = conv_sw_plan(sp.tc[i], h->enc, g, src, coff, h->d_blob + op.w16_off,
+                       reinterpret_cast<const float*>(h->d_blob + op.b_off), dst);
     if (!e && !sp.tc[i].halo && (h->halo_mode & 2) && op.kind != CTD_OP_DETECT)
       e = conv_hs_plan(sp.tc[i], h->enc, g, src, coff, h->d_blob + op.w16_off,
                        reinterpret_cast<const float*>(h->d_blob + op.b_off), dst);

@@ -75,7 +75,7 @@ struct alignas(64) ConvTcParams {
 
 struct ConvTcPlan {
   ConvTcParams p;
-  int halo = 0;                       // 1: launch conv_halo_kernel, 2: conv_hs_kernel (halo A, streamed B)
+  int halo = 0;                       // 1: conv_halo_kernel, 2: conv_hs_kernel (halo A, streamed B), 3: conv_sw_kernel
   int block_n;
   dim3 grid;
   size_t smem_bytes;
@@ -101,6 +101,11 @@ const char* conv_halo_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom
 // Halo activations + STREAMED weights for the wide stride-1 3x3 convolutions / deconvolution phases whose weights
 // do not fit in shared memory (BN = 128 / 256).  Sets plan.halo = 2 when eligible.
 const char* conv_hs_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
+                         const int src_coff[], const void* w16, const float* bias, __half* dst);
+// Swapped operands for the 128-wide stride-1 3x3 convolutions / deconvolution phases: the 128 output channels are the
+// MMA's M (weights = A operand), 256 PIXELS (8 x 32 tile, halo views) are its N, so one instruction does twice the
+// work of the pixel-major form at N = 128; the epilogue transposes through shared memory.  Sets plan.halo = 3.
+const char* conv_sw_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
                          const int src_coff[], const void* w16, const float* bias, __half* dst);
 // Stem through the halo kernel (window map of conv_tc_plan_stem, halo in y only).
 const char* conv_halo_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void* s2d, int n, int ph, int pw,
