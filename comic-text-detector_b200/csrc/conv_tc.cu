@@ -965,12 +965,14 @@ struct SwCfg {
   static constexpr size_t kSmem = size_t(kActStages) * kActStageBytes + size_t(kWStages) * kWBytes + kStoreBytes + 512 + 512;
 };
 
-template <int ACT>
-__device__ __forceinline__ void sw_store_chunk(const uint32_t (&v)[32], float bias, uint32_t buf, int co) {
+template <int ACT, bool RES>
+__device__ __forceinline__ void sw_store_chunk(const uint32_t (&v)[32], const unsigned short (&res)[32], float bias, uint32_t buf,
+                                               int co) {
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    const __half hv = __float2half_rn(apply_act<ACT>(__uint_as_float(v[j]) + bias));
-    const unsigned short bits = __half_as_ushort(hv);
+    float f = apply_act<ACT>(__uint_as_float(v[j]) + bias);
+    if constexpr (RES) f += __half2float(__ushort_as_half(res[j]));
+    const unsigned short bits = __half_as_ushort(__float2half_rn(f));
     asm volatile("st.shared.b16 [%0], %1;" ::"r"(buf + uint32_t(j) * 256u + uint32_t(co) * 2u), "h"(bits) : "memory");
   }
 }
@@ -1119,19 +1121,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_sw_kernel(const __grid_const
       const CUtensorMap* om = &p.o_map[phase];
 #pragma unroll 1
       for (int c = 0; c < 8; ++c, ++nchunk) {         // 32 pixels = tile rows 4c .. 4c+3
+        // Bottleneck residual: this thread's channel of the 32 pixels of the chunk (a warp reads 64 contiguous bytes
+        // per pixel), issued before the TMEM read so the loads are in flight under it
+        unsigned short res[32];
+        if (g.residual) {
+          const int ph_y = phase >> 1, ph_x = phase & 1;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int gy = y0 + 4 * c + (j >> 3), gx = x0 + (j & 7);
+            const bool ok = gy < g.gh && gx < g.gw;
+            const size_t off = ((size_t(img) * g.dst_h + size_t(ok ? gy * g.out_mul + ph_y : 0)) * g.dst_w +
+                                size_t(ok ? gx * g.out_mul + ph_x : 0)) * g.dst_cstride + g.dst_coff + co;
+            res[j] = *reinterpret_cast<const unsigned short*>(p.dst + off);
+          }
+        }
         uint32_t v[32];
         tmem_ld_32x32(tmem_row + uint32_t(c * 32), v);
         tmem_ld_wait();
         const uint32_t buf = buf0 + uint32_t(nchunk & 1) * Cfg::kChunkBytes;
         if (lead) tma_store_wait_read1();             // the store that used this buffer two chunks ago has drained
         named_barrier_sync(1 + group, 128);
+#define CTD_SW(ACT)                                                                  \
+  if (g.residual) sw_store_chunk<ACT, true>(v, res, bias, buf, co);                  \
+  else sw_store_chunk<ACT, false>(v, res, bias, buf, co);
         switch (g.act) {
-          case CTD_ACT_SILU: sw_store_chunk<CTD_ACT_SILU>(v, bias, buf, co); break;
-          case CTD_ACT_LEAKY: sw_store_chunk<CTD_ACT_LEAKY>(v, bias, buf, co); break;
-          case CTD_ACT_RELU: sw_store_chunk<CTD_ACT_RELU>(v, bias, buf, co); break;
-          case CTD_ACT_SIGMOID: sw_store_chunk<CTD_ACT_SIGMOID>(v, bias, buf, co); break;
-          default: sw_store_chunk<CTD_ACT_NONE>(v, bias, buf, co); break;
+          case CTD_ACT_SILU: CTD_SW(CTD_ACT_SILU) break;
+          case CTD_ACT_LEAKY: CTD_SW(CTD_ACT_LEAKY) break;
+          case CTD_ACT_RELU: CTD_SW(CTD_ACT_RELU) break;
+          case CTD_ACT_SIGMOID: CTD_SW(CTD_ACT_SIGMOID) break;
+          default: CTD_SW(CTD_ACT_NONE) break;
         }
+#undef CTD_SW
         fence_proxy_async();
         named_barrier_sync(1 + group, 128);
         if (lead) {
@@ -1176,6 +1196,7 @@ static const char* encode_map_noswizzle(PFN_encodeTiled enc, CUtensorMap* m, con
 }
 
 static int g_num_sms = 148;
+static int g_sw_residual = 0;   // CTD_SW_RESIDUAL=1 routes residual 128-wide layers through conv_sw_kernel too
 static int g_use_pdl = 0;   // CTD_PDL=1 enables programmatic dependent launch (measured: no gain once a second
                             // workspace fills the tails -- early dependents park on SMs the other batch could use)
 
@@ -1462,7 +1483,10 @@ const char* conv_hs_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
 const char* conv_sw_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
                          const int src_coff[], const void* w16, const float* bias, __half* dst) {
   plan.halo = 0;
-  if (dst == nullptr || g.in_stride != 1 || g.residual) return nullptr;
+  if (dst == nullptr || g.in_stride != 1) return nullptr;
+  // The kernel handles Bottleneck residuals (tests/test_gpu_kernels.py), but its channel-major 2-byte residual loads
+  // make those layers slower than conv_hs_kernel (measured 6.32 -> 6.44 ms per step): leave them there.
+  if (g.residual && !g_sw_residual) return nullptr;
   if (!((g.n_phase == 1 && g.taps == 9) || (g.n_phase == 4 && g.taps == 4))) return nullptr;
   if (g.cout_pad != 128 || g.cout != 128) return nullptr;
   for (int s = 0; s < g.n_src; ++s)
@@ -1588,6 +1612,8 @@ cudaError_t conv_tc_init() {
   {
     const char* pdl = getenv("CTD_PDL");
     g_use_pdl = (pdl && pdl[0] == '1') ? 1 : 0;
+    const char* swr = getenv("CTD_SW_RESIDUAL");
+    g_sw_residual = (swr && swr[0] == '1') ? 1 : 0;
   }
   int dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) {
