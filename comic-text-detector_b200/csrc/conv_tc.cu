@@ -1487,6 +1487,7 @@ const char* conv_sw_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
   // The kernel handles Bottleneck residuals (tests/test_gpu_kernels.py), but its channel-major 2-byte residual loads
   // make those layers slower than conv_hs_kernel (measured 6.32 -> 6.44 ms per step): leave them there.
   if (g.residual && !g_sw_residual) return nullptr;
+  // (1x1 layers were tried here too: without halo reuse the transposed epilogue costs more than the wider MMA saves)
   if (!((g.n_phase == 1 && g.taps == 9) || (g.n_phase == 4 && g.taps == 4))) return nullptr;
   if (g.cout_pad != 128 || g.cout != 128) return nullptr;
   for (int s = 0; s < g.n_src; ++s)

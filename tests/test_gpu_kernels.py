@@ -47,6 +47,7 @@ CONV_CASES = [
     ([256], 256, 3, 1, cc.ACT_LEAKY, True, 64, 64, 1),       # halo A + streamed weights, BN=256, residual
     ([128], 128, 3, 1, cc.ACT_SILU, True, 64, 64, 2),        # swapped-operand kernel (128 couts = M) with residual
     ([64, 64], 128, 3, 1, cc.ACT_RELU, False, 128, 64, 1),   # swapped-operand kernel, two sources
+    ([128, 64], 128, 1, 1, cc.ACT_SILU, False, 64, 192, 1),  # swapped-operand kernel, 1x1 over two sources
     ([128, 128], 512, 3, 1, cc.ACT_SILU, False, 64, 128, 1),  # same, two sources x two N blocks
 ]
 
