@@ -278,12 +278,20 @@ __global__ void accumulate_kernel(int h, int w, const float* __restrict__ pred_a
   const int leader = __ffs(peers) - 1;
   double s = 0.0;
   int c = 0;
+  if (__all_sync(0xffffffffu, peers == 0xffffffffu)) {
+    // the common case, one (component, row) run covers the whole warp: 5-step tree instead of 32 shuffles
+    s = (double)v;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    c = 32;   // only lane 0 (the leader) holds the full sum, and only the leader uses it
+  } else {
 #pragma unroll 4
-  for (int l = 0; l < 32; ++l) {
-    const float ov = __shfl_sync(0xffffffffu, v, l);
-    if ((peers >> l) & 1u) {
-      s += (double)ov;
-      ++c;
+    for (int l = 0; l < 32; ++l) {
+      const float ov = __shfl_sync(0xffffffffu, v, l);
+      if ((peers >> l) & 1u) {
+        s += (double)ov;
+        ++c;
+      }
     }
   }
   if (live && key >= 0 && lane == leader) {
