@@ -88,26 +88,35 @@ CTD_HD void hull_start_maxx(IPt* hull, int n, IPt* tmp) {
 // OpenCV rotatingCalipers(CALIPERS_MINAREARECT) + minAreaRect wrapper, float32 arithmetic in OpenCV's
 // order, followed by the angle normalisation of OpenCV >= 4.5 (angle in [-90, 0), width/height swapped
 // accordingly).  hull: n >= 3 strictly convex vertices.  vect/inv: scratch of n entries each.
-CTD_HD RRect min_area_rect(const IPt* hull, int n, float* vx, float* vy, float* inv) {
-  int left = 0, bottom = 0, right = 0, top = 0;
+// first pass of minAreaRect: per-edge vectors / inverse lengths and the four extreme vertices (FIRST index of each
+// extreme, like OpenCV's strict comparisons).  Element-wise work: the GPU runs it across the warp (segrep.cu).
+struct MarExt { int left, bottom, right, top; };
+CTD_HD void mar_edge(const IPt* hull, int n, int i, float* vx, float* vy, float* inv) {
+  const int j = (i + 1 < n) ? i + 1 : 0;
+  const float p0x = (float)hull[i].x, p0y = (float)hull[i].y, px = (float)hull[j].x, py = (float)hull[j].y;
+  const double dx = (double)px - (double)p0x, dy = (double)py - (double)p0y;
+  vx[i] = (float)dx;
+  vy[i] = (float)dy;
+  inv[i] = (float)D_DIV(1.0, sqrt(D_ADD(D_MUL(dx, dx), D_MUL(dy, dy))));
+}
+CTD_HD MarExt mar_prepass(const IPt* hull, int n, float* vx, float* vy, float* inv) {
+  MarExt e{0, 0, 0, 0};
   float left_x, right_x, top_y, bottom_y;
-  float p0x = (float)hull[0].x, p0y = (float)hull[0].y;
-  left_x = right_x = p0x;
-  top_y = bottom_y = p0y;
+  left_x = right_x = (float)hull[0].x;
+  top_y = bottom_y = (float)hull[0].y;
   for (int i = 0; i < n; ++i) {
-    if (p0x < left_x) { left_x = p0x; left = i; }
-    if (p0x > right_x) { right_x = p0x; right = i; }
-    if (p0y > top_y) { top_y = p0y; top = i; }
-    if (p0y < bottom_y) { bottom_y = p0y; bottom = i; }
-    const int j = (i + 1 < n) ? i + 1 : 0;
-    const float px = (float)hull[j].x, py = (float)hull[j].y;
-    const double dx = (double)px - (double)p0x, dy = (double)py - (double)p0y;
-    vx[i] = (float)dx;
-    vy[i] = (float)dy;
-    inv[i] = (float)D_DIV(1.0, sqrt(D_ADD(D_MUL(dx, dx), D_MUL(dy, dy))));
-    p0x = px;
-    p0y = py;
+    const float p0x = (float)hull[i].x, p0y = (float)hull[i].y;
+    if (p0x < left_x) { left_x = p0x; e.left = i; }
+    if (p0x > right_x) { right_x = p0x; e.right = i; }
+    if (p0y > top_y) { top_y = p0y; e.top = i; }
+    if (p0y < bottom_y) { bottom_y = p0y; e.bottom = i; }
+    mar_edge(hull, n, i, vx, vy, inv);
   }
+  return e;
+}
+
+CTD_HD RRect mar_core(const IPt* hull, int n, const float* vx, const float* vy, const float* inv, MarExt ext) {
+  const int left = ext.left, bottom = ext.bottom, right = ext.right, top = ext.top;
   float orientation = 0.f;
   {
     double ax = vx[n - 1], ay = vy[n - 1];
@@ -195,6 +204,11 @@ CTD_HD RRect min_area_rect(const IPt* hull, int n, float* vx, float* vy, float* 
   }
   r.angle = ang;
   return r;
+}
+
+CTD_HD RRect min_area_rect(const IPt* hull, int n, float* vx, float* vy, float* inv) {
+  const MarExt e = mar_prepass(hull, n, vx, vy, inv);
+  return mar_core(hull, n, vx, vy, inv, e);
 }
 
 // cv2.boxPoints (RotatedRect::points)

@@ -371,6 +371,57 @@ struct ContourScratch {
   float f0[ctdgeom::kMaxHull], f1[ctdgeom::kMaxHull], f2[ctdgeom::kMaxHull];
 };
 
+// ---- warp-cooperative pieces of the per-contour geometry (bit-identical to the serial forms in geom.h) ------------
+// rotate so that hull[0] is the max-x (ties: max-y) vertex; all 32 lanes, hull/tmp in shared memory
+__device__ __forceinline__ void hull_start_maxx_warp(IPt* hull, int n, IPt* tmp, int lane) {
+  if (n < 3) return;
+  int bx = INT_MIN, by = INT_MIN, bi = 0;
+  for (int i = lane; i < n; i += 32) {
+    const IPt q = hull[i];
+    if (q.x > bx || (q.x == bx && q.y > by)) { bx = q.x; by = q.y; bi = i; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const int ox = __shfl_xor_sync(0xffffffffu, bx, off), oy = __shfl_xor_sync(0xffffffffu, by, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+    if (ox > bx || (ox == bx && oy > by)) { bx = ox; by = oy; bi = oi; }   // hull vertices are distinct: no index ties
+  }
+  if (bi == 0) return;   // warp-uniform
+  for (int i = lane; i < n; i += 32) { int j = i + bi; if (j >= n) j -= n; tmp[i] = hull[j]; }
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) hull[i] = tmp[i];
+  __syncwarp();
+}
+
+// first pass of min_area_rect across the warp: per-edge vectors / inverse lengths (element-wise, same expressions as
+// ctdgeom::mar_edge) and the FIRST index of each extreme
+__device__ __forceinline__ ctdgeom::MarExt mar_prepass_warp(const IPt* hull, int n, float* vx, float* vy, float* inv, int lane) {
+  float lx = 3.402823466e+38f, rx = -3.402823466e+38f, ty = -3.402823466e+38f, by = 3.402823466e+38f;
+  int li = 0x7fffffff, ri = 0x7fffffff, ti = 0x7fffffff, bi = 0x7fffffff;
+  for (int i = lane; i < n; i += 32) {
+    const float px = (float)hull[i].x, py = (float)hull[i].y;
+    if (px < lx) { lx = px; li = i; }
+    if (px > rx) { rx = px; ri = i; }
+    if (py > ty) { ty = py; ti = i; }
+    if (py < by) { by = py; bi = i; }
+    ctdgeom::mar_edge(hull, n, i, vx, vy, inv);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    float o; int oi;
+    o = __shfl_xor_sync(0xffffffffu, lx, off); oi = __shfl_xor_sync(0xffffffffu, li, off);
+    if (o < lx || (o == lx && oi < li)) { lx = o; li = oi; }
+    o = __shfl_xor_sync(0xffffffffu, rx, off); oi = __shfl_xor_sync(0xffffffffu, ri, off);
+    if (o > rx || (o == rx && oi < ri)) { rx = o; ri = oi; }
+    o = __shfl_xor_sync(0xffffffffu, ty, off); oi = __shfl_xor_sync(0xffffffffu, ti, off);
+    if (o > ty || (o == ty && oi < ti)) { ty = o; ti = oi; }
+    o = __shfl_xor_sync(0xffffffffu, by, off); oi = __shfl_xor_sync(0xffffffffu, bi, off);
+    if (o < by || (o == by && oi < bi)) { by = o; bi = oi; }
+  }
+  __syncwarp();
+  return ctdgeom::MarExt{li, bi, ri, ti};
+}
+
 // Longest-job-first order: the serial per-contour geometry costs roughly in proportion to the rows a contour spans,
 // and the kernel is bound by its longest contour.  One CTA per page sorts (rows desc, id asc) with a bitonic network
 // so that contour_kernel starts the tall contours first and fills the tail with the small ones.
@@ -492,13 +543,30 @@ __global__ void __launch_bounds__(32 * kContourWarps) contour_kernel(int h, int 
     }
     __syncwarp();
   }
+  // ---- geometry: the element-wise parts run across the warp, the calipers / offset / hull stay on lane 0 ----------
+  overflow = __shfl_sync(0xffffffffu, int(overflow), 0) != 0;
+  k = __shfl_sync(0xffffffffu, k, 0);
+  if (overflow) return;
+  if (k > 1) --k;
+  // transpose back + reverse (the chain ran in the transposed plane)
+  for (int i = lane; i < k; i += 32) S.tmp[i] = IPt{S.hull[k - 1 - i].y, S.hull[k - 1 - i].x};
+  __syncwarp();
+  for (int i = lane; i < k; i += 32) S.hull[i] = S.tmp[i];
+  __syncwarp();
+  if (k < 3) return;                                  // contour_stage1: 1-2 points / collinear -> skipped
+  hull_start_maxx_warp(S.hull, k, S.tmp, lane);
+  const ctdgeom::MarExt e1 = mar_prepass_warp(S.hull, k, S.f0, S.f1, S.f2, lane);
   int m = 0;
-  if (lane == 0 && !overflow) {
-    if (k > 1) --k;
-    // transpose back + reverse
-    for (int i = 0; i < k; ++i) S.tmp[i] = IPt{S.hull[k - 1 - i].y, S.hull[k - 1 - i].x};
-    for (int i = 0; i < k; ++i) S.hull[i] = S.tmp[i];
-    m = ctdgeom::contour_stage1(S.hull, k, S.tmp, S.off, S.f0, S.f1, S.f2, (double)unclip_ratio);
+  if (lane == 0) {
+    const ctdgeom::RRect r1 = ctdgeom::mar_core(S.hull, k, S.f0, S.f1, S.f2, e1);
+    const float sside = r1.w < r1.h ? r1.w : r1.h;
+    if (sside >= 2.f) {
+      float px[4], py[4], ox[4], oy[4];
+      ctdgeom::box_points(r1, px, py);
+      ctdgeom::order_mini_box(px, py, ox, oy);
+      m = ctdgeom::unclip_offset(ox, oy, (double)unclip_ratio, S.off, ctdgeom::kMaxOffsetPts);
+      if (m < 3) m = 0;
+    }
   }
   m = __shfl_sync(0xffffffffu, m, 0);
   if (m == 0) return;
@@ -515,9 +583,23 @@ __global__ void __launch_bounds__(32 * kContourWarps) contour_kernel(int h, int 
   __syncwarp();
   for (int i = lane; i < m; i += 32) S.off[i] = S.tmp[i];
   __syncwarp();
+  int nh2 = 0;
+  if (lane == 0) nh2 = ctdgeom::hull_sorted(S.off, m, S.hull, ctdgeom::kMaxHull);
+  nh2 = __shfl_sync(0xffffffffu, nh2, 0);
+  __syncwarp();
+  if (nh2 < 3) return;
+  hull_start_maxx_warp(S.hull, nh2, S.tmp, lane);
+  const ctdgeom::MarExt e2 = mar_prepass_warp(S.hull, nh2, S.f0, S.f1, S.f2, lane);
   if (lane != 0) return;
+  const ctdgeom::RRect r2 = ctdgeom::mar_core(S.hull, nh2, S.f0, S.f1, S.f2, e2);
+  float px[4], py[4], ox[4], oy[4];
+  ctdgeom::box_points(r2, px, py);
+  ctdgeom::order_mini_box(px, py, ox, oy);
   int16_t box[8];
-  if (!ctdgeom::contour_stage2(S.off, m, S.hull, S.tmp, S.f0, S.f1, S.f2, w, h, dst_w, dst_h, box)) return;
+  for (int q = 0; q < 4; ++q) {
+    box[2 * q] = ctdgeom::quantise(ox[q], w, dst_w);
+    box[2 * q + 1] = ctdgeom::quantise(oy[q], h, dst_h);
+  }
   // box_score_fast (db_utils.py:197-211): mean of pred over the filled contour polygon
   double sum = tot_sum[o + root];
   long long cnt = tot_cnt[o + root];
