@@ -1,23 +1,29 @@
-// tcgen05 implicit-GEMM convolution for sm_100a.
+// tcgen05 implicit-GEMM convolutions for sm_100a: four kernels on one skeleton.
 //
-//   D[128 pixels x BN couts] (fp32, TMEM) = sum over K blocks  A[128 x KB] * B[BN x KB]^T
+//   D[128 x N] (fp32, TMEM) += A[128 x 16] * B[N x 16]^T, K-major fp16 operands in 128B/64B/32B-swizzled shared memory
 //
-// * A (activations, NHWC fp16) is fetched by 4-D tiled TMA: one box = 8 rows x 16 cols of
-//   pixels x KB channels of ONE filter tap, shifted by the tap offset; out-of-bounds pixels are
-//   zero-filled by the TMA unit, which implements the convolution padding.  The box lands in
-//   shared memory as 128 rows of KB*2 bytes with the 128B (or 64B) hardware swizzle, i.e.
-//   exactly the canonical K-major UMMA operand layout - there is no im2col buffer anywhere.
-//   torch.cat inputs are K-concatenated: each source buffer has its own tensor map.
-//   Stride-2 convolutions read through four "parity" maps (even/odd rows x even/odd columns).
-//   ConvTranspose 4x4 s2 p1 runs as 4 sub-pixel phases (blockIdx.z), each a 2x2-tap convolution.
-// * B (weights, packed [cout][tap][cin] fp16, BN folded) is fetched by 2-D tiled TMA.
-// * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread, tcgen05.mma
-//   cta_group::1 kind::f16, M=128,N=BN,K=16), warps 2-5 = epilogue (tcgen05.ld 32x32b ->
-//   bias + activation (+ residual) -> fp16 NHWC store at a channel offset, or the Detect decode).
-//   A multi-stage mbarrier ring (full/empty) couples TMA and MMA; tcgen05.commit frees slots.
+// Skeleton (all kernels): persistent, one CTA per SM; warp 0 = TMA producer (one elected thread), warp 1 = ONE thread
+// issuing tcgen05.mma cta_group::1 kind::f16 (M=128, K=16) in a straight-line loop (issue_kblock: descriptors are
+// precomputed and advanced with 64-bit adds), warp 2 = TMEM allocator, warps 4-11 = two epilogue warpgroups on
+// alternate tiles (tcgen05.ld 32x32b -> bias + activation (+ residual) -> fp16); mbarrier full/empty rings between
+// the roles, tcgen05.commit frees ring slots and publishes accumulators, a ring of TMEM accumulator stages lets the
+// epilogue of tile i run under the main loop of the following tiles; >= 64-channel slices leave through a swizzled
+// staging tile and one TMA store per 64 channels.  Activations are 4-D TMA boxes over the NHWC buffers: out-of-bounds
+// zero-fill IS the convolution padding, there is no im2col buffer; torch.cat inputs are K-concatenated from up to
+// 3 tensor maps; ConvTranspose 4x4 s2 p1 runs as 4 sub-pixel phases of 2x2 taps.
 //
-// Reference semantics: Conv.forward_fuse (models/yolov5/common.py:48-49), Bottleneck add
-// (common.py:104), ConvTranspose2d+BN+ReLU (basemodel.py:26-28), Detect (yolo.py:23-44).
+//   conv_tc_kernel<BN>    one 16x8-pixel x 64-channel box per (tap, K block) + the matching weight box; stride 2
+//                         through four parity maps; Detect heads decode sigmoid / boxes in the epilogue
+//   conv_halo_kernel<BN>  weights RESIDENT in smem; one halo box per K block, every filter tap is a matrix-descriptor
+//                         view into it (start row (dy+1)*W+(dx+1), SBO = W rows, base_offset 0); 3x3 s1/s2, deconv
+//                         phases, 1x1, the stem (window map over the space-to-depth page) and the seg tail (BN=16)
+//   conv_hs_kernel<BN>    halo activations + weights STREAMED through their own ring (BN = 128 / 256)
+//   conv_sw_kernel        operands swapped for 128 output channels: weights are the M=128 operand, 256 pixels (8x32
+//                         tile, halo views) the N operand; channel-major accumulators, transposed epilogue
+//
+// Reference semantics: Conv.forward_fuse (models/yolov5/common.py:48-49), Bottleneck add (common.py:104),
+// ConvTranspose2d+BN+ReLU (basemodel.py:26-28), Detect (yolo.py:23-44), UnetHead's final ConvT + Sigmoid
+// (basemodel.py:57-60) + postprocess_mask (inference.py:96-99).
 #include <cstdlib>
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -30,7 +36,6 @@ namespace ctd {
 
 constexpr int kTileW = 16, kTileH = 8;  // 128 grid pixels per tile
 constexpr int kThreads = 384;           // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warps 4-11 epilogue
-constexpr int kEpiWarps = 8;            // two warpgroups of 4 (one warp per TMEM lane quadrant) on alternate tiles
 constexpr int kEpiWarp0 = 4;
 
 template <int BN>
