@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libctd_b200.so")
 MAX_SRC = 3
 ABI_VERSION = 1
-PREC_FP16_TC, PREC_FP32_SIMT, PREC_FP16_SIMT = 0, 1, 2
+PREC_FP16_TC, PREC_FP32_SIMT, PREC_FP16_SIMT, PREC_SPLIT_TC = 0, 1, 2, 3
 
 
 class CtdOp(C.Structure):
@@ -38,13 +38,21 @@ class CtdDeviceOutputs(C.Structure):
                [("results_bytes", C.c_size_t)]
 
 
+# numpy mirror of `ctd_block` (include/ctd_b200.h)
+BLOCK_DTYPE = np.dtype([("xyxy", np.int32, (4,)), ("language", np.int32), ("vertical", np.int32), ("angle", np.int32),
+                        ("merged", np.int32), ("n_lines", np.int32), ("line_off", np.int32), ("n_dist", np.int32),
+                        ("dist_off", np.int32), ("font_is_float", np.int32), ("reserved", np.int32),
+                        ("font_size", np.float64), ("vec", np.float64, (2,)), ("norm", np.float64),
+                        ("weight", np.float64)], align=True)
+
 EXPORTS = ["ctd_create", "ctd_destroy", "ctd_last_error", "ctd_forward", "ctd_get_net_outputs", "ctd_get_mask_u8",
            "ctd_get_detections", "ctd_get_db_components", "ctd_last_forward_ms", "ctd_last_launch_count",
            "ctd_debug_read_buffer", "ctd_debug_write_buffer", "ctd_connected_components", "ctd_nms",
            "ctd_timer_start", "ctd_timer_stop", "ctd_profile_forward", "ctd_get_device_outputs",
            "ctd_get_text_lines", "ctd_seg_represent", "ctd_refine_mask", "ctd_submit", "ctd_collect",
            "ctd_results_bytes", "ctd_join", "ctd_forward_resized", "ctd_get_mask_u8_resized",
-           "ctd_resize_linear_u8"]
+           "ctd_resize_linear_u8", "ctd_debug_run_ops", "ctd_get_nms_status", "ctd_group_output",
+           "ctd_expand_textwindow"]
 
 _lib = None
 
@@ -94,8 +102,13 @@ def load_library():
     lib.ctd_forward_resized.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32]
     lib.ctd_get_mask_u8_resized.argtypes = [vp, i32, i32, i32, i32, vp]
     lib.ctd_resize_linear_u8.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32]
+    lib.ctd_debug_run_ops.argtypes = [vp, vp, i32, i32, i32, i32, i32]
+    lib.ctd_get_nms_status.argtypes = [vp, vp, C.POINTER(i32)]
+    lib.ctd_group_output.argtypes = [vp, vp, i32, vp, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, C.POINTER(i32)]
+    lib.ctd_expand_textwindow.argtypes = [i32, i32, vp, i32, vp]
     for name in EXPORTS[3:]:
         getattr(lib, name).restype = C.c_int
+    lib.ctd_expand_textwindow.restype = None
     _lib = lib
     return lib
 
@@ -211,6 +224,13 @@ class Engine:
         self._ck(self.lib.ctd_get_detections(self.h, _ptr(det), _ptr(cnt)))
         return [det[i, :cnt[i]].copy() for i in range(n)]
 
+    def nms_status(self, n=1):
+        """(candidates per page before the capacity cut, capacity): see ctd_get_nms_status."""
+        tot = np.zeros((n,), np.int32)
+        cap = C.c_int32()
+        self._ck(self.lib.ctd_get_nms_status(self.h, _ptr(tot), C.byref(cap)))
+        return tot, cap.value
+
     def db_components(self, want_bitmap=True, want_labels=True):
         n, h, w = self.shape
         bm = np.empty((n, h, w), np.uint8) if want_bitmap else None
@@ -319,6 +339,13 @@ class Engine:
         ch = self.program.bufs[tensor["buf"]][0]
         assert arr.shape == (n, h // tensor["down"], w // tensor["down"], ch), arr.shape
         self._ck(self.lib.ctd_debug_write_buffer(self.h, tensor["buf"], _ptr(arr), n, h, w))
+
+    def debug_run_ops(self, first, last, n, h, w, pages=None):
+        """run ops [first, last] only, on the current buffer contents (see ctd_debug_run_ops)."""
+        if pages is not None:
+            pages = np.ascontiguousarray(pages, dtype=np.uint8)
+        self._ck(self.lib.ctd_debug_run_ops(self.h, _ptr(pages), n, h, w, first, last))
+        self.shape = (n, h, w)
 
     # ---- stand-alone array kernels --------------------------------------------------------
     def connected_components(self, img, stats_cap=0):

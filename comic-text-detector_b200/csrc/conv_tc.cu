@@ -62,6 +62,59 @@ __device__ __forceinline__ float apply_act(float v) {
   else return v;
 }
 
+// Split-fp16 mode: full-precision activation functions (expf / true division: the fast intrinsics above carry
+// ~1e-6 relative error, 16 fp32 ulps, which the 1e-3 end-to-end budget of this mode cannot afford).
+template <int ACT>
+__device__ __forceinline__ float apply_act_precise(float v) {
+  if constexpr (ACT == CTD_ACT_SILU) return v / (1.0f + expf(-v));
+  else if constexpr (ACT == CTD_ACT_LEAKY) return fmaxf(v, 0.1f * v);
+  else if constexpr (ACT == CTD_ACT_RELU) return fmaxf(v, 0.f);
+  else if constexpr (ACT == CTD_ACT_SIGMOID) return 1.0f / (1.0f + expf(-v));
+  else return v;
+}
+
+// Split-fp16 mode epilogue: `ncols` (multiple of 4, <= 32) accumulator columns -> bias + activation (+ fp32 residual
+// read from the destination) -> FP32 NHWC, 16-byte stores.
+template <int ACT>
+__device__ __forceinline__ void epilogue_chunk_f32(const uint32_t* v, const float* __restrict__ bias_s,
+                                                   float* __restrict__ out, int ncols, bool residual) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (q * 4 >= ncols) break;
+    const float4 b = *reinterpret_cast<const float4*>(bias_s + q * 4);
+    float4 o;
+    o.x = apply_act_precise<ACT>(__uint_as_float(v[q * 4 + 0]) + b.x);
+    o.y = apply_act_precise<ACT>(__uint_as_float(v[q * 4 + 1]) + b.y);
+    o.z = apply_act_precise<ACT>(__uint_as_float(v[q * 4 + 2]) + b.z);
+    o.w = apply_act_precise<ACT>(__uint_as_float(v[q * 4 + 3]) + b.w);
+    if (residual) {
+      const float4 r = *reinterpret_cast<const float4*>(out + q * 4);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
+    *reinterpret_cast<float4*>(out + q * 4) = o;
+  }
+}
+
+template <int BN, int ACT>
+__device__ __forceinline__ void epilogue_store_f32(uint32_t tmem_row, const float* __restrict__ bias_s,
+                                                   float* __restrict__ out, int cout_left, bool valid, bool residual) {
+  if constexpr (BN >= 32) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v0[32];
+      tmem_ld_32x32(tmem_row + uint32_t(c0), v0);
+      tmem_ld_wait();
+      const int left = cout_left - c0;
+      if (valid && left > 0) epilogue_chunk_f32<ACT>(v0, bias_s + c0, out + c0, left < 32 ? left : 32, residual);
+    }
+  } else {
+    uint32_t t16[16];
+    tmem_ld_32x16(tmem_row, t16);
+    tmem_ld_wait();
+    if (valid && cout_left > 0) epilogue_chunk_f32<ACT>(t16, bias_s, out, cout_left < 16 ? cout_left : 16, residual);
+  }
+}
+
 // One 32-column chunk of the accumulator row owned by this thread: bias + activation (+ residual)
 // -> fp16 -> four 16-byte stores.  Straight-line code (no per-element branches), bias from smem.
 template <int ACT, bool RES>
@@ -258,7 +311,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t stage_tx = 128u * row_bytes + uint32_t(BN) * row_bytes;
   int kblocks_per_tap = 0;
   for (int s = 0; s < g.n_src; ++s) kblocks_per_tap += p.src_kblocks[s];
-  const int its_per_tile = g.taps * kblocks_per_tap;
+  const int n_terms = p.split ? 3 : 1;   // split-fp16 mode: (hi,hi) + (lo,hi) + (hi,lo) per K block
+  const int its_per_tile = g.taps * kblocks_per_tap * n_terms;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int n_nblk = g.cout_pad / BN;
   const int spatial_tiles = g.n_img * tiles_per_img;
@@ -315,15 +369,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const int q = p.tap_map[phase][tap];
           int kglob = tap * g.cin_total;
           for (int s = 0; s < g.n_src; ++s) {
-            for (int cb = 0; cb < p.src_kblocks[s]; ++cb, ++it) {
-              const int stage = it % Cfg::kStages;
-              const uint32_t par = ((it / Cfg::kStages) & 1) ^ 1;
-              mbar_wait_relaxed(empty_bar + 8 * stage, par);
-              mbar_arrive_expect_tx(full_bar + 8 * stage, stage_tx);
-              tma_load_4d(a_base + stage * Cfg::kABytes, &p.a_map[s][q], full_bar + 8 * stage, cb * kb, x0 + dx,
-                          y0 + dy, img);
-              tma_load_2d(b_base + stage * Cfg::kBBytes, &p.b_map, full_bar + 8 * stage, kglob + cb * kb,
-                          phase * g.cout_pad + nblk * BN);
+            for (int cb = 0; cb < p.src_kblocks[s]; ++cb) {
+              for (int term = 0; term < n_terms; ++term, ++it) {
+                // term 0: A hi x B hi; 1: A lo x B hi; 2: A hi x B lo (small terms ride in the same accumulator)
+                const int stage = it % Cfg::kStages;
+                const uint32_t par = ((it / Cfg::kStages) & 1) ^ 1;
+                mbar_wait_relaxed(empty_bar + 8 * stage, par);
+                mbar_arrive_expect_tx(full_bar + 8 * stage, stage_tx);
+                tma_load_4d(a_base + stage * Cfg::kABytes, &p.a_map[s][q], full_bar + 8 * stage, cb * kb, x0 + dx,
+                            y0 + dy, img + (term == 1 ? p.split_img_off : 0));
+                tma_load_2d(b_base + stage * Cfg::kBBytes, &p.b_map, full_bar + 8 * stage, kglob + cb * kb,
+                            phase * g.cout_pad + nblk * BN + (term == 2 ? p.split_row_off : 0));
+              }
             }
             kglob += g.src_c[s];
           }
@@ -386,7 +443,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + uint32_t(as * BN) + (uint32_t(quad * 32) << 16);
       const float* bias_t = bias_s + nblk * BN;
-      if (p.dst != nullptr) {
+      if (p.dst != nullptr && p.split) {
+        // split-fp16 mode: FP32 destination (same element offsets, 4-byte elements)
+        float* out32 = reinterpret_cast<float*>(p.dst) +
+                       (size_t(img) * g.dst_h * g.dst_w + size_t(valid ? oy : 0) * g.dst_w + (valid ? ox : 0)) * g.dst_cstride +
+                       g.dst_coff + nblk * BN;
+        const int cout_left = g.cout - nblk * BN;
+        const bool res = g.residual != 0;
+        switch (g.act) {
+          case CTD_ACT_SILU: epilogue_store_f32<BN, CTD_ACT_SILU>(tmem_row, bias_t, out32, cout_left, valid, res); break;
+          case CTD_ACT_LEAKY: epilogue_store_f32<BN, CTD_ACT_LEAKY>(tmem_row, bias_t, out32, cout_left, valid, res); break;
+          case CTD_ACT_RELU: epilogue_store_f32<BN, CTD_ACT_RELU>(tmem_row, bias_t, out32, cout_left, valid, res); break;
+          case CTD_ACT_SIGMOID: epilogue_store_f32<BN, CTD_ACT_SIGMOID>(tmem_row, bias_t, out32, cout_left, valid, res); break;
+          default: epilogue_store_f32<BN, CTD_ACT_NONE>(tmem_row, bias_t, out32, cout_left, valid, res); break;
+        }
+      } else if (p.dst != nullptr) {
         const int cout_left = g.cout - nblk * BN;
         bool done_tma = false;
         if constexpr (BN >= 64) {
@@ -1214,10 +1285,14 @@ static int pick_block_n(int cout_pad) {
 }
 
 const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
-                         const int src_coff[], const void* w16, const float* bias, __half* dst) {
+                         const int src_coff[], const void* w16, const float* bias, __half* dst, int split) {
   ConvTcParams& p = plan.p;
   memset(&p, 0, sizeof(p));
   p.g = g;
+  p.split = split ? 1 : 0;
+  p.split_img_off = g.n_img;
+  p.split_row_off = g.n_phase * g.cout_pad;
+  const int n_planes = split ? 2 : 1;   // hi | lo planes: images [0,n) | [n,2n) of the same buffer
   int kb = 64;
   for (int s = 0; s < g.n_src; ++s) {
     if (g.src_c[s] % 64 != 0 && kb > 32) kb = 32;
@@ -1237,7 +1312,7 @@ const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
     const size_t cs = size_t(g.src_cstride[s]);
     const char* base = static_cast<const char*>(src_ptr[s]) + size_t(src_coff[s]) * 2;
     if (g.in_stride == 1) {
-      cuuint64_t dims[4] = {cuuint64_t(g.src_c[s]), cuuint64_t(sw), cuuint64_t(sh), cuuint64_t(g.n_img)};
+      cuuint64_t dims[4] = {cuuint64_t(g.src_c[s]), cuuint64_t(sw), cuuint64_t(sh), cuuint64_t(g.n_img * n_planes)};
       cuuint64_t str[3] = {cs * 2, cs * 2 * sw, cs * 2 * sw * sh};
       cuuint32_t box[4] = {cuuint32_t(kb), kTileW, kTileH, 1};
       if (const char* e = encode_map(enc, &p.a_map[s][0], base, 4, dims, str, box, kb)) return e;
@@ -1245,7 +1320,7 @@ const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
       // parity views: pixel (2*yh+yp, 2*xh+xp)
       for (int q = 0; q < 4; ++q) {
         const int yp = q >> 1, xp = q & 1;
-        cuuint64_t dims[4] = {cuuint64_t(g.src_c[s]), cuuint64_t(sw / 2), cuuint64_t(sh / 2), cuuint64_t(g.n_img)};
+        cuuint64_t dims[4] = {cuuint64_t(g.src_c[s]), cuuint64_t(sw / 2), cuuint64_t(sh / 2), cuuint64_t(g.n_img * n_planes)};
         cuuint64_t str[3] = {cs * 2 * 2, cs * 2 * sw * 2, cs * 2 * sw * sh};
         cuuint32_t box[4] = {cuuint32_t(kb), kTileW, kTileH, 1};
         const char* b2 = base + (size_t(yp) * sw + xp) * cs * 2;
@@ -1270,7 +1345,9 @@ const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
   const int bn = pick_block_n(g.cout_pad);
   plan.block_n = bn;
   p.use_tma_store = 0;
-  if (bn >= 64 && dst != nullptr && g.cout % 64 == 0) {
+  if (split && ((g.dst_coff % 4) != 0 || (g.dst_cstride % 4) != 0 || (dst != nullptr && g.cout % 4 != 0)))
+    return "conv_tc (split): fp32 destination slice must be 16-byte aligned";
+  if (!split && bn >= 64 && dst != nullptr && g.cout % 64 == 0) {
     // destination slice as a 4-D tensor (channels of this op, x, y, image); deconv phases are parity views
     const size_t cs = size_t(g.dst_cstride);
     for (int ph = 0; ph < g.n_phase; ++ph) {
@@ -1284,7 +1361,7 @@ const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
     p.use_tma_store = 1;
   }
   {
-    cuuint64_t dims[2] = {cuuint64_t(g.k_total), cuuint64_t(g.n_phase) * cuuint64_t(g.cout_pad)};
+    cuuint64_t dims[2] = {cuuint64_t(g.k_total), cuuint64_t(g.n_phase) * cuuint64_t(g.cout_pad) * n_planes};
     cuuint64_t str[1] = {cuuint64_t(g.k_total) * 2};
     cuuint32_t box[2] = {cuuint32_t(kb), cuuint32_t(bn)};
     if (const char* e = encode_map(enc, &p.b_map, w16, 2, dims, str, box, kb)) return e;

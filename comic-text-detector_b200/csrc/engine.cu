@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <map>
 #include <string>
@@ -41,6 +42,12 @@ struct ctd_handle {
   char* d_blob = nullptr;
   size_t blob_bytes = 0;
   std::vector<void*> d_buf;
+  // split-fp16 mode (CTD_PREC_SPLIT_TC): d_buf holds the FP32 master copy of every activation; d_buf16[i] holds its
+  // fp16 hi | lo planes ([2*n][h][w][C], refreshed after every op that writes the buffer) = the MMA operands;
+  // d_wsplit holds per GEMM op the fp16 weight rows hi then lo (wsplit_off[op], bytes).
+  std::vector<void*> d_buf16;
+  char* d_wsplit = nullptr;
+  std::vector<size_t> wsplit_off;
   int elem = 2;  // bytes per activation element
   uint8_t* d_pages = nullptr;
   float* d_blks = nullptr;
@@ -57,6 +64,8 @@ struct ctd_handle {
   void* d_segrep_scratch = nullptr;
   void* d_refine_scratch = nullptr;
   size_t refine_scratch_cap = 0;
+  void* d_cc_scratch = nullptr;      // ctd_connected_components: grow-on-demand, any image size
+  size_t cc_scratch_cap = 0;
   uint8_t* d_io_scratch = nullptr;   // page upload / resized mask staging of the resize entry points
   size_t io_scratch_cap = 0;
   int16_t* d_line_boxes = nullptr;
@@ -113,9 +122,11 @@ extern "C" void ctd_destroy(ctd_handle* h) {
   for (auto& kv : h->plans)
     if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
   for (void* p : h->d_buf) cudaFree(p);
+  for (void* p : h->d_buf16) cudaFree(p);
+  cudaFree(h->d_wsplit);
   cudaFree(h->d_blob); cudaFree(h->d_pages); cudaFree(h->d_blks); cudaFree(h->d_mask); cudaFree(h->d_mask_u8);
   cudaFree(h->d_lines); cudaFree(h->d_bitmap); cudaFree(h->d_labels);
-  cudaFree(h->d_ccl_scratch); cudaFree(h->d_nms_ws); cudaFree(h->d_segrep_scratch); cudaFree(h->d_refine_scratch); cudaFree(h->d_io_scratch);
+  cudaFree(h->d_ccl_scratch); cudaFree(h->d_nms_ws); cudaFree(h->d_segrep_scratch); cudaFree(h->d_refine_scratch); cudaFree(h->d_cc_scratch); cudaFree(h->d_io_scratch);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->tev0) cudaEventDestroy(h->tev0);
@@ -184,7 +195,7 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
     const char* ov = getenv("CTD_OVERLAP");
     h->overlap = have_db && !(ov && ov[0] == '0');
   }
-  h->elem = cfg->precision == CTD_PREC_FP32_SIMT ? 4 : 2;
+  h->elem = (cfg->precision == CTD_PREC_FP32_SIMT || cfg->precision == CTD_PREC_SPLIT_TC) ? 4 : 2;
   auto bail = [&](int code) { std::string e = h->err; ctd_destroy(h); g_create_error = e; return code; };
 #define CKC(expr)                                                                                        \
   do {                                                                                                   \
@@ -232,6 +243,43 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
     const size_t bytes = nb * (mh / bufs[i].down) * (mw / bufs[i].down + 4) * bufs[i].channels * h->elem;
     CKC(cudaMalloc(&h->d_buf[i], bytes));
     CKC(cudaMemset(h->d_buf[i], 0, bytes));
+  }
+  if (cfg->precision == CTD_PREC_SPLIT_TC) {
+    h->d_buf16.assign(n_bufs, nullptr);
+    for (int i = 0; i < n_bufs; ++i) {
+      const size_t bytes = 2 * nb * (mh / bufs[i].down) * (mw / bufs[i].down + 4) * bufs[i].channels * 2;
+      CKC(cudaMalloc(&h->d_buf16[i], bytes));
+      CKC(cudaMemset(h->d_buf16[i], 0, bytes));
+    }
+    // weights: hi rows (the blob's fp16 copy = fp16(w32)) followed by lo rows fp16(w32 - hi), per GEMM op
+    h->wsplit_off.assign(size_t(n_ops), 0);
+    std::vector<__half> ws;
+    const char* hb = static_cast<const char*>(blob);
+    for (int i = 0; i < n_ops; ++i) {
+      const ctd_op& op = ops[i];
+      if (op.kind != CTD_OP_CONV && op.kind != CTD_OP_DECONV4 && op.kind != CTD_OP_DETECT) continue;
+      int cin = 0;
+      for (int k = 0; k < op.n_src; ++k) cin += op.src_c[k];
+      const int taps = op.kind == CTD_OP_DECONV4 ? 4 : op.ksize * op.ksize;
+      const int nph = op.kind == CTD_OP_DECONV4 ? 4 : 1;
+      const size_t cnt = size_t(nph) * op.cout_pad * taps * cin;
+      if (size_t(op.w32_off) + cnt * 4 > blob_bytes || size_t(op.w16_off) + cnt * 2 > blob_bytes) {
+        fail(h, CTD_E_INVALID, "op %d: weights outside the blob", i);
+        return bail(CTD_E_INVALID);
+      }
+      while (ws.size() % 128) ws.push_back(__float2half(0.f));   // 256-byte aligned rows for the tensor map
+      h->wsplit_off[size_t(i)] = ws.size() * 2;
+      const float* w32 = reinterpret_cast<const float*>(hb + op.w32_off);
+      const size_t base = ws.size();
+      ws.resize(base + 2 * cnt);
+      for (size_t k = 0; k < cnt; ++k) {
+        const __half hi = __float2half_rn(w32[k]);
+        ws[base + k] = hi;
+        ws[base + cnt + k] = __float2half_rn(w32[k] - __half2float(hi));
+      }
+    }
+    CKC(cudaMalloc(&h->d_wsplit, ws.size() * 2 + 256));
+    CKC(cudaMemcpy(h->d_wsplit, ws.data(), ws.size() * 2, cudaMemcpyHostToDevice));
   }
   const size_t px = nb * mh * mw;
   const int no = 5 + cfg->nc;
@@ -302,6 +350,41 @@ static int op_geom(ctd_handle* h, const ctd_op& op, int n, int ph, int pw, ConvG
 static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
   sp.tc.resize(h->ops.size());
   sp.has_tc.assign(h->ops.size(), 0);
+  if (h->cfg.precision == CTD_PREC_SPLIT_TC) {
+    // every GEMM-shaped op through conv_tc_kernel in split-fp16 form; stem / tails / thin ops stay on the fp32
+    // CUDA-core kernels (run_one_op)
+    for (size_t i = 0; i < h->ops.size(); ++i) {
+      const ctd_op& op = h->ops[i];
+      if (op.kind != CTD_OP_CONV && op.kind != CTD_OP_DECONV4 && op.kind != CTD_OP_DETECT) continue;
+      ConvGeom g;
+      if (int rc = op_geom(h, op, n, ph, pw, g)) return rc;
+      const void* src[CTD_MAX_SRC];
+      int coff[CTD_MAX_SRC];
+      for (int s = 0; s < op.n_src; ++s) {
+        src[s] = h->d_buf16[op.src_buf[s]];
+        coff[s] = op.src_coff[s];
+      }
+      __half* dst = op.kind == CTD_OP_DETECT ? nullptr : static_cast<__half*>(h->d_buf[op.dst_buf]);
+      const char* e = conv_tc_plan(sp.tc[i], h->enc, g, src, coff, h->d_wsplit + h->wsplit_off[i],
+                                   reinterpret_cast<const float*>(h->d_blob + op.b_off), dst, 1);
+      if (e) return fail(h, CTD_E_INVALID, "op %zu: %s", i, e);
+      if (op.kind == CTD_OP_DETECT) {
+        ConvTcParams& p = sp.tc[i].p;
+        p.blks = h->d_blks;
+        p.blks_rows_per_img = rows_per_image(ph, pw);
+        int row0 = 0;
+        for (int l = 0; l < op.aux; ++l) row0 += 3 * (ph / (8 << l)) * (pw / (8 << l));
+        p.level_row0 = row0;
+        p.nc = h->cfg.nc;
+        float hp[7];
+        cudaMemcpy(hp, h->d_blob + op.p_off, sizeof(hp), cudaMemcpyDeviceToHost);
+        p.det_stride = hp[0];
+        for (int k = 0; k < 6; ++k) p.anchor_wh[k] = hp[1 + k];
+      }
+      sp.has_tc[i] = 1;
+    }
+    return CTD_OK;
+  }
   if (h->cfg.precision != CTD_PREC_FP16_TC) return CTD_OK;
   for (size_t i = 0; i < h->ops.size(); ++i) {
     const ctd_op& op = h->ops[i];
@@ -449,10 +532,37 @@ static int run_op_thin(ctd_handle* h, const ctd_op& op, int n, int ph, int pw) {
   }
 }
 
+// split-fp16 mode: refresh the fp16 hi | lo planes of the channel slice op `i` has just written
+static int split_written_slice(ctd_handle* h, const ctd_op& op, int n, int ph, int pw, int* cnt) {
+  int buf = op.dst_buf, coff = op.dst_coff, c = op.cout;
+  if (op.kind == CTD_OP_SPPF_POOL) { buf = op.src_buf[0]; coff = op.src_coff[0] + op.src_c[0]; c = 3 * op.src_c[0]; }
+  else if (op.kind == CTD_OP_AVGPOOL2 || op.kind == CTD_OP_UPSAMPLE2) c = op.src_c[0];
+  else if (op.kind == CTD_OP_S2D) c = 16;
+  if (buf < 0 || c <= 0) return CTD_OK;
+  const ctd_bufdesc& b = h->bufs[buf];
+  const size_t npix = size_t(n) * (ph / b.down) * (pw / b.down);
+  __half* hi = static_cast<__half*>(h->d_buf16[buf]) + coff;
+  CK(split_planes_launch(static_cast<const float*>(h->d_buf[buf]) + coff, hi, hi + npix * b.channels, npix, c, b.channels,
+                         h->stream));
+  ++*cnt;
+  return CTD_OK;
+}
+
 static int run_one_op(ctd_handle* h, size_t i, int n, int ph, int pw, ShapePlan& sp, int* cnt) {
   const ctd_op& op = h->ops[i];
   const bool gemm = op.kind == CTD_OP_CONV || op.kind == CTD_OP_DECONV4 || op.kind == CTD_OP_DETECT;
   int rc = CTD_OK;
+  if (h->cfg.precision == CTD_PREC_SPLIT_TC) {
+    if (gemm) {
+      cudaError_t e = conv_tc_launch(sp.tc[i], h->stream);
+      rc = e == cudaSuccess ? CTD_OK : fail(h, CTD_E_CUDA, "conv_tc (split) op %zu: %s", i, cudaGetErrorString(e));
+    } else {
+      rc = run_op_thin<float>(h, op, n, ph, pw);
+    }
+    ++*cnt;
+    if (rc) return rc;
+    return split_written_slice(h, op, n, ph, pw, cnt);
+  }
   if (op.kind == CTD_OP_STEM && h->cfg.precision == CTD_PREC_FP16_TC) {
     // tensor-core stem: space-to-depth pre-pass into the padded window buffer, then the implicit GEMM
     cudaError_t e = s2d_launch<__half>(h->d_pages, n, ph, pw, static_cast<__half*>(h->d_buf[op.src_buf[0]]), 16, 0,
@@ -512,13 +622,13 @@ static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* lau
                       h->d_det_count, h->side2));
         CK(cudaEventRecord(h->ev_join2, h->side2));
         nms_forked = true;
-        cnt += 4;
+        cnt += 5;
       }
     }
     if (!nms_forked) {
       CK(nms_launch(h->d_blks, n, rows, h->cfg.nc, h->cfg.conf_thresh, h->cfg.nms_thresh, h->nms, h->d_det,
                     h->d_det_count, h->stream));
-      cnt += 4;
+      cnt += 5;
     } else {
       CK(cudaStreamWaitEvent(h->stream, h->ev_join2, 0));
     }
@@ -536,7 +646,7 @@ static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* lau
   // post-processing on the same stream
   CK(nms_launch(h->d_blks, n, rows, h->cfg.nc, h->cfg.conf_thresh, h->cfg.nms_thresh, h->nms, h->d_det,
                 h->d_det_count, h->stream));
-  cnt += 4;
+  cnt += 5;
   if (record) CK(cudaEventRecord(h->op_events[evi++], h->stream));
   CK(ccl_launch(h->d_bitmap, n, ph, pw, h->d_labels, h->d_ccl_scratch, h->d_nlabels, h->stream));
   cnt += 8;
@@ -562,7 +672,7 @@ static int prepare_forward(ctd_handle* h, int32_t n, int32_t ph, int32_t pw, Sha
     it = h->plans.emplace(key, std::move(sp)).first;
   }
   ShapePlan& sp = it->second;
-  if (h->cfg.use_graph && !sp.graph && h->cfg.precision == CTD_PREC_FP16_TC) {
+  if (h->cfg.use_graph && !sp.graph && (h->cfg.precision == CTD_PREC_FP16_TC || h->cfg.precision == CTD_PREC_SPLIT_TC)) {
     // DETECT params are fetched with a blocking memcpy in the SIMT path: plans are already built, so
     // capture only sees kernel launches (TC path).  SIMT paths run un-captured.
     cudaGraph_t graph;
@@ -766,6 +876,18 @@ extern "C" int ctd_get_detections(ctd_handle* h, float* det, int32_t* det_count)
   return CTD_OK;
 }
 
+extern "C" int ctd_get_nms_status(ctd_handle* h, int32_t* cand_total, int32_t* cap) {
+  if (!h) return CTD_E_INVALID;
+  CK(cudaSetDevice(h->cfg.device));
+  if (cap) *cap = h->nms.cap;
+  if (cand_total) {
+    const int n = h->have_forward ? h->n : 1;
+    CK(cudaMemcpyAsync(cand_total, h->nms.cand_total, size_t(n) * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return CTD_OK;
+}
+
 extern "C" int ctd_get_db_components(ctd_handle* h, uint8_t* bitmap, int32_t* labels, int32_t* n_labels) {
   NEED_FWD();
   const size_t px = size_t(h->n) * h->ph * h->pw;
@@ -930,34 +1052,77 @@ extern "C" int ctd_debug_write_buffer(ctd_handle* h, int32_t buf, const float* i
   if (e == cudaSuccess) {
     if (h->elem == 4) from_f32_kernel<float><<<unsigned((elems + 255) / 256), 256, 0, h->stream>>>(tmp, static_cast<float*>(h->d_buf[buf]), elems);
     else from_f32_kernel<__half><<<unsigned((elems + 255) / 256), 256, 0, h->stream>>>(tmp, static_cast<__half*>(h->d_buf[buf]), elems);
-    e = cudaStreamSynchronize(h->stream);
+    if (h->cfg.precision == CTD_PREC_SPLIT_TC) {
+      const size_t npix = elems / b.channels;
+      __half* hi = static_cast<__half*>(h->d_buf16[buf]);
+      e = split_planes_launch(static_cast<const float*>(h->d_buf[buf]), hi, hi + elems, npix, b.channels, b.channels, h->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   }
   cudaFree(tmp);
   CK(e);
   return CTD_OK;
 }
 
+extern "C" int ctd_debug_run_ops(ctd_handle* h, const uint8_t* pages, int32_t n, int32_t ph, int32_t pw, int32_t first_op,
+                                 int32_t last_op) {
+  if (!h) return CTD_E_INVALID;
+  if (first_op < 0 || last_op >= int(h->ops.size()) || first_op > last_op) return fail(h, CTD_E_INVALID, "bad op range");
+  if (n < 1 || n > h->cfg.max_batch || ph % 64 || pw % 64 || ph > h->cfg.max_h || pw > h->cfg.max_w || ph < 64 || pw < 64)
+    return fail(h, CTD_E_SHAPE, "bad shape");
+  CK(cudaSetDevice(h->cfg.device));
+  auto key = std::make_tuple(int(n), int(ph), int(pw));
+  auto it = h->plans.find(key);
+  if (it == h->plans.end()) {
+    ShapePlan sp;
+    if (int rc = build_plans(h, n, ph, pw, sp)) return rc;
+    it = h->plans.emplace(key, std::move(sp)).first;
+  }
+  if (pages) CK(cudaMemcpyAsync(h->d_pages, pages, size_t(n) * ph * pw * 3, cudaMemcpyHostToDevice, h->stream));
+  int cnt = 0;
+  for (int i = first_op; i <= last_op; ++i)
+    if (int rc = run_one_op(h, size_t(i), n, ph, pw, it->second, &cnt)) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  h->n = n; h->ph = ph; h->pw = pw;
+  h->have_forward = true;
+  h->last_launches = cnt;
+  return CTD_OK;
+}
+
 extern "C" int ctd_connected_components(ctd_handle* h, const uint8_t* img, int32_t ih, int32_t iw, int32_t* labels,
                                         int32_t* stats, int32_t stats_cap, int32_t* n_labels) {
   if (!h || !img || !labels || !n_labels) return CTD_E_INVALID;
-  if (size_t(ih) * iw > size_t(h->cfg.max_batch) * h->cfg.max_h * h->cfg.max_w)
-    return fail(h, CTD_E_CAPACITY, "image larger than the workspace");
+  if (ih < 1 || iw < 1 || size_t(ih) * iw > (size_t(1) << 28)) return fail(h, CTD_E_SHAPE, "bad image size %dx%d", ih, iw);
   CK(cudaSetDevice(h->cfg.device));
   const size_t px = size_t(ih) * iw;
-  // reuse the page-sized scratch: bitmap <- img
-  CK(cudaMemcpyAsync(h->d_bitmap, img, px, cudaMemcpyHostToDevice, h->stream));
-  CK(ccl_launch(h->d_bitmap, 1, ih, iw, h->d_labels, h->d_ccl_scratch, h->d_nlabels, h->stream));
-  CK(cudaMemcpyAsync(labels, h->d_labels, px * 4, cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaMemcpyAsync(n_labels, h->d_nlabels, 4, cudaMemcpyDeviceToHost, h->stream));
+  // own grow-on-demand scratch (any page size, independent of the net-input workspace; the results of the last
+  // forward stay intact): bitmap | labels | 3 ints/px of CCL scratch (reused for the stats table) | n_labels
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t o_lab = al(px), o_scr = o_lab + al(px * 4);
+  const size_t scr_bytes = al(std::max(px * 12, size_t(stats_cap > 0 ? stats_cap : 0) * 5 * 4));
+  const size_t o_nl = o_scr + scr_bytes, need = o_nl + 256;
+  if (need > h->cc_scratch_cap) {
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_cc_scratch);
+    h->d_cc_scratch = nullptr;
+    h->cc_scratch_cap = 0;
+    CK(cudaMalloc(&h->d_cc_scratch, need + need / 4));
+    h->cc_scratch_cap = need + need / 4;
+  }
+  uint8_t* base = static_cast<uint8_t*>(h->d_cc_scratch);
+  uint8_t* d_bitmap = base;
+  int32_t* d_labels = reinterpret_cast<int32_t*>(base + o_lab);
+  int32_t* d_scr = reinterpret_cast<int32_t*>(base + o_scr);
+  int32_t* d_nl = reinterpret_cast<int32_t*>(base + o_nl);
+  CK(cudaMemcpyAsync(d_bitmap, img, px, cudaMemcpyHostToDevice, h->stream));
+  CK(ccl_launch(d_bitmap, 1, ih, iw, d_labels, d_scr, d_nl, h->stream));
+  CK(cudaMemcpyAsync(labels, d_labels, px * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(n_labels, d_nl, 4, cudaMemcpyDeviceToHost, h->stream));
   if (stats && stats_cap > 0) {
-    int32_t* d_stats = reinterpret_cast<int32_t*>(h->d_ccl_scratch);  // scratch is free again after ccl_launch
-    if (size_t(stats_cap) * 5 > size_t(h->cfg.max_batch) * h->cfg.max_h * h->cfg.max_w * 3)
-      return fail(h, CTD_E_CAPACITY, "stats_cap too large");
-    CK(ccl_stats_launch(h->d_labels, ih, iw, d_stats, stats_cap, h->stream));
-    CK(cudaMemcpyAsync(stats, d_stats, size_t(stats_cap) * 5 * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(ccl_stats_launch(d_labels, ih, iw, d_scr, stats_cap, h->stream));   // scratch is free again after ccl_launch
+    CK(cudaMemcpyAsync(stats, d_scr, size_t(stats_cap) * 5 * 4, cudaMemcpyDeviceToHost, h->stream));
   }
   CK(cudaStreamSynchronize(h->stream));
-  h->have_forward = false;  // the page outputs were clobbered
   return CTD_OK;
 }
 

@@ -71,6 +71,13 @@ struct alignas(64) ConvTcParams {
   // ConvT 4x4 s2 (C -> 1); sigmoid -> f32 mask + truncated u8 mask at (2y+py, 2x+px)
   float* seg_f32;
   uint8_t* seg_u8;
+  // split-fp16 mode (CTD_PREC_SPLIT_TC, conv_tc_kernel only): every fp32 operand x is carried as two fp16 planes
+  // hi = fp16(x), lo = fp16(x - hi); a K block issues (hi,hi) + (lo,hi) + (hi,lo) into the same fp32 accumulator
+  // (~22 significant bits per operand), and the epilogue writes FP32.  Activation planes: image n_img + i of the
+  // same tensor map holds the lo plane of image i; weight lo rows follow the hi rows (row + split_row_off).
+  int split;
+  int split_img_off;
+  int split_row_off;
 };
 
 struct ConvTcPlan {
@@ -86,8 +93,10 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // Builds tensor maps + launch shape.  Returns nullptr on success, else an error string.
+// split != 0: split-fp16 mode (see ConvTcParams::split): src_ptr are the [2*n_img][h][w][C] fp16 hi|lo plane buffers,
+// w16 holds hi rows then lo rows, dst is an FP32 NHWC buffer.
 const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& g, const void* const src_ptr[],
-                         const int src_coff[], const void* w16, const float* bias, __half* dst);
+                         const int src_coff[], const void* w16, const float* bias, __half* dst, int split = 0);
 // Stem in tensor-core form: 3 filter rows x (4-pixel window x 16 channels) over the padded space-to-depth page
 // (`s2d`: [n][ph/2][pw/2 + 4][16] fp16), output [n][ph/2][pw/2][cstride] at channel offset `dst_coff`.
 const char* conv_tc_plan_stem(ConvTcPlan& plan, PFN_encodeTiled enc, const void* s2d, int n, int ph, int pw,
@@ -137,6 +146,10 @@ cudaError_t stem_launch(const uint8_t* pages, int n, int h, int w, const float* 
 template <typename T>
 cudaError_t s2d_launch(const uint8_t* pages, int n, int h, int w, T* dst, int dst_cstride, int dst_coff, int pitch_px,
                        int xoff, cudaStream_t s);
+// fp32 NHWC channel slice -> fp16 hi / lo planes (split-fp16 mode): hi = fp16(x), lo = fp16(x - hi).
+// src / hi / lo point at the first channel of the slice; `cstride` elements between pixels (same in all three).
+cudaError_t split_planes_launch(const float* src, __half* hi, __half* lo, size_t npix, int c, int cstride,
+                                cudaStream_t s);
 template <typename T>
 cudaError_t avgpool2_launch(const T* src, int n, int h, int w, int c, int src_cstride, T* dst, int dst_cstride,
                             cudaStream_t s);
@@ -159,7 +172,8 @@ cudaError_t db_tail_launch(const T* src, int n, int h, int w, int cstride, const
 // post-processing (postproc.cu)
 struct NmsWorkspace {
   float* cand;     // [n][cap][6]
-  int* cand_count; // [n]
+  int* cand_count; // [n] candidates in `cand` (<= cap after nms_overflow_kernel)
+  int* cand_total; // [n] candidates the page really had (> cap: the best `cap` by score were kept)
   float* sorted;   // [n][cap][6]
   unsigned long long* mask;  // [n][cap][cap/64]
   int cap;

@@ -15,7 +15,7 @@ constexpr int kMaxDet = 300;    // max_det (yolov5_utils.py:125)
 constexpr float kMaxWh = 4096.f;  // class offset (yolov5_utils.py:143,198)
 
 size_t nms_workspace_bytes(int n, int cap) {
-  return size_t(n) * cap * kCandStride * 4 * 2 + size_t(n) * 4 * 4 + size_t(n) * cap * (cap / 64) * 8;
+  return size_t(n) * cap * kCandStride * 4 * 2 + size_t(n) * 4 * 8 + size_t(n) * cap * (cap / 64) * 8;
 }
 void nms_workspace_bind(NmsWorkspace& ws, void* base, int n, int cap) {
   char* p = static_cast<char*>(base);
@@ -27,6 +27,8 @@ void nms_workspace_bind(NmsWorkspace& ws, void* base, int n, int cap) {
   ws.sorted = reinterpret_cast<float*>(p);
   p += size_t(n) * cap * kCandStride * 4;
   ws.cand_count = reinterpret_cast<int*>(p);
+  p += size_t(n) * 4 * 4;
+  ws.cand_total = reinterpret_cast<int*>(p);
 }
 
 // yolov5_utils.py:136,152,169-182: obj > conf -> cls *= obj -> xywh2xyxy -> best class -> conf > thres
@@ -60,6 +62,110 @@ __global__ void nms_filter_kernel(const float* __restrict__ blks, int rows, int 
   o[5] = float(bj);
   o[6] = __int_as_float(r);
   o[7] = 0.f;
+}
+
+// Overflow path (more candidates than the workspace holds, `cap`): the atomicAdd slots above are claimed in
+// scheduling order, so WHICH rows survived would be nondeterministic.  The reference keeps every candidate up to
+// max_nms = 30000 and beyond that the highest scores (yolov5_utils.py:143,191-194); here the cap is lower, so on
+// overflow this kernel rebuilds the page's candidate list as exactly the `cap` best rows by (score descending, row
+// ascending) -- a 3-level radix select over the score bits, then an ordered compaction -- and records the true
+// candidate count so the host can see that the cap was hit (ctd_get_nms_status).  One CTA per page; returns at once
+// when the page did not overflow.
+__device__ __forceinline__ unsigned nms_score_key(const float* __restrict__ x, int no, float conf_thres, int* cls) {
+  const float obj = x[4];
+  if (!(obj > conf_thres)) return 0u;
+  float best = -INFINITY;
+  int bj = 0;
+  for (int j = 5; j < no; ++j) {
+    const float c = __fmul_rn(x[j], obj);
+    if (c > best) {
+      best = c;
+      bj = j - 5;
+    }
+  }
+  if (!(best > conf_thres)) return 0u;
+  *cls = bj;
+  return __float_as_uint(best);   // positive floats: the bit pattern is monotone in the value
+}
+
+__global__ void __launch_bounds__(1024) nms_overflow_kernel(const float* __restrict__ blks, int rows, int no,
+                                                            float conf_thres, float* __restrict__ cand,
+                                                            int* __restrict__ cand_count, int* __restrict__ cand_total,
+                                                            int cap) {
+  __shared__ int hist[2048];
+  __shared__ unsigned s_prefix, s_maskbits;
+  __shared__ int s_need, s_base_take, s_base_tie;
+  __shared__ int wsum_take[32], wsum_tie[32];
+  const int img = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int total = cand_count[img];
+  if (t == 0) cand_total[img] = total;
+  if (total <= cap) return;
+  const float* pb = blks + size_t(img) * rows * no;
+  if (t == 0) { s_prefix = 0u; s_maskbits = 0u; s_need = cap; }
+  const int shifts[3] = {21, 10, 0}, nbins[3] = {2048, 2048, 1024};
+  for (int lvl = 0; lvl < 3; ++lvl) {
+    for (int i = t; i < 2048; i += 1024) hist[i] = 0;
+    __syncthreads();
+    const unsigned prefix = s_prefix, maskbits = s_maskbits;
+    for (int r = t; r < rows; r += 1024) {
+      int cls;
+      const unsigned key = nms_score_key(pb + size_t(r) * no, no, conf_thres, &cls);
+      if (key != 0u && (key & maskbits) == prefix) atomicAdd(&hist[(key >> shifts[lvl]) & unsigned(nbins[lvl] - 1)], 1);
+    }
+    __syncthreads();
+    if (t == 0) {
+      int need = s_need, cum = 0, digit = 0;
+      for (int b = nbins[lvl] - 1; b >= 0; --b) {
+        if (cum + hist[b] >= need) { digit = b; break; }
+        cum += hist[b];
+      }
+      s_need = need - cum;                       // still to take among keys sharing the extended prefix
+      s_prefix = prefix | (unsigned(digit) << shifts[lvl]);
+      s_maskbits = maskbits | (unsigned(nbins[lvl] - 1) << shifts[lvl]);
+    }
+    __syncthreads();
+  }
+  const unsigned T = s_prefix;                   // key of the cap-th best score
+  const int need_ties = s_need;                  // rows with key == T to take, lowest row index first
+  if (t == 0) { s_base_take = 0; s_base_tie = 0; }
+  __syncthreads();
+  float* out = cand + size_t(img) * cap * kCandStride;
+  for (int r0 = 0; r0 < rows; r0 += 1024) {
+    const int r = r0 + t;
+    int cls = 0;
+    unsigned key = 0u;
+    if (r < rows) key = nms_score_key(pb + size_t(r) * no, no, conf_thres, &cls);
+    const bool tie = key == T && key != 0u;
+    const unsigned tb = __ballot_sync(0xffffffffu, tie);
+    if (lane == 0) wsum_tie[wid] = __popc(tb);
+    __syncthreads();
+    int tie_rank = s_base_tie + __popc(tb & ((1u << lane) - 1u));
+    for (int w2 = 0; w2 < wid; ++w2) tie_rank += wsum_tie[w2];
+    const bool take = key > T || (tie && tie_rank < need_ties);
+    const unsigned kb = __ballot_sync(0xffffffffu, take);
+    if (lane == 0) wsum_take[wid] = __popc(kb);
+    __syncthreads();
+    if (take) {
+      int slot = s_base_take + __popc(kb & ((1u << lane) - 1u));
+      for (int w2 = 0; w2 < wid; ++w2) slot += wsum_take[w2];
+      if (slot < cap) {
+        const float* x = pb + size_t(r) * no;
+        float* o = out + size_t(slot) * kCandStride;
+        const float hw = x[2] / 2.f, hh = x[3] / 2.f;
+        o[0] = x[0] - hw; o[1] = x[1] - hh; o[2] = x[0] + hw; o[3] = x[1] + hh;
+        o[4] = __uint_as_float(key); o[5] = float(cls); o[6] = __int_as_float(r); o[7] = 0.f;
+      }
+    }
+    __syncthreads();
+    if (t == 0) {
+      int a = 0, b = 0;
+      for (int w2 = 0; w2 < 32; ++w2) { a += wsum_take[w2]; b += wsum_tie[w2]; }
+      s_base_take += a;
+      s_base_tie += b;
+    }
+    __syncthreads();
+  }
+  if (t == 0) cand_count[img] = cap;
 }
 
 // stable descending sort by score (ties: original row order) -- torchvision nms_kernel sorts with
@@ -225,6 +331,7 @@ cudaError_t nms_launch(const float* blks, int n, int rows, int nc, float conf, f
   if (e != cudaSuccess) return e;
   // rows of `mask` below the diagonal block are never read; words at/after are always written
   nms_filter_kernel<<<dim3((rows + 255) / 256, n), 256, 0, s>>>(blks, rows, 5 + nc, conf, ws.cand, ws.cand_count, ws.cap);
+  nms_overflow_kernel<<<n, 1024, 0, s>>>(blks, rows, 5 + nc, conf, ws.cand, ws.cand_count, ws.cand_total, ws.cap);
   if (ws.cap == 4096) nms_sort_kernel<4096><<<n, 1024, 0, s>>>(ws.cand, ws.cand_count, ws.sorted, ws.cap);
   else if (ws.cap == 1024) nms_sort_kernel<1024><<<n, 1024, 0, s>>>(ws.cand, ws.cand_count, ws.sorted, ws.cap);
   else return cudaErrorInvalidValue;

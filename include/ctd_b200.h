@@ -94,7 +94,10 @@ typedef struct ctd_bufdesc {
 enum ctd_precision {
   CTD_PREC_FP16_TC = 0,   /* fp16 storage, tcgen05 implicit GEMM, fp32 accumulate (default) */
   CTD_PREC_FP32_SIMT = 1, /* fp32 storage + CUDA-core fp32 kernels ("vs reference fp32" config) */
-  CTD_PREC_FP16_SIMT = 2  /* fp16 storage + CUDA-core kernels (bisecting aid)               */
+  CTD_PREC_FP16_SIMT = 2, /* fp16 storage + CUDA-core kernels (bisecting aid)               */
+  CTD_PREC_SPLIT_TC = 3   /* fp32 storage; tcgen05 with every operand split into fp16 hi + lo planes
+                             (hi*hi + lo*hi + hi*lo, fp32 accumulate: ~22 significant bits) -- the
+                             tensor-core path that meets the 1e-3 "vs reference fp32" tolerance  */
 };
 
 typedef struct ctd_config {
@@ -144,6 +147,13 @@ CTD_API int ctd_get_mask_u8(ctd_handle* h, uint8_t* mask_u8);
  * [x1,y1,x2,y2,conf,cls] f32, score-descending, at most 300 per page.
  * det: HOST f32 [n][300][6]; det_count: HOST i32 [n].                                      */
 CTD_API int ctd_get_detections(ctd_handle* h, float* det, int32_t* det_count);
+/* Candidate capacity of the NMS stage.  The reference keeps up to max_nms = 30000 candidates per page
+ * (yolov5_utils.py:143,191-194); this engine holds *cap = 4096.  A page with more rows above conf_thresh keeps
+ * exactly the 4096 best by (score descending, row ascending) -- deterministic, and identical to the reference
+ * whenever the reference's own 300-detection cut (max_det) is reached inside those rows.  cand_total: HOST i32 [n],
+ * the number of candidates each page of the last forward (or the last ctd_nms call, n = 1) really had, so a caller
+ * can detect cand_total[i] > *cap.  Either pointer may be NULL.                                */
+CTD_API int ctd_get_nms_status(ctd_handle* h, int32_t* cand_total, int32_t* cap);
 
 /* `SegDetectorRepresenter.binarize` + connected components of the shrink map
  * (db_utils.py:71-72 and the labelling findContours/connectedComponents imply):
@@ -208,6 +218,13 @@ CTD_API int ctd_debug_read_buffer(ctd_handle* h, int32_t buf, float* out, size_t
  * storage type) for a forward of shape (n, ph, pw); used with programs that have no STEM op.  */
 CTD_API int ctd_debug_write_buffer(ctd_handle* h, int32_t buf, const float* in, int32_t n, int32_t ph, int32_t pw);
 
+/* Debug/unit tests: run only ops [first_op, last_op] of the program on the CURRENT buffer contents (fill sources
+ * with ctd_debug_write_buffer, read the result with ctd_debug_read_buffer): one launch plan of the real network at
+ * the real shape, checked in isolation.  `pages` (HOST u8 [n][ph][pw][3]) may be NULL unless the range contains
+ * the STEM op.  Synchronous, never graph-captured, no post-processing.                              */
+CTD_API int ctd_debug_run_ops(ctd_handle* h, const uint8_t* pages, int32_t n, int32_t ph, int32_t pw, int32_t first_op,
+                              int32_t last_op);
+
 /* ---- measurement / interop ------------------------------------------------------------------
  * CUDA-event timer on the ENGINE stream (bench.py times K forwards between start and stop).    */
 CTD_API int ctd_timer_start(ctd_handle* h);
@@ -256,6 +273,43 @@ CTD_API int ctd_seg_represent(ctd_handle* h, const float* pred, int32_t ih, int3
  * out HOST u8 [ih][iw] = mask_refined.  ih*iw must be a multiple of 4.                                */
 CTD_API int ctd_refine_mask(ctd_handle* h, const uint8_t* img, const uint8_t* mask, int32_t ih, int32_t iw,
                             const int32_t* windows, int32_t n_win, int32_t refine_mode, uint8_t* out);
+
+/* ---- line -> block grouping (host C++, no GPU needed) ---------------------------------------------
+ * `group_output(blks, lines, im_w, im_h, mask, sort_blklist)` (utils/textblock.py:421-508) with its callees
+ * examine_textblk / split_textblk / try_merge_textline / merge_textlines / sort_textblk_list (267-419) and
+ * TextBlock.adjust_bbox / sort_lines (87-105).  One record per resulting TextBlock, field for field
+ * (utils/textblock.py:12-85; only the fields group_output assigns are carried).                      */
+typedef struct ctd_block {
+  int32_t xyxy[4];       /* TextBlock.xyxy                                                  */
+  int32_t language;      /* index into LANG_LIST = ['eng', 'ja', 'unknown'] (textblock.py:9) */
+  int32_t vertical;      /* TextBlock.vertical                                              */
+  int32_t angle;         /* TextBlock.angle (degrees)                                       */
+  int32_t merged;        /* TextBlock.merged                                                */
+  int32_t n_lines;       /* len(TextBlock.lines); rows line_off .. line_off+n_lines-1 of `lines_out` */
+  int32_t line_off;
+  int32_t n_dist;        /* len(TextBlock.distance) (differs from n_lines for split blocks: the reference
+                            deep-copies the parent's distance array, textblock.py:397,412)   */
+  int32_t dist_off;
+  int32_t font_is_float; /* python type of font_size: int until try_merge_textline averages it */
+  int32_t reserved;
+  double font_size;      /* TextBlock.font_size                                             */
+  double vec[2];         /* TextBlock.vec                                                   */
+  double norm;           /* TextBlock.norm                                                  */
+  double weight;         /* TextBlock.weight (reading-order key, -1 when sort_blklist = 0)  */
+} ctd_block;
+
+/* blk_xyxy i32 [n_blk][4], blk_cls i32 [n_blk]: the detector rows after postprocess_yolo (inference.py:101-114);
+ * lines i32 [n_lines][4][2]: the kept text-line quads in page coordinates; mask u8 [im_h][im_w] or NULL.
+ * Results: blocks_out[*n_blocks], lines_out i32 [..][4][2], dist_out f64 [..].  Returns CTD_E_CAPACITY (with
+ * *n_blocks set) when an output array is too small: blocks <= n_blk + n_lines, lines <= n_lines + n_blk,
+ * distances <= (n_lines + n_blk) * max lines per block.  Pure host code, thread-safe, needs no handle. */
+CTD_API int ctd_group_output(const int32_t* blk_xyxy, const int32_t* blk_cls, int32_t n_blk, const int32_t* lines,
+                             int32_t n_lines, int32_t im_w, int32_t im_h, const uint8_t* mask, int32_t sort_blklist,
+                             ctd_block* blocks_out, int32_t blocks_cap, int32_t* lines_out, int32_t lines_cap,
+                             double* dist_out, int32_t dist_cap, int32_t* n_blocks);
+/* `expand_textwindow(img.shape, xyxy, expand_r)` (utils/imgproc_utils.py:151-161) followed by the index
+ * normalisation of the python slice `img[y1:y2, x1:x2]` (negative bounds wrap, then clamp): win = x1,y1,x2,y2.  */
+CTD_API void ctd_expand_textwindow(int32_t im_w, int32_t im_h, const int32_t* xyxy, int32_t expand_r, int32_t* win);
 
 /* utils/yolov5_utils.py:124-218 on a caller-supplied prediction tensor (HOST f32
  * [rows][5+nc]); output as ctd_get_detections for one page.                                */

@@ -26,18 +26,43 @@ def _blob(prog, off, count, dtype):
     return torch.from_numpy(np.frombuffer(prog.blob, dtype=dtype, count=count, offset=off).copy())
 
 
-def run_program(prog, pages, use_fp16_weights=False):
-    """pages u8 [n][h][w][3] -> (blks, mask, lines) like the engine's net outputs."""
-    n, h, w, _ = pages.shape
-    bufs = [torch.zeros(n, c, h // d, w // d) for c, d in prog.bufs]  # NCHW here
-    nc = prog.nc
-    no = 5 + nc
-    rows = 3 * ((h // 8) * (w // 8) + (h // 16) * (w // 16) + (h // 32) * (w // 32))
-    blks = torch.zeros(n, rows, no)
-    mask = lines = None
-    for op in prog.ops:
+class Interp:
+    """Step-by-step interpreter.  storage='f32': exact fp32 reference of the program.  storage='f16': emulation of
+    the tensor-core engine's numerics -- fp16 weights, every activation rounded to fp16 when it is stored, fp32
+    accumulation, the stem in its space-to-depth window form, the seg tail in its 3x3 / 4-phase fp16 form."""
+
+    def __init__(self, prog, pages, storage="f32"):
+        self.prog, self.pages, self.f16 = prog, pages, storage == "f16"
+        n, h, w, _ = pages.shape
+        self.n, self.h, self.w = n, h, w
+        self.bufs = [torch.zeros(n, c, h // d, w // d) for c, d in prog.bufs]  # NCHW here
+        self.no = 5 + prog.nc
+        rows = 3 * ((h // 8) * (w // 8) + (h // 16) * (w // 16) + (h // 32) * (w // 32))
+        self.blks = torch.zeros(n, rows, self.no)
+        self.mask = self.lines = None
+
+    def q(self, x):
+        return x.half().float() if self.f16 else x
+
+    def buf_nhwc(self, b):
+        return np.ascontiguousarray(self.bufs[b].permute(0, 2, 3, 1).numpy())
+
+    def written(self, op):
+        """(buf, coff, c) of the slice op writes, or None for ops writing engine outputs."""
         k = op["kind"]
-        srcs = [bufs[op["src_buf"][i]][:, op["src_coff"][i]:op["src_coff"][i] + op["src_c"][i]] for i in range(op["n_src"])]
+        if k == cc.OP_SPPF_POOL:
+            return op["src_buf"][0], op["src_coff"][0] + op["src_c"][0], 3 * op["src_c"][0]
+        if op["dst_buf"] < 0:
+            return None
+        c = op["cout"] if k in (cc.OP_STEM, cc.OP_CONV, cc.OP_DECONV4) else (16 if k == cc.OP_S2D else op["src_c"][0])
+        return op["dst_buf"], op["dst_coff"], c
+
+    def step(self, i):
+        prog, pages, bufs, n, h, w, no = self.prog, self.pages, self.bufs, self.n, self.h, self.w, self.no
+        use_fp16_weights = self.f16
+        op = prog.ops[i]
+        k = op["kind"]
+        srcs = [bufs[op["src_buf"][j]][:, op["src_coff"][j]:op["src_coff"][j] + op["src_c"][j]] for j in range(op["n_src"])]
         if k == cc.OP_STEM and use_fp16_weights:
             # tensor-core form of the stem: window-layout fp16 weights over the space-to-depth page
             x = torch.from_numpy(np.ascontiguousarray(pages.transpose(0, 3, 1, 2)).astype(np.float32) / 255).half().float()
@@ -49,8 +74,8 @@ def run_program(prog, pages, use_fp16_weights=False):
             wt = ww.permute(0, 3, 1, 2)  # [co][ch][a][b]
             b = _blob(prog, op["b_off"], op["cout"], np.float32)
             y = _act(F.conv2d(s2d, wt, b, 1, 1), op["act"])
-            bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["cout"]] = y
-            continue
+            bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["cout"]] = self.q(y)
+            return
         cin = sum(op["src_c"][:op["n_src"]])
         if k == cc.OP_STEM:
             x = torch.from_numpy(np.ascontiguousarray(pages.transpose(0, 3, 1, 2)).astype(np.float32) / 255)
@@ -64,7 +89,7 @@ def run_program(prog, pages, use_fp16_weights=False):
             for dy in range(2):
                 for dx in range(2):
                     y[:, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3] = x[:, :, dy::2, dx::2]
-            bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + 16] = y
+            bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + 16] = self.q(y)
         elif k in (cc.OP_CONV, cc.OP_DETECT):
             ks, st = op["ksize"], op["stride"]
             K = ks * ks * cin
@@ -80,7 +105,7 @@ def run_program(prog, pages, use_fp16_weights=False):
                 dst = bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["cout"]]
                 if op["residual"]:
                     y = y + dst
-                bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["cout"]] = y
+                bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["cout"]] = self.q(y)
             else:
                 prm = _blob(prog, op["p_off"], 7, np.float32)
                 stride, anch = float(prm[0]), prm[1:].view(3, 2)
@@ -92,7 +117,7 @@ def run_program(prog, pages, use_fp16_weights=False):
                 out[..., 0:2] = (y[..., 0:2] * 2 - 0.5 + grid) * stride
                 out[..., 2:4] = (y[..., 2:4] * 2) ** 2 * anch.view(1, 3, 1, 1, 2)
                 r0 = sum(3 * (h // (8 << l)) * (w // (8 << l)) for l in range(op["aux"]))
-                blks[:, r0:r0 + 3 * ny * nx] = out.reshape(bs, -1, no)
+                self.blks[:, r0:r0 + 3 * ny * nx] = out.reshape(bs, -1, no)
         elif k == cc.OP_DECONV4:
             K = 4 * cin
             wk = (_blob(prog, op["w16_off"], 4 * op["cout_pad"] * K, np.float16).float() if use_fp16_weights
@@ -112,9 +137,9 @@ def run_program(prog, pages, use_fp16_weights=False):
                     acc += torch.einsum("nchw,oc->nohw", xs, wk[ph, :op["cout"], t])
                 out[:, :, py::2, px::2] = acc
             y = _act(out + b.view(1, -1, 1, 1), op["act"])
-            bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["cout"]] = y
+            bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["cout"]] = self.q(y)
         elif k == cc.OP_AVGPOOL2:
-            bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["src_c"][0]] = F.avg_pool2d(srcs[0], 2, 2)
+            bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["src_c"][0]] = self.q(F.avg_pool2d(srcs[0], 2, 2))
         elif k == cc.OP_SPPF_POOL:
             c = op["src_c"][0]
             c0 = op["src_coff"][0]
@@ -127,8 +152,19 @@ def run_program(prog, pages, use_fp16_weights=False):
             bufs[op["dst_buf"]][:, op["dst_coff"]:op["dst_coff"] + op["src_c"][0]] = F.interpolate(srcs[0], scale_factor=2, mode="nearest")
         elif k == cc.OP_SEG_TAIL:
             c = op["src_c"][0]
-            wt = _blob(prog, op["p_off"], c * 16, np.float32).view(c, 1, 4, 4)
-            mask = torch.sigmoid(F.conv_transpose2d(srcs[0], wt, None, 2, 1))
+            if use_fp16_weights and op["w16_off"] > 0:
+                # tensor-core form: 3x3 conv with the 4 sub-pixel phases as output channels, fp16 weights
+                wc = _blob(prog, op["w16_off"], 16 * 9 * c, np.float16).float().view(16, 3, 3, c)[:4].permute(0, 3, 1, 2)
+                y = F.conv2d(srcs[0], wc, None, 1, 1)                       # [n][4][h][w], phase = py*2+px
+                nb, _, ih, iw = y.shape
+                out = torch.zeros(nb, 1, 2 * ih, 2 * iw)
+                for py in range(2):
+                    for px in range(2):
+                        out[:, 0, py::2, px::2] = y[:, py * 2 + px]
+                self.mask = torch.sigmoid(out)
+            else:
+                wt = _blob(prog, op["p_off"], c * 16, np.float32).view(c, 1, 4, 4)
+                self.mask = torch.sigmoid(F.conv_transpose2d(srcs[0], wt, None, 2, 1))
         elif k == cc.OP_DB_TAIL:
             prm = _blob(prog, op["p_off"], 2 * 1105, np.float32)
             outs = []
@@ -139,5 +175,16 @@ def run_program(prog, pages, use_fp16_weights=False):
                 x = srcs[0][:, b_ * 16:(b_ + 1) * 16]
                 t = F.relu(F.conv_transpose2d(x, w3, b3, 2))
                 outs.append(torch.sigmoid(F.conv_transpose2d(t, w6, b6, 2)))
-            lines = torch.cat(outs, 1)
-    return blks, mask, lines
+            self.lines = torch.cat(outs, 1)
+
+
+def run_program(prog, pages, use_fp16_weights=False, storage=None):
+    """pages u8 [n][h][w][3] -> (blks, mask, lines) like the engine's net outputs.  storage='f16' emulates the
+    tensor-core engine (fp16 weights AND fp16 activation storage); use_fp16_weights alone keeps fp32 activations."""
+    it = Interp(prog, pages, storage or "f32")
+    if use_fp16_weights and storage is None:
+        it.f16 = True
+        it.q = lambda x: x          # historical mode: fp16 weights, fp32 activations
+    for i in range(len(prog.ops)):
+        it.step(i)
+    return it.blks, it.mask, it.lines

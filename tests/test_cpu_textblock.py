@@ -1,6 +1,9 @@
-"""not-gpu: host-side line -> block grouping (comic-text-detector_b200/textblock.py) against the
-unmodified reference `utils.textblock.group_output` on identical random inputs (build container), and
-against golden results the reference produced (tests/golden/group_output.json, everywhere)."""
+"""not-gpu: the native line -> block grouping (`ctd_group_output`, csrc/group.cpp, called through
+comic-text-detector_b200/textblock.py) AND the oracle's python restatement (oracle/textblock_ref.py) against the
+unmodified reference `utils.textblock.group_output` on identical random inputs (build container), and against golden
+results the reference produced (tests/golden/group_output.json, everywhere).  Integer fields, structure and order must
+be identical; float fields are compared to 1e-12 relative for the native code (glibc acos/sin vs numpy's SIMD
+kernels may differ in the last ulp) and exactly for the python restatement."""
 import json
 import os
 import sys
@@ -10,7 +13,7 @@ import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from ctd_b200 import textblock as tb  # noqa: E402
-from oracle import ref_shim  # noqa: E402
+from oracle import ref_shim, textblock_ref  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "group_output.json")
 needs_ref = pytest.mark.skipif(not ref_shim.available(), reason="/root/reference not present on this box")
@@ -65,22 +68,72 @@ def _run(fn, case):
     return [blk_summary(b) for b in fn(blks, lines, w, h, mask.copy())]
 
 
+FLOAT_KEYS = ("font_size", "distance", "vec", "norm", "weight")
+
+
+def assert_same_blocks(got, ref, rel=1e-12):
+    """integer fields / structure exactly, float fields to `rel` (NaN == NaN)."""
+    assert len(got) == len(ref), (len(got), len(ref))
+    for i, (g, r) in enumerate(zip(got, ref)):
+        for k in r:
+            if k in FLOAT_KEYS:
+                a, b = np.atleast_1d(np.array(g[k], np.float64)), np.atleast_1d(np.array(r[k], np.float64))
+                assert a.shape == b.shape, (i, k, a.shape, b.shape)
+                assert np.allclose(a, b, rtol=rel, atol=0, equal_nan=True), (i, k, g[k], r[k])
+            else:
+                assert g[k] == r[k], (i, k, g[k], r[k])
+
+
 @needs_ref
 @pytest.mark.parametrize("seed", range(24))
-def test_group_output_equals_reference(seed):
+def test_python_restatement_equals_reference(seed):
     ns = ref_shim.load()
     case = make_case(seed)
-    assert _run(tb.group_output, case) == _run(ns.textblock.group_output, case)
+    assert _run(textblock_ref.group_output, case) == _run(ns.textblock.group_output, case)
 
 
-def test_group_output_golden():
+@needs_ref
+@pytest.mark.parametrize("seed", range(64))
+def test_native_group_output_equals_reference(seed):
+    ns = ref_shim.load()
+    case = make_case(seed) if seed < 48 else make_case(seed, 1536, 1024)     # landscape pages halve the grid width
+    assert_same_blocks(_run(tb.group_output, case), _run(ns.textblock.group_output, case))
+
+
+def test_native_group_output_golden():
     gold = json.load(open(GOLD))
     for seed, ref in gold.items():
-        assert _run(tb.group_output, make_case(int(seed))) == ref, seed
+        assert_same_blocks(_run(tb.group_output, make_case(int(seed))), ref)
+
+
+@pytest.mark.parametrize("seed", range(100, 140))
+def test_native_group_output_equals_python_restatement(seed):
+    """runs everywhere (also on the GPU box, where /root/reference is absent)"""
+    case = make_case(seed) if seed % 3 else make_case(seed, 1400, 904)
+    assert_same_blocks(_run(tb.group_output, case), _run(textblock_ref.group_output, case))
+
+
+def test_group_output_edge_inputs():
+    mask = np.zeros((64, 64), np.uint8)
+    none = (np.zeros((0, 4), np.int32), np.zeros((0,), np.int32), np.zeros((0,), np.float32))
+    assert tb.group_output(none, [], 64, 64, mask) == []
+    # one detector box, no lines, no mask under it -> dropped; with mask -> one synthetic line (xywh2xyxypoly)
+    one = (np.array([[8, 8, 40, 24]], np.int32), np.array([0], np.int32), np.array([0.9], np.float32))
+    assert tb.group_output(one, [], 64, 64, mask) == []
+    mask[:] = 255
+    out = tb.group_output(one, [], 64, 64, mask)
+    ref = textblock_ref.group_output(one, [], 64, 64, mask)
+    assert_same_blocks([blk_summary(b) for b in out], [blk_summary(b) for b in ref])
+    assert out[0].lines == [[[6, 8], [42, 8], [42, 24], [6, 24]]] or len(out[0].lines) == 1
+    # a box hanging off the page: python slice semantics on the mask (negative indices wrap)
+    off = (np.array([[-20, -10, 30, 30]], np.int32), np.array([1], np.int32), np.array([0.9], np.float32))
+    a = [blk_summary(b) for b in tb.group_output(off, [], 64, 64, mask)]
+    b = [blk_summary(b) for b in textblock_ref.group_output(off, [], 64, 64, mask)]
+    assert_same_blocks(a, b)
 
 
 def test_quads_intersect():
     sq = [(0, 0), (4, 0), (4, 3), (0, 3)]
-    assert tb.quads_intersect(sq, [(4, 3), (6, 3), (6, 5), (4, 5)])
-    assert not tb.quads_intersect(sq, [(5, 0), (6, 0), (6, 1), (5, 1)])
-    assert tb.quads_intersect(sq, [(1, 1), (2, 1), (2, 2), (1, 2)])
+    assert textblock_ref.quads_intersect(sq, [(4, 3), (6, 3), (6, 5), (4, 5)])
+    assert not textblock_ref.quads_intersect(sq, [(5, 0), (6, 0), (6, 1), (5, 1)])
+    assert textblock_ref.quads_intersect(sq, [(1, 1), (2, 1), (2, 2), (1, 2)])

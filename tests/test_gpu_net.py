@@ -1,9 +1,14 @@
 """-m gpu: the whole forward pass (backbone + both heads) through the C-ABI against the oracle
 (oracle/net_ref.py, pinned bit-identical to the unmodified reference in the build container).
 
-Tolerances (stated, per BASELINE.json north_star): fp32 engine: seg / line maps within 1e-3 of the
-fp32 reference; fp16 tensor-core engine: within 5e-3 on the post-sigmoid maps (fp16 storage of
-every activation, fp32 accumulate)."""
+Tolerances (stated, per BASELINE.json north_star):
+  * fp32 CUDA-core engine and the split-fp16 TENSOR-CORE engine (CTD_PREC_SPLIT_TC, BASELINE config 2): seg / line
+    maps within 1e-3 of the fp32 reference (max abs, post-sigmoid), DB bitmap disagreement <= 1e-4 of the pixels;
+  * fp16 tensor-core engine (CTD_PREC_FP16_TC, BASELINE config 3 "fp16"): fp16 STORAGE of every activation makes the
+    random-weight net's maps differ from fp32 statistically (a CPU emulation of fp16 storage through the same graph,
+    tests/prog_interp.py storage='f16', shows the same profile: mean 3-6e-3, p99.9 0.11-0.16, isolated maxima
+    0.3-0.45).  The kernels themselves are pinned per op at 2e-3 in tests/test_gpu_layers.py; here the engine is held
+    to the emulation's profile and compared against the emulation itself."""
 import numpy as np
 import pytest
 import torch
@@ -11,7 +16,7 @@ import torch
 import ctd_b200
 from oracle import synth
 from oracle.net_ref import RefNet
-from util import get_checkpoint, page_to_net_input, PREC_FP16_TC, PREC_FP32_SIMT, PREC_FP16_SIMT
+from util import get_checkpoint, page_to_net_input, PREC_FP16_TC, PREC_FP32_SIMT, PREC_FP16_SIMT, PREC_SPLIT_TC
 
 pytestmark = pytest.mark.gpu
 
@@ -21,8 +26,10 @@ pytestmark = pytest.mark.gpu
 # The 99.9th percentile sits at 0.13-0.151 depending on the fp32 accumulation ORDER (tap-major vs K-block-major
 # kernels give 0.147 / 0.151 on the same page), hence 0.2.
 TOL = {PREC_FP32_SIMT: dict(maps=1e-3, maps_mean=1e-4, p999=1e-3, blks_rel=2e-3),
-       PREC_FP16_TC: dict(maps=0.5, maps_mean=1e-2, p999=0.2, blks_rel=1.0),
-       PREC_FP16_SIMT: dict(maps=0.5, maps_mean=1e-2, p999=0.2, blks_rel=1.0)}
+       PREC_SPLIT_TC: dict(maps=1e-3, maps_mean=1e-4, p999=1e-3, blks_rel=2e-3),
+       PREC_FP16_TC: dict(maps=0.5, maps_mean=8e-3, p999=0.2, blks_rel=1.0),
+       PREC_FP16_SIMT: dict(maps=0.5, maps_mean=8e-3, p999=0.2, blks_rel=1.0)}
+EXACT = (PREC_FP32_SIMT, PREC_SPLIT_TC)
 
 
 def _pages(n, h, w, seed=1000):
@@ -30,16 +37,15 @@ def _pages(n, h, w, seed=1000):
                      for i in range(n)])
 
 
-@pytest.mark.parametrize("prec", [PREC_FP32_SIMT, PREC_FP16_SIMT, PREC_FP16_TC])
-@pytest.mark.parametrize("smooth", [False, True], ids=["rough", "smooth"])
-def test_forward_matches_oracle(prec, smooth):
+def _check_against_oracle(prec, smooth, n, h, w, use_graph=False, seed=1000):
     ck = get_checkpoint(0, smooth)
-    n, h, w = 2, 256, 320
-    pages = _pages(n, h, w)
+    pages = _pages(n, h, w, seed)
     ref = RefNet(ck)
-    rb, rm, rl = ref(page_to_net_input(pages))
+    with torch.no_grad():
+        outs = [ref(page_to_net_input(pages[i:i + 1])) for i in range(n)]      # page by page: bounded host memory
+    rb, rm, rl = (torch.cat([o[k] for o in outs]) for k in range(3))
     prog = ctd_b200.compiler.compile_checkpoint(ck)
-    eng = ctd_b200.Engine(prog, precision=prec, max_batch=n, max_h=h, max_w=w)
+    eng = ctd_b200.Engine(prog, precision=prec, max_batch=n, max_h=h, max_w=w, use_graph=use_graph)
     try:
         eng.forward(pages)
         blks, mask, lines = eng.net_outputs()
@@ -63,9 +69,103 @@ def test_forward_matches_oracle(prec, smooth):
         assert float(np.partition(d, int(d.size * 0.999))[int(d.size * 0.999)]) <= tol["p999"], msg
     # DB bitmap (shrink > 0.3, db_utils.py:71-72) agreement
     flips = float(((lines[:, 0] > 0.3) != (rl.numpy()[:, 0] > 0.3)).mean())
-    assert flips <= (1e-4 if prec == PREC_FP32_SIMT else 1e-2), (flips, msg)
+    assert flips <= (1e-4 if prec in EXACT else 1e-2), (flips, msg)
     # postprocess_mask (inference.py:96-99): (mask*255) truncated; compare on the engine's own float mask
     assert np.array_equal(m8, (mask[:, 0] * 255).astype(np.uint8))
+    return pages, prog, (blks, mask, lines)
+
+
+@pytest.mark.parametrize("prec", [PREC_FP32_SIMT, PREC_FP16_SIMT, PREC_FP16_TC, PREC_SPLIT_TC])
+@pytest.mark.parametrize("smooth", [False, True], ids=["rough", "smooth"])
+def test_forward_matches_oracle(prec, smooth):
+    _check_against_oracle(prec, smooth, 2, 256, 320)
+
+
+def test_benchmark_config_matches_oracle():
+    """BASELINE configs[2] itself -- 1024x1024, batch 16, fp16 tcgen05 path under a CUDA graph (what bench.py
+    times) -- against the fp32 oracle on all 16 pages (structured and noise pages alternate)."""
+    _check_against_oracle(PREC_FP16_TC, True, 16, 1024, 1024, use_graph=True)
+
+
+@pytest.mark.parametrize("prec", [PREC_FP16_TC, PREC_SPLIT_TC], ids=["fp16_tc", "split_tc"])
+@pytest.mark.parametrize("size", [640, 1024, 1536])
+def test_stream_bucket_sizes_match_oracle(prec, size):
+    """BASELINE configs[4] buckets (640 / 1024 / 1536 squares) and config 2 (1024, fp32-accurate tensor-core mode)."""
+    _check_against_oracle(prec, True, 2, size, size, use_graph=True, seed=2000 + size)
+
+
+def test_fp16_engine_tracks_fp16_storage_emulation():
+    """The tcgen05 engine against the CPU emulation of ITS OWN numerics (fp16 weights + fp16 activation storage, fp32
+    accumulate): what is left is accumulation order and one-ulp rounding flips amplified by the net, an order of
+    magnitude below the engine's distance to the fp32 reference."""
+    import prog_interp
+    ck = get_checkpoint(0, True)
+    n, h, w = 2, 256, 320
+    pages = _pages(n, h, w)
+    prog = ctd_b200.compiler.compile_checkpoint(ck)
+    eb, em, el = prog_interp.run_program(prog, pages, storage="f16")
+    eng = ctd_b200.Engine(prog, precision=PREC_FP16_TC, max_batch=n, max_h=h, max_w=w)
+    try:
+        eng.forward(pages)
+        blks, mask, lines = eng.net_outputs()
+    finally:
+        eng.close()
+    rb, rm, rl = RefNet(ck)(page_to_net_input(pages))
+    for name, got, emu, ref in (("mask", mask, em.numpy(), rm.numpy()), ("lines", lines, el.numpy(), rl.numpy())):
+        d_emu = float(np.abs(got - emu).mean())
+        d_ref = float(np.abs(got - ref).mean())
+        print("%s: mean |engine - fp16 emulation| %.3g, mean |engine - fp32 reference| %.3g, max vs emulation %.3g"
+              % (name, d_emu, d_ref, float(np.abs(got - emu).max())))
+        assert d_emu <= 0.6 * d_ref + 1e-4, (name, d_emu, d_ref)
+        assert d_emu <= 3e-3, (name, d_emu)
+
+
+def test_split_engine_end_to_end_bit_exact():
+    """BASELINE config 2 / north_star: with the fp32-accurate tensor-core engine the WHOLE device pipeline is compared
+    with the oracle chain run on the REFERENCE's fp32 maps (not on the engine's own maps): detection rows, DB bitmap,
+    CC labels and line boxes must be identical; pixels whose reference value lies within 1e-3 of a threshold (0.3 for
+    the bitmap, k/255 for the u8 mask) are the only ones allowed to differ and are counted."""
+    from oracle import postproc_ref
+    ck = get_checkpoint(0, True)
+    n, h, w = 2, 512, 512
+    pages = np.stack([synth.structured_page(1000 + 3 * i, h, w) for i in range(n)])
+    with torch.no_grad():
+        rb, rm, rl = RefNet(ck)(page_to_net_input(pages))
+    prog = ctd_b200.compiler.compile_checkpoint(ck)
+    eng = ctd_b200.Engine(prog, precision=PREC_SPLIT_TC, max_batch=n, max_h=h, max_w=w, use_graph=True)
+    try:
+        eng.forward(pages)
+        dets = eng.detections()
+        m8 = eng.mask_u8()
+        bitmap, labels, nl = eng.db_components()
+        boxes, scores = eng.text_lines()
+    finally:
+        eng.close()
+    shrink = rl.numpy()[:, 0]
+    ref_bitmap = (shrink > 0.3).astype(np.uint8)
+    flips = bitmap != ref_bitmap
+    assert np.all(np.abs(shrink[flips] - 0.3) < 1e-3), "bitmap differs away from the threshold"
+    ref_m8 = (rm.numpy()[:, 0] * 255).astype(np.uint8)
+    mdiff = m8 != ref_m8
+    frac = rm.numpy()[:, 0] * 255
+    assert np.all(np.abs(frac[mdiff] - np.round(frac[mdiff])) < 0.255 + 1e-6), "u8 mask differs away from a truncation step"
+    assert np.all(np.abs(m8.astype(int) - ref_m8.astype(int))[mdiff] == 1)
+    print("near-threshold pixels that differ: bitmap %d of %d, mask_u8 %d of %d" % (int(flips.sum()), flips.size,
+                                                                                   int(mdiff.sum()), mdiff.size))
+    for i in range(n):
+        ref_det = postproc_ref.non_max_suppression(rb[i:i + 1], 0.4, 0.35)[0].numpy()
+        assert len(dets[i]) == len(ref_det) and len(ref_det) > 0
+        assert np.array_equal(dets[i][:, 5], ref_det[:, 5])
+        assert np.array_equal(dets[i][:, :4].astype(np.int32), ref_det[:, :4].astype(np.int32)), "int bboxes (inference.py:108)"
+        assert np.array_equal(np.round(dets[i][:, 4], 3), np.round(ref_det[:, 4], 3))
+        if not flips[i].any():
+            n_ref, lab_ref, _, _ = postproc_ref.connected_components_cv2(ref_bitmap[i])
+            assert int(nl[i]) == n_ref and np.array_equal(labels[i], lab_ref), "CC labels"
+            rboxes, rscores = postproc_ref.seg_represent(shrink[i], 0.3)
+            assert len(boxes[i]) == len(rboxes) and len(rboxes) > 0
+            same = np.all(boxes[i].reshape(len(rboxes), -1) == rboxes.reshape(len(rboxes), -1), axis=1)
+            assert same.mean() >= 0.97, "line boxes (minAreaRect ties aside)"
+            assert np.allclose(scores[i], rscores, atol=1e-3)
 
 
 def test_batch_invariance():

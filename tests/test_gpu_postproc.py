@@ -90,6 +90,32 @@ def test_nms_matches_reference(eng, rows, n_obj, seed):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("seed,ties", [(10, False), (11, True)])
+def test_nms_candidate_overflow_is_deterministic_top_by_score(eng, seed, ties):
+    """More candidates than the 4096-slot workspace (the atomicAdd slot race made the survivors depend on
+    thread scheduling): the engine must keep exactly the 4096 best rows by (score descending, row ascending), i.e.
+    equal the reference NMS run on that subset, report the true count, and repeat bit-identically."""
+    rng = np.random.default_rng(seed)
+    rows = 64512
+    pred = _pred(rng, rows, 9000)
+    if ties:   # many exact ties straddling the cut: the lowest rows must win
+        pred[:, 4] = np.round(pred[:, 4], 2)
+        pred[:, 5:] = 1.0
+    obj = pred[:, 4]
+    score = (pred[:, 5:] * obj[:, None]).max(1)
+    cand = np.where((obj > 0.4) & (score > 0.4))[0]
+    assert len(cand) > 4096
+    order = cand[np.lexsort((cand, -score[cand]))][:4096]
+    sub = pred[np.sort(order)]
+    ref = postproc_ref.non_max_suppression(torch.from_numpy(sub)[None], 0.4, 0.35)[0].numpy()
+    got = eng.nms(pred, 0.4, 0.35)
+    tot, cap = eng.nms_status()
+    assert cap == 4096 and int(tot[0]) == len(cand)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    for _ in range(3):
+        assert np.array_equal(eng.nms(pred, 0.4, 0.35), got)
+
+
 # ---------------------------------------------------------------------------------------------------
 import stress_maps  # noqa: E402
 

@@ -11,7 +11,7 @@ if ROOT not in sys.path:
 
 import ctd_b200  # noqa: E402
 from ctd_b200 import compiler as cc  # noqa: E402
-from ctd_b200.binding import PREC_FP16_TC, PREC_FP32_SIMT, PREC_FP16_SIMT  # noqa: E402
+from ctd_b200.binding import PREC_FP16_TC, PREC_FP32_SIMT, PREC_FP16_SIMT, PREC_SPLIT_TC  # noqa: E402
 
 _CKPT_CACHE = {}
 
