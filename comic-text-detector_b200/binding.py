@@ -9,7 +9,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libctd_b200.so")
 MAX_SRC = 3
-ABI_VERSION = 1
+ABI_VERSION = 2
 PREC_FP16_TC, PREC_FP32_SIMT, PREC_FP16_SIMT, PREC_SPLIT_TC = 0, 1, 2, 3
 
 
@@ -45,6 +45,15 @@ BLOCK_DTYPE = np.dtype([("xyxy", np.int32, (4,)), ("language", np.int32), ("vert
                         ("font_size", np.float64), ("vec", np.float64, (2,)), ("norm", np.float64),
                         ("weight", np.float64)], align=True)
 
+class CtdResultsLayout(C.Structure):
+    _fields_ = [("max_batch", C.c_int32), ("max_h", C.c_int32), ("max_w", C.c_int32), ("reserved", C.c_int32)] + \
+               [(k, C.c_size_t) for k in ("total_bytes", "phase_a_bytes", "mask_u8", "det", "det_count", "n_labels",
+                                          "line_boxes", "line_scores", "line_count", "mask_refined", "blocks",
+                                          "blocks_stride", "blk_records_off", "blk_lines_off", "blk_dist_off")]
+
+
+MAX_BLOCKS, MAX_BLOCK_DIST = 1300, 8192   # CTD_MAX_BLOCKS / CTD_MAX_BLOCK_DIST
+
 EXPORTS = ["ctd_create", "ctd_destroy", "ctd_last_error", "ctd_forward", "ctd_get_net_outputs", "ctd_get_mask_u8",
            "ctd_get_detections", "ctd_get_db_components", "ctd_last_forward_ms", "ctd_last_launch_count",
            "ctd_debug_read_buffer", "ctd_debug_write_buffer", "ctd_connected_components", "ctd_nms",
@@ -52,7 +61,7 @@ EXPORTS = ["ctd_create", "ctd_destroy", "ctd_last_error", "ctd_forward", "ctd_ge
            "ctd_get_text_lines", "ctd_seg_represent", "ctd_refine_mask", "ctd_submit", "ctd_collect",
            "ctd_results_bytes", "ctd_join", "ctd_forward_resized", "ctd_get_mask_u8_resized",
            "ctd_resize_linear_u8", "ctd_debug_run_ops", "ctd_get_nms_status", "ctd_group_output",
-           "ctd_expand_textwindow"]
+           "ctd_expand_textwindow", "ctd_detect_page", "ctd_results_layout", "ctd_submit_full", "ctd_device_arena"]
 
 _lib = None
 
@@ -106,6 +115,10 @@ def load_library():
     lib.ctd_get_nms_status.argtypes = [vp, vp, C.POINTER(i32)]
     lib.ctd_group_output.argtypes = [vp, vp, i32, vp, i32, i32, i32, vp, i32, vp, i32, vp, i32, vp, i32, C.POINTER(i32)]
     lib.ctd_expand_textwindow.argtypes = [i32, i32, vp, i32, vp]
+    lib.ctd_detect_page.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, i32, vp, i32, C.POINTER(i32)]
+    lib.ctd_results_layout.argtypes = [vp, C.POINTER(CtdResultsLayout)]
+    lib.ctd_submit_full.argtypes = [vp, i32, vp, i32, i32, i32, i32, i32, vp]
+    lib.ctd_device_arena.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
     for name in EXPORTS[3:]:
         getattr(lib, name).restype = C.c_int
     lib.ctd_expand_textwindow.restype = None
@@ -320,6 +333,43 @@ class Engine:
         (results_bytes() bytes; unpack with multigpu.unpack_arena)."""
         self._ck(self.lib.ctd_submit(self.h, slot, C.c_void_p(pages_ptr), n, h, w, C.c_void_p(results_ptr)))
         self.shape = (n, h, w)
+
+    def results_layout(self):
+        """byte offsets of the result arena (ctd_results_layout): dict of ints."""
+        lay = CtdResultsLayout()
+        self._ck(self.lib.ctd_results_layout(self.h, C.byref(lay)))
+        return {k: int(getattr(lay, k)) for k, _t in CtdResultsLayout._fields_}
+
+    def submit_full(self, slot, pages_ptr, n, h, w, results_ptr, refine_mode=0, pages_on_device=False):
+        """asynchronous full pipeline (network + post-processing + group_output + refine_mask) of a batch of
+        net-sized pages into HOST `results` (results_layout()['total_bytes'] bytes, pinned): see ctd_submit_full."""
+        self._ck(self.lib.ctd_submit_full(self.h, slot, C.c_void_p(pages_ptr), n, h, w, int(bool(pages_on_device)),
+                                          int(refine_mode), C.c_void_p(results_ptr)))
+        self.shape = (n, h, w)
+
+    def device_arena(self, slot):
+        """(device pointer of slot's complete result arena copy, cudaStream_t its last writes were enqueued on)."""
+        base, st = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.ctd_device_arena(self.h, slot, C.byref(base), C.byref(st)))
+        return base.value, st.value
+
+    def detect_page(self, page, net_h, net_w, refine_mode=0, keep_undetected=False):
+        """the whole of TextDetector.__call__ for one page of any size (ctd_detect_page): returns
+        (mask u8 [ih,iw], mask_refined u8 [ih,iw], block records, lines i32 [.,8], distances f64)."""
+        page = np.ascontiguousarray(page, dtype=np.uint8)
+        ih, iw, c = page.shape
+        assert c == 3
+        mask = np.empty((ih, iw), np.uint8)
+        refined = np.empty((ih, iw), np.uint8)
+        rec = np.zeros((MAX_BLOCKS,), BLOCK_DTYPE)
+        lines = np.zeros((MAX_BLOCKS, 8), np.int32)
+        dist = np.zeros((MAX_BLOCK_DIST,), np.float64)
+        nb = C.c_int32()
+        self._ck(self.lib.ctd_detect_page(self.h, _ptr(page), ih, iw, net_h, net_w, int(refine_mode), int(bool(keep_undetected)),
+                                          _ptr(mask), _ptr(refined), _ptr(rec), MAX_BLOCKS, _ptr(lines), MAX_BLOCKS, _ptr(dist),
+                                          MAX_BLOCK_DIST, C.byref(nb)))
+        self.shape = (1, net_h, net_w)
+        return mask, refined, rec[:nb.value], lines, dist
 
     def collect(self, slot):
         self._ck(self.lib.ctd_collect(self.h, slot))

@@ -397,7 +397,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       int stage = 0, ti = 0;
       uint32_t full_par = 0;
       uint64_t ad = a_desc0, bd = b_desc0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      if constexpr (BN <= 64) {
+        if (p.split) {
+          // Split-fp16 mode with PROMOTED accumulation.  The tensor core adds into its fp32 accumulator with
+          // truncation: over the K/16 x 3 MMAs of a deep layer the one-sided errors add up to ~K/16 ulps (measured
+          // 3e-5 relative on the 3x3 256->256 layers, 200x a CUDA-core fp32 FMA chain).  So every hi x hi MMA (K = 16)
+          // writes a FRESH accumulator from a ring of kRing TMEM slots and the epilogue threads sum the slots in fp32
+          // registers with round-to-nearest; the small cross terms (lo x hi, hi x lo: 2^-12 of the sum, their
+          // truncation is 2^-36) accumulate in TMEM as usual, in one slot per tile parity (slots 0 / 1).
+          constexpr int kRing = Cfg::kAccStages - 2;
+          uint32_t rc = 0;   // hi x hi MMAs issued so far (ring position)
+          for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+            const int xs = ti & 1;
+            mbar_wait(tmem_empty_bar + 8 * xs, ((ti >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_x = tmem_base + uint32_t(xs * BN);
+            bool cross_started = false;
+            for (int k_it = 0; k_it < its_per_tile; ++k_it) {
+              mbar_wait(full_bar + 8 * stage, full_par);
+              tc_fence_after();
+              if (k_it % 3 == 0) {
+                for (int ks = 0; ks < ksteps; ++ks, ++rc) {
+                  const uint32_t slot = 2u + rc % kRing;
+                  mbar_wait(tmem_empty_bar + 8 * slot, ((rc / kRing) & 1u) ^ 1u);
+                  tc_fence_after();
+                  umma_f16(tmem_base + slot * BN, ad + 2 * ks, bd + 2 * ks, idesc, 0u);
+                  umma_commit(tmem_full_bar + 8 * slot);
+                }
+              } else {
+                issue_kblock(tmem_x, ad, bd, idesc, cross_started ? 1u : 0u, ksteps);
+                cross_started = true;
+              }
+              umma_commit(empty_bar + 8 * stage);
+              if (++stage == Cfg::kStages) {
+                stage = 0; full_par ^= 1u; ad = a_desc0; bd = b_desc0;
+              } else {
+                ad += uint64_t(Cfg::kABytes >> 4); bd += uint64_t(Cfg::kBBytes >> 4);
+              }
+            }
+            umma_commit(tmem_full_bar + 8 * xs);
+          }
+          ti = -1;   // skip the plain loop below
+        }
+      }
+      for (int t = blockIdx.x; ti >= 0 && t < total_tiles; t += gridDim.x, ++ti) {
         const int as = ti % Cfg::kAccStages;
         mbar_wait(tmem_empty_bar + 8 * as, ((ti / Cfg::kAccStages) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
@@ -439,25 +482,91 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if constexpr (BN >= 64) {
         if (p.use_tma_store && g.residual) load_res_chunk(rc, out);
       }
+      const float* bias_t = bias_s + nblk * BN;
+      if constexpr (BN <= 64) {
+        if (p.split) {
+          // promoted accumulation (see the MMA issuer): sum the hi x hi ring slots of this tile and its cross-term
+          // slot in fp32 registers, then bias / activation / residual -> FP32 destination (or the Detect decode)
+          constexpr int kRing = Cfg::kAccStages - 2;
+          const int cpt = (its_per_tile / 3) * (kb / 16);        // hi x hi MMAs per tile
+          const uint32_t lane_off = uint32_t(quad * 32) << 16;
+          float acc[BN];
+#pragma unroll
+          for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+          uint32_t rc = uint32_t(ti) * uint32_t(cpt);
+          for (int c = 0; c <= cpt; ++c, ++rc) {
+            const bool last = c == cpt;                            // the cross-term slot comes last
+            const uint32_t slot = last ? uint32_t(ti & 1) : 2u + rc % kRing;
+            const uint32_t par = last ? uint32_t((ti >> 1) & 1) : ((rc / kRing) & 1u);
+            mbar_wait_relaxed(tmem_full_bar + 8 * slot, par);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + slot * BN + lane_off;
+            if constexpr (BN >= 32) {
+#pragma unroll
+              for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(trow + uint32_t(c0), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[c0 + j] = __fadd_rn(acc[c0 + j], __uint_as_float(v[j]));
+              }
+            } else {
+              uint32_t v[16];
+              tmem_ld_32x16(trow, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[j] = __fadd_rn(acc[j], __uint_as_float(v[j]));
+            }
+            tc_fence_before();
+            mbar_arrive(tmem_empty_bar + 8 * slot);
+          }
+          const uint32_t* accu = reinterpret_cast<const uint32_t*>(acc);
+          if (p.dst != nullptr) {
+            float* out32 = reinterpret_cast<float*>(p.dst) +
+                           (size_t(img) * g.dst_h * g.dst_w + size_t(valid ? oy : 0) * g.dst_w + (valid ? ox : 0)) * g.dst_cstride +
+                           g.dst_coff + nblk * BN;
+            const int cout_left = g.cout - nblk * BN;
+            const bool res = g.residual != 0;
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+              const int left = cout_left - c0;
+              if (!valid || left <= 0) continue;
+              const int nc = left < 32 ? left : 32;
+              switch (g.act) {
+                case CTD_ACT_SILU: epilogue_chunk_f32<CTD_ACT_SILU>(accu + c0, bias_t + c0, out32 + c0, nc, res); break;
+                case CTD_ACT_LEAKY: epilogue_chunk_f32<CTD_ACT_LEAKY>(accu + c0, bias_t + c0, out32 + c0, nc, res); break;
+                case CTD_ACT_RELU: epilogue_chunk_f32<CTD_ACT_RELU>(accu + c0, bias_t + c0, out32 + c0, nc, res); break;
+                case CTD_ACT_SIGMOID: epilogue_chunk_f32<CTD_ACT_SIGMOID>(accu + c0, bias_t + c0, out32 + c0, nc, res); break;
+                default: epilogue_chunk_f32<CTD_ACT_NONE>(accu + c0, bias_t + c0, out32 + c0, nc, res); break;
+              }
+            }
+          } else if (valid) {
+            // Detect decode (yolo.py:36-44): columns = anchor*(5+nc) + o
+            const int no = 5 + p.nc;
+            float* rows = p.blks + (size_t(img) * p.blks_rows_per_img + p.level_row0) * no;
+#pragma unroll
+            for (int j = 0; j < BN; ++j) {
+              const int col = nblk * BN + j;
+              if (col < g.cout) {
+                const int a = col / no, o = col - a * no;
+                const float sg = 1.0f / (1.0f + expf(-(acc[j] + bias_t[j])));
+                float r;
+                if (o == 0) r = (sg * 2.0f - 0.5f + float(gx)) * p.det_stride;
+                else if (o == 1) r = (sg * 2.0f - 0.5f + float(gy)) * p.det_stride;
+                else if (o == 2) r = (sg * 2.0f) * (sg * 2.0f) * p.anchor_wh[2 * a];
+                else if (o == 3) r = (sg * 2.0f) * (sg * 2.0f) * p.anchor_wh[2 * a + 1];
+                else r = sg;
+                rows[(size_t(a) * g.gh * g.gw + size_t(gy) * g.gw + gx) * no + o] = r;
+              }
+            }
+          }
+          continue;
+        }
+      }
       mbar_wait_relaxed(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + uint32_t(as * BN) + (uint32_t(quad * 32) << 16);
-      const float* bias_t = bias_s + nblk * BN;
-      if (p.dst != nullptr && p.split) {
-        // split-fp16 mode: FP32 destination (same element offsets, 4-byte elements)
-        float* out32 = reinterpret_cast<float*>(p.dst) +
-                       (size_t(img) * g.dst_h * g.dst_w + size_t(valid ? oy : 0) * g.dst_w + (valid ? ox : 0)) * g.dst_cstride +
-                       g.dst_coff + nblk * BN;
-        const int cout_left = g.cout - nblk * BN;
-        const bool res = g.residual != 0;
-        switch (g.act) {
-          case CTD_ACT_SILU: epilogue_store_f32<BN, CTD_ACT_SILU>(tmem_row, bias_t, out32, cout_left, valid, res); break;
-          case CTD_ACT_LEAKY: epilogue_store_f32<BN, CTD_ACT_LEAKY>(tmem_row, bias_t, out32, cout_left, valid, res); break;
-          case CTD_ACT_RELU: epilogue_store_f32<BN, CTD_ACT_RELU>(tmem_row, bias_t, out32, cout_left, valid, res); break;
-          case CTD_ACT_SIGMOID: epilogue_store_f32<BN, CTD_ACT_SIGMOID>(tmem_row, bias_t, out32, cout_left, valid, res); break;
-          default: epilogue_store_f32<BN, CTD_ACT_NONE>(tmem_row, bias_t, out32, cout_left, valid, res); break;
-        }
-      } else if (p.dst != nullptr) {
+      if (p.dst != nullptr) {
         const int cout_left = g.cout - nblk * BN;
         bool done_tma = false;
         if constexpr (BN >= 64) {
@@ -988,10 +1097,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_hs_kernel(const __grid_const
                     g.dst_coff + nblk * BN;
       ResChunk rc;
       if (g.residual) load_res_chunk(rc, out);
+      const float* bias_t = bias_s + nblk * BN;
       mbar_wait_relaxed(tmem_full_bar + 8 * as, (ti / Cfg::kAccStages) & 1);
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + uint32_t(as * BN) + (uint32_t(quad * 32) << 16);
-      const float* bias_t = bias_s + nblk * BN;
       const uint32_t stage_base = store_base + uint32_t(group) * (128u * 128u);
       const bool lead = (threadIdx.x & 127) == 0;
       const CUtensorMap* om = &p.o_map[phase];
@@ -1342,7 +1451,8 @@ const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
         p.tap_map[ph][t] = 0;
       }
     }
-  const int bn = pick_block_n(g.cout_pad);
+  int bn = pick_block_n(g.cout_pad);
+  if (split && bn > 64) bn = 64;   // promoted accumulation keeps a BN-float row per epilogue thread in registers
   plan.block_n = bn;
   p.use_tma_store = 0;
   if (split && ((g.dst_coff % 4) != 0 || (g.dst_cstride % 4) != 0 || (dst != nullptr && g.cout % 4 != 0)))

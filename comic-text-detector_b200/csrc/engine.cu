@@ -15,87 +15,15 @@
 #include <tuple>
 #include <vector>
 
-#include "kernels.h"
+#include "engine.h"
 
 using namespace ctd;
 
 namespace {
 thread_local std::string g_create_error;
-
-struct ShapePlan {
-  std::vector<ConvTcPlan> tc;  // index = op index (unused entries default)
-  std::vector<char> has_tc;
-  cudaGraphExec_t graph = nullptr;
-  int launches = 0;
-};
 }  // namespace
 
-struct ctd_handle {
-  ctd_config cfg{};
-  std::vector<ctd_op> ops;
-  std::vector<ctd_bufdesc> bufs;
-  std::string err;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
-  std::vector<cudaEvent_t> op_events;
-  PFN_encodeTiled enc = nullptr;
-  char* d_blob = nullptr;
-  size_t blob_bytes = 0;
-  std::vector<void*> d_buf;
-  // split-fp16 mode (CTD_PREC_SPLIT_TC): d_buf holds the FP32 master copy of every activation; d_buf16[i] holds its
-  // fp16 hi | lo planes ([2*n][h][w][C], refreshed after every op that writes the buffer) = the MMA operands;
-  // d_wsplit holds per GEMM op the fp16 weight rows hi then lo (wsplit_off[op], bytes).
-  std::vector<void*> d_buf16;
-  char* d_wsplit = nullptr;
-  std::vector<size_t> wsplit_off;
-  int elem = 2;  // bytes per activation element
-  uint8_t* d_pages = nullptr;
-  float* d_blks = nullptr;
-  float* d_mask = nullptr;
-  uint8_t* d_mask_u8 = nullptr;   // start of the contiguous result arena: mask_u8 | det | det_count | n_labels
-  size_t results_bytes = 0;
-  float* d_lines = nullptr;
-  uint8_t* d_bitmap = nullptr;
-  float* d_det = nullptr;
-  int* d_det_count = nullptr;
-  int32_t* d_labels = nullptr;
-  int32_t* d_nlabels = nullptr;
-  int32_t* d_ccl_scratch = nullptr;
-  void* d_segrep_scratch = nullptr;
-  void* d_refine_scratch = nullptr;
-  size_t refine_scratch_cap = 0;
-  void* d_cc_scratch = nullptr;      // ctd_connected_components: grow-on-demand, any image size
-  size_t cc_scratch_cap = 0;
-  uint8_t* d_io_scratch = nullptr;   // page upload / resized mask staging of the resize entry points
-  size_t io_scratch_cap = 0;
-  int16_t* d_line_boxes = nullptr;
-  float* d_line_scores = nullptr;
-  int32_t* d_line_count = nullptr;
-  void* d_nms_ws = nullptr;
-  NmsWorkspace nms{};
-  std::map<std::tuple<int, int, int>, ShapePlan> plans;
-  // pipelined host path (ctd_submit / ctd_collect): two staging slots, copy streams either side of compute
-  cudaStream_t copy_in = nullptr, copy_out = nullptr;
-  uint8_t* d_stage_in[2] = {nullptr, nullptr};
-  uint8_t* d_stage_out[2] = {nullptr, nullptr};
-  cudaEvent_t ev_in_done[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
-  cudaEvent_t ev_out_ready[2] = {nullptr, nullptr}, ev_out_done[2] = {nullptr, nullptr};
-  bool slot_busy[2] = {false, false};
-  // overlapped schedule: post-processing of the DB maps / the Detect rows runs on side streams under the
-  // remaining network ops (see run_ops)
-  int halo_mode = 7;   // CTD_HALO bit mask (0 routes every conv through conv_tc_kernel, for A/B measurements)
-  bool overlap = false;
-  cudaStream_t side = nullptr, side2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
-  cudaEvent_t ev_xjoin = nullptr;   // ctd_join (never part of a captured graph)
-  std::vector<char> db_ancestor;   // op feeds the DB tail (computed once in ctd_create)
-  // last forward
-  int n = 0, ph = 0, pw = 0;
-  int last_launches = 0;
-  bool have_forward = false;
-};
-
-static int fail(ctd_handle* h, int code, const char* fmt, ...) {
+int ctd_fail(ctd_handle* h, int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -109,7 +37,7 @@ static int fail(ctd_handle* h, int code, const char* fmt, ...) {
 #define CK(expr)                                                                                      \
   do {                                                                                                \
     cudaError_t _e = (expr);                                                                          \
-    if (_e != cudaSuccess) return fail(h, CTD_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    if (_e != cudaSuccess) return ctd_fail(h, CTD_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
 static int rows_per_image(int ph, int pw) { return 3 * ((ph / 8) * (pw / 8) + (ph / 16) * (pw / 16) + (ph / 32) * (pw / 32)); }
@@ -119,6 +47,7 @@ extern "C" const char* ctd_last_error(const ctd_handle* h) { return h ? h->err.c
 extern "C" void ctd_destroy(ctd_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
+  ctd_pipeline_shutdown(h);
   for (auto& kv : h->plans)
     if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
   for (void* p : h->d_buf) cudaFree(p);
@@ -155,16 +84,16 @@ extern "C" void ctd_destroy(ctd_handle* h) {
 extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op* ops, int32_t n_ops,
                           const ctd_bufdesc* bufs, int32_t n_bufs, const void* blob, size_t blob_bytes) {
   ctd_handle* h = nullptr;
-  if (!out || !cfg || !ops || !bufs || !blob) return fail(nullptr, CTD_E_INVALID, "null argument");
+  if (!out || !cfg || !ops || !bufs || !blob) return ctd_fail(nullptr, CTD_E_INVALID, "null argument");
   *out = nullptr;
-  if (cfg->abi_version != CTD_ABI_VERSION) return fail(nullptr, CTD_E_INVALID, "ABI version mismatch");
-  if (cfg->max_h % 64 || cfg->max_w % 64 || cfg->max_batch < 1) return fail(nullptr, CTD_E_SHAPE, "bad max shape");
+  if (cfg->abi_version != CTD_ABI_VERSION) return ctd_fail(nullptr, CTD_E_INVALID, "ABI version mismatch");
+  if (cfg->max_h % 64 || cfg->max_w % 64 || cfg->max_batch < 1) return ctd_fail(nullptr, CTD_E_SHAPE, "bad max shape");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= cfg->device)
-    return fail(nullptr, CTD_E_NO_DEVICE, "no CUDA device %d (this engine has no CPU fallback)", cfg->device);
+    return ctd_fail(nullptr, CTD_E_NO_DEVICE, "no CUDA device %d (this engine has no CPU fallback)", cfg->device);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
-    return fail(nullptr, CTD_E_NO_DEVICE, "device %d is not sm_100 (compute %d.%d)", cfg->device, prop.major, prop.minor);
+    return ctd_fail(nullptr, CTD_E_NO_DEVICE, "device %d is not sm_100 (compute %d.%d)", cfg->device, prop.major, prop.minor);
   h = new ctd_handle();
   h->cfg = *cfg;
   h->ops.assign(ops, ops + n_ops);
@@ -201,7 +130,7 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
   do {                                                                                                   \
     cudaError_t _e = (expr);                                                                             \
     if (_e != cudaSuccess) {                                                                             \
-      fail(h, CTD_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);          \
+      ctd_fail(h, CTD_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);          \
       return bail(CTD_E_CUDA);                                                                           \
     }                                                                                                    \
   } while (0)
@@ -228,7 +157,7 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
     cudaDriverEntryPointQueryResult qres;
     CKC(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess) {
-      fail(h, CTD_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+      ctd_fail(h, CTD_E_CUDA, "cuTensorMapEncodeTiled not available from the driver");
       return bail(CTD_E_CUDA);
     }
     h->enc = reinterpret_cast<PFN_encodeTiled>(fn);
@@ -264,7 +193,7 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
       const int nph = op.kind == CTD_OP_DECONV4 ? 4 : 1;
       const size_t cnt = size_t(nph) * op.cout_pad * taps * cin;
       if (size_t(op.w32_off) + cnt * 4 > blob_bytes || size_t(op.w16_off) + cnt * 2 > blob_bytes) {
-        fail(h, CTD_E_INVALID, "op %d: weights outside the blob", i);
+        ctd_fail(h, CTD_E_INVALID, "op %d: weights outside the blob", i);
         return bail(CTD_E_INVALID);
       }
       while (ws.size() % 128) ws.push_back(__float2half(0.f));   // 256-byte aligned rows for the tensor map
@@ -291,17 +220,26 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
   CKC(cudaMalloc(&h->d_labels, px * 4));
   {
     auto al = [](size_t v) { return (v + 255) / 256 * 256; };
-    const size_t o_det = al(px), o_cnt = o_det + al(nb * 300 * 6 * 4), o_nl = o_cnt + al(nb * 4);
-    const size_t o_lb = o_nl + al(nb * 4), o_ls = o_lb + al(nb * 1000 * 8 * 2), o_lc = o_ls + al(nb * 1000 * 4);
-    h->results_bytes = o_lc + al(nb * 4);
+    ArenaLayout& L = h->layout;
+    L.det = al(px); L.cnt = L.det + al(nb * 300 * 6 * 4); L.nl = L.cnt + al(nb * 4);
+    L.lb = L.nl + al(nb * 4); L.ls = L.lb + al(nb * 1000 * 8 * 2); L.lc = L.ls + al(nb * 1000 * 4);
+    L.a_bytes = L.lc + al(nb * 4);
+    L.refined = L.a_bytes;
+    L.blocks = L.refined + al(px);
+    L.rec_off = 64;
+    L.lines_off = L.rec_off + al(size_t(CTD_MAX_BLOCKS) * sizeof(ctd_block));
+    L.dist_off = L.lines_off + al(size_t(CTD_MAX_BLOCKS) * 32);
+    L.blocks_stride = L.dist_off + al(size_t(CTD_MAX_BLOCK_DIST) * 8);
+    L.total = L.blocks + nb * L.blocks_stride;
+    h->results_bytes = L.total;
     CKC(cudaMalloc(&h->d_mask_u8, h->results_bytes));
     CKC(cudaMemset(h->d_mask_u8, 0, h->results_bytes));
-    h->d_det = reinterpret_cast<float*>(h->d_mask_u8 + o_det);
-    h->d_det_count = reinterpret_cast<int*>(h->d_mask_u8 + o_cnt);
-    h->d_nlabels = reinterpret_cast<int32_t*>(h->d_mask_u8 + o_nl);
-    h->d_line_boxes = reinterpret_cast<int16_t*>(h->d_mask_u8 + o_lb);
-    h->d_line_scores = reinterpret_cast<float*>(h->d_mask_u8 + o_ls);
-    h->d_line_count = reinterpret_cast<int32_t*>(h->d_mask_u8 + o_lc);
+    h->d_det = reinterpret_cast<float*>(h->d_mask_u8 + L.det);
+    h->d_det_count = reinterpret_cast<int*>(h->d_mask_u8 + L.cnt);
+    h->d_nlabels = reinterpret_cast<int32_t*>(h->d_mask_u8 + L.nl);
+    h->d_line_boxes = reinterpret_cast<int16_t*>(h->d_mask_u8 + L.lb);
+    h->d_line_scores = reinterpret_cast<float*>(h->d_mask_u8 + L.ls);
+    h->d_line_count = reinterpret_cast<int32_t*>(h->d_mask_u8 + L.lc);
   }
   CKC(cudaMalloc(&h->d_ccl_scratch, px * 4 * 3));
   CKC(cudaMalloc(&h->d_segrep_scratch, segrep_scratch_bytes(int(nb), int(mh), int(mw), 1000)));
@@ -326,7 +264,7 @@ static int op_geom(ctd_handle* h, const ctd_op& op, int n, int ph, int pw, ConvG
   g.cin_total = 0;
   for (int s = 0; s < op.n_src; ++s) {
     const ctd_bufdesc& b = h->bufs[op.src_buf[s]];
-    if (b.down != sb.down) return fail(h, CTD_E_INVALID, "op sources differ in resolution");
+    if (b.down != sb.down) return ctd_fail(h, CTD_E_INVALID, "op sources differ in resolution");
     g.src_c[s] = op.src_c[s];
     g.src_cstride[s] = b.channels;
     g.cin_total += op.src_c[s];
@@ -367,7 +305,7 @@ static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
       __half* dst = op.kind == CTD_OP_DETECT ? nullptr : static_cast<__half*>(h->d_buf[op.dst_buf]);
       const char* e = conv_tc_plan(sp.tc[i], h->enc, g, src, coff, h->d_wsplit + h->wsplit_off[i],
                                    reinterpret_cast<const float*>(h->d_blob + op.b_off), dst, 1);
-      if (e) return fail(h, CTD_E_INVALID, "op %zu: %s", i, e);
+      if (e) return ctd_fail(h, CTD_E_INVALID, "op %zu: %s", i, e);
       if (op.kind == CTD_OP_DETECT) {
         ConvTcParams& p = sp.tc[i].p;
         p.blks = h->d_blks;
@@ -393,7 +331,7 @@ static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
           sp.tc[i], h->enc, h->d_buf[op.src_buf[0]], n, ph, pw, h->d_blob + op.w16_off,
           reinterpret_cast<const float*>(h->d_blob + op.b_off), static_cast<__half*>(h->d_buf[op.dst_buf]),
           h->bufs[op.dst_buf].channels, op.dst_coff, op.cout, op.act);
-      if (e) return fail(h, CTD_E_INVALID, "stem: %s", e);
+      if (e) return ctd_fail(h, CTD_E_INVALID, "stem: %s", e);
       sp.has_tc[i] = 1;
       continue;
     }
@@ -407,7 +345,7 @@ static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
       int coff[CTD_MAX_SRC] = {op.src_coff[0]};
       const char* e = conv_halo_plan(sp.tc[i], h->enc, g, src, coff, h->d_blob + op.w16_off, nullptr, nullptr, h->d_mask,
                                      h->d_mask_u8);
-      if (e) return fail(h, CTD_E_INVALID, "seg tail: %s", e);
+      if (e) return ctd_fail(h, CTD_E_INVALID, "seg tail: %s", e);
       sp.has_tc[i] = sp.tc[i].halo ? 1 : 0;
       continue;
     }
@@ -435,7 +373,7 @@ static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
     if (!e && !sp.tc[i].halo)
       e = conv_tc_plan(sp.tc[i], h->enc, g, src, coff, h->d_blob + op.w16_off,
                        reinterpret_cast<const float*>(h->d_blob + op.b_off), dst);
-    if (e) return fail(h, CTD_E_INVALID, "op %zu: %s", i, e);
+    if (e) return ctd_fail(h, CTD_E_INVALID, "op %zu: %s", i, e);
     if (op.kind == CTD_OP_DETECT) {
       ConvTcParams& p = sp.tc[i].p;
       p.blks = h->d_blks;
@@ -487,7 +425,7 @@ static int run_op_simt(ctd_handle* h, const ctd_op& op, int n, int ph, int pw) {
       CK(conv_simt_launch<T>(p, s));
       return CTD_OK;
     }
-    default: return fail(h, CTD_E_INVALID, "run_op_simt: bad kind %d", op.kind);
+    default: return ctd_fail(h, CTD_E_INVALID, "run_op_simt: bad kind %d", op.kind);
   }
 }
 
@@ -528,7 +466,7 @@ static int run_op_thin(ctd_handle* h, const ctd_op& op, int n, int ph, int pw) {
       CK(db_tail_launch<T>(src, n, sh, sw, sb->channels, reinterpret_cast<const float*>(h->d_blob + op.p_off),
                            h->d_lines, h->d_bitmap, h->cfg.db_thresh, s));
       return CTD_OK;
-    default: return fail(h, CTD_E_INVALID, "run_op_thin: bad kind %d", op.kind);
+    default: return ctd_fail(h, CTD_E_INVALID, "run_op_thin: bad kind %d", op.kind);
   }
 }
 
@@ -555,7 +493,7 @@ static int run_one_op(ctd_handle* h, size_t i, int n, int ph, int pw, ShapePlan&
   if (h->cfg.precision == CTD_PREC_SPLIT_TC) {
     if (gemm) {
       cudaError_t e = conv_tc_launch(sp.tc[i], h->stream);
-      rc = e == cudaSuccess ? CTD_OK : fail(h, CTD_E_CUDA, "conv_tc (split) op %zu: %s", i, cudaGetErrorString(e));
+      rc = e == cudaSuccess ? CTD_OK : ctd_fail(h, CTD_E_CUDA, "conv_tc (split) op %zu: %s", i, cudaGetErrorString(e));
     } else {
       rc = run_op_thin<float>(h, op, n, ph, pw);
     }
@@ -568,15 +506,15 @@ static int run_one_op(ctd_handle* h, size_t i, int n, int ph, int pw, ShapePlan&
     cudaError_t e = s2d_launch<__half>(h->d_pages, n, ph, pw, static_cast<__half*>(h->d_buf[op.src_buf[0]]), 16, 0,
                                        pw / 2 + 4, 1, h->stream);
     if (e == cudaSuccess) e = conv_tc_launch(sp.tc[i], h->stream);
-    rc = e == cudaSuccess ? CTD_OK : fail(h, CTD_E_CUDA, "stem op %zu: %s", i, cudaGetErrorString(e));
+    rc = e == cudaSuccess ? CTD_OK : ctd_fail(h, CTD_E_CUDA, "stem op %zu: %s", i, cudaGetErrorString(e));
     ++*cnt;
   } else if (op.kind == CTD_OP_SEG_TAIL && h->cfg.precision == CTD_PREC_FP16_TC && sp.has_tc[i]) {
     cudaError_t e = conv_tc_launch(sp.tc[i], h->stream);
-    rc = e == cudaSuccess ? CTD_OK : fail(h, CTD_E_CUDA, "seg tail op %zu: %s", i, cudaGetErrorString(e));
+    rc = e == cudaSuccess ? CTD_OK : ctd_fail(h, CTD_E_CUDA, "seg tail op %zu: %s", i, cudaGetErrorString(e));
   } else if (gemm) {
     if (h->cfg.precision == CTD_PREC_FP16_TC) {
       cudaError_t e = conv_tc_launch(sp.tc[i], h->stream);
-      rc = e == cudaSuccess ? CTD_OK : fail(h, CTD_E_CUDA, "conv_tc op %zu: %s", i, cudaGetErrorString(e));
+      rc = e == cudaSuccess ? CTD_OK : ctd_fail(h, CTD_E_CUDA, "conv_tc op %zu: %s", i, cudaGetErrorString(e));
     } else if (h->cfg.precision == CTD_PREC_FP32_SIMT) {
       rc = run_op_simt<float>(h, op, n, ph, pw);
     } else {
@@ -659,10 +597,10 @@ static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* lau
 }
 
 // shape checks + plan lookup + (first time) graph capture; the forward itself is enqueue_forward()
-static int prepare_forward(ctd_handle* h, int32_t n, int32_t ph, int32_t pw, ShapePlan** out) {
-  if (n < 1 || n > h->cfg.max_batch) return fail(h, CTD_E_CAPACITY, "batch %d exceeds max_batch %d", n, h->cfg.max_batch);
+int prepare_forward(ctd_handle* h, int32_t n, int32_t ph, int32_t pw, ShapePlan** out) {
+  if (n < 1 || n > h->cfg.max_batch) return ctd_fail(h, CTD_E_CAPACITY, "batch %d exceeds max_batch %d", n, h->cfg.max_batch);
   if (ph % 64 || pw % 64 || ph > h->cfg.max_h || pw > h->cfg.max_w || ph < 64 || pw < 64)
-    return fail(h, CTD_E_SHAPE, "page %dx%d must be a multiple of 64 and <= %dx%d", ph, pw, h->cfg.max_h, h->cfg.max_w);
+    return ctd_fail(h, CTD_E_SHAPE, "page %dx%d must be a multiple of 64 and <= %dx%d", ph, pw, h->cfg.max_h, h->cfg.max_w);
   CK(cudaSetDevice(h->cfg.device));
   auto key = std::make_tuple(int(n), int(ph), int(pw));
   auto it = h->plans.find(key);
@@ -688,7 +626,7 @@ static int prepare_forward(ctd_handle* h, int32_t n, int32_t ph, int32_t pw, Sha
   return CTD_OK;
 }
 
-static int enqueue_forward(ctd_handle* h, int32_t n, int32_t ph, int32_t pw, ShapePlan& sp) {
+int enqueue_forward(ctd_handle* h, int32_t n, int32_t ph, int32_t pw, ShapePlan& sp) {
   if (sp.graph) {
     CK(cudaGraphLaunch(sp.graph, h->stream));
   } else {
@@ -718,7 +656,7 @@ extern "C" int ctd_forward(ctd_handle* h, const uint8_t* pages, int32_t n, int32
 //               compute: [wait H2D] stage_in -> d_pages (D2D), forward, arena -> stage_out[slot] (D2D)
 //               copy_out: [wait arena copy] D2H stage_out[slot] -> results_host
 // so the H2D of batch i+1 and the D2H of batch i-1 run under the forward of batch i.
-static int ensure_pipeline(ctd_handle* h) {
+int ensure_pipeline(ctd_handle* h) {
   if (h->copy_in) return CTD_OK;
   CK(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
@@ -737,8 +675,8 @@ static int ensure_pipeline(ctd_handle* h) {
 extern "C" int ctd_submit(ctd_handle* h, int32_t slot, const uint8_t* pages_host, int32_t n, int32_t ph, int32_t pw,
                           void* results_host) {
   if (!h || !pages_host || !results_host || slot < 0 || slot > 1) return CTD_E_INVALID;
-  if (h->cfg.debug_skip_postproc) return fail(h, CTD_E_INVALID, "ctd_submit needs the full pipeline");
-  if (h->slot_busy[slot]) return fail(h, CTD_E_INVALID, "slot %d has an uncollected submission", slot);
+  if (h->cfg.debug_skip_postproc) return ctd_fail(h, CTD_E_INVALID, "ctd_submit needs the full pipeline");
+  if (h->slot_busy[slot]) return ctd_fail(h, CTD_E_INVALID, "slot %d has an uncollected submission", slot);
   ShapePlan* sp = nullptr;
   if (int rc = prepare_forward(h, n, ph, pw, &sp)) return rc;
   if (int rc = ensure_pipeline(h)) return rc;
@@ -752,10 +690,10 @@ extern "C" int ctd_submit(ctd_handle* h, int32_t slot, const uint8_t* pages_host
   CK(cudaEventRecord(h->ev_in_free[slot], h->stream));
   if (int rc = enqueue_forward(h, n, ph, pw, *sp)) return rc;
   CK(cudaStreamWaitEvent(h->stream, h->ev_out_done[slot], 0));  // previous D2H of this slot has drained
-  CK(cudaMemcpyAsync(h->d_stage_out[slot], h->d_mask_u8, h->results_bytes, cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_stage_out[slot], h->d_mask_u8, h->layout.a_bytes, cudaMemcpyDeviceToDevice, h->stream));
   CK(cudaEventRecord(h->ev_out_ready[slot], h->stream));
   CK(cudaStreamWaitEvent(h->copy_out, h->ev_out_ready[slot], 0));
-  CK(cudaMemcpyAsync(results_host, h->d_stage_out[slot], h->results_bytes, cudaMemcpyDeviceToHost, h->copy_out));
+  CK(cudaMemcpyAsync(results_host, h->d_stage_out[slot], h->layout.a_bytes, cudaMemcpyDeviceToHost, h->copy_out));
   CK(cudaEventRecord(h->ev_out_done[slot], h->copy_out));
   h->slot_busy[slot] = true;
   return CTD_OK;
@@ -763,14 +701,19 @@ extern "C" int ctd_submit(ctd_handle* h, int32_t slot, const uint8_t* pages_host
 
 extern "C" int ctd_collect(ctd_handle* h, int32_t slot) {
   if (!h || slot < 0 || slot > 1) return CTD_E_INVALID;
-  if (!h->slot_busy[slot]) return fail(h, CTD_E_INVALID, "slot %d has nothing in flight", slot);
+  if (!h->slot_busy[slot]) return ctd_fail(h, CTD_E_INVALID, "slot %d has nothing in flight", slot);
   CK(cudaSetDevice(h->cfg.device));
+  if (h->slot_full[slot]) {
+    const int rc = ctd_collect_full(h, slot);
+    h->slot_busy[slot] = false;
+    return rc;
+  }
   CK(cudaEventSynchronize(h->ev_out_done[slot]));
   h->slot_busy[slot] = false;
   return CTD_OK;
 }
 
-static int ensure_io_scratch(ctd_handle* h, size_t bytes) {
+int ensure_io_scratch(ctd_handle* h, size_t bytes) {
   if (bytes <= h->io_scratch_cap) return CTD_OK;
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(h->d_io_scratch);
@@ -785,7 +728,7 @@ extern "C" int ctd_forward_resized(ctd_handle* h, const uint8_t* page, int32_t i
                                    int32_t unpad_w, int32_t net_h, int32_t net_w) {
   if (!h || !page) return CTD_E_INVALID;
   if (ih < 1 || iw < 1 || unpad_h < 1 || unpad_w < 1 || unpad_h > net_h || unpad_w > net_w)
-    return fail(h, CTD_E_SHAPE, "letterbox %dx%d -> %dx%d does not fit the %dx%d net input", ih, iw, unpad_h, unpad_w, net_h, net_w);
+    return ctd_fail(h, CTD_E_SHAPE, "letterbox %dx%d -> %dx%d does not fit the %dx%d net input", ih, iw, unpad_h, unpad_w, net_h, net_w);
   ShapePlan* sp = nullptr;
   if (int rc = prepare_forward(h, 1, net_h, net_w, &sp)) return rc;
   const size_t bytes = size_t(ih) * iw * 3;
@@ -799,9 +742,9 @@ extern "C" int ctd_forward_resized(ctd_handle* h, const uint8_t* page, int32_t i
 extern "C" int ctd_get_mask_u8_resized(ctd_handle* h, int32_t crop_h, int32_t crop_w, int32_t out_h, int32_t out_w,
                                        uint8_t* mask_out) {
   if (!h || !mask_out) return CTD_E_INVALID;
-  if (!h->have_forward) return fail(h, CTD_E_INVALID, "no forward pass has been run on this handle");
+  if (!h->have_forward) return ctd_fail(h, CTD_E_INVALID, "no forward pass has been run on this handle");
   if (crop_h < 1 || crop_w < 1 || crop_h > h->ph || crop_w > h->pw || out_h < 1 || out_w < 1)
-    return fail(h, CTD_E_SHAPE, "bad crop %dx%d of the %dx%d mask", crop_h, crop_w, h->ph, h->pw);
+    return ctd_fail(h, CTD_E_SHAPE, "bad crop %dx%d of the %dx%d mask", crop_h, crop_w, h->ph, h->pw);
   CK(cudaSetDevice(h->cfg.device));
   const size_t bytes = size_t(out_h) * out_w;
   if (int rc = ensure_io_scratch(h, bytes)) return rc;
@@ -814,7 +757,7 @@ extern "C" int ctd_get_mask_u8_resized(ctd_handle* h, int32_t crop_h, int32_t cr
 extern "C" int ctd_resize_linear_u8(ctd_handle* h, const uint8_t* src, int32_t sh, int32_t sw, int32_t channels, uint8_t* dst,
                                     int32_t dh, int32_t dw) {
   if (!h || !src || !dst) return CTD_E_INVALID;
-  if ((channels != 1 && channels != 3) || sh < 1 || sw < 1 || dh < 1 || dw < 1) return fail(h, CTD_E_SHAPE, "bad resize shape");
+  if ((channels != 1 && channels != 3) || sh < 1 || sw < 1 || dh < 1 || dw < 1) return ctd_fail(h, CTD_E_SHAPE, "bad resize shape");
   CK(cudaSetDevice(h->cfg.device));
   const size_t sb = size_t(sh) * sw * channels, db = size_t(dh) * dw * channels;
   const size_t so = (sb + 255) / 256 * 256;
@@ -829,7 +772,7 @@ extern "C" int ctd_resize_linear_u8(ctd_handle* h, const uint8_t* src, int32_t s
 extern "C" int ctd_join(ctd_handle* h, ctd_handle* other) {
   if (!h || !other) return CTD_E_INVALID;
   if (h == other) return CTD_OK;
-  if (h->cfg.device != other->cfg.device) return fail(h, CTD_E_INVALID, "ctd_join: handles live on different devices");
+  if (h->cfg.device != other->cfg.device) return ctd_fail(h, CTD_E_INVALID, "ctd_join: handles live on different devices");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaEventRecord(other->ev_xjoin, other->stream));
   CK(cudaStreamWaitEvent(h->stream, other->ev_xjoin, 0));
@@ -844,7 +787,7 @@ extern "C" int ctd_results_bytes(ctd_handle* h, size_t* bytes) {
 
 #define NEED_FWD()                                                                     \
   if (!h) return CTD_E_INVALID;                                                        \
-  if (!h->have_forward) return fail(h, CTD_E_INVALID, "no forward pass has been run"); \
+  if (!h->have_forward) return ctd_fail(h, CTD_E_INVALID, "no forward pass has been run"); \
   CK(cudaSetDevice(h->cfg.device));
 
 extern "C" int ctd_get_net_outputs(ctd_handle* h, float* blks, float* mask, float* lines) {
@@ -912,7 +855,7 @@ extern "C" int ctd_seg_represent(ctd_handle* h, const float* pred, int32_t ih, i
                                  float* scores, int32_t* count) {
   if (!h || !pred || !boxes || !scores || !count) return CTD_E_INVALID;
   if (ih < 1 || iw < 1 || size_t(ih) * iw > size_t(h->cfg.max_h) * h->cfg.max_w || ih > 2048 || iw > 2048)
-    return fail(h, CTD_E_CAPACITY, "map larger than the workspace");
+    return ctd_fail(h, CTD_E_CAPACITY, "map larger than the workspace");
   CK(cudaSetDevice(h->cfg.device));
   const size_t px = size_t(ih) * iw;
   CK(cudaMemcpyAsync(h->d_lines, pred, px * 4, cudaMemcpyHostToDevice, h->stream));
@@ -962,9 +905,9 @@ extern "C" int ctd_profile_forward(ctd_handle* h, const uint8_t* pages, int32_t 
                                    int32_t pages_on_device, float* op_ms, int32_t cap) {
   if (!h || !pages || !op_ms) return CTD_E_INVALID;
   const int need = int(h->ops.size()) + 2;
-  if (cap < need) return fail(h, CTD_E_INVALID, "op_ms needs %d entries", need);
+  if (cap < need) return ctd_fail(h, CTD_E_INVALID, "op_ms needs %d entries", need);
   if (n < 1 || n > h->cfg.max_batch || ph % 64 || pw % 64 || ph > h->cfg.max_h || pw > h->cfg.max_w)
-    return fail(h, CTD_E_SHAPE, "bad shape");
+    return ctd_fail(h, CTD_E_SHAPE, "bad shape");
   CK(cudaSetDevice(h->cfg.device));
   while (int(h->op_events.size()) < need + 1) {
     cudaEvent_t e;
@@ -1018,10 +961,10 @@ __global__ void to_f32_kernel(const T* src, float* dst, size_t n) {
 
 extern "C" int ctd_debug_read_buffer(ctd_handle* h, int32_t buf, float* out, size_t out_elems) {
   NEED_FWD();
-  if (buf < 0 || buf >= int(h->bufs.size()) || !out) return fail(h, CTD_E_INVALID, "bad buffer id");
+  if (buf < 0 || buf >= int(h->bufs.size()) || !out) return ctd_fail(h, CTD_E_INVALID, "bad buffer id");
   const ctd_bufdesc& b = h->bufs[buf];
   const size_t elems = size_t(h->n) * (h->ph / b.down) * (h->pw / b.down) * b.channels;
-  if (out_elems < elems) return fail(h, CTD_E_INVALID, "buffer %d holds %zu elements", buf, elems);
+  if (out_elems < elems) return ctd_fail(h, CTD_E_INVALID, "buffer %d holds %zu elements", buf, elems);
   float* tmp = nullptr;
   CK(cudaMalloc(&tmp, elems * 4));
   if (h->elem == 4) to_f32_kernel<float><<<unsigned((elems + 255) / 256), 256, 0, h->stream>>>(static_cast<float*>(h->d_buf[buf]), tmp, elems);
@@ -1041,8 +984,8 @@ __global__ void from_f32_kernel(const float* src, T* dst, size_t n) {
 
 extern "C" int ctd_debug_write_buffer(ctd_handle* h, int32_t buf, const float* in, int32_t n, int32_t ph, int32_t pw) {
   if (!h || !in) return CTD_E_INVALID;
-  if (buf < 0 || buf >= int(h->bufs.size())) return fail(h, CTD_E_INVALID, "bad buffer id");
-  if (n < 1 || n > h->cfg.max_batch || ph > h->cfg.max_h || pw > h->cfg.max_w) return fail(h, CTD_E_CAPACITY, "shape");
+  if (buf < 0 || buf >= int(h->bufs.size())) return ctd_fail(h, CTD_E_INVALID, "bad buffer id");
+  if (n < 1 || n > h->cfg.max_batch || ph > h->cfg.max_h || pw > h->cfg.max_w) return ctd_fail(h, CTD_E_CAPACITY, "shape");
   CK(cudaSetDevice(h->cfg.device));
   const ctd_bufdesc& b = h->bufs[buf];
   const size_t elems = size_t(n) * (ph / b.down) * (pw / b.down) * b.channels;
@@ -1067,9 +1010,9 @@ extern "C" int ctd_debug_write_buffer(ctd_handle* h, int32_t buf, const float* i
 extern "C" int ctd_debug_run_ops(ctd_handle* h, const uint8_t* pages, int32_t n, int32_t ph, int32_t pw, int32_t first_op,
                                  int32_t last_op) {
   if (!h) return CTD_E_INVALID;
-  if (first_op < 0 || last_op >= int(h->ops.size()) || first_op > last_op) return fail(h, CTD_E_INVALID, "bad op range");
+  if (first_op < 0 || last_op >= int(h->ops.size()) || first_op > last_op) return ctd_fail(h, CTD_E_INVALID, "bad op range");
   if (n < 1 || n > h->cfg.max_batch || ph % 64 || pw % 64 || ph > h->cfg.max_h || pw > h->cfg.max_w || ph < 64 || pw < 64)
-    return fail(h, CTD_E_SHAPE, "bad shape");
+    return ctd_fail(h, CTD_E_SHAPE, "bad shape");
   CK(cudaSetDevice(h->cfg.device));
   auto key = std::make_tuple(int(n), int(ph), int(pw));
   auto it = h->plans.find(key);
@@ -1089,16 +1032,12 @@ extern "C" int ctd_debug_run_ops(ctd_handle* h, const uint8_t* pages, int32_t n,
   return CTD_OK;
 }
 
-extern "C" int ctd_connected_components(ctd_handle* h, const uint8_t* img, int32_t ih, int32_t iw, int32_t* labels,
-                                        int32_t* stats, int32_t stats_cap, int32_t* n_labels) {
-  if (!h || !img || !labels || !n_labels) return CTD_E_INVALID;
-  if (ih < 1 || iw < 1 || size_t(ih) * iw > (size_t(1) << 28)) return fail(h, CTD_E_SHAPE, "bad image size %dx%d", ih, iw);
-  CK(cudaSetDevice(h->cfg.device));
+int cc_device(ctd_handle* h, const uint8_t* d_img, int ih, int iw, int stats_cap, int32_t** d_stats, int32_t* n_labels) {
   const size_t px = size_t(ih) * iw;
   // own grow-on-demand scratch (any page size, independent of the net-input workspace; the results of the last
-  // forward stay intact): bitmap | labels | 3 ints/px of CCL scratch (reused for the stats table) | n_labels
+  // forward stay intact): labels | 3 ints/px of CCL scratch (reused for the stats table) | n_labels
   auto al = [](size_t v) { return (v + 255) / 256 * 256; };
-  const size_t o_lab = al(px), o_scr = o_lab + al(px * 4);
+  const size_t o_scr = al(px * 4);
   const size_t scr_bytes = al(std::max(px * 12, size_t(stats_cap > 0 ? stats_cap : 0) * 5 * 4));
   const size_t o_nl = o_scr + scr_bytes, need = o_nl + 256;
   if (need > h->cc_scratch_cap) {
@@ -1110,61 +1049,29 @@ extern "C" int ctd_connected_components(ctd_handle* h, const uint8_t* img, int32
     h->cc_scratch_cap = need + need / 4;
   }
   uint8_t* base = static_cast<uint8_t*>(h->d_cc_scratch);
-  uint8_t* d_bitmap = base;
-  int32_t* d_labels = reinterpret_cast<int32_t*>(base + o_lab);
+  int32_t* d_labels = reinterpret_cast<int32_t*>(base);
   int32_t* d_scr = reinterpret_cast<int32_t*>(base + o_scr);
   int32_t* d_nl = reinterpret_cast<int32_t*>(base + o_nl);
-  CK(cudaMemcpyAsync(d_bitmap, img, px, cudaMemcpyHostToDevice, h->stream));
-  CK(ccl_launch(d_bitmap, 1, ih, iw, d_labels, d_scr, d_nl, h->stream));
-  CK(cudaMemcpyAsync(labels, d_labels, px * 4, cudaMemcpyDeviceToHost, h->stream));
+  CK(ccl_launch(d_img, 1, ih, iw, d_labels, d_scr, d_nl, h->stream));
+  if (stats_cap > 0) CK(ccl_stats_launch(d_labels, ih, iw, d_scr, stats_cap, h->stream));   // scratch is free after ccl_launch
   CK(cudaMemcpyAsync(n_labels, d_nl, 4, cudaMemcpyDeviceToHost, h->stream));
-  if (stats && stats_cap > 0) {
-    CK(ccl_stats_launch(d_labels, ih, iw, d_scr, stats_cap, h->stream));   // scratch is free again after ccl_launch
-    CK(cudaMemcpyAsync(stats, d_scr, size_t(stats_cap) * 5 * 4, cudaMemcpyDeviceToHost, h->stream));
-  }
   CK(cudaStreamSynchronize(h->stream));
+  if (d_stats) *d_stats = d_scr;
   return CTD_OK;
 }
 
-extern "C" int ctd_refine_mask(ctd_handle* h, const uint8_t* img, const uint8_t* mask, int32_t ih, int32_t iw,
-                               const int32_t* windows, int32_t n_win, int32_t refine_mode, uint8_t* out) {
-  if (!h || !img || !mask || !out || (n_win > 0 && !windows)) return CTD_E_INVALID;
-  if (ih < 1 || iw < 1 || (size_t(ih) * iw) % 4) return fail(h, CTD_E_SHAPE, "ih*iw must be a multiple of 4");
+extern "C" int ctd_connected_components(ctd_handle* h, const uint8_t* img, int32_t ih, int32_t iw, int32_t* labels,
+                                        int32_t* stats, int32_t stats_cap, int32_t* n_labels) {
+  if (!h || !img || !labels || !n_labels) return CTD_E_INVALID;
+  if (ih < 1 || iw < 1 || size_t(ih) * iw > (size_t(1) << 28)) return ctd_fail(h, CTD_E_SHAPE, "bad image size %dx%d", ih, iw);
   CK(cudaSetDevice(h->cfg.device));
-  struct Win { int x1, y1, x2, y2; long long off; };
-  std::vector<Win> wins;
-  size_t total = 0;
-  for (int i = 0; i < n_win; ++i) {
-    Win w{windows[4 * i], windows[4 * i + 1], windows[4 * i + 2], windows[4 * i + 3], (long long)total};
-    if (w.x1 < 0 || w.y1 < 0 || w.x2 > iw || w.y2 > ih) return fail(h, CTD_E_INVALID, "window %d outside the image", i);
-    if (w.x2 > w.x1 && w.y2 > w.y1) total += size_t(w.x2 - w.x1) * (w.y2 - w.y1);
-    total = (total + 3) / 4 * 4;
-    wins.push_back(w);
-  }
   const size_t px = size_t(ih) * iw;
-  const size_t need = refine_scratch_bytes(total) + px * 5 + wins.size() * sizeof(Win) + 1024;
-  if (need > h->refine_scratch_cap) {
-    cudaFree(h->d_refine_scratch);
-    h->d_refine_scratch = nullptr;
-    h->refine_scratch_cap = 0;
-    CK(cudaMalloc(&h->d_refine_scratch, need + need / 4));
-    h->refine_scratch_cap = need + need / 4;
-  }
-  char* base = static_cast<char*>(h->d_refine_scratch);
-  uint8_t* d_img = reinterpret_cast<uint8_t*>(base);
-  uint8_t* d_mask = d_img + px * 3;
-  uint8_t* d_out = d_mask + px;
-  char* d_wins = reinterpret_cast<char*>(d_out + px);
-  d_wins = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(d_wins) + 255) / 256 * 256);
-  char* d_scr = d_wins + (wins.size() * sizeof(Win) + 255) / 256 * 256;
-  CK(cudaMemcpyAsync(d_img, img, px * 3, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(d_mask, mask, px, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemsetAsync(d_out, 0, px, h->stream));
-  if (!wins.empty()) {
-    CK(cudaMemcpyAsync(d_wins, wins.data(), wins.size() * sizeof(Win), cudaMemcpyHostToDevice, h->stream));
-    CK(refine_launch(d_img, d_mask, ih, iw, d_wins, int(wins.size()), total, d_scr, refine_mode, d_out, h->stream));
-  }
-  CK(cudaMemcpyAsync(out, d_out, px, cudaMemcpyDeviceToHost, h->stream));
+  if (int rc = ensure_io_scratch(h, px + 256)) return rc;
+  CK(cudaMemcpyAsync(h->d_io_scratch, img, px, cudaMemcpyHostToDevice, h->stream));
+  int32_t* d_stats = nullptr;
+  if (int rc = cc_device(h, h->d_io_scratch, ih, iw, (stats && stats_cap > 0) ? stats_cap : 0, &d_stats, n_labels)) return rc;
+  CK(cudaMemcpyAsync(labels, h->d_cc_scratch, px * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (stats && stats_cap > 0) CK(cudaMemcpyAsync(stats, d_stats, size_t(stats_cap) * 5 * 4, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return CTD_OK;
 }
@@ -1174,7 +1081,7 @@ extern "C" int ctd_nms(ctd_handle* h, const float* pred, int32_t rows, float con
   if (!h || !pred || !det || !det_count) return CTD_E_INVALID;
   const int no = 5 + h->cfg.nc;
   if (rows > rows_per_image(h->cfg.max_h, h->cfg.max_w) * h->cfg.max_batch)
-    return fail(h, CTD_E_CAPACITY, "too many prediction rows");
+    return ctd_fail(h, CTD_E_CAPACITY, "too many prediction rows");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaMemcpyAsync(h->d_blks, pred, size_t(rows) * no * 4, cudaMemcpyHostToDevice, h->stream));
   CK(nms_launch(h->d_blks, 1, rows, h->cfg.nc, conf_thresh, iou_thresh, h->nms, h->d_det, h->d_det_count, h->stream));

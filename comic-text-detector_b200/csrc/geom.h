@@ -137,18 +137,20 @@ CTD_HD RRect mar_core(const IPt* hull, int n, const float* vx, const float* vy, 
   int b_left = 0, b_bottom = 0;
   float b_a = 1.f, b_b = 0.f, b_w = 0.f, b_h = 0.f;
   for (int k = 0; k < n; ++k) {
-    const float dp0 = F_ADD(F_MUL(base_a, vx[seq[0]]), F_MUL(base_b, vy[seq[0]]));
-    const float dp1 = F_ADD(F_MUL(-base_b, vx[seq[1]]), F_MUL(base_a, vy[seq[1]]));
-    const float dp2 = F_SUB(F_MUL(-base_a, vx[seq[2]]), F_MUL(base_b, vy[seq[2]]));
-    const float dp3 = F_SUB(F_MUL(base_b, vx[seq[3]]), F_MUL(base_a, vy[seq[3]]));
-    float maxcos = F_MUL(dp0, inv[seq[0]]);
+    // OpenCV >= 4.5.2 (rotcalipers.cpp): the caliper side that meets its polygon edge first is found from the SIGN of
+    // cross products of the four edge vectors rotated into a common frame (bottom: as is, right: 90 deg clockwise,
+    // top: 180 deg, left: 90 deg counter-clockwise), not from float cosines -- exact for integer hull vertices
+    float rvx[4], rvy[4];
+    rvx[0] = vx[seq[0]];  rvy[0] = vy[seq[0]];
+    rvx[1] = vy[seq[1]];  rvy[1] = -vx[seq[1]];
+    rvx[2] = -vx[seq[2]]; rvy[2] = -vy[seq[2]];
+    rvx[3] = -vy[seq[3]]; rvy[3] = vx[seq[3]];
     int main_element = 0;
-    float c = F_MUL(dp1, inv[seq[1]]);
-    if (c > maxcos) { main_element = 1; maxcos = c; }
-    c = F_MUL(dp2, inv[seq[2]]);
-    if (c > maxcos) { main_element = 2; maxcos = c; }
-    c = F_MUL(dp3, inv[seq[3]]);
-    if (c > maxcos) { main_element = 3; maxcos = c; }
+    for (int i = 1; i < 4; ++i) {
+      // firstVecIsRight(rot[i], rot[main]): rotate rot[i] 90 deg clockwise, dot with rot[main] < 0
+      const float tx = rvy[i], ty = -rvx[i];
+      if (F_ADD(F_MUL(tx, rvx[main_element]), F_MUL(ty, rvy[main_element])) < 0.f) main_element = i;
+    }
     const int pindex = seq[main_element];
     const float lead_x = F_MUL(vx[pindex], inv[pindex]);
     const float lead_y = F_MUL(vy[pindex], inv[pindex]);
@@ -189,19 +191,15 @@ CTD_HD RRect mar_core(const IPt* hull, int n, const float* vx, const float* vy, 
   r.cy = F_ADD(py, F_MUL(F_ADD(o1y, o2y), 0.5f));
   r.w = (float)sqrt(D_ADD(D_MUL((double)o1x, (double)o1x), D_MUL((double)o1y, (double)o1y)));
   r.h = (float)sqrt(D_ADD(D_MUL((double)o2x, (double)o2x), D_MUL((double)o2y, (double)o2y)));
-  double vxx = (double)o1x, vyy = (double)o1y;
-  float ang = (float)D_DIV(D_MUL((double)(float)atan2(vyy, vxx), 180.0), kPi);
-  // normalise into [-90, 0): every quarter turn swaps width and height
+  // OpenCV 4.13 minAreaRect: the angle is formed in DOUBLE from the first side vector, brought into [-90, 0) by
+  // quarter turns (each swaps width and height) and only then rounded to float -- pinned against cv2 on 20k random
+  // hulls (tests/test_cpu_geom.py): f32(atan2(y, x) * 180 / pi - 90) for the first-quadrant vectors the calipers emit.
+  double deg = D_DIV(D_MUL(atan2((double)o1y, (double)o1x), 180.0), kPi);
   int nsw = 0;
-  double aa = ang;
-  while (aa >= 0) { aa -= 90; ++nsw; }
-  while (aa < -90) { aa += 90; --nsw; }
-  if (nsw != 0) {
-    if (nsw & 1) { const float t = r.w; r.w = r.h; r.h = t; }
-    int q = ((nsw % 4) + 4) % 4;
-    for (int i = 0; i < q; ++i) { const double t = vxx; vxx = vyy; vyy = -t; }
-    ang = (float)D_DIV(D_MUL((double)(float)atan2(vyy, vxx), 180.0), kPi);
-  }
+  while (deg >= 0) { deg = D_SUB(deg, 90.0); ++nsw; }
+  while (deg < -90) { deg = D_ADD(deg, 90.0); ++nsw; }
+  if (nsw & 1) { const float t = r.w; r.w = r.h; r.h = t; }
+  const float ang = (float)deg;
   r.angle = ang;
   return r;
 }

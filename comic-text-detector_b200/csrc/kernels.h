@@ -202,7 +202,12 @@ cudaError_t binarize_launch(const float* pred, size_t count, float thresh, uint8
 cudaError_t resize_linear_u8_launch(const uint8_t* src, int sh, int sw, size_t src_pitch, int channels, uint8_t* dst,
                                     int dh, int dw, int canvas_h, int canvas_w, cudaStream_t s);
 size_t refine_scratch_bytes(size_t total_px);
-cudaError_t refine_launch(const uint8_t* d_img, const uint8_t* d_mask, int H, int W, const void* d_wins, int n_wins,
-                          size_t total_px, void* scratch, int refine_mode, uint8_t* d_out, cudaStream_t s);
+// d_wins: RefineWin records {x1,y1,x2,y2,(int64) plane offset,(int) page,(int) pad} = 32 bytes; idx_small / idx_large:
+// device index lists into d_wins (windows above refine_large_px() pixels are processed by a CTA cluster each).
+cudaError_t refine_launch(const uint8_t* d_img, const uint8_t* d_mask, int H, int W, const void* d_wins, const int* d_idx_small,
+                          int n_small, const int* d_idx_large, int n_large, size_t total_px, void* scratch, int refine_mode,
+                          uint8_t* d_out, cudaStream_t s);
+int refine_large_px();
+size_t refine_win_bytes();
 
 }  // namespace ctd

@@ -3,22 +3,64 @@
 // per-channel Otsu candidate, polarity by min xor-sum, candidate-by-candidate connected-component merge
 // against the eroded/thresholded mask, 3x3 dilation (inpaint mode), hole filling, OR into the page mask.
 //
-// One CTA per block window; phases are separated by __syncthreads(); all per-window planes live in a
-// scratch arena (L2 resident).  Integer arithmetic throughout except the float64 numpy/OpenCV formulas that
-// are replicated literally (np.histogram bin mapping, np.linspace edges, cv2 Otsu, cvRound of inRange bounds).
+// One GROUP of CTAs per block window: a single CTA for small windows, a thread-block CLUSTER of kRefCluster CTAs for
+// large ones (a 1024x1024 window took 78 ms on one CTA: the phases are latency-bound sweeps over the window).  The
+// phases are separated by group barriers (__syncthreads / barrier.cluster); every per-window plane lives in a
+// global scratch arena (L2 resident), the per-window histograms / sums are reduced across the cluster through
+// distributed shared memory and every CTA then takes the (deterministic) scalar decisions redundantly.  Windows of
+// ALL pages of a batch are processed by one launch per group size (RefineWin::page selects the image / mask / output
+// planes).  Integer arithmetic throughout except the float64 numpy/OpenCV formulas that are replicated literally
+// (np.histogram bin mapping, np.linspace edges, cv2 Otsu, cvRound of inRange bounds).
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <limits.h>
 #include <math.h>
 
 #include "kernels.h"
 
+namespace cg = cooperative_groups;
+
 namespace ctd {
 
 constexpr int kRefThreads = 512;
+constexpr int kRefCluster = 8;          // CTAs per large window (portable cluster size)
+constexpr int kRefLargePx = 24 * 1024;  // windows with more pixels go to the cluster kernel
+
+// one window group: CL CTAs (cluster) of kRefThreads threads
+template <int CL>
+struct Grp {
+  __device__ static __forceinline__ int rank() { return CL == 1 ? 0 : int(cg::this_cluster().block_rank()); }
+  __device__ static __forceinline__ int tid() { return rank() * kRefThreads + int(threadIdx.x); }
+  static constexpr int size = CL * kRefThreads;
+  __device__ static __forceinline__ void sync() {
+    if constexpr (CL == 1) __syncthreads();
+    else cg::this_cluster().sync();
+  }
+  // every CTA ends up with the cluster-wide sum of its `n`-entry shared array (n <= 1024); `tmp` is shared scratch
+  template <typename T>
+  __device__ static __forceinline__ void allreduce(T* arr, int n, T* tmp) {
+    if constexpr (CL == 1) {
+      __syncthreads();
+    } else {
+      cg::cluster_group cl = cg::this_cluster();
+      cl.sync();                       // local accumulation finished everywhere
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        T sum = 0;
+        for (int r = 0; r < CL; ++r) sum += *cl.map_shared_rank(arr + i, r);
+        tmp[i] = sum;
+      }
+      cl.sync();                       // everybody has read everybody
+      for (int i = threadIdx.x; i < n; i += blockDim.x) arr[i] = tmp[i];
+      __syncthreads();
+    }
+  }
+};
 
 struct RefineWin {
   int x1, y1, x2, y2;     // window (python slice semantics: rows y1..y2-1, cols x1..x2-1)
   long long off;          // pixel offset of this window's planes inside each scratch plane
+  int page;               // page of the batch the window belongs to
+  int pad;
 };
 
 struct RefinePlanes {
@@ -31,19 +73,29 @@ struct RefinePlanes {
   int* acc;               // [4*total] per-root: area, gain, loss, maxidx
 };
 
+// XSM: the union-find array is updated by CTAs on other SMs (cluster groups): parent reads bypass L1 (a stale parent
+// would still be an ancestor -- parents only decrease -- but the chase would take longer and the final flatten must
+// see the final tree)
+template <bool XSM>
+__device__ __forceinline__ int rf_load(const int* p) {
+  if constexpr (XSM) return __ldcg(p);
+  else return *p;
+}
+template <bool XSM>
 __device__ __forceinline__ int rf_find(const int* L, int a) {
-  int p = L[a];
+  int p = rf_load<XSM>(L + a);
   while (p != a) {
     a = p;
-    p = L[a];
+    p = rf_load<XSM>(L + a);
   }
   return a;
 }
+template <bool XSM>
 __device__ __forceinline__ void rf_union(int* L, int a, int b) {
   bool done;
   do {
-    a = rf_find(L, a);
-    b = rf_find(L, b);
+    a = rf_find<XSM>(L, a);
+    b = rf_find<XSM>(L, b);
     if (a < b) {
       const int old = atomicMin(&L[b], a);
       done = old == b;
@@ -58,14 +110,20 @@ __device__ __forceinline__ void rf_union(int* L, int a, int b) {
   } while (!done);
 }
 
-// 8-connectivity labelling of plane `src` (non-zero = foreground) inside one window by the whole CTA.
+// 8-connectivity labelling of plane `src` (non-zero = foreground) inside one window by the whole group.
 // Afterwards L[i] = root (smallest index of the component) or -1.
-__device__ void cta_ccl(const uint8_t* __restrict__ src, int rw, int rh, int* __restrict__ L) {
-  // rows: run starts (one thread per row, sequential inside the row)
-  for (int y = threadIdx.x; y < rh; y += blockDim.x) {
+template <int CL>
+__device__ void grp_ccl(const uint8_t* __restrict__ src, int rw, int rh, int* __restrict__ L) {
+  using G = Grp<CL>;
+  // run starts: one thread per 64-pixel row segment (sequential inside the segment), then the segment seams
+  constexpr int kSegW = 64;
+  const int segs = (rw + kSegW - 1) / kSegW;
+  for (int t = G::tid(); t < rh * segs; t += G::size) {
+    const int y = t / segs, x0 = (t - y * segs) * kSegW;
+    const int x1 = min(rw, x0 + kSegW);
     int start = -1;
     const int base = y * rw;
-    for (int x = 0; x < rw; ++x) {
+    for (int x = x0; x < x1; ++x) {
       if (src[base + x]) {
         if (start < 0) start = base + x;
         L[base + x] = start;
@@ -75,26 +133,34 @@ __device__ void cta_ccl(const uint8_t* __restrict__ src, int rw, int rh, int* __
       }
     }
   }
-  __syncthreads();
+  G::sync();
   const int n = rw * rh;
+  if (segs > 1) {
+    for (int t = G::tid(); t < rh * (segs - 1); t += G::size) {
+      const int y = t / (segs - 1), x = ((t - y * (segs - 1)) + 1) * kSegW;
+      const int i = y * rw + x;
+      if (src[i] && src[i - 1]) rf_union<(CL > 1)>(L, i, i - 1);
+    }
+    G::sync();
+  }
   // contacts with the row above; all predicates read `src` (L is being rewritten by the unions)
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = G::tid(); i < n; i += G::size) {
     if (!src[i] || i < rw) continue;
     const int x = i % rw;
     const int up = i - rw;
     if (src[up]) {
       // only the first pixel of each (current run x upper run) overlap issues the union
       const bool first = x == 0 || !src[i - 1] || !src[up - 1];
-      if (first) rf_union(L, i, up);
+      if (first) rf_union<(CL > 1)>(L, i, up);
     } else {
-      if (x > 0 && src[up - 1]) rf_union(L, i, up - 1);
-      if (x + 1 < rw && src[up + 1]) rf_union(L, i, up + 1);
+      if (x > 0 && src[up - 1]) rf_union<(CL > 1)>(L, i, up - 1);
+      if (x + 1 < rw && src[up + 1]) rf_union<(CL > 1)>(L, i, up + 1);
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-    if (L[i] >= 0) L[i] = rf_find(L, i);
-  __syncthreads();
+  G::sync();
+  for (int i = G::tid(); i < n; i += G::size)
+    if (L[i] >= 0) L[i] = rf_find<(CL > 1)>(L, i);
+  G::sync();
 }
 
 __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* sm) {
@@ -107,24 +173,26 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 // merge step shared by the candidate loop and the hole filling (textmask.py:92-108 / 118-131):
 // a label is OR-ed into `merged` iff that lowers xor(merged, pred) inside the label's bounding box, i.e.
 // iff among the label's pixels not yet in `merged` more have pred == 255 than pred == 0.
-__device__ void cta_merge_labels(const int* __restrict__ L, const uint8_t* __restrict__ predm, uint8_t* __restrict__ merged,
+template <int CL>
+__device__ void grp_merge_labels(const int* __restrict__ L, const uint8_t* __restrict__ predm, uint8_t* __restrict__ merged,
                                  int* __restrict__ acc, int n, int rw, bool small_bbox_rule, int area_thresh) {
+  using G = Grp<CL>;
   int* area = acc;
   int* gain = acc + n;
   int* loss = acc + 2 * n;
   int* maxi = acc + 3 * n;
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
+  for (int i = G::tid(); i < n; i += G::size)
     if (L[i] == i) { area[i] = 0; gain[i] = 0; loss[i] = 0; maxi[i] = -1; }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  G::sync();
+  for (int i = G::tid(); i < n; i += G::size) {
     const int r = L[i];
     if (r < 0) continue;
     atomicAdd(&area[r], 1);
     atomicMax(&maxi[r], i);
     if (merged[i] == 0) atomicAdd(predm[i] ? &gain[r] : &loss[r], 1);
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  G::sync();
+  for (int i = G::tid(); i < n; i += G::size) {
     const int r = L[i];
     if (r < 0) continue;
     bool ok;
@@ -138,16 +206,22 @@ __device__ void cta_merge_labels(const int* __restrict__ L, const uint8_t* __res
     }
     if (ok && gain[r] > loss[r]) merged[i] = 255;
   }
-  __syncthreads();
+  G::sync();
 }
 
-__global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask,
-                                                             int H, int W, const RefineWin* __restrict__ wins, RefinePlanes P,
-                                                             int refine_mode, uint32_t* __restrict__ out_words) {
-  const RefineWin win = wins[blockIdx.x];
+template <int CL>
+__global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __restrict__ img_all, const uint8_t* __restrict__ mask_all,
+                                                             int H, int W, const RefineWin* __restrict__ wins,
+                                                             const int* __restrict__ win_idx, RefinePlanes P,
+                                                             int refine_mode, uint32_t* __restrict__ out_all) {
+  using G = Grp<CL>;
+  const RefineWin win = wins[win_idx[blockIdx.x / CL]];
   const int rw = win.x2 - win.x1, rh = win.y2 - win.y1;
-  if (rw <= 0 || rh <= 0) return;
+  if (rw <= 0 || rh <= 0) return;     // uniform over the group
   const int n = rw * rh;
+  const uint8_t* img = img_all + size_t(win.page) * H * W * 3;
+  const uint8_t* mask = mask_all + size_t(win.page) * H * W;
+  uint32_t* out_words = out_all + size_t(win.page) * H * W / 4;
   uint8_t* grey = P.grey + win.off;
   uint8_t* cand = P.cand + win.off;
   uint8_t* predm = P.predm + win.off;
@@ -156,8 +230,11 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __re
   int* L = P.L + win.off;
   int* acc = P.acc + 4 * win.off;
 
-  __shared__ int hist_g[256];          // grey histogram of the eroded-mask pixels
-  __shared__ int hist_c[3][256];       // per-channel histograms of the whole window (Otsu)
+  __shared__ int hist_all[1024];       // [0,256): grey histogram of the eroded-mask pixels; then the per-channel
+  int* hist_g = hist_all;              // histograms of the whole window (Otsu), B | G | R
+  int (*hist_c)[256] = reinterpret_cast<int (*)[256]>(hist_all + 256);
+  __shared__ int red_tmp[1024];        // staging of the cluster all-reduce
+  __shared__ unsigned long long red_tmp64[12];
   __shared__ int cnt255[256];          // np.histogram(bins=255) counts
   __shared__ int order[256];
   __shared__ double edges[256];
@@ -165,7 +242,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __re
   __shared__ int lo[3], hi[3], otsu_t[3];
   __shared__ unsigned long long xs[12];  // xor sums: [k][pos/neg] for 3 colours, then 3 channels
   __shared__ int proc_kind[4], proc_neg[4], s_nproc;
-  __shared__ int top2[2], s_area0;
+  __shared__ int top2[2], s_area0, ctop[2];
 
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     hist_g[i] = 0; hist_c[0][i] = 0; hist_c[1][i] = 0; hist_c[2][i] = 0; cnt255[i] = 0;
@@ -174,7 +251,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __re
   __syncthreads();
 
   // ---- phase 0: grey, eroded candidates, pred mask, histograms ---------------------------------
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = G::tid(); i < n; i += G::size) {
     const int y = i / rw, x = i - y * rw;
     const size_t gp = size_t(win.y1 + y) * W + win.x1 + x;
     const int b = img[gp * 3], g = img[gp * 3 + 1], r = img[gp * 3 + 2];
@@ -200,7 +277,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __re
     predm[i] = mc > 60 ? 255 : 0;                  // textmask.py:86-89
     merged[i] = 0;
   }
-  __syncthreads();
+  G::allreduce(hist_all, 1024, red_tmp);     // also orders the plane writes above before every later phase
 
   // ---- phase 1: np.histogram(bins=255) of the candidate grey values, top-k colours, Otsu ---------
   if (threadIdx.x == 0) {
@@ -293,7 +370,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __re
 #pragma unroll
     for (int k = 0; k < 12; ++k) loc[k] = 0ull;
     const int ncol = s_ncol;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = G::tid(); i < n; i += G::size) {
       const int y = i / rw, x = i - y * rw;
       const size_t gp = size_t(win.y1 + y) * W + win.x1 + x;
       const int mk = mask[gp];
@@ -314,7 +391,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __re
 #pragma unroll
     for (int k = 0; k < 12; ++k) block_sum_u64(loc[k], &xs[k]);
   }
-  __syncthreads();
+  G::allreduce(xs, 12, red_tmp64);
   if (threadIdx.x == 0) {
     // minxor_thresh (textmask.py:29-41): negative wins only if strictly smaller
     unsigned long long best[4];
@@ -349,7 +426,7 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __re
   // ---- phase 3: candidates in order: label, test every label, merge -------------------------------
   for (int c = 0; c < s_nproc; ++c) {
     const int kind = proc_kind[c], neg = proc_neg[c];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = G::tid(); i < n; i += G::size) {
       int t;
       if (kind < 3) {
         const int gr = grey[i];
@@ -361,14 +438,14 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __re
       }
       cand[i] = (uint8_t)(neg ? 255 - t : t);
     }
-    __syncthreads();
-    cta_ccl(cand, rw, rh, L);
-    cta_merge_labels(L, predm, merged, acc, n, rw, true, 0);
+    G::sync();
+    grp_ccl<CL>(cand, rw, rh, L);
+    grp_merge_labels<CL>(L, predm, merged, acc, n, rw, true, 0);
   }
 
   // ---- phase 4: dilate 3x3 (inpaint mode) ------------------------------------------------------------
   if (refine_mode == 0) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = G::tid(); i < n; i += G::size) {
       const int y = i / rw, x = i - y * rw;
       int m = 0;
       for (int dy = -1; dy <= 1; ++dy) {
@@ -382,34 +459,34 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __re
       }
       tmp[i] = (uint8_t)m;
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) merged[i] = tmp[i];
-    __syncthreads();
+    G::sync();
+    for (int i = G::tid(); i < n; i += G::size) merged[i] = tmp[i];
+    G::sync();
   }
 
   // ---- phase 5: fill holes: components of the inverse smaller than the 2nd largest area -------------
   if (threadIdx.x == 0) { top2[0] = -1; top2[1] = -1; s_area0 = 0; }
-  for (int i = threadIdx.x; i < n; i += blockDim.x) tmp[i] = merged[i] ? 0 : 255;
-  __syncthreads();
-  cta_ccl(tmp, rw, rh, L);
+  for (int i = G::tid(); i < n; i += G::size) tmp[i] = merged[i] ? 0 : 255;
+  G::sync();
+  grp_ccl<CL>(tmp, rw, rh, L);
   {
     int* area = acc;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int i = G::tid(); i < n; i += G::size)
       if (L[i] == i) area[i] = 0;
-    __syncthreads();
+    G::sync();
     int a0 = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = G::tid(); i < n; i += G::size) {
       if (L[i] >= 0) atomicAdd(&area[L[i]], 1);
       else ++a0;
     }
     if (a0) atomicAdd(&s_area0, a0);
-    __syncthreads();
+    G::allreduce(&s_area0, 1, red_tmp);
     // two largest areas over all labels INCLUDING label 0 (the pixels where the inverse is 0), as a multiset
     int m1 = -1, m2 = -1;
     auto push = [&](int a) { if (a > m1) { m2 = m1; m1 = a; } else if (a > m2) m2 = a; };
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int i = G::tid(); i < n; i += G::size)
       if (L[i] == i) push(area[i]);
-    if (threadIdx.x == 0) push(s_area0);
+    if (G::tid() == 0) push(s_area0);
     for (int o = 16; o > 0; o >>= 1) {
       const int a1 = __shfl_down_sync(0xffffffffu, m1, o), a2 = __shfl_down_sync(0xffffffffu, m2, o);
       push(a1);
@@ -425,18 +502,35 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __re
           const int a = wtop[wv][e];
           if (a > t1) { t2 = t1; t1 = a; } else if (a > t2) t2 = a;
         }
+      ctop[0] = t1; ctop[1] = t2;
+    }
+    G::sync();
+    if (threadIdx.x == 0) {   // merge the per-CTA pairs (multiset union of the two largest)
+      int t1 = -1, t2 = -1;
+      if constexpr (CL == 1) {
+        t1 = ctop[0]; t2 = ctop[1];
+      } else {
+        cg::cluster_group cl = cg::this_cluster();
+        for (int r = 0; r < CL; ++r) {
+          const int* rc = cl.map_shared_rank(ctop, r);
+          for (int e = 0; e < 2; ++e) {
+            const int a = rc[e];
+            if (a > t1) { t2 = t1; t1 = a; } else if (a > t2) t2 = a;
+          }
+        }
+      }
       top2[0] = t1; top2[1] = t2;
     }
-    __syncthreads();
+    G::sync();   // also keeps ctop alive until every CTA has read it
   }
   {
     // sorted_area[-2] if more than one label else sorted_area[-1] (textmask.py:114-118); label 0 always exists
     const int thresh = top2[1] >= 0 ? top2[1] : top2[0];
-    cta_merge_labels(L, predm, merged, acc, n, rw, false, thresh);
+    grp_merge_labels<CL>(L, predm, merged, acc, n, rw, false, thresh);
   }
 
   // ---- phase 6: mask_refined[window] |= merged (textmask.py:168); windows may overlap -> atomic OR ----
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = G::tid(); i < n; i += G::size) {
     if (!merged[i]) continue;
     const int y = i / rw, x = i - y * rw;
     const size_t gp = size_t(win.y1 + y) * W + win.x1 + x;
@@ -446,9 +540,12 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __re
 
 size_t refine_scratch_bytes(size_t total_px) { return total_px * (5 + 4 + 16) + 4096; }
 
-cudaError_t refine_launch(const uint8_t* d_img, const uint8_t* d_mask, int H, int W, const void* d_wins, int n_wins,
-                          size_t total_px, void* scratch, int refine_mode, uint8_t* d_out, cudaStream_t s) {
-  if (n_wins <= 0) return cudaSuccess;
+// wins: n_wins RefineWin records on the device; idx_small / idx_large: indices into `wins` (device), split by the
+// host at kRefLargePx pixels.  img / mask / out hold `H*W`-pixel planes per page (H*W % 4 == 0).
+cudaError_t refine_launch(const uint8_t* d_img, const uint8_t* d_mask, int H, int W, const void* d_wins, const int* d_idx_small,
+                          int n_small, const int* d_idx_large, int n_large, size_t total_px, void* scratch, int refine_mode,
+                          uint8_t* d_out, cudaStream_t s) {
+  if (n_small <= 0 && n_large <= 0) return cudaSuccess;
   char* p = static_cast<char*>(scratch);
   RefinePlanes P;
   P.L = reinterpret_cast<int*>(p); p += total_px * 4;
@@ -458,9 +555,29 @@ cudaError_t refine_launch(const uint8_t* d_img, const uint8_t* d_mask, int H, in
   P.predm = reinterpret_cast<uint8_t*>(p); p += total_px;
   P.merged = reinterpret_cast<uint8_t*>(p); p += total_px;
   P.tmp = reinterpret_cast<uint8_t*>(p);
-  refine_kernel<<<n_wins, kRefThreads, 0, s>>>(d_img, d_mask, H, W, static_cast<const RefineWin*>(d_wins), P, refine_mode,
-                                               reinterpret_cast<uint32_t*>(d_out));
+  const RefineWin* wins = static_cast<const RefineWin*>(d_wins);
+  uint32_t* out = reinterpret_cast<uint32_t*>(d_out);
+  if (n_large > 0) {
+    // large windows first: they are the critical path, the single-CTA windows fill in around them
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(n_large) * kRefCluster, 1, 1);
+    cfg.blockDim = dim3(kRefThreads, 1, 1);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kRefCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, refine_kernel<kRefCluster>, d_img, d_mask, H, W, wins, d_idx_large, P, refine_mode, out);
+    if (e != cudaSuccess) return e;
+  }
+  if (n_small > 0)
+    refine_kernel<1><<<n_small, kRefThreads, 0, s>>>(d_img, d_mask, H, W, wins, d_idx_small, P, refine_mode, out);
   return cudaGetLastError();
 }
+int refine_large_px() { return kRefLargePx; }
+size_t refine_win_bytes() { return sizeof(RefineWin); }
 
 }  // namespace ctd

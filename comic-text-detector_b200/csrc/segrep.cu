@@ -193,11 +193,18 @@ __global__ void __launch_bounds__(256) flag_scan_seg_kernel(int hw, int* __restr
   if (threadIdx.x == 255) segsum[page * nseg + seg] = woff + incl;
 }
 __global__ void __launch_bounds__(1024) flag_scan_top_kernel(int* __restrict__ segsum, int nseg, int* __restrict__ total) {
+  // exclusive scan of up to 4096 segment sums: 4 consecutive entries per thread, block scan of the per-thread sums
   __shared__ int part[1024];
   const int page = blockIdx.x;
   int* sgs = segsum + page * nseg;
-  const int v = threadIdx.x < nseg ? sgs[threadIdx.x] : 0;
-  part[threadIdx.x] = v;
+  int v[4], loc = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = threadIdx.x * 4 + k;
+    v[k] = i < nseg ? sgs[i] : 0;
+    loc += v[k];
+  }
+  part[threadIdx.x] = loc;
   __syncthreads();
   for (int off = 1; off < 1024; off <<= 1) {
     int u = 0;
@@ -206,7 +213,13 @@ __global__ void __launch_bounds__(1024) flag_scan_top_kernel(int* __restrict__ s
     part[threadIdx.x] += u;
     __syncthreads();
   }
-  if (threadIdx.x < nseg) sgs[threadIdx.x] = part[threadIdx.x] - v;
+  int run = part[threadIdx.x] - loc;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = threadIdx.x * 4 + k;
+    if (i < nseg) sgs[i] = run;
+    run += v[k];
+  }
   if (threadIdx.x == 1023) total[page] = part[1023];
 }
 // cid[root pixel] = position in OpenCV's list if < max_candidates else -1; contour table
@@ -628,8 +641,8 @@ size_t segrep_scratch_bytes(int n, int h, int w, int max_cand) {
          + hw * 8 * 3          // own_sum, tot_sum, ring_sum
          + size_t(n) * max_cand * h * 4 * 2   // rowmin, rowmax
          + size_t(n) * max_cand * 16          // c_root, c_yrange, perm
-         + size_t(n) * 2048 * 4               // segsum + totals
-         + 8192;
+         + size_t(n) * 8192 * 4               // segsum (<= 4096 per page) + totals
+         + 65536;                             // 256-byte alignment slack of the 17 sub-arrays
 }
 
 cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_page_stride, const int* Lf, int n, int h,
@@ -652,11 +665,11 @@ cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_
   int* c_root = reinterpret_cast<int*>(take(size_t(n) * max_cand * 4));
   int* c_yrange = reinterpret_cast<int*>(take(size_t(n) * max_cand * 8));
   int* perm = reinterpret_cast<int*>(take(size_t(n) * max_cand * 4));
-  int* segsum = reinterpret_cast<int*>(take(size_t(n) * 1024 * 4));
+  int* segsum = reinterpret_cast<int*>(take(size_t(n) * 4096 * 4));
   int* total = reinterpret_cast<int*>(take(size_t(n) * 4));
   ContourScratch* cs = nullptr;
   const int nseg = int((hw + kSeg - 1) / kSeg);
-  if (nseg > 1024) return cudaErrorInvalidValue;
+  if (nseg > 4096) return cudaErrorInvalidValue;
 
   dim3 tgrid((w + 31) / 32, (h + 31) / 32, n);
   dim3 grid(unsigned((hw + 255) / 256), n);

@@ -5,9 +5,9 @@ Same constructor and call signature as the reference's `inference.TextDetector`
 conf_thresh=0.4, mask_thresh=0.3, act='leaky')` and
 `detector(img, refine_mode=REFINEMASK_INPAINT, keep_undetected_mask=False) -> (mask, mask_refined, blk_list)`.
 
-Everything with per-pixel or per-contour work runs in libctd_b200.so (network, NMS, mask u8, DB binarize,
-connected components, contour boxes + scores, refine_mask); the host keeps what the reference does with
-a handful of numbers per block (ratio scaling, `group_output`, window expansion) -- SURVEY section 7.
+Everything runs in libctd_b200.so: network, NMS, mask u8, DB binarize, connected components, contour boxes + scores,
+refine_mask on the GPU; ratio scaling, `group_output` and the window expansion in host C++ (csrc/group.cpp,
+csrc/pipeline.cu).  This module is the reference-shaped Python surface over `ctd_detect_page`.
 """
 from pathlib import Path
 from typing import List
@@ -16,7 +16,7 @@ import numpy as np
 
 from . import compiler
 from .binding import Engine, PREC_FP16_TC, PREC_FP32_SIMT
-from .textblock import TextBlock, group_output, overlap_area
+from .textblock import TextBlock, blocks_from_records, group_output, overlap_area  # noqa: F401
 
 REFINEMASK_INPAINT = 0
 REFINEMASK_ANNOTATION = 1
@@ -84,75 +84,11 @@ class TextDetector:
         self.net.close()
 
     def __call__(self, img, refine_mode=REFINEMASK_INPAINT, keep_undetected_mask=False):
-        eng = self.net
-        # preprocess_img (inference.py:72-83): the BGR<->RGB double flip cancels, the net sees BGR.  The letterbox
-        # resize + padding run on the GPU (cv2-exact INTER_LINEAR); net-sized pages skip the resize kernel.
-        im_h, im_w = img.shape[:2]
-        _r, new_unpad, dw, dh = letterbox_geometry((im_h, im_w), self.input_size)
-        if (im_h, im_w) == tuple(self.input_size):
-            eng.forward(np.ascontiguousarray(img)[None])
-        else:
-            eng.forward_resized(img, new_unpad[1], new_unpad[0], self.input_size[0], self.input_size[1])
-        resize_ratio = (im_w / (self.input_size[0] - dw), im_h / (self.input_size[1] - dh))
-
-        # postprocess_yolo (inference.py:101-114) on the GPU NMS rows
-        det = eng.detections()[0]
-        det[..., [0, 2]] = det[..., [0, 2]] * resize_ratio[0]
-        det[..., [1, 3]] = det[..., [1, 3]] * resize_ratio[1]
-        blks = (det[..., 0:4].astype(np.int32), det[..., 5].astype(np.int32), np.round(det[..., 4], 3))
-
-        boxes, scores = eng.text_lines()                          # SegDetectorRepresenter (inference.py:158)
-        keep = np.where(scores[0] > 0.6)                          # box_thresh (inference.py:159-161)
-        lines = boxes[0][keep]
-
-        # postprocess_mask + crop + cv2.resize back to the page (inference.py:85-99,164-168), all on the GPU
-        mask = eng.mask_u8_resized(self.input_size[0] - dh, self.input_size[1] - dw, im_h, im_w)
-        if lines.size == 0:
-            lines = []
-        else:
-            lines = lines.astype(np.float64)
-            lines[..., 0] *= resize_ratio[0]
-            lines[..., 1] *= resize_ratio[1]
-            lines = lines.astype(np.int32)
-        blk_list = group_output(blks, lines, im_w, im_h, mask)
-        mask_refined = self._refine(img, mask, blk_list, refine_mode)
-        if keep_undetected_mask:
-            mask_refined = self._refine_undetected(img, mask, mask_refined, blk_list, refine_mode)
-        return mask, mask_refined, blk_list
-
-    # ---- textmask.py:159-169 ---------------------------------------------------------------------
-    def _refine(self, img, mask, blk_list: List[TextBlock], refine_mode):
-        wins = np.array([expand_textwindow(img.shape, blk.xyxy, expand_r=16) for blk in blk_list], np.int32).reshape(-1, 4)
-        h, w = img.shape[:2]
-        if (h * w) % 4 == 0:
-            return self.net.refine_mask(img, mask, wins, refine_mode)
-        # the kernel wants h*w % 4 == 0: pad the columns with zeros (windows lie inside the page, so their
-        # contents and therefore the result are unchanged) and crop the padding off again
-        wp = (w + 3) // 4 * 4
-        img_p = np.zeros((h, wp, 3), np.uint8)
-        img_p[:, :w] = img
-        mask_p = np.zeros((h, wp), np.uint8)
-        mask_p[:, :w] = mask
-        return np.ascontiguousarray(self.net.refine_mask(img_p, mask_p, wins, refine_mode)[:, :w])
-
-    # ---- textmask.py:135-156 ---------------------------------------------------------------------
-    def _refine_undetected(self, img, mask_pred, mask_refined, blk_list, refine_mode):
-        mask_pred[np.where(mask_refined > 30)] = 0                 # in place, like the reference (App. D #13)
-        pred_t = np.where(mask_pred > 30, 255, 0).astype(np.uint8)  # cv2.threshold(.., 30, 255, BINARY)
-        n, labels, stats = self.net.connected_components(pred_t, stats_cap=int(pred_t.size // 4 + 2))
-        valid = np.where(stats[:, -1] > 50)[0]
-        seg_blks = []
-        if len(valid) > 0:
-            for li in valid[1:]:
-                x, y, w, h, area = stats[li]
-                bbox = [x, y, x + w, y + h]
-                score = -1
-                for blk in blk_list:
-                    s = overlap_area(blk.xyxy, bbox)
-                    if s > score:
-                        score = s
-                if score / w / h < 0.5:
-                    seg_blks.append(TextBlock(bbox))
-        if len(seg_blks) > 0:
-            mask_refined = np.bitwise_or(mask_refined, self._refine(img, mask_pred, seg_blks, refine_mode))
-        return mask_refined
+        """reference inference.py:141-178.  One native call (`ctd_detect_page`): letterbox (cv2-exact INTER_LINEAR) +
+        network + NMS + mask u8 + DB boxes on the GPU, postprocess_yolo casts / box_thresh / group_output on the host
+        in C++, refine_mask (and refine_undetected_mask) on the GPU with the page and its mask resident in HBM; this
+        method only turns the block records into `TextBlock` objects."""
+        img = np.ascontiguousarray(img)
+        mask, mask_refined, rec, lines, dist = self.net.detect_page(img, self.input_size[0], self.input_size[1], refine_mode,
+                                                                    keep_undetected_mask)
+        return mask, mask_refined, blocks_from_records(rec, lines, dist)

