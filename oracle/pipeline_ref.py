@@ -8,7 +8,7 @@ import torch
 from oracle import postproc_ref
 
 
-def refine_undetected_mask(img, mask_pred, mask_refined, blk_xyxy, make_window_list, refine_mode):
+def refine_undetected_mask(img, mask_pred, mask_refined, blk_xyxy, make_window_list, refine_mode, tie_order="stable"):
     """utils/textmask.py:135-156 (mutates mask_pred in place like the reference)."""
     import cv2
     mask_pred[np.where(mask_refined > 30)] = 0
@@ -29,12 +29,12 @@ def refine_undetected_mask(img, mask_pred, mask_refined, blk_xyxy, make_window_l
             if score / w / h < 0.5:
                 extra.append([int(v) for v in bbox])
     if len(extra) > 0:
-        mask_refined = cv2.bitwise_or(mask_refined, postproc_ref.refine_mask(img, mask_pred, extra, refine_mode))
+        mask_refined = cv2.bitwise_or(mask_refined, postproc_ref.refine_mask(img, mask_pred, extra, refine_mode, tie_order))
     return mask_refined
 
 
 def postprocess_page(img, blks, mask_f32, lines_f32, group_output_fn, conf_thresh=0.4, nms_thresh=0.35,
-                     refine_mode=0, keep_undetected_mask=False):
+                     refine_mode=0, keep_undetected_mask=False, tie_order="stable"):
     """img u8 [H,W,3]; blks f32 [A,7]; mask_f32 [H,W]; lines_f32 [2,H,W] -> (mask u8, mask_refined u8, blk_list)."""
     im_h, im_w = img.shape[:2]
     det = postproc_ref.non_max_suppression(torch.as_tensor(blks)[None], conf_thresh, nms_thresh)[0].numpy()
@@ -55,7 +55,7 @@ def postprocess_page(img, blks, mask_f32, lines_f32, group_output_fn, conf_thres
         lines = lines.astype(np.int32)
     blk_list = group_output_fn(b, lines, im_w, im_h, mask)
     wins = [blk.xyxy for blk in blk_list]
-    mask_refined = postproc_ref.refine_mask(img, mask, wins, refine_mode)
+    mask_refined = postproc_ref.refine_mask(img, mask, wins, refine_mode, tie_order)
     if keep_undetected_mask:
-        mask_refined = refine_undetected_mask(img, mask, mask_refined, wins, None, refine_mode)
+        mask_refined = refine_undetected_mask(img, mask, mask_refined, wins, None, refine_mode, tie_order)
     return mask, mask_refined, blk_list

@@ -145,9 +145,11 @@ def expand_textwindow(img_size, xyxy, expand_r=8):
     return [x1, y1, x2, y2]
 
 
-def _topk_color(color_list, bins, k=3, color_var=10, bin_tol=0.001):
-    """textmask.py:16-27 (stable tie order, see header)."""
-    idx = np.argsort(bins * -1, kind="stable")
+def _topk_color(color_list, bins, k=3, color_var=10, bin_tol=0.001, tie_order="stable"):
+    """textmask.py:16-27.  tie_order='stable': ties of the histogram sort broken by ascending bin index (the documented
+    normalisation the CUDA kernel follows); 'numpy': `np.argsort(bins * -1)` exactly as the reference calls it (unstable,
+    its tie order depends on numpy's SIMD build) -- used to pin the oracle against the unmodified reference."""
+    idx = np.argsort(bins * -1, kind="stable") if tie_order == "stable" else np.argsort(bins * -1)
     color_list, bins = color_list[idx], bins[idx]
     top = [color_list[0]]
     tol = np.sum(bins) * bin_tol
@@ -169,7 +171,7 @@ def _minxor(threshed, mask):
     return (neg, neg_sum) if neg_sum < pos_sum else (threshed, pos_sum)
 
 
-def candidate_masks(im, msk):
+def candidate_masks(im, msk, tie_order="stable"):
     """get_topk_masklist + get_otsuthresh_masklist (textmask.py:43-71) -> list of [mask, xor_sum]"""
     import cv2
     grey = cv2.cvtColor(im, cv2.COLOR_BGR2GRAY)
@@ -177,7 +179,7 @@ def candidate_masks(im, msk):
     px = grey[np.where(cv2.erode(msk, np.ones((3, 3), np.uint8), iterations=1) > 127)]
     counts, edges = np.histogram(px, bins=255)
     out = []
-    for color in _topk_color(edges, counts, color_var=10, k=3):
+    for color in _topk_color(edges, counts, color_var=10, k=3, tie_order=tie_order):
         c_top = min(color + 30, 255)
         c_bottom = c_top - 60
         t, s = _minxor(cv2.inRange(grey, c_bottom, c_top), msk)
@@ -228,7 +230,7 @@ def merge_masks(mask_list, pred_mask, refine_mode=REFINEMASK_INPAINT):
     return merged
 
 
-def refine_mask(img, pred_mask, windows_xyxy, refine_mode=REFINEMASK_INPAINT):
+def refine_mask(img, pred_mask, windows_xyxy, refine_mode=REFINEMASK_INPAINT, tie_order="stable"):
     """refine_mask (textmask.py:159-169); `windows_xyxy` = [blk.xyxy for blk in blk_list]."""
     import cv2
     out = np.zeros_like(pred_mask)
@@ -236,6 +238,6 @@ def refine_mask(img, pred_mask, windows_xyxy, refine_mode=REFINEMASK_INPAINT):
         bx1, by1, bx2, by2 = expand_textwindow(img.shape, xyxy, expand_r=16)
         im = np.ascontiguousarray(img[by1:by2, bx1:bx2])
         msk = np.ascontiguousarray(pred_mask[by1:by2, bx1:bx2])
-        merged = merge_masks(candidate_masks(im, msk), msk, refine_mode)
+        merged = merge_masks(candidate_masks(im, msk, tie_order), msk, refine_mode)
         out[by1:by2, bx1:bx2] = cv2.bitwise_or(out[by1:by2, bx1:bx2], merged)
     return out
