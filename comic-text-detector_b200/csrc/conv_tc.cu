@@ -405,10 +405,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           // writes a FRESH accumulator from a ring of kRing TMEM slots and the epilogue threads sum the slots in fp32
           // registers with round-to-nearest; the small cross terms (lo x hi, hi x lo: 2^-12 of the sum, their
           // truncation is 2^-36) accumulate in TMEM as usual, in one slot per tile parity (slots 0 / 1).
-          constexpr int kRing = Cfg::kAccStages - 2;
-          uint32_t rc = 0;   // hi x hi MMAs issued so far (ring position)
+          // Each epilogue warpgroup owns its own ring (and cross-term slot): a slot's uses are then consumed by ONE
+          // warpgroup in production order, which the parity protocol needs (a consumer that starts waiting for use u
+          // of a slot before use u-1 has even been produced would see "previous phase complete" and run ahead).
+          constexpr int kRing = (Cfg::kAccStages - 2) / 2;
+          const uint32_t cpt_m = uint32_t(its_per_tile / 3) * uint32_t(ksteps);
           for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
             const int xs = ti & 1;
+            uint32_t rc = uint32_t(ti >> 1) * cpt_m;   // hi x hi MMAs issued so far for this warpgroup's tiles
             mbar_wait(tmem_empty_bar + 8 * xs, ((ti >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t tmem_x = tmem_base + uint32_t(xs * BN);
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               tc_fence_after();
               if (k_it % 3 == 0) {
                 for (int ks = 0; ks < ksteps; ++ks, ++rc) {
-                  const uint32_t slot = 2u + rc % kRing;
+                  const uint32_t slot = 2u + uint32_t(xs * kRing) + rc % kRing;
                   mbar_wait(tmem_empty_bar + 8 * slot, ((rc / kRing) & 1u) ^ 1u);
                   tc_fence_after();
                   umma_f16(tmem_base + slot * BN, ad + 2 * ks, bd + 2 * ks, idesc, 0u);
@@ -487,16 +491,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (p.split) {
           // promoted accumulation (see the MMA issuer): sum the hi x hi ring slots of this tile and its cross-term
           // slot in fp32 registers, then bias / activation / residual -> FP32 destination (or the Detect decode)
-          constexpr int kRing = Cfg::kAccStages - 2;
+          constexpr int kRing = (Cfg::kAccStages - 2) / 2;       // this warpgroup's ring (see the MMA issuer)
           const int cpt = (its_per_tile / 3) * (kb / 16);        // hi x hi MMAs per tile
           const uint32_t lane_off = uint32_t(quad * 32) << 16;
           float acc[BN];
 #pragma unroll
           for (int j = 0; j < BN; ++j) acc[j] = 0.f;
-          uint32_t rc = uint32_t(ti) * uint32_t(cpt);
+          uint32_t rc = uint32_t(ti >> 1) * uint32_t(cpt);
           for (int c = 0; c <= cpt; ++c, ++rc) {
             const bool last = c == cpt;                            // the cross-term slot comes last
-            const uint32_t slot = last ? uint32_t(ti & 1) : 2u + rc % kRing;
+            const uint32_t slot = last ? uint32_t(ti & 1) : 2u + uint32_t((ti & 1) * kRing) + rc % kRing;
             const uint32_t par = last ? uint32_t((ti >> 1) & 1) : ((rc / kRing) & 1u);
             mbar_wait_relaxed(tmem_full_bar + 8 * slot, par);
             tc_fence_after();

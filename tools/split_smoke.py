@@ -8,7 +8,8 @@ from util import get_checkpoint
 prec = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 ck = get_checkpoint(0, True)
 prog = ctd_b200.compiler.compile_checkpoint(ck)
-n, h, w = 1, 128, 128
+size = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+n, h, w = 1, size, size
 pages = np.stack([synth.structured_page(1000 + i, h, w) for i in range(n)])
 eng = ctd_b200.Engine(prog, precision=prec, max_batch=n, max_h=h, max_w=w)
 eng.forward(pages)

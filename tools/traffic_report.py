@@ -1,6 +1,8 @@
 """Aggregate an ncu CSV (`--metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv`) of
 tools/profile_forward.py: per-kernel DRAM bytes and time of the LAST forward, and the totals of the tensor-core
-convolution kernels (what bench.py reports as roofline.traffic).  Usage: traffic_report.py CSV [n_forwards] [out.json]"""
+convolution kernels (what bench.py reports as roofline.traffic).  With a 4th argument also writes the per-kernel table of
+every NON-conv kernel (post-processing, refine_mask, thin layers): launches, time, DRAM bytes and achieved GB/s per batch.
+Usage: traffic_report.py CSV [n_forwards] [conv_out.json] [postproc_out.json]"""
 import collections
 import csv
 import json
@@ -45,8 +47,19 @@ def main():
     tot["dram_bytes"] = tot["dram_read_bytes"] + tot["dram_write_bytes"]
     print("tensor-core conv kernels: %d launches, %.1f us, DRAM %.1f MB read + %.1f MB written per forward" % (
         tot["launches"], tot["us"], tot["dram_read_bytes"] / 1e6, tot["dram_write_bytes"] / 1e6))
-    if len(sys.argv) > 3:
+    if len(sys.argv) > 3 and sys.argv[3] != "-":
         json.dump(tot, open(sys.argv[3], "w"), indent=1)
+    if len(sys.argv) > 4:
+        rows = []
+        for k, (c, t, rdb, wrb) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            if any(x in k for x in ("conv_tc", "conv_halo", "conv_hs", "conv_sw")):
+                continue
+            rows.append({"kernel": k, "launches": c, "us": round(t, 1), "dram_read_MB": round(rdb / 1e6, 2),
+                         "dram_write_MB": round(wrb / 1e6, 2),
+                         "achieved_GBps": round((rdb + wrb) / (t * 1e-6) / 1e9, 1) if t > 0 else None})
+        json.dump({"what": "non-conv kernels of one batch (ncu dram__bytes_* and gpu__time_duration per launch, summed per kernel); "
+                           "achieved_GBps = DRAM bytes / kernel time; HBM peak 6572 GB/s (MEASURED_PEAKS.json)",
+                   "kernels": rows}, open(sys.argv[4], "w"), indent=1)
 
 
 if __name__ == "__main__":
