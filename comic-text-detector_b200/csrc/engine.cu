@@ -545,7 +545,7 @@ static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* lau
     CK(segrep_launch(h->d_bitmap, h->d_lines, size_t(2) * ph * pw, h->d_ccl_scratch, n, ph, pw, 1000, 1.5f,
                      h->d_segrep_scratch, h->d_line_boxes, h->d_line_scores, h->d_line_count, h->side));
     CK(cudaEventRecord(h->ev_join, h->side));
-    cnt += 22;
+    cnt += 23;
     size_t last_detect = h->ops.size();
     for (size_t i = 0; i < h->ops.size(); ++i)
       if (!h->db_ancestor[i] && h->ops[i].kind == CTD_OP_DETECT) last_detect = i;
@@ -590,7 +590,7 @@ static int run_ops(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp, int* lau
   cnt += 8;
   CK(segrep_launch(h->d_bitmap, h->d_lines, size_t(2) * ph * pw, h->d_ccl_scratch, n, ph, pw, 1000, 1.5f,
                    h->d_segrep_scratch, h->d_line_boxes, h->d_line_scores, h->d_line_count, h->stream));
-  cnt += 14;
+  cnt += 15;
   if (record) CK(cudaEventRecord(h->op_events[evi++], h->stream));
   *launches = cnt;
   return CTD_OK;

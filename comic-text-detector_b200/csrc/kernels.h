@@ -209,5 +209,13 @@ cudaError_t refine_launch(const uint8_t* d_img, const uint8_t* d_mask, int H, in
                           uint8_t* d_out, cudaStream_t s);
 int refine_large_px();
 size_t refine_win_bytes();
+// phase-synchronous form (refine_mk.cu): one kernel per phase over all window pixels of the batch, windows cut into
+// chunks of whole rows {win, y0, rows, pad} by the host; d_state: refine_mk_state_bytes(n_wins) bytes of per-window state
+size_t refine_mk_state_bytes(int n_wins);
+size_t refine_mk_chunk_bytes();
+int refine_mk_chunk_px();
+cudaError_t refine_mk_launch(const uint8_t* d_img, const uint8_t* d_mask, int H, int W, const void* d_wins, int n_wins,
+                             const void* d_chunks, int n_chunks, void* d_state, size_t total_px, void* scratch, int refine_mode,
+                             uint8_t* d_out, cudaStream_t s);
 
 }  // namespace ctd

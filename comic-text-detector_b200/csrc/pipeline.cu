@@ -47,12 +47,17 @@ void RefineJob::add(int x1, int y1, int x2, int y2, int page, int iw, int ih) {
   const size_t a = (x2 > x1 && y2 > y1) ? size_t(x2 - x1) * (y2 - y1) : 0;
   if (a == 0) return;                                    // empty slice: the reference's loop body is a no-op
   HostWin w{x1, y1, x2, y2, (long long)total_px, page, 0};
-  (a > size_t(refine_large_px()) ? idx_large : idx_small).push_back(int(wins.size()));
+  const int wi = int(wins.size());
+  (a > size_t(refine_large_px()) ? idx_large : idx_small).push_back(wi);
+  const int rw = x2 - x1, rh = y2 - y1;
+  const int rows_per = std::max(1, refine_mk_chunk_px() / rw);
+  for (int y0 = 0; y0 < rh; y0 += rows_per) chunks.push_back(HostChunk{wi, y0, std::min(rows_per, rh - y0), 0});
   wins.push_back(w);
   total_px = (total_px + a + 3) / 4 * 4;
 }
 size_t RefineJob::table_bytes() const {
-  return (wins.size() * sizeof(HostWin) + 255) / 256 * 256 + ((idx_small.size() + idx_large.size()) * 4 + 255) / 256 * 256;
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  return al(wins.size() * sizeof(HostWin)) + al((idx_small.size() + idx_large.size()) * 4) + al(chunks.size() * sizeof(HostChunk));
 }
 
 // uploads the window tables of `job` into the (grown on demand) refine scratch and launches the refine kernels:
@@ -61,10 +66,15 @@ size_t RefineJob::table_bytes() const {
 int launch_refine(ctd_handle* h, const RefineJob& job, const uint8_t* d_img, const uint8_t* d_mask, int ih, int iw,
                   int refine_mode, uint8_t* d_out, cudaStream_t st, char* pinned) {
   if (job.wins.empty()) return CTD_OK;
-  static_assert(sizeof(HostWin) == 32, "RefineWin layout");
-  if (refine_win_bytes() != sizeof(HostWin)) return ctd_fail(h, CTD_E_INVALID, "RefineWin layout mismatch");
+  static_assert(sizeof(HostWin) == 32 && sizeof(HostChunk) == 16, "RefineWin / Chunk layout");
+  if (refine_win_bytes() != sizeof(HostWin) || refine_mk_chunk_bytes() != sizeof(HostChunk))
+    return ctd_fail(h, CTD_E_INVALID, "RefineWin / Chunk layout mismatch");
+  const char* rf_env = getenv("CTD_REFINE");                   // CTD_REFINE=coop: the cooperative kernels of refine.cu
+  const bool coop = rf_env && rf_env[0] == 'c';
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
   const size_t tb = job.table_bytes();   // a multiple of 256
-  const size_t need = tb + refine_scratch_bytes(job.total_px);
+  const size_t sb = refine_mk_state_bytes(int(job.wins.size()));
+  const size_t need = tb + sb + refine_scratch_bytes(job.total_px);
   if (need > h->refine_scratch_cap) {
     CK(cudaDeviceSynchronize());         // the old scratch may still be in use by an earlier launch
     cudaFree(h->d_refine_scratch);
@@ -74,7 +84,8 @@ int launch_refine(ctd_handle* h, const RefineJob& job, const uint8_t* d_img, con
     h->refine_scratch_cap = need + need / 2;
   }
   char* base = static_cast<char*>(h->d_refine_scratch);
-  const size_t wb = (job.wins.size() * sizeof(HostWin) + 255) / 256 * 256;
+  const size_t wb = al(job.wins.size() * sizeof(HostWin));
+  const size_t ib = al((job.idx_small.size() + job.idx_large.size()) * 4);
   std::vector<char> local;
   char* stage = pinned;
   if (!stage) { local.resize(tb); stage = local.data(); }
@@ -82,11 +93,16 @@ int launch_refine(ctd_handle* h, const RefineJob& job, const uint8_t* d_img, con
   int* hidx = reinterpret_cast<int*>(stage + wb);
   if (!job.idx_small.empty()) memcpy(hidx, job.idx_small.data(), job.idx_small.size() * 4);
   if (!job.idx_large.empty()) memcpy(hidx + job.idx_small.size(), job.idx_large.data(), job.idx_large.size() * 4);
+  memcpy(stage + wb + ib, job.chunks.data(), job.chunks.size() * sizeof(HostChunk));
   CK(cudaMemcpyAsync(base, stage, tb, cudaMemcpyHostToDevice, st));
   if (!pinned) CK(cudaStreamSynchronize(st));   // pageable staging dies with this frame
   const int* d_idx = reinterpret_cast<const int*>(base + wb);
-  CK(refine_launch(d_img, d_mask, ih, iw, base, d_idx, int(job.idx_small.size()), d_idx + job.idx_small.size(),
-                   int(job.idx_large.size()), job.total_px, base + tb, refine_mode, d_out, st));
+  if (coop)
+    CK(refine_launch(d_img, d_mask, ih, iw, base, d_idx, int(job.idx_small.size()), d_idx + job.idx_small.size(),
+                     int(job.idx_large.size()), job.total_px, base + tb + sb, refine_mode, d_out, st));
+  else
+    CK(refine_mk_launch(d_img, d_mask, ih, iw, base, int(job.wins.size()), base + wb + ib, int(job.chunks.size()), base + tb,
+                        job.total_px, base + tb + sb, refine_mode, d_out, st));
   return CTD_OK;
 }
 
@@ -253,9 +269,9 @@ static void pipe_worker(ctd_handle* h) {
       uint8_t* d_arena = h->d_stage_out[slot];
       CK(cudaMemcpyAsync(d_arena + L.blocks, res + L.blocks, size_t(n) * L.blocks_stride, cudaMemcpyHostToDevice, st));
       CK(cudaMemsetAsync(d_arena + L.refined, 0, size_t(n) * px, st));
-      if (rj.table_bytes() > h->pipe_pinned_cap) return ctd_fail(h, CTD_E_CAPACITY, "refine window table larger than its staging buffer");
+      char* stage_tab = rj.table_bytes() <= h->pipe_pinned_cap ? h->pipe_pinned[slot] : nullptr;   // else: pageable + sync
       const uint8_t* d_pages = job.pages_dev ? job.pages_dev : h->d_stage_in[slot];
-      if (int r2 = launch_refine(h, rj, d_pages, d_arena, ph, pw, job.refine_mode, d_arena + L.refined, st, h->pipe_pinned[slot]))
+      if (int r2 = launch_refine(h, rj, d_pages, d_arena, ph, pw, job.refine_mode, d_arena + L.refined, st, stage_tab))
         return r2;
       CK(cudaMemcpyAsync(res + L.refined, d_arena + L.refined, size_t(n) * px, cudaMemcpyDeviceToHost, st));
       CK(cudaEventRecord(h->ev_post_done[slot], st));
@@ -280,7 +296,8 @@ static int ensure_full_pipeline(ctd_handle* h) {
   CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   CK(cudaStreamCreateWithPriority(&h->post, cudaStreamNonBlocking, hi));
   // window tables: <= CTD_MAX_BLOCKS windows per page, 32-byte record + 4-byte index
-  h->pipe_pinned_cap = (size_t(h->cfg.max_batch) * CTD_MAX_BLOCKS * 36 + 1024 + 255) / 256 * 256;
+  // <= CTD_MAX_BLOCKS windows per page (32 + 4 bytes each) and <= area / chunk + rows chunks per window (16 bytes)
+  h->pipe_pinned_cap = size_t(h->cfg.max_batch) * (size_t(CTD_MAX_BLOCKS) * 36 + size_t(CTD_MAX_BLOCKS) * 16 * 8) + (size_t(8) << 20);
   for (int i = 0; i < 2; ++i) {
     CK(cudaHostAlloc(reinterpret_cast<void**>(&h->pipe_pinned[i]), h->pipe_pinned_cap, cudaHostAllocDefault));
     CK(cudaEventCreateWithFlags(&h->ev_post_done[i], cudaEventDisableTiming));

@@ -22,7 +22,9 @@ namespace cg = cooperative_groups;
 
 namespace ctd {
 
-constexpr int kRefThreads = 512;
+constexpr int kRefThreads = 512;         // single-CTA windows
+constexpr int kRefThreadsCluster = 1024; // cluster windows: the sweeps are latency-bound, one pixel per thread-iteration
+constexpr int ref_threads(int cl) { return cl > 1 ? kRefThreadsCluster : kRefThreads; }
 constexpr int kRefCluster = 8;          // CTAs per large window (portable cluster size)
 constexpr int kRefLargePx = 24 * 1024;  // windows with more pixels go to the cluster kernel
 
@@ -30,8 +32,9 @@ constexpr int kRefLargePx = 24 * 1024;  // windows with more pixels go to the cl
 template <int CL>
 struct Grp {
   __device__ static __forceinline__ int rank() { return CL == 1 ? 0 : int(cg::this_cluster().block_rank()); }
-  __device__ static __forceinline__ int tid() { return rank() * kRefThreads + int(threadIdx.x); }
-  static constexpr int size = CL * kRefThreads;
+  static constexpr int threads = ref_threads(CL);
+  __device__ static __forceinline__ int tid() { return rank() * threads + int(threadIdx.x); }
+  static constexpr int size = CL * threads;
   __device__ static __forceinline__ void sync() {
     if constexpr (CL == 1) __syncthreads();
     else cg::this_cluster().sync();
@@ -89,6 +92,19 @@ __device__ __forceinline__ int rf_find(const int* L, int a) {
     p = rf_load<XSM>(L + a);
   }
   return a;
+}
+// find + full path compression: every node on the path is pointed at the root (atomicMin: a concurrent union may
+// already have lowered it further, and a root found here may meanwhile have become a child -- it is still an ancestor)
+template <bool XSM>
+__device__ __forceinline__ int rf_find_compress(int* L, int a) {
+  const int r = rf_find<XSM>(L, a);
+  while (a != r) {
+    const int p = rf_load<XSM>(L + a);
+    if (p <= r) break;
+    atomicMin(&L[a], r);
+    a = p;
+  }
+  return r;
 }
 template <bool XSM>
 __device__ __forceinline__ void rf_union(int* L, int a, int b) {
@@ -158,8 +174,20 @@ __device__ void grp_ccl(const uint8_t* __restrict__ src, int rw, int rh, int* __
     }
   }
   G::sync();
-  for (int i = G::tid(); i < n; i += G::size)
-    if (L[i] >= 0) L[i] = rf_find<(CL > 1)>(L, i);
+  // flatten in two steps.  The chain nodes of the forest are the segment-run starts (every other pixel points at its
+  // run start): on a window that is mostly one component the unions above can leave a chain as long as the window is
+  // high, and letting each of its ~10^6 pixels walk it alone was the single largest cost of the kernel.  Step 1 walks
+  // from the run starts only and compresses the path for everybody; step 2 is then one or two hops per pixel.
+  for (int i = G::tid(); i < n; i += G::size) {
+    if (!src[i]) continue;
+    const int x = i % rw;
+    if ((x % kSegW) == 0 || !src[i - 1]) rf_find_compress<(CL > 1)>(L, i);
+  }
+  G::sync();
+  for (int i = G::tid(); i < n; i += G::size) {
+    const int p = L[i];
+    if (p >= 0) L[i] = rf_find<(CL > 1)>(L, p);
+  }
   G::sync();
 }
 
@@ -229,7 +257,7 @@ __device__ void grp_merge_labels(const int* __restrict__ L, const uint8_t* __res
 }
 
 template <int CL>
-__global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __restrict__ img_all, const uint8_t* __restrict__ mask_all,
+__global__ void __launch_bounds__(ref_threads(CL)) refine_kernel(const uint8_t* __restrict__ img_all, const uint8_t* __restrict__ mask_all,
                                                              int H, int W, const RefineWin* __restrict__ wins,
                                                              const int* __restrict__ win_idx, RefinePlanes P,
                                                              int refine_mode, uint32_t* __restrict__ out_all) {
@@ -523,12 +551,12 @@ __global__ void __launch_bounds__(kRefThreads) refine_kernel(const uint8_t* __re
       push(a1);
       push(a2);
     }
-    __shared__ int wtop[kRefThreads / 32][2];
+    __shared__ int wtop[G::threads / 32][2];
     if ((threadIdx.x & 31) == 0) { wtop[threadIdx.x >> 5][0] = m1; wtop[threadIdx.x >> 5][1] = m2; }
     __syncthreads();
     if (threadIdx.x == 0) {
       int t1 = -1, t2 = -1;
-      for (int wv = 0; wv < kRefThreads / 32; ++wv)
+      for (int wv = 0; wv < G::threads / 32; ++wv)
         for (int e = 0; e < 2; ++e) {
           const int a = wtop[wv][e];
           if (a > t1) { t2 = t1; t1 = a; } else if (a > t2) t2 = a;
@@ -592,7 +620,7 @@ cudaError_t refine_launch(const uint8_t* d_img, const uint8_t* d_mask, int H, in
     // large windows first: they are the critical path, the single-CTA windows fill in around them
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(n_large) * kRefCluster, 1, 1);
-    cfg.blockDim = dim3(kRefThreads, 1, 1);
+    cfg.blockDim = dim3(kRefThreadsCluster, 1, 1);
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -1,0 +1,641 @@
+// refine_mask on the GPU, phase-synchronous form (reference utils/textmask.py:159-169 and callees 16-132).
+//
+// csrc/refine.cu runs ONE cooperative kernel with a CTA (or an 8-CTA cluster) per block window and barriers between
+// the phases.  Measured on the synthetic 1024^2 pages: every phase is a latency-bound sweep with one pixel per thread
+// iteration, a 1 Mpx window keeps 8 SMs busy for 15 ms while the other 140 idle, and a batch of 16 pages (~50 Mpx of
+// overlapping windows) cost 29 ms -- 4.5x the network.  Here every phase is its own kernel over ALL window pixels of
+// the batch: the windows are cut into chunks of whole rows (<= kChunkPx pixels, table built by the host, which knows
+// the window sizes), one CTA per chunk, so a giant window is spread over the whole GPU and the kernel boundary is the
+// barrier.  Per-window reductions (histograms, xor sums, the two largest hole areas) go through a small per-window
+// state record in global memory; per-window scalar decisions are one-CTA-per-window kernels.  Same arithmetic, same
+// scratch planes and the same union-find (global atomics) as refine.cu -- results are bit-identical
+// (tests/test_gpu_refine.py runs both).
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <math.h>
+
+#include "kernels.h"
+
+namespace ctd {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kSegW = 64;          // run starts are found per 64-pixel row segment (one thread each)
+
+struct RefineWin {
+  int x1, y1, x2, y2;
+  long long off;
+  int page, pad;
+};
+struct Chunk { int win, y0, rows, pad; };
+
+struct WinState {
+  int hist[4][256];               // [0] grey of the eroded-mask pixels, [1..3] B, G, R of the whole window
+  unsigned long long xs[12];      // xor sums: [k][pos/neg] for 3 colours, then 3 channels
+  int lo[3], hi[3], otsu_t[3], ncol;
+  int nproc, proc_kind[4], proc_neg[4];
+  int area0, max1, cnt1, max2;
+  int pad[2];
+};
+
+struct Ctx {
+  const uint8_t* img_all;
+  const uint8_t* mask_all;
+  uint32_t* out_all;
+  const RefineWin* wins;
+  const Chunk* chunks;
+  WinState* st;
+  int H, W, mode;
+  // planes (window-pixel indexed)
+  int* L;
+  int* acc;
+  uint8_t *grey, *cand, *predm, *merged, *tmp;
+};
+
+struct View {
+  RefineWin win;
+  int w, rw, rh, y0, rows, i0, cnt;
+  const uint8_t* img;
+  const uint8_t* mask;
+};
+
+__device__ __forceinline__ View view_of(const Ctx& c, int chunk) {
+  View v;
+  const Chunk ch = c.chunks[chunk];
+  v.w = ch.win;
+  v.win = c.wins[ch.win];
+  v.rw = v.win.x2 - v.win.x1;
+  v.rh = v.win.y2 - v.win.y1;
+  v.y0 = ch.y0;
+  v.rows = ch.rows;
+  v.i0 = ch.y0 * v.rw;
+  v.cnt = ch.rows * v.rw;
+  v.img = c.img_all + size_t(v.win.page) * c.H * c.W * 3;
+  v.mask = c.mask_all + size_t(v.win.page) * c.H * c.W;
+  return v;
+}
+
+// ---- union-find on a window's L plane (other CTAs update it: parent reads bypass L1) -------------------------------
+__device__ __forceinline__ int uf_find(const int* L, int a) {
+  int p = __ldcg(L + a);
+  while (p != a) {
+    a = p;
+    p = __ldcg(L + a);
+  }
+  return a;
+}
+__device__ __forceinline__ int uf_find_compress(int* L, int a) {
+  const int r = uf_find(L, a);
+  while (a != r) {
+    const int p = __ldcg(L + a);
+    if (p <= r) break;
+    atomicMin(&L[a], r);
+    a = p;
+  }
+  return r;
+}
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+  bool done;
+  do {
+    a = uf_find(L, a);
+    b = uf_find(L, b);
+    if (a < b) {
+      const int old = atomicMin(&L[b], a);
+      done = old == b;
+      b = old;
+    } else if (b < a) {
+      const int old = atomicMin(&L[a], b);
+      done = old == a;
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+
+__device__ __forceinline__ void hist_add(int* hist, int bin) {
+  const unsigned peers = __match_any_sync(0xffffffffu, bin);
+  if (bin >= 0 && int(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+}
+
+// ---- phase 0: grey, pred mask (cross erosion > 60), merged = 0, histograms ------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_phase0(Ctx c) {
+  __shared__ int sh[4][256];
+  const View v = view_of(c, blockIdx.x);
+  for (int i = threadIdx.x; i < 1024; i += kThreads) (&sh[0][0])[i] = 0;
+  __syncthreads();
+  uint8_t* grey = c.grey + v.win.off;
+  uint8_t* predm = c.predm + v.win.off;
+  uint8_t* merged = c.merged + v.win.off;
+  for (int k0 = 0; k0 < v.cnt; k0 += kThreads) {
+    const int k = k0 + threadIdx.x;
+    const bool in = k < v.cnt;
+    int b = -1, g = -1, r = -1, gr = 0, m3 = 255, mc = 255;
+    if (in) {
+      const int i = v.i0 + k;
+      const int y = i / v.rw, x = i - y * v.rw;
+      const size_t gp = size_t(v.win.y1 + y) * c.W + v.win.x1 + x;
+      b = v.img[gp * 3]; g = v.img[gp * 3 + 1]; r = v.img[gp * 3 + 2];
+      gr = (b * 1868 + g * 9617 + r * 4899 + 8192) >> 14;  // cv2.COLOR_BGR2GRAY, 8u fixed point
+      grey[i] = (uint8_t)gr;
+      // erosions of the mask CROP (window borders ignore the outside: BORDER_CONSTANT with +inf)
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= v.rh) continue;
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int xx = x + dx;
+          if (xx < 0 || xx >= v.rw) continue;
+          const int mv = v.mask[size_t(v.win.y1 + yy) * c.W + v.win.x1 + xx];
+          m3 = min(m3, mv);
+          if (dx == 0 || dy == 0) mc = min(mc, mv);
+        }
+      }
+      predm[i] = mc > 60 ? 255 : 0;                  // textmask.py:86-89
+      merged[i] = 0;
+    }
+    hist_add(sh[1], b);
+    hist_add(sh[2], g);
+    hist_add(sh[3], r);
+    hist_add(sh[0], (in && m3 > 127) ? gr : -1);     // textmask.py:60
+  }
+  __syncthreads();
+  int* gh = &c.st[v.w].hist[0][0];
+  for (int i = threadIdx.x; i < 1024; i += kThreads) {
+    const int val = (&sh[0][0])[i];
+    if (val) atomicAdd(&gh[i], val);
+  }
+}
+
+// ---- phase 1 (one CTA per window): np.histogram(bins=255), top-k colours, Otsu ---------------------------------------
+__global__ void __launch_bounds__(kThreads) k_decide1(Ctx c) {
+  __shared__ int cnt255[256];
+  __shared__ int order[256];
+  __shared__ double edges[256];
+  __shared__ int s_first, s_last, s_total;
+  WinState& st = c.st[blockIdx.x];
+  const RefineWin win = c.wins[blockIdx.x];
+  const int n = (win.x2 - win.x1) * (win.y2 - win.y1);
+  const int* hist_g = st.hist[0];
+  for (int i = threadIdx.x; i < 256; i += kThreads) cnt255[i] = 0;
+  if (threadIdx.x == 0) {
+    int first = -1, last = -1, total = 0;
+    for (int v = 0; v < 256; ++v)
+      if (hist_g[v]) { if (first < 0) first = v; last = v; total += hist_g[v]; }
+    s_first = first; s_last = last; s_total = total;
+  }
+  __syncthreads();
+  {
+    // outer edges (numpy _get_outer_edges): empty -> (0,1); equal -> (v-0.5, v+0.5)
+    double fe, le;
+    if (s_total == 0) { fe = 0.0; le = 1.0; }
+    else if (s_first == s_last) { fe = s_first - 0.5; le = s_last + 0.5; }
+    else { fe = s_first; le = s_last; }
+    const double step = (le - fe) / 255.0;  // np.linspace(fe, le, 256): arange * step + start, last = stop
+    for (int i = threadIdx.x; i < 256; i += kThreads) edges[i] = (i == 255) ? le : __dadd_rn(__dmul_rn((double)i, step), fe);
+    __syncthreads();
+    for (int v = threadIdx.x; v < 256; v += kThreads) {
+      if (!hist_g[v]) continue;
+      const double a = (double)v;
+      const double f = ((a - fe) / (le - fe)) * 255.0;  // numpy fast path: (tmp_a - first_edge) / norm_denom * n_bins
+      int idx = (int)f;
+      if (idx == 255) idx = 254;
+      if (a < edges[idx]) --idx;
+      if (a >= edges[idx + 1] && idx != 254) ++idx;
+      atomicAdd(&cnt255[idx], hist_g[v]);
+    }
+  }
+  __syncthreads();
+  // stable descending order of the 255 bins (documented normalisation of np.argsort's tie order)
+  for (int b = threadIdx.x; b < 255; b += kThreads) {
+    int rank = 0;
+    const int cb = cnt255[b];
+    for (int q = 0; q < 255; ++q) rank += (cnt255[q] > cb) || (cnt255[q] == cb && q < b);
+    order[rank] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // get_topk_color (textmask.py:16-27): colour = LEFT EDGE of the bin (textmask.py:61-62 swaps the names)
+    double top[3];
+    int nt = 1;
+    top[0] = edges[order[0]];
+    const double tol = (double)s_total * 0.001;
+    for (int j = 1; j < 255; ++j) {
+      const double col = edges[order[j]];
+      double dmin = 1e300;
+      for (int t = 0; t < nt; ++t) dmin = fmin(dmin, fabs(top[t] - col));
+      if (dmin > 10.0) top[nt++] = col;
+      if (nt >= 3 || (double)cnt255[order[j]] < tol) break;
+    }
+    st.ncol = nt;
+    for (int t = 0; t < nt; ++t) {
+      const double c_top = fmin(top[t] + 30.0, 255.0);
+      const double c_bot = c_top - 60.0;
+      // cv2.inRange with float bounds on 8u data: cvRound (half to even) + saturate
+      st.lo[t] = (int)fmin(fmax(rint(c_bot), 0.0), 255.0);
+      st.hi[t] = (int)fmin(fmax(rint(c_top), 0.0), 255.0);
+    }
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 35) {
+    // cv2.threshold(..., THRESH_OTSU): getThreshVal_Otsu_8u
+    const int* hh = st.hist[1 + threadIdx.x - 32];
+    const double scale = 1.0 / (double)n;
+    double mu = 0;
+    for (int i = 0; i < 256; ++i) mu = __dadd_rn(mu, __dmul_rn((double)i, (double)hh[i]));
+    mu = __dmul_rn(mu, scale);
+    double mu1 = 0, q1 = 0, max_sigma = 0;
+    int max_val = 0;
+    for (int i = 0; i < 256; ++i) {
+      const double p_i = __dmul_rn((double)hh[i], scale);
+      mu1 = __dmul_rn(mu1, q1);
+      q1 = __dadd_rn(q1, p_i);
+      const double q2 = 1.0 - q1;
+      if (fmin(q1, q2) < 1.1920929e-07 || fmax(q1, q2) > 1.0 - 1.1920929e-07) continue;
+      // explicit roundings: the x86 build of OpenCV has no FMA contraction here
+      mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
+      const double mu2 = __ddiv_rn(__dsub_rn(mu, __dmul_rn(q1, mu1)), q2);
+      const double dm = __dsub_rn(mu1, mu2);
+      const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), dm), dm);
+      if (sigma > max_sigma) { max_sigma = sigma; max_val = i; }
+    }
+    st.otsu_t[threadIdx.x - 32] = max_val;
+  }
+}
+
+// ---- phase 2: xor sums of every candidate and of its negative against the mask crop -----------------------------------
+__global__ void __launch_bounds__(kThreads) k_xor(Ctx c) {
+  __shared__ unsigned long long sx[12];
+  const View v = view_of(c, blockIdx.x);
+  const WinState& st = c.st[v.w];
+  if (threadIdx.x < 12) sx[threadIdx.x] = 0ull;
+  __syncthreads();
+  const uint8_t* grey = c.grey + v.win.off;
+  const int ncol = st.ncol;
+  int lo[3], hi[3], ot[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { lo[k] = st.lo[k]; hi[k] = st.hi[k]; ot[k] = st.otsu_t[k]; }
+  unsigned long long loc[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) loc[k] = 0ull;
+  for (int k0 = threadIdx.x; k0 < v.cnt; k0 += kThreads) {
+    const int i = v.i0 + k0;
+    const int y = i / v.rw, x = i - y * v.rw;
+    const size_t gp = size_t(v.win.y1 + y) * c.W + v.win.x1 + x;
+    const int mk = v.mask[gp];
+    const int gr = grey[i];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k < ncol) {
+        const int t = (gr >= lo[k] && gr <= hi[k]) ? 255 : 0;
+        loc[2 * k] += (unsigned)(t ^ mk);
+        loc[2 * k + 1] += (unsigned)((255 - t) ^ mk);
+      }
+      const int ch = v.img[gp * 3 + k];
+      const int t2 = ch > ot[k] ? 255 : 0;
+      loc[6 + 2 * k] += (unsigned)(t2 ^ mk);
+      loc[6 + 2 * k + 1] += (unsigned)((255 - t2) ^ mk);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    unsigned long long s = loc[k];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&sx[k], s);
+  }
+  __syncthreads();
+  if (threadIdx.x < 12 && sx[threadIdx.x]) atomicAdd(&c.st[v.w].xs[threadIdx.x], sx[threadIdx.x]);
+}
+
+// candidate order (one thread per window): minxor_thresh + sort
+__global__ void k_decide2(Ctx c, int n_wins) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_wins) return;
+  WinState& st = c.st[w];
+  const unsigned long long* xs = st.xs;
+  // minxor_thresh (textmask.py:29-41): negative wins only if strictly smaller
+  unsigned long long best[4];
+  int kind[4], neg[4], np_ = 0;
+  for (int k = 0; k < st.ncol; ++k) {
+    const bool ng = xs[2 * k + 1] < xs[2 * k];
+    best[np_] = ng ? xs[2 * k + 1] : xs[2 * k];
+    kind[np_] = k; neg[np_] = ng; ++np_;
+  }
+  // Otsu: best channel (stable sort by xor sum -> first minimum in B,G,R order)  (textmask.py:43-54)
+  int bc = 0, bneg = 0;
+  unsigned long long bv = ~0ull;
+  for (int ch = 0; ch < 3; ++ch) {
+    const bool ng = xs[6 + 2 * ch + 1] < xs[6 + 2 * ch];
+    const unsigned long long val = ng ? xs[6 + 2 * ch + 1] : xs[6 + 2 * ch];
+    if (val < bv) { bv = val; bc = ch; bneg = ng; }
+  }
+  best[np_] = bv; kind[np_] = 3 + bc; neg[np_] = bneg; ++np_;
+  // mask_list.sort(key=xor_sum) (textmask.py:74): stable insertion sort
+  for (int i = 1; i < np_; ++i) {
+    const unsigned long long val = best[i];
+    const int kk = kind[i], nn = neg[i];
+    int j = i - 1;
+    while (j >= 0 && best[j] > val) { best[j + 1] = best[j]; kind[j + 1] = kind[j]; neg[j + 1] = neg[j]; --j; }
+    best[j + 1] = val; kind[j + 1] = kk; neg[j + 1] = nn;
+  }
+  for (int i = 0; i < np_; ++i) { st.proc_kind[i] = kind[i]; st.proc_neg[i] = neg[i]; }
+  st.nproc = np_;
+  st.area0 = 0; st.max1 = -1; st.cnt1 = 0; st.max2 = -1;
+}
+
+// ---- labelling of a source plane: candidate `round` (0..3) or, round == 4, the inverse of `merged` (hole filling) -----
+// pass A: source pixels + run starts, one thread per 64-pixel row segment
+__global__ void __launch_bounds__(kThreads) k_source(Ctx c, int round) {
+  const View v = view_of(c, blockIdx.x);
+  const WinState& st = c.st[v.w];
+  if (round < 4 && round >= st.nproc) return;
+  uint8_t* cand = c.cand + v.win.off;
+  int* L = c.L + v.win.off;
+  const uint8_t* grey = c.grey + v.win.off;
+  const uint8_t* merged = c.merged + v.win.off;
+  int kind = 0, neg = 0, lo = 0, hi = 0, ot = 0;
+  if (round < 4) {
+    kind = st.proc_kind[round]; neg = st.proc_neg[round];
+    if (kind < 3) { lo = st.lo[kind]; hi = st.hi[kind]; } else ot = st.otsu_t[kind - 3];
+  }
+  const int segs = (v.rw + kSegW - 1) / kSegW;
+  for (int t = threadIdx.x; t < v.rows * segs; t += kThreads) {
+    const int yl = t / segs, x0 = (t - yl * segs) * kSegW;
+    const int y = v.y0 + yl;
+    const int x1 = min(v.rw, x0 + kSegW);
+    const int base = y * v.rw;
+    const size_t gp0 = size_t(v.win.y1 + y) * c.W + v.win.x1;
+    int start = -1;
+    for (int x = x0; x < x1; ++x) {
+      int s;
+      if (round == 4) {
+        s = merged[base + x] ? 0 : 255;
+      } else {
+        int tv;
+        if (kind < 3) {
+          const int gr = grey[base + x];
+          tv = (gr >= lo && gr <= hi) ? 255 : 0;
+        } else {
+          tv = v.img[(gp0 + x) * 3 + (kind - 3)] > ot ? 255 : 0;
+        }
+        s = neg ? 255 - tv : tv;
+      }
+      cand[base + x] = (uint8_t)s;
+      if (s) {
+        if (start < 0) start = base + x;
+        L[base + x] = start;
+      } else {
+        start = -1;
+        L[base + x] = -1;
+      }
+    }
+  }
+}
+// pass B: segment seams and contacts with the row above
+__global__ void __launch_bounds__(kThreads) k_union(Ctx c, int round) {
+  const View v = view_of(c, blockIdx.x);
+  if (round < 4 && round >= c.st[v.w].nproc) return;
+  const uint8_t* src = c.cand + v.win.off;
+  int* L = c.L + v.win.off;
+  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
+    const int i = v.i0 + k;
+    if (!src[i]) continue;
+    const int x = i % v.rw;
+    if (x > 0 && (x % kSegW) == 0 && src[i - 1]) uf_union(L, i, i - 1);
+    if (i < v.rw) continue;
+    const int up = i - v.rw;
+    if (src[up]) {
+      // only the first pixel of each (current run x upper run) overlap issues the union
+      const bool first = x == 0 || !src[i - 1] || !src[up - 1];
+      if (first) uf_union(L, i, up);
+    } else {
+      if (x > 0 && src[up - 1]) uf_union(L, i, up - 1);
+      if (x + 1 < v.rw && src[up + 1]) uf_union(L, i, up + 1);
+    }
+  }
+}
+// pass C: compress from the chain nodes (segment-run starts); pass D: every pixel takes its parent's root
+__global__ void __launch_bounds__(kThreads) k_flat1(Ctx c, int round) {
+  const View v = view_of(c, blockIdx.x);
+  if (round < 4 && round >= c.st[v.w].nproc) return;
+  const uint8_t* src = c.cand + v.win.off;
+  int* L = c.L + v.win.off;
+  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
+    const int i = v.i0 + k;
+    if (!src[i]) continue;
+    const int x = i % v.rw;
+    if ((x % kSegW) == 0 || !src[i - 1]) uf_find_compress(L, i);
+  }
+}
+__global__ void __launch_bounds__(kThreads) k_flat2(Ctx c, int round) {
+  const View v = view_of(c, blockIdx.x);
+  if (round < 4 && round >= c.st[v.w].nproc) return;
+  int* L = c.L + v.win.off;
+  int* acc = c.acc + 4 * v.win.off;
+  const int n = v.rw * v.rh;
+  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
+    const int i = v.i0 + k;
+    const int p = __ldcg(L + i);
+    if (p < 0) continue;
+    const int r = uf_find(L, p);
+    L[i] = r;
+    if (r == i) { acc[i] = 0; acc[n + i] = 0; acc[2 * n + i] = 0; acc[3 * n + i] = -1; }   // area, gain, loss, maxi
+  }
+}
+
+// ---- merge step (textmask.py:92-108 / 118-131): per-label sums, then the labels that lower xor(merged, pred) -----------
+__global__ void __launch_bounds__(kThreads) k_macc(Ctx c, int round) {
+  const View v = view_of(c, blockIdx.x);
+  WinState& st = c.st[v.w];
+  if (round < 4 && round >= st.nproc) return;
+  const int* L = c.L + v.win.off;
+  const uint8_t* predm = c.predm + v.win.off;
+  const uint8_t* merged = c.merged + v.win.off;
+  int* acc = c.acc + 4 * v.win.off;
+  const int n = v.rw * v.rh;
+  int* area = acc; int* gain = acc + n; int* loss = acc + 2 * n; int* maxi = acc + 3 * n;
+  int a0 = 0;
+  for (int k0 = 0; k0 < v.cnt; k0 += kThreads) {
+    const int k = k0 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int i = v.i0 + k;
+    const int r = k < v.cnt ? L[i] : -2;
+    const bool un = r >= 0 && merged[i] == 0;
+    const bool pg = un && predm[i] != 0;
+    const unsigned peers = __match_any_sync(0xffffffffu, r);
+    const unsigned bg = __ballot_sync(0xffffffffu, pg), bl = __ballot_sync(0xffffffffu, un && !pg);
+    if (r >= 0 && lane == __ffs(peers) - 1) {
+      atomicAdd(&area[r], __popc(peers));
+      atomicMax(&maxi[r], i - lane + 31 - __clz(peers));
+      const int g_ = __popc(peers & bg), l_ = __popc(peers & bl);
+      if (g_) atomicAdd(&gain[r], g_);
+      if (l_) atomicAdd(&loss[r], l_);
+    }
+    if (r == -1) ++a0;
+  }
+  if (round == 4) {   // label 0 of the inverse = the pixels already in `merged`
+    for (int o = 16; o > 0; o >>= 1) a0 += __shfl_down_sync(0xffffffffu, a0, o);
+    if ((threadIdx.x & 31) == 0 && a0) atomicAdd(&st.area0, a0);
+  }
+}
+// hole filling only: the two largest areas over all labels incl. label 0, as a multiset (max1 with its multiplicity, max2)
+__global__ void __launch_bounds__(kThreads) k_top_a(Ctx c) {
+  const View v = view_of(c, blockIdx.x);
+  WinState& st = c.st[v.w];
+  const int* L = c.L + v.win.off;
+  const int* area = c.acc + 4 * v.win.off;
+  int m = -1;
+  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
+    const int i = v.i0 + k;
+    if (L[i] == i) m = max(m, area[i]);
+  }
+  if (v.y0 == 0 && threadIdx.x == 0) m = max(m, st.area0);
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m >= 0) atomicMax(&st.max1, m);
+}
+__global__ void __launch_bounds__(kThreads) k_top_b(Ctx c) {
+  const View v = view_of(c, blockIdx.x);
+  WinState& st = c.st[v.w];
+  const int* L = c.L + v.win.off;
+  const int* area = c.acc + 4 * v.win.off;
+  const int m1 = st.max1;
+  int m2 = -1, c1 = 0;
+  auto push = [&](int a) { if (a == m1) ++c1; else m2 = max(m2, a); };
+  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
+    const int i = v.i0 + k;
+    if (L[i] == i) push(area[i]);
+  }
+  if (v.y0 == 0 && threadIdx.x == 0) push(st.area0);
+  for (int o = 16; o > 0; o >>= 1) {
+    m2 = max(m2, __shfl_down_sync(0xffffffffu, m2, o));
+    c1 += __shfl_down_sync(0xffffffffu, c1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c1) atomicAdd(&st.cnt1, c1);
+    if (m2 >= 0) atomicMax(&st.max2, m2);
+  }
+}
+__global__ void __launch_bounds__(kThreads) k_mapply(Ctx c, int round) {
+  const View v = view_of(c, blockIdx.x);
+  const WinState& st = c.st[v.w];
+  if (round < 4 && round >= st.nproc) return;
+  const int* L = c.L + v.win.off;
+  uint8_t* merged = c.merged + v.win.off;
+  const int* acc = c.acc + 4 * v.win.off;
+  const int n = v.rw * v.rh;
+  const int* area = acc; const int* gain = acc + n; const int* loss = acc + 2 * n; const int* maxi = acc + 3 * n;
+  // sorted_area[-2] if more than one label else sorted_area[-1] (textmask.py:114-118); label 0 always exists
+  const int second = st.cnt1 >= 2 ? st.max1 : st.max2;
+  const int thresh = second >= 0 ? second : st.max1;
+  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
+    const int i = v.i0 + k;
+    const int r = L[i];
+    if (r < 0) continue;
+    bool ok;
+    if (round < 4) {
+      // `if w * h < 3: continue` (textmask.py:97): bounding boxes 1x1, 1x2, 2x1
+      const int a = area[r];
+      const bool tiny = a == 1 || (a == 2 && (maxi[r] == r + 1 || maxi[r] == r + v.rw));
+      ok = !tiny;
+    } else {
+      ok = area[r] < thresh;  // textmask.py:120
+    }
+    if (ok && gain[r] > loss[r]) merged[i] = 255;
+  }
+}
+
+// ---- dilate 3x3 (inpaint mode) into tmp, copy back -----------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_dilate(Ctx c) {
+  const View v = view_of(c, blockIdx.x);
+  const uint8_t* merged = c.merged + v.win.off;
+  uint8_t* tmp = c.tmp + v.win.off;
+  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
+    const int i = v.i0 + k;
+    const int y = i / v.rw, x = i - y * v.rw;
+    int m = 0;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= v.rh) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= v.rw) continue;
+        m = max(m, (int)merged[yy * v.rw + xx]);
+      }
+    }
+    tmp[i] = (uint8_t)m;
+  }
+}
+__global__ void __launch_bounds__(kThreads) k_copyback(Ctx c) {
+  const View v = view_of(c, blockIdx.x);
+  uint8_t* merged = c.merged + v.win.off;
+  const uint8_t* tmp = c.tmp + v.win.off;
+  for (int k = threadIdx.x; k < v.cnt; k += kThreads) merged[v.i0 + k] = tmp[v.i0 + k];
+}
+// mask_refined[window] |= merged (textmask.py:168); windows may overlap -> atomic OR
+__global__ void __launch_bounds__(kThreads) k_or(Ctx c) {
+  const View v = view_of(c, blockIdx.x);
+  const uint8_t* merged = c.merged + v.win.off;
+  uint32_t* out_words = c.out_all + size_t(v.win.page) * c.H * c.W / 4;
+  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
+    const int i = v.i0 + k;
+    if (!merged[i]) continue;
+    const int y = i / v.rw, x = i - y * v.rw;
+    const size_t gp = size_t(v.win.y1 + y) * c.W + v.win.x1 + x;
+    atomicOr(&out_words[gp >> 2], 0xffu << (8 * (gp & 3)));
+  }
+}
+
+}  // namespace
+
+size_t refine_mk_state_bytes(int n_wins) { return (size_t(n_wins) * sizeof(WinState) + 255) / 256 * 256; }
+size_t refine_mk_chunk_bytes() { return sizeof(Chunk); }
+int refine_mk_chunk_px() { return 4096; }
+
+// d_wins: n_wins RefineWin records; d_chunks: n_chunks {win, y0, rows, pad} (whole rows, <= refine_mk_chunk_px() pixels
+// each unless a single row is longer); d_state: refine_mk_state_bytes(n_wins) bytes (zeroed here); scratch planes as in
+// refine_launch.  img / mask / out hold H*W-pixel planes per page.
+cudaError_t refine_mk_launch(const uint8_t* d_img, const uint8_t* d_mask, int H, int W, const void* d_wins, int n_wins,
+                             const void* d_chunks, int n_chunks, void* d_state, size_t total_px, void* scratch, int refine_mode,
+                             uint8_t* d_out, cudaStream_t s) {
+  if (n_wins <= 0 || n_chunks <= 0) return cudaSuccess;
+  Ctx c;
+  c.img_all = d_img; c.mask_all = d_mask; c.out_all = reinterpret_cast<uint32_t*>(d_out);
+  c.wins = static_cast<const RefineWin*>(d_wins);
+  c.chunks = static_cast<const Chunk*>(d_chunks);
+  c.st = static_cast<WinState*>(d_state);
+  c.H = H; c.W = W; c.mode = refine_mode;
+  char* p = static_cast<char*>(scratch);
+  c.L = reinterpret_cast<int*>(p); p += total_px * 4;
+  c.acc = reinterpret_cast<int*>(p); p += total_px * 16;
+  c.grey = reinterpret_cast<uint8_t*>(p); p += total_px;
+  c.cand = reinterpret_cast<uint8_t*>(p); p += total_px;
+  c.predm = reinterpret_cast<uint8_t*>(p); p += total_px;
+  c.merged = reinterpret_cast<uint8_t*>(p); p += total_px;
+  c.tmp = reinterpret_cast<uint8_t*>(p);
+  cudaError_t e = cudaMemsetAsync(d_state, 0, refine_mk_state_bytes(n_wins), s);
+  if (e != cudaSuccess) return e;
+  const unsigned g = unsigned(n_chunks);
+  k_phase0<<<g, kThreads, 0, s>>>(c);
+  k_decide1<<<unsigned(n_wins), kThreads, 0, s>>>(c);
+  k_xor<<<g, kThreads, 0, s>>>(c);
+  k_decide2<<<unsigned((n_wins + 127) / 128), 128, 0, s>>>(c, n_wins);
+  for (int round = 0; round < 5; ++round) {
+    if (round == 4 && refine_mode == 0) {
+      k_dilate<<<g, kThreads, 0, s>>>(c);
+      k_copyback<<<g, kThreads, 0, s>>>(c);
+    }
+    k_source<<<g, kThreads, 0, s>>>(c, round);
+    k_union<<<g, kThreads, 0, s>>>(c, round);
+    k_flat1<<<g, kThreads, 0, s>>>(c, round);
+    k_flat2<<<g, kThreads, 0, s>>>(c, round);
+    k_macc<<<g, kThreads, 0, s>>>(c, round);
+    if (round == 4) {
+      k_top_a<<<g, kThreads, 0, s>>>(c);
+      k_top_b<<<g, kThreads, 0, s>>>(c);
+    }
+    k_mapply<<<g, kThreads, 0, s>>>(c, round);
+  }
+  k_or<<<g, kThreads, 0, s>>>(c);
+  return cudaGetLastError();
+}
+
+}  // namespace ctd

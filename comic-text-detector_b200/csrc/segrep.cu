@@ -377,12 +377,18 @@ __global__ void tree_kernel(int h, int w, const int* __restrict__ Lf_all, const 
 }
 
 // ---- per-contour geometry: one thread per candidate -------------------------------------------------
-struct ContourScratch {
-  IPt hull[ctdgeom::kMaxHull];
-  IPt tmp[ctdgeom::kMaxHull];
-  IPt off[ctdgeom::kMaxOffsetPts];
-  float f0[ctdgeom::kMaxHull], f1[ctdgeom::kMaxHull], f2[ctdgeom::kMaxHull];
+// CAP = vertex capacity of the hull / offset buffers.  The kernel runs twice: CAP = 128 for every contour (4.5 KB of
+// shared memory per warp -> 48 contours in flight per SM instead of 12; the per-contour work is serial, latency-bound
+// lane-0 code, so contours in flight is what sets the pace), then CAP = ctdgeom::kMaxHull for the few contours whose
+// hull or offset polygon did not fit (collected in an overflow list by the first pass).
+template <int CAP>
+struct ContourScratchT {
+  IPt hull[CAP];
+  IPt tmp[CAP];
+  IPt off[CAP];
+  float f0[CAP], f1[CAP], f2[CAP];
 };
+struct ContourScratch;   // (unused global-memory variant of the first design)
 
 // ---- warp-cooperative pieces of the per-contour geometry (bit-identical to the serial forms in geom.h) ------------
 // rotate so that hull[0] is the max-x (ties: max-y) vertex; all 32 lanes, hull/tmp in shared memory
@@ -472,6 +478,7 @@ __global__ void __launch_bounds__(1024) contour_order_kernel(int max_cand, const
 // One WARP per candidate (lane 0 runs the serial geometry; the working set lives in shared memory instead
 // of per-thread local memory), 4 candidates per CTA.
 constexpr int kContourWarps = 4;
+template <int CAP>
 __global__ void __launch_bounds__(32 * kContourWarps) contour_kernel(int h, int w, int max_cand, const int* __restrict__ total,
                                                      const int* __restrict__ c_root, const int* __restrict__ rowmin,
                                                      const int* __restrict__ rowmax, const int* __restrict__ c_yrange,
@@ -480,9 +487,10 @@ __global__ void __launch_bounds__(32 * kContourWarps) contour_kernel(int h, int 
                                                      const int* __restrict__ ring_cnt, ContourScratch* __restrict__ scratch,
                                                      int16_t* __restrict__ boxes, float* __restrict__ scores,
                                                      int* __restrict__ n_out, int dst_w, int dst_h, float unclip_ratio,
-                                                     const int* __restrict__ perm, int n_pages) {
+                                                     const int* __restrict__ perm, int n_pages,
+                                                     int* __restrict__ ovf_count, int* __restrict__ ovf_list, int second) {
   extern __shared__ __align__(16) unsigned char csm[];
-  ContourScratch& S = reinterpret_cast<ContourScratch*>(csm)[threadIdx.x >> 5];
+  ContourScratchT<CAP>& S = reinterpret_cast<ContourScratchT<CAP>*>(csm)[threadIdx.x >> 5];
   (void)scratch;
   // 1-D grid, page fastest: every page's tallest contours are scheduled before anybody's small ones
   const int page = int(blockIdx.x) % n_pages;
@@ -490,9 +498,19 @@ __global__ void __launch_bounds__(32 * kContourWarps) contour_kernel(int h, int 
   const int lane = threadIdx.x & 31;
   int ncont = total[page];
   if (ncont > max_cand) ncont = max_cand;
-  if (slot == 0 && lane == 0) n_out[page] = ncont;
+  if (!second && slot == 0 && lane == 0) n_out[page] = ncont;
   if (slot >= max_cand) return;
-  const int c = perm[page * max_cand + slot];
+  int c;
+  if (second) {
+    if (slot >= ovf_count[page]) return;   // warp-uniform: only the contours the first pass could not hold
+    c = ovf_list[page * max_cand + slot];
+  } else {
+    c = perm[page * max_cand + slot];
+  }
+  // a contour that overflows this pass's buffers is handed to the next pass (its row stays zero if there is none)
+  auto defer = [&]() {
+    if (!second && lane == 0) ovf_list[page * max_cand + atomicAdd(&ovf_count[page], 1)] = c;
+  };
   int16_t* bo = boxes + (size_t(page) * max_cand + c) * 8;
   float* so = scores + size_t(page) * max_cand + c;
   if (lane < 8) bo[lane] = 0;
@@ -525,7 +543,7 @@ __global__ void __launch_bounds__(32 * kContourWarps) contour_kernel(int h, int 
         for (int q = 0; q < (a == b ? 1 : 2); ++q) {
           const IPt pt{y0 + e, q == 0 ? a : b};
           while (k >= 2 && ctdgeom::cross3(S.hull[k - 2], S.hull[k - 1], pt) <= 0) --k;
-          if (k >= ctdgeom::kMaxHull) { overflow = true; break; }
+          if (k >= CAP) { overflow = true; break; }
           S.hull[k++] = pt;
         }
       }
@@ -549,7 +567,7 @@ __global__ void __launch_bounds__(32 * kContourWarps) contour_kernel(int h, int 
           const IPt pt{y1 - e, q == 0 ? b : a};
           if (first) { first = false; continue; }  // the very last point of the forward pass
           while (k >= lower && ctdgeom::cross3(S.hull[k - 2], S.hull[k - 1], pt) <= 0) --k;
-          if (k >= ctdgeom::kMaxHull) { overflow = true; break; }
+          if (k >= CAP) { overflow = true; break; }
           S.hull[k++] = pt;
         }
       }
@@ -559,7 +577,7 @@ __global__ void __launch_bounds__(32 * kContourWarps) contour_kernel(int h, int 
   // ---- geometry: the element-wise parts run across the warp, the calipers / offset / hull stay on lane 0 ----------
   overflow = __shfl_sync(0xffffffffu, int(overflow), 0) != 0;
   k = __shfl_sync(0xffffffffu, k, 0);
-  if (overflow) return;
+  if (overflow) { defer(); return; }
   if (k > 1) --k;
   // transpose back + reverse (the chain ran in the transposed plane)
   for (int i = lane; i < k; i += 32) S.tmp[i] = IPt{S.hull[k - 1 - i].y, S.hull[k - 1 - i].x};
@@ -570,6 +588,7 @@ __global__ void __launch_bounds__(32 * kContourWarps) contour_kernel(int h, int 
   hull_start_maxx_warp(S.hull, k, S.tmp, lane);
   const ctdgeom::MarExt e1 = mar_prepass_warp(S.hull, k, S.f0, S.f1, S.f2, lane);
   int m = 0;
+  __syncwarp();   // S.off / S.tmp of the previous use are dead for every lane before lane 0 rewrites S.off
   if (lane == 0) {
     const ctdgeom::RRect r1 = ctdgeom::mar_core(S.hull, k, S.f0, S.f1, S.f2, e1);
     const float sside = r1.w < r1.h ? r1.w : r1.h;
@@ -577,11 +596,13 @@ __global__ void __launch_bounds__(32 * kContourWarps) contour_kernel(int h, int 
       float px[4], py[4], ox[4], oy[4];
       ctdgeom::box_points(r1, px, py);
       ctdgeom::order_mini_box(px, py, ox, oy);
-      m = ctdgeom::unclip_offset(ox, oy, (double)unclip_ratio, S.off, ctdgeom::kMaxOffsetPts);
-      if (m < 3) m = 0;
+      m = ctdgeom::unclip_offset(ox, oy, (double)unclip_ratio, S.off, CAP);
+      if (m >= 0 && m < 3) m = 0;
     }
   }
   m = __shfl_sync(0xffffffffu, m, 0);
+  __syncwarp();   // lane 0's S.off writes are visible to the lanes that rank-sort them (racecheck: shfl is no fence)
+  if (m < 0) { defer(); return; }   // more offset vertices than this pass holds
   if (m == 0) return;
   // cooperative rank sort of the offset points by (x, y) into S.tmp, then back
   for (int i = lane; i < m; i += 32) {
@@ -597,9 +618,10 @@ __global__ void __launch_bounds__(32 * kContourWarps) contour_kernel(int h, int 
   for (int i = lane; i < m; i += 32) S.off[i] = S.tmp[i];
   __syncwarp();
   int nh2 = 0;
-  if (lane == 0) nh2 = ctdgeom::hull_sorted(S.off, m, S.hull, ctdgeom::kMaxHull);
+  if (lane == 0) nh2 = ctdgeom::hull_sorted(S.off, m, S.hull, CAP);
   nh2 = __shfl_sync(0xffffffffu, nh2, 0);
   __syncwarp();
+  if (nh2 < 0) { defer(); return; }
   if (nh2 < 3) return;
   hull_start_maxx_warp(S.hull, nh2, S.tmp, lane);
   const ctdgeom::MarExt e2 = mar_prepass_warp(S.hull, nh2, S.f0, S.f1, S.f2, lane);
@@ -640,7 +662,7 @@ size_t segrep_scratch_bytes(int n, int h, int w, int max_cand) {
          + hw * 4 * 2          // tot_cnt, ring_cnt
          + hw * 8 * 3          // own_sum, tot_sum, ring_sum
          + size_t(n) * max_cand * h * 4 * 2   // rowmin, rowmax
-         + size_t(n) * max_cand * 16          // c_root, c_yrange, perm
+         + size_t(n) * max_cand * 20          // c_root, c_yrange, perm, overflow list
          + size_t(n) * 8192 * 4               // segsum (<= 4096 per page) + totals
          + 65536;                             // 256-byte alignment slack of the 17 sub-arrays
 }
@@ -667,6 +689,8 @@ cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_
   int* perm = reinterpret_cast<int*>(take(size_t(n) * max_cand * 4));
   int* segsum = reinterpret_cast<int*>(take(size_t(n) * 4096 * 4));
   int* total = reinterpret_cast<int*>(take(size_t(n) * 4));
+  int* ovf_count = reinterpret_cast<int*>(take(size_t(n) * 4));
+  int* ovf_list = reinterpret_cast<int*>(take(size_t(n) * max_cand * 4));
   ContourScratch* cs = nullptr;
   const int nseg = int((hw + kSeg - 1) / kSeg);
   if (nseg > 4096) return cudaErrorInvalidValue;
@@ -691,14 +715,21 @@ cudaError_t segrep_launch(const uint8_t* bitmap, const float* pred, size_t pred_
   accumulate_kernel<<<grid, 256, 0, s>>>(h, w, pred, pred_page_stride, Lf, Lb, parent, flag, own_sum, own_cnt, ring_sum,
                                          ring_cnt, rowmin, rowmax, c_yrange, max_cand);
   tree_kernel<<<grid, 256, 0, s>>>(h, w, Lf, Lb, parent, own_sum, own_cnt, tot_sum, tot_cnt);
-  const size_t csmem = sizeof(ContourScratch) * kContourWarps;
+  constexpr int kCapSmall = 128, kCapLarge = ctdgeom::kMaxHull;
+  const size_t sm_small = sizeof(ContourScratchT<kCapSmall>) * kContourWarps, sm_large = sizeof(ContourScratchT<kCapLarge>) * kContourWarps;
   // per device, so set on every launch (cheap; a process may own engines on several GPUs)
-  cudaFuncSetAttribute(contour_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(csmem));
+  cudaFuncSetAttribute(contour_kernel<kCapLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sm_large));
   if (max_cand > 1024) return cudaErrorInvalidValue;
   contour_order_kernel<<<n, 1024, 0, s>>>(max_cand, total, c_yrange, perm);
-  contour_kernel<<<unsigned((max_cand + kContourWarps - 1) / kContourWarps) * unsigned(n), 32 * kContourWarps, csmem, s>>>(
+  e = cudaMemsetAsync(ovf_count, 0, size_t(n) * 4, s);
+  if (e != cudaSuccess) return e;
+  const unsigned cgrid = unsigned((max_cand + kContourWarps - 1) / kContourWarps) * unsigned(n);
+  contour_kernel<kCapSmall><<<cgrid, 32 * kContourWarps, sm_small, s>>>(
       h, w, max_cand, total, c_root, rowmin, rowmax, c_yrange, tot_sum, tot_cnt, ring_sum, ring_cnt, cs, boxes, scores,
-      n_contours, w, h, unclip_ratio, perm, n);
+      n_contours, w, h, unclip_ratio, perm, n, ovf_count, ovf_list, 0);
+  contour_kernel<kCapLarge><<<cgrid, 32 * kContourWarps, sm_large, s>>>(
+      h, w, max_cand, total, c_root, rowmin, rowmax, c_yrange, tot_sum, tot_cnt, ring_sum, ring_cnt, cs, boxes, scores,
+      n_contours, w, h, unclip_ratio, perm, n, ovf_count, ovf_list, 1);
   return cudaGetLastError();
 }
 

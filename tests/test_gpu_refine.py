@@ -1,5 +1,9 @@
 """-m gpu: refine_mask (utils/textmask.py:159-169) on the GPU, bit-exact against the oracle restatement
-(which equals the unmodified reference except for the documented stable tie order of np.argsort)."""
+(which equals the unmodified reference except for the documented stable tie order of np.argsort).  Both device
+implementations are tested: the phase-synchronous kernels of csrc/refine_mk.cu (default) and the cooperative
+one-CTA / one-cluster-per-window kernels of csrc/refine.cu (CTD_REFINE=coop)."""
+import os
+
 import cv2
 import numpy as np
 import pytest
@@ -37,9 +41,20 @@ def make_case(seed, size=512, nblk=10):
     return img, mask, wins
 
 
+@pytest.fixture(params=["mk", "coop"])
+def impl(request):
+    old = os.environ.get("CTD_REFINE")
+    os.environ["CTD_REFINE"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("CTD_REFINE", None)
+    else:
+        os.environ["CTD_REFINE"] = old
+
+
 @pytest.mark.parametrize("mode", [0, 1], ids=["inpaint", "annotation"])
 @pytest.mark.parametrize("seed", range(6))
-def test_refine_mask_matches_oracle(eng, seed, mode):
+def test_refine_mask_matches_oracle(eng, impl, seed, mode):
     img, mask, wins = make_case(seed)
     ref = postproc_ref.refine_mask(img, mask.copy(), wins, mode)
     ex = [postproc_ref.expand_textwindow(img.shape, w, expand_r=16) for w in wins]
@@ -47,7 +62,7 @@ def test_refine_mask_matches_oracle(eng, seed, mode):
     assert np.array_equal(got, ref), int((got != ref).sum())
 
 
-def test_refine_mask_edge_cases(eng):
+def test_refine_mask_edge_cases(eng, impl):
     img, mask, _ = make_case(3, 256, 4)
     # window covering the whole page, an empty-mask window, a 1-pixel-high window, no windows at all
     wins = [[0, 0, 255, 255], [200, 200, 240, 240], [10, 10, 60, 11]]
@@ -57,3 +72,17 @@ def test_refine_mask_edge_cases(eng):
         ex = [postproc_ref.expand_textwindow(img.shape, w, expand_r=16) for w in wins]
         assert np.array_equal(eng.refine_mask(img, mask, ex, mode), ref)
     assert not eng.refine_mask(img, mask, np.zeros((0, 4), np.int32), 0).any()
+
+
+def test_refine_large_windows_both_implementations_agree(eng):
+    """a 1024x1024 page with overlapping page-sized windows (cluster kernel / many chunks per window): the two device
+    implementations must agree bit for bit (the oracle takes minutes at this size)"""
+    img, mask, wins = make_case(11, 1024, 30)
+    wins += [[0, 0, 1023, 1023], [100, 50, 900, 1000], [0, 300, 1023, 700]]
+    ex = [postproc_ref.expand_textwindow(img.shape, w, expand_r=16) for w in wins]
+    out = {}
+    for name in ("mk", "coop"):
+        os.environ["CTD_REFINE"] = name
+        out[name] = eng.refine_mask(img, mask, ex, 0)
+    os.environ.pop("CTD_REFINE", None)
+    assert out["mk"].any() and np.array_equal(out["mk"], out["coop"]), int((out["mk"] != out["coop"]).sum())
