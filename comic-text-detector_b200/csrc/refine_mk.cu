@@ -21,7 +21,6 @@ namespace ctd {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kSegW = 64;          // run starts are found per 64-pixel row segment (one thread each)
 
 struct RefineWin {
   int x1, y1, x2, y2;
@@ -343,12 +342,49 @@ __global__ void k_decide2(Ctx c, int n_wins) {
 }
 
 // ---- labelling of a source plane: candidate `round` (0..3) or, round == 4, the inverse of `merged` (hole filling) -----
-// pass A: source pixels + run starts, one thread per 64-pixel row segment
-__global__ void __launch_bounds__(kThreads) k_source(Ctx c, int round) {
+// Level 1, one CTA per chunk (whole rows, <= kChunkPx pixels), everything in SHARED memory: source pixels (coalesced),
+// run starts by warp ballot, seams between warps and the contacts between the rows of the chunk united in a shared
+// union-find, one root per chunk-local component written to L (tmp = 1 marks those roots: they are the chain nodes of
+// the global forest).  Level 2: only the first row of every chunk issues global unions with the row above it.
+// Level 3: compress from the chain nodes, then every pixel takes its (chunk-local) parent's root.
+constexpr int kChunkPx = 8192;
+constexpr int kLabelThreads = 512;
+
+__device__ __forceinline__ int suf_find(const int* L, int a) {
+  int p = L[a];
+  while (p != a) {
+    a = p;
+    p = L[a];
+  }
+  return a;
+}
+__device__ __forceinline__ void suf_union(int* L, int a, int b) {
+  bool done;
+  do {
+    a = suf_find(L, a);
+    b = suf_find(L, b);
+    if (a < b) {
+      const int old = atomicMin(&L[b], a);
+      done = old == b;
+      b = old;
+    } else if (b < a) {
+      const int old = atomicMin(&L[a], b);
+      done = old == a;
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+
+__global__ void __launch_bounds__(kLabelThreads) k_label_local(Ctx c, int round) {
+  __shared__ int Ls[kChunkPx];
+  __shared__ uint8_t fs[kChunkPx];
   const View v = view_of(c, blockIdx.x);
   const WinState& st = c.st[v.w];
   if (round < 4 && round >= st.nproc) return;
   uint8_t* cand = c.cand + v.win.off;
+  uint8_t* rootflag = c.tmp + v.win.off;
   int* L = c.L + v.win.off;
   const uint8_t* grey = c.grey + v.win.off;
   const uint8_t* merged = c.merged + v.win.off;
@@ -357,54 +393,79 @@ __global__ void __launch_bounds__(kThreads) k_source(Ctx c, int round) {
     kind = st.proc_kind[round]; neg = st.proc_neg[round];
     if (kind < 3) { lo = st.lo[kind]; hi = st.hi[kind]; } else ot = st.otsu_t[kind - 3];
   }
-  const int segs = (v.rw + kSegW - 1) / kSegW;
-  for (int t = threadIdx.x; t < v.rows * segs; t += kThreads) {
-    const int yl = t / segs, x0 = (t - yl * segs) * kSegW;
-    const int y = v.y0 + yl;
-    const int x1 = min(v.rw, x0 + kSegW);
-    const int base = y * v.rw;
-    const size_t gp0 = size_t(v.win.y1 + y) * c.W + v.win.x1;
-    int start = -1;
-    for (int x = x0; x < x1; ++x) {
-      int s;
+  const int lane = threadIdx.x & 31;
+  // pass 1: source value per pixel (coalesced), run starts inside each warp's 32 consecutive pixels
+  for (int k0 = 0; k0 < v.cnt; k0 += kLabelThreads) {
+    const int k = k0 + threadIdx.x;
+    const bool in = k < v.cnt;
+    int sv = 0, x = 0;
+    if (in) {
+      const int i = v.i0 + k;
+      const int y = i / v.rw;
+      x = i - y * v.rw;
       if (round == 4) {
-        s = merged[base + x] ? 0 : 255;
+        sv = merged[i] ? 0 : 255;
       } else {
         int tv;
         if (kind < 3) {
-          const int gr = grey[base + x];
+          const int gr = grey[i];
           tv = (gr >= lo && gr <= hi) ? 255 : 0;
         } else {
-          tv = v.img[(gp0 + x) * 3 + (kind - 3)] > ot ? 255 : 0;
+          tv = v.img[(size_t(v.win.y1 + y) * c.W + v.win.x1 + x) * 3 + (kind - 3)] > ot ? 255 : 0;
         }
-        s = neg ? 255 - tv : tv;
+        sv = neg ? 255 - tv : tv;
       }
-      cand[base + x] = (uint8_t)s;
-      if (s) {
-        if (start < 0) start = base + x;
-        L[base + x] = start;
-      } else {
-        start = -1;
-        L[base + x] = -1;
-      }
+      cand[i] = (uint8_t)sv;
+    }
+    const bool fg = in && sv != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, fg);
+    // a run starts at a foreground pixel whose left neighbour (same row, same warp) is not foreground
+    const bool starts = fg && (lane == 0 || x == 0 || !((m >> (lane - 1)) & 1u));
+    const unsigned sb = __ballot_sync(0xffffffffu, starts);
+    if (in) {
+      fs[k] = (uint8_t)sv;
+      Ls[k] = fg ? (k - lane) + (31 - __clz(sb & (0xffffffffu >> (31 - lane)))) : -1;
     }
   }
+  __syncthreads();
+  // pass 2: seams between warps, contacts with the row above inside the chunk
+  for (int k = threadIdx.x; k < v.cnt; k += kLabelThreads) {
+    if (!fs[k]) continue;
+    const int x = (v.i0 + k) % v.rw;
+    if ((k & 31) == 0 && x > 0 && k > 0 && fs[k - 1]) suf_union(Ls, k, k - 1);
+    if (k < v.rw) continue;
+    const int up = k - v.rw;
+    if (fs[up]) {
+      // only the first pixel of each (current run x upper run) overlap issues the union
+      const bool first = x == 0 || !fs[k - 1] || !fs[up - 1];
+      if (first) suf_union(Ls, k, up);
+    } else {
+      if (x > 0 && fs[up - 1]) suf_union(Ls, k, up - 1);
+      if (x + 1 < v.rw && fs[up + 1]) suf_union(Ls, k, up + 1);
+    }
+  }
+  __syncthreads();
+  // pass 3: chunk-local roots to global memory (window-local pixel indices)
+  for (int k = threadIdx.x; k < v.cnt; k += kLabelThreads) {
+    const int i = v.i0 + k;
+    int r = -1;
+    if (fs[k]) r = suf_find(Ls, k);
+    L[i] = r < 0 ? -1 : v.i0 + r;
+    rootflag[i] = (r == k) ? 1 : 0;
+  }
 }
-// pass B: segment seams and contacts with the row above
-__global__ void __launch_bounds__(kThreads) k_union(Ctx c, int round) {
+// level 2: the first row of every chunk against the last row of the chunk above
+__global__ void __launch_bounds__(kThreads) k_union_border(Ctx c, int round) {
   const View v = view_of(c, blockIdx.x);
   if (round < 4 && round >= c.st[v.w].nproc) return;
+  if (v.y0 == 0) return;
   const uint8_t* src = c.cand + v.win.off;
   int* L = c.L + v.win.off;
-  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
-    const int i = v.i0 + k;
+  for (int x = threadIdx.x; x < v.rw; x += kThreads) {
+    const int i = v.i0 + x;
     if (!src[i]) continue;
-    const int x = i % v.rw;
-    if (x > 0 && (x % kSegW) == 0 && src[i - 1]) uf_union(L, i, i - 1);
-    if (i < v.rw) continue;
     const int up = i - v.rw;
     if (src[up]) {
-      // only the first pixel of each (current run x upper run) overlap issues the union
       const bool first = x == 0 || !src[i - 1] || !src[up - 1];
       if (first) uf_union(L, i, up);
     } else {
@@ -413,17 +474,15 @@ __global__ void __launch_bounds__(kThreads) k_union(Ctx c, int round) {
     }
   }
 }
-// pass C: compress from the chain nodes (segment-run starts); pass D: every pixel takes its parent's root
+// level 3a: compress from the chain nodes (chunk-local roots); 3b: every pixel takes its parent's root
 __global__ void __launch_bounds__(kThreads) k_flat1(Ctx c, int round) {
   const View v = view_of(c, blockIdx.x);
   if (round < 4 && round >= c.st[v.w].nproc) return;
-  const uint8_t* src = c.cand + v.win.off;
+  const uint8_t* rootflag = c.tmp + v.win.off;
   int* L = c.L + v.win.off;
   for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
     const int i = v.i0 + k;
-    if (!src[i]) continue;
-    const int x = i % v.rw;
-    if ((x % kSegW) == 0 || !src[i - 1]) uf_find_compress(L, i);
+    if (rootflag[i]) uf_find_compress(L, i);
   }
 }
 __global__ void __launch_bounds__(kThreads) k_flat2(Ctx c, int round) {
@@ -588,7 +647,7 @@ __global__ void __launch_bounds__(kThreads) k_or(Ctx c) {
 
 size_t refine_mk_state_bytes(int n_wins) { return (size_t(n_wins) * sizeof(WinState) + 255) / 256 * 256; }
 size_t refine_mk_chunk_bytes() { return sizeof(Chunk); }
-int refine_mk_chunk_px() { return 4096; }
+int refine_mk_chunk_px() { return kChunkPx; }
 
 // d_wins: n_wins RefineWin records; d_chunks: n_chunks {win, y0, rows, pad} (whole rows, <= refine_mk_chunk_px() pixels
 // each unless a single row is longer); d_state: refine_mk_state_bytes(n_wins) bytes (zeroed here); scratch planes as in
@@ -623,8 +682,8 @@ cudaError_t refine_mk_launch(const uint8_t* d_img, const uint8_t* d_mask, int H,
       k_dilate<<<g, kThreads, 0, s>>>(c);
       k_copyback<<<g, kThreads, 0, s>>>(c);
     }
-    k_source<<<g, kThreads, 0, s>>>(c, round);
-    k_union<<<g, kThreads, 0, s>>>(c, round);
+    k_label_local<<<g, kLabelThreads, 0, s>>>(c, round);
+    k_union_border<<<g, kThreads, 0, s>>>(c, round);
     k_flat1<<<g, kThreads, 0, s>>>(c, round);
     k_flat2<<<g, kThreads, 0, s>>>(c, round);
     k_macc<<<g, kThreads, 0, s>>>(c, round);
