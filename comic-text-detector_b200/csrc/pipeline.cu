@@ -70,7 +70,9 @@ int launch_refine(ctd_handle* h, const RefineJob& job, const uint8_t* d_img, con
   if (refine_win_bytes() != sizeof(HostWin) || refine_mk_chunk_bytes() != sizeof(HostChunk))
     return ctd_fail(h, CTD_E_INVALID, "RefineWin / Chunk layout mismatch");
   const char* rf_env = getenv("CTD_REFINE");                   // CTD_REFINE=coop: the cooperative kernels of refine.cu
-  const bool coop = rf_env && rf_env[0] == 'c';
+  bool coop = rf_env && rf_env[0] == 'c';
+  for (const HostWin& w : job.wins)                            // a window row must fit one chunk of the phase kernels
+    if (w.x2 - w.x1 > refine_mk_chunk_px()) coop = true;
   auto al = [](size_t v) { return (v + 255) / 256 * 256; };
   const size_t tb = job.table_bytes();   // a multiple of 256
   const size_t sb = refine_mk_state_bytes(int(job.wins.size()));

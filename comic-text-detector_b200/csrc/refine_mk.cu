@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(kThreads) k_phase0(Ctx c) {
 }
 
 // ---- phase 1 (one CTA per window): np.histogram(bins=255), top-k colours, Otsu ---------------------------------------
-__global__ void __launch_bounds__(kThreads) k_decide1(Ctx c) {
+constexpr int kDecideThreads = 64;   // mostly serial per-window work: small CTAs so that many windows are resident per SM
+__global__ void __launch_bounds__(kDecideThreads) k_decide1(Ctx c) {
   __shared__ int cnt255[256];
   __shared__ int order[256];
   __shared__ double edges[256];
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(kThreads) k_decide1(Ctx c) {
   const RefineWin win = c.wins[blockIdx.x];
   const int n = (win.x2 - win.x1) * (win.y2 - win.y1);
   const int* hist_g = st.hist[0];
-  for (int i = threadIdx.x; i < 256; i += kThreads) cnt255[i] = 0;
+  for (int i = threadIdx.x; i < 256; i += kDecideThreads) cnt255[i] = 0;
   if (threadIdx.x == 0) {
     int first = -1, last = -1, total = 0;
     for (int v = 0; v < 256; ++v)
@@ -191,9 +192,9 @@ __global__ void __launch_bounds__(kThreads) k_decide1(Ctx c) {
     else if (s_first == s_last) { fe = s_first - 0.5; le = s_last + 0.5; }
     else { fe = s_first; le = s_last; }
     const double step = (le - fe) / 255.0;  // np.linspace(fe, le, 256): arange * step + start, last = stop
-    for (int i = threadIdx.x; i < 256; i += kThreads) edges[i] = (i == 255) ? le : __dadd_rn(__dmul_rn((double)i, step), fe);
+    for (int i = threadIdx.x; i < 256; i += kDecideThreads) edges[i] = (i == 255) ? le : __dadd_rn(__dmul_rn((double)i, step), fe);
     __syncthreads();
-    for (int v = threadIdx.x; v < 256; v += kThreads) {
+    for (int v = threadIdx.x; v < 256; v += kDecideThreads) {
       if (!hist_g[v]) continue;
       const double a = (double)v;
       const double f = ((a - fe) / (le - fe)) * 255.0;  // numpy fast path: (tmp_a - first_edge) / norm_denom * n_bins
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(kThreads) k_decide1(Ctx c) {
   }
   __syncthreads();
   // stable descending order of the 255 bins (documented normalisation of np.argsort's tie order)
-  for (int b = threadIdx.x; b < 255; b += kThreads) {
+  for (int b = threadIdx.x; b < 255; b += kDecideThreads) {
     int rank = 0;
     const int cb = cnt255[b];
     for (int q = 0; q < 255; ++q) rank += (cnt255[q] > cb) || (cnt255[q] == cb && q < b);
@@ -386,6 +387,8 @@ __global__ void __launch_bounds__(kLabelThreads) k_label_local(Ctx c, int round)
   uint8_t* cand = c.cand + v.win.off;
   uint8_t* rootflag = c.tmp + v.win.off;
   int* L = c.L + v.win.off;
+  int* acc = c.acc + 4 * v.win.off;
+  const int n = v.rw * v.rh;
   const uint8_t* grey = c.grey + v.win.off;
   const uint8_t* merged = c.merged + v.win.off;
   int kind = 0, neg = 0, lo = 0, hi = 0, ot = 0;
@@ -452,6 +455,9 @@ __global__ void __launch_bounds__(kLabelThreads) k_label_local(Ctx c, int round)
     if (fs[k]) r = suf_find(Ls, k);
     L[i] = r < 0 ? -1 : v.i0 + r;
     rootflag[i] = (r == k) ? 1 : 0;
+    // every global root is one of these chunk-local roots: their per-label sums start at zero here, so that the
+    // flatten pass can accumulate right away
+    if (r == k) { acc[i] = 0; acc[n + i] = 0; acc[2 * n + i] = 0; acc[3 * n + i] = -1; }   // area, gain, loss, maxi
   }
 }
 // level 2: the first row of every chunk against the last row of the chunk above
@@ -485,28 +491,14 @@ __global__ void __launch_bounds__(kThreads) k_flat1(Ctx c, int round) {
     if (rootflag[i]) uf_find_compress(L, i);
   }
 }
-__global__ void __launch_bounds__(kThreads) k_flat2(Ctx c, int round) {
-  const View v = view_of(c, blockIdx.x);
-  if (round < 4 && round >= c.st[v.w].nproc) return;
-  int* L = c.L + v.win.off;
-  int* acc = c.acc + 4 * v.win.off;
-  const int n = v.rw * v.rh;
-  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
-    const int i = v.i0 + k;
-    const int p = __ldcg(L + i);
-    if (p < 0) continue;
-    const int r = uf_find(L, p);
-    L[i] = r;
-    if (r == i) { acc[i] = 0; acc[n + i] = 0; acc[2 * n + i] = 0; acc[3 * n + i] = -1; }   // area, gain, loss, maxi
-  }
-}
-
 // ---- merge step (textmask.py:92-108 / 118-131): per-label sums, then the labels that lower xor(merged, pred) -----------
-__global__ void __launch_bounds__(kThreads) k_macc(Ctx c, int round) {
+// level 3b fused with the accumulation: every pixel takes its (chunk-local) parent's root, writes it back and adds
+// itself to the root's sums (warp-aggregated: the 32 consecutive pixels of a warp mostly share a label)
+__global__ void __launch_bounds__(kThreads) k_flat2_macc(Ctx c, int round) {
   const View v = view_of(c, blockIdx.x);
   WinState& st = c.st[v.w];
   if (round < 4 && round >= st.nproc) return;
-  const int* L = c.L + v.win.off;
+  int* L = c.L + v.win.off;
   const uint8_t* predm = c.predm + v.win.off;
   const uint8_t* merged = c.merged + v.win.off;
   int* acc = c.acc + 4 * v.win.off;
@@ -517,7 +509,12 @@ __global__ void __launch_bounds__(kThreads) k_macc(Ctx c, int round) {
     const int k = k0 + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int i = v.i0 + k;
-    const int r = k < v.cnt ? L[i] : -2;
+    int r = -2;
+    if (k < v.cnt) {
+      const int p = __ldcg(L + i);
+      r = p < 0 ? -1 : uf_find(L, p);
+      if (p >= 0 && r != p) L[i] = r;
+    }
     const bool un = r >= 0 && merged[i] == 0;
     const bool pg = un && predm[i] != 0;
     const unsigned peers = __match_any_sync(0xffffffffu, r);
@@ -674,7 +671,7 @@ cudaError_t refine_mk_launch(const uint8_t* d_img, const uint8_t* d_mask, int H,
   if (e != cudaSuccess) return e;
   const unsigned g = unsigned(n_chunks);
   k_phase0<<<g, kThreads, 0, s>>>(c);
-  k_decide1<<<unsigned(n_wins), kThreads, 0, s>>>(c);
+  k_decide1<<<unsigned(n_wins), kDecideThreads, 0, s>>>(c);
   k_xor<<<g, kThreads, 0, s>>>(c);
   k_decide2<<<unsigned((n_wins + 127) / 128), 128, 0, s>>>(c, n_wins);
   for (int round = 0; round < 5; ++round) {
@@ -685,8 +682,7 @@ cudaError_t refine_mk_launch(const uint8_t* d_img, const uint8_t* d_mask, int H,
     k_label_local<<<g, kLabelThreads, 0, s>>>(c, round);
     k_union_border<<<g, kThreads, 0, s>>>(c, round);
     k_flat1<<<g, kThreads, 0, s>>>(c, round);
-    k_flat2<<<g, kThreads, 0, s>>>(c, round);
-    k_macc<<<g, kThreads, 0, s>>>(c, round);
+    k_flat2_macc<<<g, kThreads, 0, s>>>(c, round);
     if (round == 4) {
       k_top_a<<<g, kThreads, 0, s>>>(c);
       k_top_b<<<g, kThreads, 0, s>>>(c);
