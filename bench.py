@@ -227,6 +227,7 @@ def main():
                 ghost = [torch.empty((res_bytes,), dtype=torch.uint8).pin_memory() for _ in range(world)] if rank == 0 else None
                 gathered[(ei, slot)] = (res_t, glist, ghost)
     gstream = torch.cuda.Stream() if world > 1 else None
+    gather_done = {}
 
     def finish(ei, slot):
         engs[ei].collect(slot)
@@ -234,6 +235,9 @@ def main():
             res_t, glist, ghost = gathered[(ei, slot)]
             with torch.cuda.stream(gstream):
                 dist.gather(res_t, gather_list=glist, dst=0)
+                ev = torch.cuda.Event()
+                ev.record(gstream)          # the slot's device arena may be overwritten once the gather has read it
+                gather_done[(ei, slot)] = ev
                 if rank == 0 and not state["on_device"]:
                     for g, hbuf in zip(glist, ghost):
                         hbuf.copy_(g, non_blocking=True)
@@ -244,6 +248,8 @@ def main():
         ei, slot = k % n_eng, (k // n_eng) & 1
         if len(pending) == 2 * n_eng:
             finish(*pending.pop(0))
+        if (ei, slot) in gather_done:
+            gather_done.pop((ei, slot)).synchronize()
         src = dev_pages.data_ptr() if state["on_device"] else host_pages.data_ptr()
         engs[ei].submit_full(slot, src, B, H, W, out_arena[ei][slot].data_ptr(), pages_on_device=state["on_device"])
         pending.append((ei, slot))
