@@ -15,6 +15,8 @@ def load(path):
     for r in rd:
         if len(r) < len(hdr):
             continue
+        if "Metric Name" in idx and r[idx["Metric Name"]] != "gpu__time_duration.sum":
+            continue   # multi-metric lists (traffic captures): one row per metric and launch
         u = r[idx["Metric Unit"]]
         t = float(r[idx["Metric Value"]].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(u, 1e-3)
         data.append((r[idx["Kernel Name"]], t, r[idx["Grid Size"]]))
