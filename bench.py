@@ -51,6 +51,10 @@ def conv_flops(prog, n, h, w):
         if kind == 0:  # stem: 6x6 s2 conv 3 -> cout (algorithmic FLOPs, not the zero-padded tensor-core K)
             out.append(2.0 * (h // 2) * (w // 2) * n * 108 * o["cout"])
             continue
+        if kind == 10:  # fused Bottleneck: 1x1 c -> c plus 3x3 c -> c on the same pixels
+            down = prog.bufs[o["src_buf"][0]][1]
+            out.append(2.0 * (h // down) * (w // down) * n * 10 * o["cout"] * o["cout"])
+            continue
         if kind not in (1, 2, 6, 7):
             out.append(0.0)
             continue
@@ -194,7 +198,7 @@ def main():
     warm = max(3, args.warmup)
 
     ck = synth.make_checkpoint(0, smooth=True)
-    prog = ctd_b200.compiler.compile_checkpoint(ck)
+    prog = ctd_b200.compiler.compile_checkpoint(ck, fuse=ctd_b200.compiler.fuse_default(True))
     n_eng = max(1, args.engines)
     engs = [ctd_b200.Engine(prog, device=local, max_batch=B, max_h=H, max_w=W, use_graph=True) for _ in range(n_eng)]
     eng = engs[0]
@@ -346,7 +350,7 @@ def main():
     op_ms2, _, _ = eng.profile_forward(dev_ptr=dev_pages.data_ptr(), shape=(B, H, W))
     op_ms = np.minimum(op_ms, op_ms2)
     fl = conv_flops(prog, B, H, W)
-    tc_idx = [i for i, o in enumerate(prog.ops) if o["kind"] in (0, 1, 2, 6, 7)]
+    tc_idx = [i for i, o in enumerate(prog.ops) if o["kind"] in (0, 1, 2, 6, 7, 10)]
     tc_ms = float(sum(op_ms[i] for i in tc_idx))
     tc_flops = float(sum(fl[i] for i in tc_idx))
     peaks = {}
@@ -399,7 +403,7 @@ def main():
                             % (n_eng, "; + NCCL gather of all ranks' arenas and rank 0's D2H of them" if world > 1 else "")},
             "net_only": {"value": net_val, "unit": "pages/s", "ms_per_step": ms_net / args.steps,
                          "what": "round-1 step: network + NMS + CCL + line boxes only (ctd_forward on resident pages), no group_output / refine_mask"},
-            "roofline": {"bound": "tensor", "kernel": "conv_tc / conv_halo / conv_hs / conv_sw kernels, the tcgen05 implicit-GEMM convolutions (%d launches per step)" % len(tc_idx),
+            "roofline": {"bound": "tensor", "kernel": "conv_tc / conv_halo / conv_hs / conv_sw / conv_bneck kernels, the tcgen05 implicit-GEMM convolutions (%d launches per step)" % len(tc_idx),
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                          "traffic": traffic, "traffic_unit": "bytes/step", "traffic_source": traffic_src,
                          "peak_source": peak_src, "flops_per_step": tc_flops, "ms_per_step": tc_ms,

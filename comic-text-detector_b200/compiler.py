@@ -16,7 +16,8 @@ import numpy as np
 
 # enum mirrors of include/ctd_b200.h
 (OP_STEM, OP_CONV, OP_DECONV4, OP_AVGPOOL2, OP_SPPF_POOL, OP_UPSAMPLE2, OP_DETECT, OP_SEG_TAIL, OP_DB_TAIL,
- OP_S2D) = range(10)
+ OP_S2D, OP_BNECK) = range(11)
+FUSED_BNECK_CHANNELS = (32, 64)   # c_ the fused Bottleneck kernel (csrc/conv_fuse.cu) is built for
 ACT_NONE, ACT_SILU, ACT_LEAKY, ACT_RELU, ACT_SIGMOID = range(5)
 MAX_SRC = 3
 
@@ -150,6 +151,19 @@ class Program:
         self._op(OP_DECONV4, srcs, dst, ksize=4, stride=2, act=act, **self._pack(wk, b, co))
         return dst
 
+    def bneck(self, src, w1, b1, w2, b2, act, residual):
+        """Fused Bottleneck (common.py:94-104): dst = [src +] act(conv3x3(act(conv1x1(src)))) into a NEW buffer
+        (the fused kernel reads the halo of src while neighbouring tiles write dst).  Blob: W1 [c][c] then W2 [c][9c]
+        (K order (ky, kx, ci)), fp16 and fp32; bias1 | bias2."""
+        c = w1.shape[0]
+        assert w1.shape == (c, c, 1, 1) and w2.shape == (c, c, 3, 3) and src["c"] == c
+        dst = self.tensor(self.newbuf(c, src["down"]), 0, c)
+        wk = np.concatenate([w1.reshape(c, c).reshape(-1), w2.transpose(0, 2, 3, 1).reshape(-1)]).astype(np.float32)
+        bb = np.concatenate([b1, b2]).astype(np.float32)
+        self._op(OP_BNECK, [src], dst, ksize=3, stride=1, act=act, residual=int(residual), cout=c, cout_pad=c,
+                 w16_off=self.add_blob(wk.astype(np.float16)), w32_off=self.add_blob(wk), b_off=self.add_blob(bb))
+        return dst
+
     def detect(self, src, w, b, level, stride, anchors_px):
         co = w.shape[0]
         wk = w.reshape(1, co, -1)
@@ -171,8 +185,16 @@ def fold_bn(w, conv_bias, sd, bn_prefix, eps, transposed=False):
     return wf, (b0 - mu) * scale + beta
 
 
-def compile_checkpoint(ckpt, head_act="leaky", stem_mode="s2d"):
-    """Returns a Program for the full TextDetBase.forward graph (basemodel.py:240-244)."""
+def fuse_default(fp16_tc):
+    """Whether a caller that builds the fp16 tensor-core engine should ask for fused ops (CTD_FUSE=0 turns it off)."""
+    import os
+    return bool(fp16_tc) and os.environ.get("CTD_FUSE", "1") != "0"
+
+
+def compile_checkpoint(ckpt, head_act="leaky", stem_mode="s2d", fuse=False):
+    """Returns a Program for the full TextDetBase.forward graph (basemodel.py:240-244).  fuse=True emits the
+    Bottlenecks with 32 / 64 channels as ONE op each (OP_BNECK, fp16 tensor-core engine only): same arithmetic and
+    the same fp16 storage points as the two-op form, so the results are bit-identical."""
     P = Program()
     cfg = ckpt["blk_det"]["cfg"]
     ysd, ssd, dsd = ckpt["blk_det"]["weights"], ckpt["text_seg"], ckpt["text_det"]
@@ -193,14 +215,20 @@ def compile_checkpoint(ckpt, head_act="leaky", stem_mode="s2d"):
         down = srcs[0]["down"]
         Y = P.newbuf(2 * c_, down)
         P.conv(srcs, np.concatenate([w1, w2], 0), np.concatenate([b1, b2], 0), 1, act, dst=P.tensor(Y, 0, 2 * c_))
+        cur = P.tensor(Y, 0, c_)
         for j in range(n):
             wa, ba = get("%s.m.%d.cv1" % (prefix, j))
             wb, bb = get("%s.m.%d.cv2" % (prefix, j))
-            t = P.conv([P.tensor(Y, 0, c_)], wa, ba, 1, act)
+            if fuse and c_ in FUSED_BNECK_CHANNELS and act != ACT_SIGMOID:
+                cur = P.bneck(cur, wa, ba, wb, bb, act, bool(shortcut))
+                continue
+            t = P.conv([cur], wa, ba, 1, act)
             # Bottleneck (common.py:103-104): x + cv2(cv1(x)), written in place over x
-            P.conv([t], wb, bb, 1, act, dst=P.tensor(Y, 0, c_), residual=bool(shortcut))
+            P.conv([t], wb, bb, 1, act, dst=cur, residual=bool(shortcut))
         w3, b3 = get(prefix + ".cv3")
-        return P.conv([P.tensor(Y, 0, 2 * c_)], w3, b3, 1, act)
+        if cur["buf"] == Y:
+            return P.conv([P.tensor(Y, 0, 2 * c_)], w3, b3, 1, act)
+        return P.conv([cur, P.tensor(Y, c_, c_)], w3, b3, 1, act)   # cv3(cat(m(cv1 x), cv2 x)): K-concatenated
 
     # ---- blk_det (yolo.py:115-134) -----------------------------------------------------------
     outs = []

@@ -163,6 +163,12 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
     h->enc = reinterpret_cast<PFN_encodeTiled>(fn);
   }
   CKC(conv_tc_init());
+  CKC(ctd::conv_bneck_init());
+  for (int i = 0; i < n_ops; ++i)
+    if (ops[i].kind == CTD_OP_BNECK && (cfg->precision != CTD_PREC_FP16_TC || !ctd::conv_bneck_supported(ops[i].cout))) {
+      ctd_fail(h, CTD_E_INVALID, "op %d: fused Bottleneck needs CTD_PREC_FP16_TC and 32 or 64 channels", i);
+      return bail(CTD_E_INVALID);
+    }
   h->blob_bytes = blob_bytes;
   CKC(cudaMalloc(&h->d_blob, blob_bytes));
   CKC(cudaMemcpy(h->d_blob, blob, blob_bytes, cudaMemcpyHostToDevice));
@@ -324,8 +330,26 @@ static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
     return CTD_OK;
   }
   if (h->cfg.precision != CTD_PREC_FP16_TC) return CTD_OK;
+  sp.bn.resize(h->ops.size());
   for (size_t i = 0; i < h->ops.size(); ++i) {
     const ctd_op& op = h->ops[i];
+    if (op.kind == CTD_OP_BNECK) {
+      // fused Bottleneck: 1x1 + 3x3 (+ residual) in one kernel, intermediate in shared memory (conv_fuse.cu)
+      const ctd_bufdesc& sb = h->bufs[op.src_buf[0]];
+      const ctd_bufdesc& db = h->bufs[op.dst_buf];
+      if (op.n_src != 1 || op.src_c[0] != op.cout || op.cout != op.cout_pad || sb.down != db.down || op.src_buf[0] == op.dst_buf)
+        return ctd_fail(h, CTD_E_INVALID, "op %zu: malformed fused Bottleneck", i);
+      int nsm = 148;
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->cfg.device);
+      const char* e = ctd::conv_bneck_plan(sp.bn[i], h->enc, n, ph / sb.down, pw / sb.down, op.cout, h->d_buf[op.src_buf[0]],
+                                           sb.channels, op.src_coff[0], h->d_blob + op.w16_off,
+                                           reinterpret_cast<const float*>(h->d_blob + op.b_off),
+                                           static_cast<__half*>(h->d_buf[op.dst_buf]), db.channels, op.dst_coff, op.act,
+                                           op.residual, nsm);
+      if (e) return ctd_fail(h, CTD_E_INVALID, "op %zu: %s", i, e);
+      sp.has_tc[i] = 1;
+      continue;
+    }
     if (op.kind == CTD_OP_STEM) {
       const char* e = ((h->halo_mode & 1) ? conv_halo_plan_stem : conv_tc_plan_stem)(
           sp.tc[i], h->enc, h->d_buf[op.src_buf[0]], n, ph, pw, h->d_blob + op.w16_off,
@@ -501,7 +525,12 @@ static int run_one_op(ctd_handle* h, size_t i, int n, int ph, int pw, ShapePlan&
     if (rc) return rc;
     return split_written_slice(h, op, n, ph, pw, cnt);
   }
-  if (op.kind == CTD_OP_STEM && h->cfg.precision == CTD_PREC_FP16_TC) {
+  if (op.kind == CTD_OP_BNECK) {
+    if (h->cfg.precision != CTD_PREC_FP16_TC || !sp.has_tc[i])
+      return ctd_fail(h, CTD_E_INVALID, "op %zu: fused Bottleneck ops run on the fp16 tensor-core engine only", i);
+    cudaError_t e = ctd::conv_bneck_launch(sp.bn[i], h->stream);
+    rc = e == cudaSuccess ? CTD_OK : ctd_fail(h, CTD_E_CUDA, "conv_bneck op %zu: %s", i, cudaGetErrorString(e));
+  } else if (op.kind == CTD_OP_STEM && h->cfg.precision == CTD_PREC_FP16_TC) {
     // tensor-core stem: space-to-depth pre-pass into the padded window buffer, then the implicit GEMM
     cudaError_t e = s2d_launch<__half>(h->d_pages, n, ph, pw, static_cast<__half*>(h->d_buf[op.src_buf[0]]), 16, 0,
                                        pw / 2 + 4, 1, h->stream);

@@ -16,6 +16,7 @@
 
 #include "kernels.h"
 
+using ctd::BneckPlan;
 using ctd::ConvTcPlan;
 using ctd::NmsWorkspace;
 using ctd::PFN_encodeTiled;
@@ -49,6 +50,7 @@ struct RefineJob {
 struct ShapePlan {
   std::vector<ConvTcPlan> tc;  // index = op index (unused entries default)
   std::vector<char> has_tc;
+  std::vector<BneckPlan> bn;   // fused Bottleneck ops (CTD_OP_BNECK), index = op index
   cudaGraphExec_t graph = nullptr;
   int launches = 0;
 };

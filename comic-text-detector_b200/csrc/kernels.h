@@ -124,6 +124,32 @@ cudaError_t conv_tc_launch(const ConvTcPlan& plan, cudaStream_t s);
 cudaError_t conv_tc_init();  // sets max dynamic smem attributes once
 
 // ---------------------------------------------------------------------------------------
+// Fused Bottleneck (conv_fuse.cu): y = [x +] act(conv3x3(act(conv1x1(x)))), c -> c -> c channels, c in {32, 64}; the
+// intermediate stays in shared memory.  w16: W1 [c][c] followed by W2 [c][9*c] (K-major fp16, K = (tap, ci));
+// bias: bias1[c] | bias2[c].  Source and destination are different buffers.
+struct alignas(64) BneckParams {
+  CUtensorMap x_map, w1_map, w2_map, o_map;
+  int n_img, gh, gw;
+  int tiles_x, tiles_y;     // 8 x 16-pixel tiles
+  int act, residual;
+  int dst_cstride, dst_coff;
+  __half* dst;
+  const float* bias;
+};
+struct BneckPlan {
+  BneckParams p;
+  int c;
+  dim3 grid;
+  size_t smem_bytes;
+};
+bool conv_bneck_supported(int c);
+const char* conv_bneck_plan(BneckPlan& plan, PFN_encodeTiled enc, int n_img, int gh, int gw, int c, const void* src,
+                            int src_cstride, int src_coff, const void* w16, const float* bias, __half* dst,
+                            int dst_cstride, int dst_coff, int act, int residual, int num_sms);
+cudaError_t conv_bneck_init();
+cudaError_t conv_bneck_launch(const BneckPlan& plan, cudaStream_t s);
+
+// ---------------------------------------------------------------------------------------
 // CUDA-core kernels (simt.cu): accurate/bisecting path and the thin layers.  T = float | __half.
 struct ConvSimtParams {
   ConvGeom g;

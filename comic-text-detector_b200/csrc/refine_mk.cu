@@ -114,11 +114,34 @@ __device__ __forceinline__ void uf_union(int* L, int a, int b) {
 }
 
 __device__ __forceinline__ void hist_add(int* hist, int bin) {
+  // flat regions (page background, solid strokes): the whole warp hits one bin -> one atomic, no match.any
+  const int b0 = __shfl_sync(0xffffffffu, bin, 0);
+  if (__all_sync(0xffffffffu, bin == b0)) {
+    if ((threadIdx.x & 31) == 0 && bin >= 0) atomicAdd(&hist[bin], 32);
+    return;
+  }
   const unsigned peers = __match_any_sync(0xffffffffu, bin);
   if (bin >= 0 && int(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
 }
 
+// i = q * d + r for 0 <= i < 2^24 (exact in float; |q error| <= 1 before the correction), else integer division.
+// Every sweep below turns window-local pixel indices into (y, x): a runtime integer division per pixel was a
+// quarter of the instructions of the lean kernels.
+struct DivW { int d; float inv; bool fast; };
+__device__ __forceinline__ DivW make_div(int d, int n) { return DivW{d, __frcp_rn(float(d)), n < (1 << 24)}; }
+__device__ __forceinline__ void divmod(int i, const DivW& dv, int& q, int& r) {
+  if (dv.fast) {
+    q = __float2int_rz(__int2float_rn(i) * dv.inv);
+    r = i - q * dv.d;
+    if (r < 0) { --q; r += dv.d; } else if (r >= dv.d) { ++q; r -= dv.d; }
+  } else {
+    q = i / dv.d;
+    r = i - q * dv.d;
+  }
+}
+
 // ---- phase 0: grey, pred mask (cross erosion > 60), merged = 0, histograms ------------------------------------------
+constexpr int kU = 4;   // pixels per thread and outer iteration: the loads of all kU pixels are issued before the first use
 __global__ void __launch_bounds__(kThreads) k_phase0(Ctx c) {
   __shared__ int sh[4][256];
   const View v = view_of(c, blockIdx.x);
@@ -127,36 +150,53 @@ __global__ void __launch_bounds__(kThreads) k_phase0(Ctx c) {
   uint8_t* grey = c.grey + v.win.off;
   uint8_t* predm = c.predm + v.win.off;
   uint8_t* merged = c.merged + v.win.off;
-  for (int k0 = 0; k0 < v.cnt; k0 += kThreads) {
-    const int k = k0 + threadIdx.x;
-    const bool in = k < v.cnt;
-    int b = -1, g = -1, r = -1, gr = 0, m3 = 255, mc = 255;
-    if (in) {
-      const int i = v.i0 + k;
-      const int y = i / v.rw, x = i - y * v.rw;
-      const size_t gp = size_t(v.win.y1 + y) * c.W + v.win.x1 + x;
-      b = v.img[gp * 3]; g = v.img[gp * 3 + 1]; r = v.img[gp * 3 + 2];
-      gr = (b * 1868 + g * 9617 + r * 4899 + 8192) >> 14;  // cv2.COLOR_BGR2GRAY, 8u fixed point
-      grey[i] = (uint8_t)gr;
-      // erosions of the mask CROP (window borders ignore the outside: BORDER_CONSTANT with +inf)
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int yy = y + dy;
-        if (yy < 0 || yy >= v.rh) continue;
-        for (int dx = -1; dx <= 1; ++dx) {
-          const int xx = x + dx;
-          if (xx < 0 || xx >= v.rw) continue;
-          const int mv = v.mask[size_t(v.win.y1 + yy) * c.W + v.win.x1 + xx];
-          m3 = min(m3, mv);
-          if (dx == 0 || dy == 0) mc = min(mc, mv);
+  const DivW dv = make_div(v.rw, v.rw * v.rh);
+  for (int k0 = 0; k0 < v.cnt; k0 += kThreads * kU) {
+    int b[kU], g[kU], r[kU], m3[kU], mc[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int k = k0 + u * kThreads + threadIdx.x;
+      b[u] = -1; g[u] = -1; r[u] = -1; m3[u] = 255; mc[u] = 255;
+      if (k < v.cnt) {
+        int y, x;
+        divmod(v.i0 + k, dv, y, x);
+        const size_t gp = size_t(v.win.y1 + y) * c.W + v.win.x1 + x;
+        b[u] = v.img[gp * 3]; g[u] = v.img[gp * 3 + 1]; r[u] = v.img[gp * 3 + 2];
+        // erosions of the mask CROP (window borders ignore the outside: BORDER_CONSTANT with +inf)
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int yy = y + dy;
+          if (yy < 0 || yy >= v.rh) continue;
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= v.rw) continue;
+            const int mv = v.mask[size_t(v.win.y1 + yy) * c.W + v.win.x1 + xx];
+            m3[u] = min(m3[u], mv);
+            if (dx == 0 || dy == 0) mc[u] = min(mc[u], mv);
+          }
         }
       }
-      predm[i] = mc > 60 ? 255 : 0;                  // textmask.py:86-89
-      merged[i] = 0;
     }
-    hist_add(sh[1], b);
-    hist_add(sh[2], g);
-    hist_add(sh[3], r);
-    hist_add(sh[0], (in && m3 > 127) ? gr : -1);     // textmask.py:60
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int k = k0 + u * kThreads + threadIdx.x;
+      const bool in = k < v.cnt;
+      int gr = 0;
+      if (in) {
+        const int i = v.i0 + k;
+        gr = (b[u] * 1868 + g[u] * 9617 + r[u] * 4899 + 8192) >> 14;  // cv2.COLOR_BGR2GRAY, 8u fixed point
+        grey[i] = (uint8_t)gr;
+        predm[i] = mc[u] > 60 ? 255 : 0;                  // textmask.py:86-89
+        merged[i] = 0;
+      }
+      if (k0 + u * kThreads < v.cnt) {   // warp-uniform: skip the histogram votes of fully idle warps
+        hist_add(sh[1], b[u]);
+        hist_add(sh[2], g[u]);
+        hist_add(sh[3], r[u]);
+        hist_add(sh[0], (in && m3[u] > 127) ? gr : -1);     // textmask.py:60
+      }
+    }
   }
   __syncthreads();
   int* gh = &c.st[v.w].hist[0][0];
@@ -277,23 +317,37 @@ __global__ void __launch_bounds__(kThreads) k_xor(Ctx c) {
   unsigned long long loc[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) loc[k] = 0ull;
-  for (int k0 = threadIdx.x; k0 < v.cnt; k0 += kThreads) {
-    const int i = v.i0 + k0;
-    const int y = i / v.rw, x = i - y * v.rw;
-    const size_t gp = size_t(v.win.y1 + y) * c.W + v.win.x1 + x;
-    const int mk = v.mask[gp];
-    const int gr = grey[i];
+  const DivW dv = make_div(v.rw, v.rw * v.rh);
+  for (int k0 = 0; k0 < v.cnt; k0 += kThreads * kU) {
+    int mk[kU], gr[kU], ch[kU][3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      if (k < ncol) {
-        const int t = (gr >= lo[k] && gr <= hi[k]) ? 255 : 0;
-        loc[2 * k] += (unsigned)(t ^ mk);
-        loc[2 * k + 1] += (unsigned)((255 - t) ^ mk);
+    for (int u = 0; u < kU; ++u) {
+      const int k = k0 + u * kThreads + threadIdx.x;
+      mk[u] = -1;
+      if (k < v.cnt) {
+        int y, x;
+        divmod(v.i0 + k, dv, y, x);
+        const size_t gp = size_t(v.win.y1 + y) * c.W + v.win.x1 + x;
+        mk[u] = v.mask[gp];
+        gr[u] = grey[v.i0 + k];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) ch[u][q] = v.img[gp * 3 + q];
       }
-      const int ch = v.img[gp * 3 + k];
-      const int t2 = ch > ot[k] ? 255 : 0;
-      loc[6 + 2 * k] += (unsigned)(t2 ^ mk);
-      loc[6 + 2 * k + 1] += (unsigned)((255 - t2) ^ mk);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (mk[u] < 0) continue;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (k < ncol) {
+          const int t = (gr[u] >= lo[k] && gr[u] <= hi[k]) ? 255 : 0;
+          loc[2 * k] += (unsigned)(t ^ mk[u]);
+          loc[2 * k + 1] += (unsigned)((255 - t) ^ mk[u]);
+        }
+        const int t2 = ch[u][k] > ot[k] ? 255 : 0;
+        loc[6 + 2 * k] += (unsigned)(t2 ^ mk[u]);
+        loc[6 + 2 * k + 1] += (unsigned)((255 - t2) ^ mk[u]);
+      }
     }
   }
 #pragma unroll
@@ -397,28 +451,43 @@ __global__ void __launch_bounds__(kLabelThreads) k_label_local(Ctx c, int round)
     if (kind < 3) { lo = st.lo[kind]; hi = st.hi[kind]; } else ot = st.otsu_t[kind - 3];
   }
   const int lane = threadIdx.x & 31;
-  // pass 1: source value per pixel (coalesced), run starts inside each warp's 32 consecutive pixels
-  for (int k0 = 0; k0 < v.cnt; k0 += kLabelThreads) {
+  const DivW dv = make_div(v.rw, kChunkPx + 1);   // chunk-local indices: k = row * rw + x, k < kChunkPx
+  constexpr int kIt = kChunkPx / kLabelThreads;    // 16 pixels per thread
+  // pass 1: source value per pixel (coalesced; ALL loads of the thread issued before the first use), then run starts
+  // inside each warp's 32 consecutive pixels
+  int raw[kIt];
+#pragma unroll
+  for (int u = 0; u < kIt; ++u) {
+    const int k = u * kLabelThreads + threadIdx.x;
+    raw[u] = 0;
+    if (k < v.cnt) {
+      const int i = v.i0 + k;
+      if (round == 4) raw[u] = merged[i];
+      else if (kind < 3) raw[u] = grey[i];
+      else {
+        int yl, x;
+        divmod(k, dv, yl, x);
+        raw[u] = v.img[(size_t(v.win.y1 + v.y0 + yl) * c.W + v.win.x1 + x) * 3 + (kind - 3)];
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kIt; ++u) {
+    const int k0 = u * kLabelThreads;
+    if (k0 >= v.cnt) break;                       // CTA-uniform
     const int k = k0 + threadIdx.x;
     const bool in = k < v.cnt;
     int sv = 0, x = 0;
     if (in) {
-      const int i = v.i0 + k;
-      const int y = i / v.rw;
-      x = i - y * v.rw;
+      int yl;
+      divmod(k, dv, yl, x);
       if (round == 4) {
-        sv = merged[i] ? 0 : 255;
+        sv = raw[u] ? 0 : 255;
       } else {
-        int tv;
-        if (kind < 3) {
-          const int gr = grey[i];
-          tv = (gr >= lo && gr <= hi) ? 255 : 0;
-        } else {
-          tv = v.img[(size_t(v.win.y1 + y) * c.W + v.win.x1 + x) * 3 + (kind - 3)] > ot ? 255 : 0;
-        }
+        const int tv = kind < 3 ? ((raw[u] >= lo && raw[u] <= hi) ? 255 : 0) : (raw[u] > ot ? 255 : 0);
         sv = neg ? 255 - tv : tv;
       }
-      cand[i] = (uint8_t)sv;
+      cand[v.i0 + k] = (uint8_t)sv;
     }
     const bool fg = in && sv != 0;
     const unsigned m = __ballot_sync(0xffffffffu, fg);
@@ -434,7 +503,8 @@ __global__ void __launch_bounds__(kLabelThreads) k_label_local(Ctx c, int round)
   // pass 2: seams between warps, contacts with the row above inside the chunk
   for (int k = threadIdx.x; k < v.cnt; k += kLabelThreads) {
     if (!fs[k]) continue;
-    const int x = (v.i0 + k) % v.rw;
+    int yl, x;
+    divmod(k, dv, yl, x);
     if ((k & 31) == 0 && x > 0 && k > 0 && fs[k - 1]) suf_union(Ls, k, k - 1);
     if (k < v.rw) continue;
     const int up = k - v.rw;
@@ -486,14 +556,24 @@ __global__ void __launch_bounds__(kThreads) k_flat1(Ctx c, int round) {
   if (round < 4 && round >= c.st[v.w].nproc) return;
   const uint8_t* rootflag = c.tmp + v.win.off;
   int* L = c.L + v.win.off;
-  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
-    const int i = v.i0 + k;
-    if (rootflag[i]) uf_find_compress(L, i);
+  constexpr int U = 8;
+  for (int k0 = 0; k0 < v.cnt; k0 += kThreads * U) {
+    uint8_t rf[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + u * kThreads + threadIdx.x;
+      rf[u] = k < v.cnt ? rootflag[v.i0 + k] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (rf[u]) uf_find_compress(L, v.i0 + k0 + u * kThreads + threadIdx.x);
   }
 }
 // ---- merge step (textmask.py:92-108 / 118-131): per-label sums, then the labels that lower xor(merged, pred) -----------
-// level 3b fused with the accumulation: every pixel takes its (chunk-local) parent's root, writes it back and adds
-// itself to the root's sums (warp-aggregated: the 32 consecutive pixels of a warp mostly share a label)
+// level 3b fused with the accumulation: every pixel takes its root, writes it back and adds itself to the root's sums
+// (warp-aggregated: the 32 consecutive pixels of a warp mostly share a label).  After k_flat1 every chunk-local root
+// points straight at its global root, and every pixel's L is a chunk-local root (k_label_local pass 3), so the root of
+// pixel i is L[L[i]]: two dependent loads, issued for kU pixels at a time.
 __global__ void __launch_bounds__(kThreads) k_flat2_macc(Ctx c, int round) {
   const View v = view_of(c, blockIdx.x);
   WinState& st = c.st[v.w];
@@ -504,29 +584,43 @@ __global__ void __launch_bounds__(kThreads) k_flat2_macc(Ctx c, int round) {
   int* acc = c.acc + 4 * v.win.off;
   const int n = v.rw * v.rh;
   int* area = acc; int* gain = acc + n; int* loss = acc + 2 * n; int* maxi = acc + 3 * n;
+  const int lane = threadIdx.x & 31;
   int a0 = 0;
-  for (int k0 = 0; k0 < v.cnt; k0 += kThreads) {
-    const int k = k0 + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const int i = v.i0 + k;
-    int r = -2;
-    if (k < v.cnt) {
-      const int p = __ldcg(L + i);
-      r = p < 0 ? -1 : uf_find(L, p);
-      if (p >= 0 && r != p) L[i] = r;
+  for (int k0 = 0; k0 < v.cnt; k0 += kThreads * kU) {
+    int p[kU], r[kU];
+    uint8_t mg[kU], pd[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int k = k0 + u * kThreads + threadIdx.x;
+      p[u] = -2; mg[u] = 1; pd[u] = 0;
+      if (k < v.cnt) {
+        const int i = v.i0 + k;
+        p[u] = __ldcg(L + i);
+        mg[u] = merged[i];
+        pd[u] = predm[i];
+      }
     }
-    const bool un = r >= 0 && merged[i] == 0;
-    const bool pg = un && predm[i] != 0;
-    const unsigned peers = __match_any_sync(0xffffffffu, r);
-    const unsigned bg = __ballot_sync(0xffffffffu, pg), bl = __ballot_sync(0xffffffffu, un && !pg);
-    if (r >= 0 && lane == __ffs(peers) - 1) {
-      atomicAdd(&area[r], __popc(peers));
-      atomicMax(&maxi[r], i - lane + 31 - __clz(peers));
-      const int g_ = __popc(peers & bg), l_ = __popc(peers & bl);
-      if (g_) atomicAdd(&gain[r], g_);
-      if (l_) atomicAdd(&loss[r], l_);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) r[u] = p[u] >= 0 ? __ldcg(L + p[u]) : (p[u] == -2 ? -2 : -1);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (k0 + u * kThreads >= v.cnt) break;      // CTA-uniform
+      const int i = v.i0 + k0 + u * kThreads + threadIdx.x;
+      const int rr = r[u];
+      if (rr >= 0 && rr != p[u]) L[i] = rr;
+      const bool un = rr >= 0 && mg[u] == 0;
+      const bool pg = un && pd[u] != 0;
+      const unsigned peers = __match_any_sync(0xffffffffu, rr);
+      const unsigned bg = __ballot_sync(0xffffffffu, pg), bl = __ballot_sync(0xffffffffu, un && !pg);
+      if (rr >= 0 && lane == __ffs(peers) - 1) {
+        atomicAdd(&area[rr], __popc(peers));
+        atomicMax(&maxi[rr], i - lane + 31 - __clz(peers));
+        const int g_ = __popc(peers & bg), l_ = __popc(peers & bl);
+        if (g_) atomicAdd(&gain[rr], g_);
+        if (l_) atomicAdd(&loss[rr], l_);
+      }
+      if (rr == -1) ++a0;
     }
-    if (r == -1) ++a0;
   }
   if (round == 4) {   // label 0 of the inverse = the pixels already in `merged`
     for (int o = 16; o > 0; o >>= 1) a0 += __shfl_down_sync(0xffffffffu, a0, o);
@@ -540,9 +634,18 @@ __global__ void __launch_bounds__(kThreads) k_top_a(Ctx c) {
   const int* L = c.L + v.win.off;
   const int* area = c.acc + 4 * v.win.off;
   int m = -1;
-  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
-    const int i = v.i0 + k;
-    if (L[i] == i) m = max(m, area[i]);
+  constexpr int U = 8;
+  for (int k0 = 0; k0 < v.cnt; k0 += kThreads * U) {
+    int l[U], a[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + u * kThreads + threadIdx.x;
+      l[u] = -1; a[u] = -1;
+      if (k < v.cnt) { l[u] = L[v.i0 + k] - (v.i0 + k); a[u] = area[v.i0 + k]; }   // l == 0: the pixel is a root
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (l[u] == 0) m = max(m, a[u]);
   }
   if (v.y0 == 0 && threadIdx.x == 0) m = max(m, st.area0);
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
@@ -556,9 +659,18 @@ __global__ void __launch_bounds__(kThreads) k_top_b(Ctx c) {
   const int m1 = st.max1;
   int m2 = -1, c1 = 0;
   auto push = [&](int a) { if (a == m1) ++c1; else m2 = max(m2, a); };
-  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
-    const int i = v.i0 + k;
-    if (L[i] == i) push(area[i]);
+  constexpr int U = 8;
+  for (int k0 = 0; k0 < v.cnt; k0 += kThreads * U) {
+    int l[U], a[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + u * kThreads + threadIdx.x;
+      l[u] = -1; a[u] = -1;
+      if (k < v.cnt) { l[u] = L[v.i0 + k] - (v.i0 + k); a[u] = area[v.i0 + k]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (l[u] == 0) push(a[u]);
   }
   if (v.y0 == 0 && threadIdx.x == 0) push(st.area0);
   for (int o = 16; o > 0; o >>= 1) {
@@ -582,61 +694,91 @@ __global__ void __launch_bounds__(kThreads) k_mapply(Ctx c, int round) {
   // sorted_area[-2] if more than one label else sorted_area[-1] (textmask.py:114-118); label 0 always exists
   const int second = st.cnt1 >= 2 ? st.max1 : st.max2;
   const int thresh = second >= 0 ? second : st.max1;
-  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
-    const int i = v.i0 + k;
-    const int r = L[i];
-    if (r < 0) continue;
-    bool ok;
-    if (round < 4) {
-      // `if w * h < 3: continue` (textmask.py:97): bounding boxes 1x1, 1x2, 2x1
-      const int a = area[r];
-      const bool tiny = a == 1 || (a == 2 && (maxi[r] == r + 1 || maxi[r] == r + v.rw));
-      ok = !tiny;
-    } else {
-      ok = area[r] < thresh;  // textmask.py:120
+  for (int k0 = 0; k0 < v.cnt; k0 += kThreads * kU) {
+    int r[kU], a[kU], g[kU], l[kU], mx[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int k = k0 + u * kThreads + threadIdx.x;
+      r[u] = k < v.cnt ? L[v.i0 + k] : -1;
     }
-    if (ok && gain[r] > loss[r]) merged[i] = 255;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      a[u] = 0; g[u] = 0; l[u] = 0; mx[u] = 0;
+      if (r[u] >= 0) { a[u] = area[r[u]]; g[u] = gain[r[u]]; l[u] = loss[r[u]]; if (round < 4) mx[u] = maxi[r[u]]; }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (r[u] < 0) continue;
+      bool ok;
+      if (round < 4) {
+        // `if w * h < 3: continue` (textmask.py:97): bounding boxes 1x1, 1x2, 2x1
+        const bool tiny = a[u] == 1 || (a[u] == 2 && (mx[u] == r[u] + 1 || mx[u] == r[u] + v.rw));
+        ok = !tiny;
+      } else {
+        ok = a[u] < thresh;  // textmask.py:120
+      }
+      if (ok && g[u] > l[u]) merged[v.i0 + k0 + u * kThreads + threadIdx.x] = 255;
+    }
   }
 }
 
-// ---- dilate 3x3 (inpaint mode) into tmp, copy back -----------------------------------------------------------------
+// ---- dilate 3x3 (inpaint mode): merged -> tmp; the caller swaps the two planes afterwards -----------------------------
 __global__ void __launch_bounds__(kThreads) k_dilate(Ctx c) {
   const View v = view_of(c, blockIdx.x);
   const uint8_t* merged = c.merged + v.win.off;
   uint8_t* tmp = c.tmp + v.win.off;
-  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
-    const int i = v.i0 + k;
-    const int y = i / v.rw, x = i - y * v.rw;
-    int m = 0;
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int yy = y + dy;
-      if (yy < 0 || yy >= v.rh) continue;
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int xx = x + dx;
-        if (xx < 0 || xx >= v.rw) continue;
-        m = max(m, (int)merged[yy * v.rw + xx]);
+  const DivW dv = make_div(v.rw, v.rw * v.rh);
+  for (int k0 = 0; k0 < v.cnt; k0 += kThreads * kU) {
+    int m[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int k = k0 + u * kThreads + threadIdx.x;
+      m[u] = 0;
+      if (k < v.cnt) {
+        int y, x;
+        divmod(v.i0 + k, dv, y, x);
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int yy = y + dy;
+          if (yy < 0 || yy >= v.rh) continue;
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= v.rw) continue;
+            m[u] = max(m[u], (int)merged[yy * v.rw + xx]);
+          }
+        }
       }
     }
-    tmp[i] = (uint8_t)m;
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int k = k0 + u * kThreads + threadIdx.x;
+      if (k < v.cnt) tmp[v.i0 + k] = (uint8_t)m[u];
+    }
   }
-}
-__global__ void __launch_bounds__(kThreads) k_copyback(Ctx c) {
-  const View v = view_of(c, blockIdx.x);
-  uint8_t* merged = c.merged + v.win.off;
-  const uint8_t* tmp = c.tmp + v.win.off;
-  for (int k = threadIdx.x; k < v.cnt; k += kThreads) merged[v.i0 + k] = tmp[v.i0 + k];
 }
 // mask_refined[window] |= merged (textmask.py:168); windows may overlap -> atomic OR
 __global__ void __launch_bounds__(kThreads) k_or(Ctx c) {
   const View v = view_of(c, blockIdx.x);
   const uint8_t* merged = c.merged + v.win.off;
   uint32_t* out_words = c.out_all + size_t(v.win.page) * c.H * c.W / 4;
-  for (int k = threadIdx.x; k < v.cnt; k += kThreads) {
-    const int i = v.i0 + k;
-    if (!merged[i]) continue;
-    const int y = i / v.rw, x = i - y * v.rw;
-    const size_t gp = size_t(v.win.y1 + y) * c.W + v.win.x1 + x;
-    atomicOr(&out_words[gp >> 2], 0xffu << (8 * (gp & 3)));
+  const DivW dv = make_div(v.rw, v.rw * v.rh);
+  constexpr int U = 8;
+  for (int k0 = 0; k0 < v.cnt; k0 += kThreads * U) {
+    uint8_t mg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = k0 + u * kThreads + threadIdx.x;
+      mg[u] = k < v.cnt ? merged[v.i0 + k] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (!mg[u]) continue;
+      int y, x;
+      divmod(v.i0 + k0 + u * kThreads + threadIdx.x, dv, y, x);
+      const size_t gp = size_t(v.win.y1 + y) * c.W + v.win.x1 + x;
+      atomicOr(&out_words[gp >> 2], 0xffu << (8 * (gp & 3)));
+    }
   }
 }
 
@@ -677,7 +819,7 @@ cudaError_t refine_mk_launch(const uint8_t* d_img, const uint8_t* d_mask, int H,
   for (int round = 0; round < 5; ++round) {
     if (round == 4 && refine_mode == 0) {
       k_dilate<<<g, kThreads, 0, s>>>(c);
-      k_copyback<<<g, kThreads, 0, s>>>(c);
+      uint8_t* t = c.merged; c.merged = c.tmp; c.tmp = t;   // the dilated plane IS `merged` from here on (no copy back)
     }
     k_label_local<<<g, kLabelThreads, 0, s>>>(c, round);
     k_union_border<<<g, kThreads, 0, s>>>(c, round);

@@ -73,9 +73,10 @@ class TextDetector:
         self.conf_thresh = conf_thresh
         self.nms_thresh = nms_thresh
         self.backend = 'b200'
-        self.program = compiler.compile_checkpoint(ckpt, head_act=act)
         if precision is None:
             precision = PREC_FP16_TC
+        # fused Bottleneck ops exist on the fp16 tensor-core engine only (bit-identical to the two-op form)
+        self.program = compiler.compile_checkpoint(ckpt, head_act=act, fuse=compiler.fuse_default(precision == PREC_FP16_TC))
         # DB threshold is hard-coded 0.3 in the reference (inference.py:139 ignores mask_thresh)
         self.net = Engine(self.program, device=device_index, precision=precision, max_batch=1, max_h=input_size[0],
                           max_w=input_size[1], conf_thresh=conf_thresh, nms_thresh=nms_thresh, db_thresh=0.3)

@@ -57,8 +57,12 @@ enum ctd_op_kind {
   CTD_OP_SEG_TAIL = 7,  /* ConvT4x4s2 64->1 + sigmoid    (basemodel.py:57-60)               */
   CTD_OP_DB_TAIL = 8,   /* ConvT2x2s2+BN+ReLU -> ConvT2x2s2 -> sigmoid, both branches
                            (basemodel.py:99-103,138-142)                                    */
-  CTD_OP_S2D = 9        /* u8 BGR page -> /255 -> 2x2 space-to-depth, 12(+4 zero) channels at 1/2 resolution:
+  CTD_OP_S2D = 9,       /* u8 BGR page -> /255 -> 2x2 space-to-depth, 12(+4 zero) channels at 1/2 resolution:
                            turns the 6x6 s2 p2 stem conv into a 3x3 s1 p1 conv for the tensor cores       */
+  CTD_OP_BNECK = 10     /* fused Bottleneck (common.py:94-104): dst = [src +] act(conv3x3(act(conv1x1(src)))), c -> c -> c
+                           channels (c = cout in {32, 64}), src and dst in DIFFERENT buffers; w16_off / w32_off: W1 [c][c]
+                           followed by W2 [c][9c] (K = (ky, kx, ci)); b_off: bias1[c] | bias2[c]; residual = the `+ src`.
+                           CTD_PREC_FP16_TC only (the compiler emits it on request, compiler.py fuse=True)              */
 };
 
 enum ctd_act { CTD_ACT_NONE = 0, CTD_ACT_SILU = 1, CTD_ACT_LEAKY = 2, CTD_ACT_RELU = 3, CTD_ACT_SIGMOID = 4 };

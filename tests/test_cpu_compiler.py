@@ -52,3 +52,30 @@ def test_program_matches_oracle(ck):
     assert float((mask - rm).abs().max()) < 1e-3
     assert float((lines - rl).abs().max()) < 1e-3
     assert float(((blks - rb).abs() / (rb.abs() + 1)).max()) < 1e-3
+
+
+def test_fused_bottleneck_program_equals_two_op_form(ck):
+    """compile_checkpoint(fuse=True) replaces the 32 / 64-channel Bottlenecks by ONE op each (OP_BNECK, a new buffer
+    instead of the in-place residual, cv3 K-concatenated from two buffers): the interpreted program computes the same
+    net, in fp32 and in the fp16-storage emulation (identical storage points -> identical numbers)."""
+    cc = ctd_b200.compiler
+    p0 = cc.compile_checkpoint(ck)
+    p1 = cc.compile_checkpoint(ck, fuse=True)
+    kinds = [o["kind"] for o in p1.ops]
+    assert kinds.count(cc.OP_BNECK) == 5 and len(p1.ops) == len(p0.ops) - 5
+    for o in p1.ops:
+        if o["kind"] == cc.OP_BNECK:
+            assert o["cout"] in cc.FUSED_BNECK_CHANNELS and o["src_buf"][0] != o["dst_buf"] and o["w16_off"] % 256 == 0
+    pages = np.stack([synth.structured_page(7, 128, 192)])
+    for storage in ("f32", "f16"):
+        b0, m0, l0 = run_program(p0, pages, storage=storage)
+        b1, m1, l1 = run_program(p1, pages, storage=storage)
+        # same math, but oneDNN may block the re-shaped convolutions differently (fp32 rounding, amplified by the
+        # random-weight net); on the GPU the two engines are bit-identical (tests/test_gpu_fuse.py)
+        dm, dl = (m0 - m1).abs(), (l0 - l1).abs()
+        print(storage, float(dm.max()), float(dm.mean()), float(dl.max()), float(dl.mean()))
+        if storage == "f32":
+            assert float(dm.max()) <= 1e-3 and float(dl.max()) <= 1e-3
+            assert float(((b0 - b1).abs() / (b0.abs() + 1)).max()) <= 1e-3
+        else:
+            assert float(dm.mean()) <= 1e-3 and float(dl.mean()) <= 1e-3

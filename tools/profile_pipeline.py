@@ -10,7 +10,7 @@ from oracle import synth
 bs = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 ck = synth.make_checkpoint(0, smooth=True)
-prog = ctd_b200.compiler.compile_checkpoint(ck)
+prog = ctd_b200.compiler.compile_checkpoint(ck, fuse=ctd_b200.compiler.fuse_default(True))
 pages = torch.from_numpy(np.stack([synth.structured_page(1000 + i) for i in range(bs)])).pin_memory()
 eng = ctd_b200.Engine(prog, max_batch=bs, max_h=1024, max_w=1024)
 out = torch.empty((eng.results_layout()["total_bytes"],), dtype=torch.uint8).pin_memory()
