@@ -328,8 +328,11 @@ def compile_checkpoint(ckpt, head_act="leaky", stem_mode="s2d", fuse=False):
             for dy, ky in TAPS[py]:
                 for dx, kx in TAPS[px]:
                     wc[py * 2 + px, dy + 1, dx + 1, :] = w6[:, 0, ky, kx]
+    # b_off (the layer has no bias): the same weights as a 1x1 GEMM over the 16 kernel positions, [ky*4+kx][ci] fp16, for the
+    # GEMM + col2im form of the tail (csrc/conv_fuse.cu)
     P._op(OP_SEG_TAIL, [u512], None, p_off=P.add_blob(w6.reshape(w6.shape[0], 16).astype(np.float32)),
-          w16_off=P.add_blob(wc.reshape(16, 9 * ci6).astype(np.float16)), cout=4, cout_pad=16)
+          w16_off=P.add_blob(wc.reshape(16, 9 * ci6).astype(np.float16)), cout=4, cout_pad=16,
+          b_off=P.add_blob(np.ascontiguousarray(w6.reshape(ci6, 16).T).astype(np.float16)))
 
     # ---- text_det: DBHead.forward (basemodel.py:106-125) ----------------------------------------
     du128 = up_c3(dsd, [f64, u64], "upconv3")

@@ -120,7 +120,8 @@ extern "C" int ctd_create(ctd_handle** out, const ctd_config* cfg, const ctd_op*
       if (op.residual && op.dst_buf >= 0 && op.dst_buf < n_bufs) needed[op.dst_buf] = 1;
     }
     const char* hm = getenv("CTD_HALO");
-    h->halo_mode = hm ? atoi(hm) : 7;   // bit 0: conv_halo_kernel (resident weights), 1: conv_hs_kernel (streamed), 2: conv_sw_kernel
+    // bit 0: conv_halo_kernel (resident weights), 1: conv_hs_kernel (streamed), 2: conv_sw_kernel, 3: seg tail as GEMM + col2im
+    h->halo_mode = hm ? atoi(hm) : 15;
     const char* ov = getenv("CTD_OVERLAP");
     h->overlap = have_db && !(ov && ov[0] == '0');
   }
@@ -359,6 +360,18 @@ static int build_plans(ctd_handle* h, int n, int ph, int pw, ShapePlan& sp) {
       sp.has_tc[i] = 1;
       continue;
     }
+    if (op.kind == CTD_OP_SEG_TAIL && (h->halo_mode & 8) && op.b_off > 0 && op.src_c[0] == 64) {
+      // final ConvT 4x4 s2 (64 -> 1) + sigmoid + u8 mask as one 1x1 GEMM over the 16 kernel positions + col2im epilogue
+      const ctd_bufdesc& sb = h->bufs[op.src_buf[0]];
+      int nsm = 148;
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->cfg.device);
+      const char* e = ctd::conv_segtail_plan(sp.seg, h->enc, n, ph / sb.down, pw / sb.down, h->d_buf[op.src_buf[0]], sb.channels,
+                                             op.src_coff[0], h->d_blob + op.b_off, h->d_mask, h->d_mask_u8, nsm);
+      if (e) return ctd_fail(h, CTD_E_INVALID, "seg tail: %s", e);
+      sp.seg_op = int(i);
+      sp.has_tc[i] = 1;
+      continue;
+    }
     if (op.kind == CTD_OP_SEG_TAIL && (h->halo_mode & 1) && op.w16_off > 0 && op.cout_pad == 16) {
       // final ConvT 4x4 s2 (C -> 1) + sigmoid + u8 mask as a 3x3 / 4-output halo convolution
       ctd_op c3 = op;
@@ -538,7 +551,7 @@ static int run_one_op(ctd_handle* h, size_t i, int n, int ph, int pw, ShapePlan&
     rc = e == cudaSuccess ? CTD_OK : ctd_fail(h, CTD_E_CUDA, "stem op %zu: %s", i, cudaGetErrorString(e));
     ++*cnt;
   } else if (op.kind == CTD_OP_SEG_TAIL && h->cfg.precision == CTD_PREC_FP16_TC && sp.has_tc[i]) {
-    cudaError_t e = conv_tc_launch(sp.tc[i], h->stream);
+    cudaError_t e = sp.seg_op == int(i) ? ctd::conv_segtail_launch(sp.seg, h->stream) : conv_tc_launch(sp.tc[i], h->stream);
     rc = e == cudaSuccess ? CTD_OK : ctd_fail(h, CTD_E_CUDA, "seg tail op %zu: %s", i, cudaGetErrorString(e));
   } else if (gemm) {
     if (h->cfg.precision == CTD_PREC_FP16_TC) {

@@ -134,6 +134,8 @@ struct alignas(64) BneckParams {
   int act, residual;
   int dst_cstride, dst_coff;
   __half* dst;
+  const __half* src;        // residual: x re-read per output pixel
+  int src_cstride, src_coff;
   const float* bias;
 };
 struct BneckPlan {
@@ -146,7 +148,25 @@ bool conv_bneck_supported(int c);
 const char* conv_bneck_plan(BneckPlan& plan, PFN_encodeTiled enc, int n_img, int gh, int gw, int c, const void* src,
                             int src_cstride, int src_coff, const void* w16, const float* bias, __half* dst,
                             int dst_cstride, int dst_coff, int act, int residual, int num_sms);
-cudaError_t conv_bneck_init();
+cudaError_t conv_bneck_init();   // also sets the attributes of conv_segtail_kernel
+
+// Seg tail (conv_fuse.cu): ConvTranspose2d(64 -> 1, 4x4, s2, p1) + sigmoid + u8 mask as ONE 1x1 GEMM over the 16 kernel
+// positions + a col2im epilogue.  w16: [16 = ky*4+kx][64 channels] fp16; source must have exactly 64 channels.
+struct alignas(64) SegTailParams {
+  CUtensorMap x_map, w_map;
+  int n_img, gh, gw;
+  int tiles_x, tiles_y;     // 16 x 12 input pixels per tile
+  float* seg_f32;
+  uint8_t* seg_u8;
+};
+struct SegTailPlan {
+  SegTailParams p;
+  dim3 grid;
+  size_t smem_bytes;
+};
+const char* conv_segtail_plan(SegTailPlan& plan, PFN_encodeTiled enc, int n_img, int gh, int gw, const void* src, int src_cstride,
+                              int src_coff, const void* w16, float* seg_f32, uint8_t* seg_u8, int num_sms);
+cudaError_t conv_segtail_launch(const SegTailPlan& plan, cudaStream_t s);
 cudaError_t conv_bneck_launch(const BneckPlan& plan, cudaStream_t s);
 
 // ---------------------------------------------------------------------------------------

@@ -432,7 +432,7 @@ __device__ __forceinline__ void suf_union(int* L, int a, int b) {
   } while (!done);
 }
 
-__global__ void __launch_bounds__(kLabelThreads) k_label_local(Ctx c, int round) {
+__global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int round) {
   __shared__ int Ls[kChunkPx];
   __shared__ uint8_t fs[kChunkPx];
   const View v = view_of(c, blockIdx.x);
@@ -455,48 +455,53 @@ __global__ void __launch_bounds__(kLabelThreads) k_label_local(Ctx c, int round)
   constexpr int kIt = kChunkPx / kLabelThreads;    // 16 pixels per thread
   // pass 1: source value per pixel (coalesced; ALL loads of the thread issued before the first use), then run starts
   // inside each warp's 32 consecutive pixels
-  int raw[kIt];
+  constexpr int kB = 8;                            // loads in flight per thread (two batches of 8 keep 3 CTAs / SM)
+#pragma unroll 1
+  for (int ub = 0; ub < kIt; ub += kB) {
+    if (ub * kLabelThreads >= v.cnt) break;        // CTA-uniform
+    int raw[kB];
 #pragma unroll
-  for (int u = 0; u < kIt; ++u) {
-    const int k = u * kLabelThreads + threadIdx.x;
-    raw[u] = 0;
-    if (k < v.cnt) {
-      const int i = v.i0 + k;
-      if (round == 4) raw[u] = merged[i];
-      else if (kind < 3) raw[u] = grey[i];
-      else {
-        int yl, x;
+    for (int u = 0; u < kB; ++u) {
+      const int k = (ub + u) * kLabelThreads + threadIdx.x;
+      raw[u] = 0;
+      if (k < v.cnt) {
+        const int i = v.i0 + k;
+        if (round == 4) raw[u] = merged[i];
+        else if (kind < 3) raw[u] = grey[i];
+        else {
+          int yl, x;
+          divmod(k, dv, yl, x);
+          raw[u] = v.img[(size_t(v.win.y1 + v.y0 + yl) * c.W + v.win.x1 + x) * 3 + (kind - 3)];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kB; ++u) {
+      const int k0 = (ub + u) * kLabelThreads;
+      if (k0 >= v.cnt) break;                       // CTA-uniform
+      const int k = k0 + threadIdx.x;
+      const bool in = k < v.cnt;
+      int sv = 0, x = 0;
+      if (in) {
+        int yl;
         divmod(k, dv, yl, x);
-        raw[u] = v.img[(size_t(v.win.y1 + v.y0 + yl) * c.W + v.win.x1 + x) * 3 + (kind - 3)];
+        if (round == 4) {
+          sv = raw[u] ? 0 : 255;
+        } else {
+          const int tv = kind < 3 ? ((raw[u] >= lo && raw[u] <= hi) ? 255 : 0) : (raw[u] > ot ? 255 : 0);
+          sv = neg ? 255 - tv : tv;
+        }
+        cand[v.i0 + k] = (uint8_t)sv;
       }
-    }
-  }
-#pragma unroll
-  for (int u = 0; u < kIt; ++u) {
-    const int k0 = u * kLabelThreads;
-    if (k0 >= v.cnt) break;                       // CTA-uniform
-    const int k = k0 + threadIdx.x;
-    const bool in = k < v.cnt;
-    int sv = 0, x = 0;
-    if (in) {
-      int yl;
-      divmod(k, dv, yl, x);
-      if (round == 4) {
-        sv = raw[u] ? 0 : 255;
-      } else {
-        const int tv = kind < 3 ? ((raw[u] >= lo && raw[u] <= hi) ? 255 : 0) : (raw[u] > ot ? 255 : 0);
-        sv = neg ? 255 - tv : tv;
+      const bool fg = in && sv != 0;
+      const unsigned m = __ballot_sync(0xffffffffu, fg);
+      // a run starts at a foreground pixel whose left neighbour (same row, same warp) is not foreground
+      const bool starts = fg && (lane == 0 || x == 0 || !((m >> (lane - 1)) & 1u));
+      const unsigned sb = __ballot_sync(0xffffffffu, starts);
+      if (in) {
+        fs[k] = (uint8_t)sv;
+        Ls[k] = fg ? (k - lane) + (31 - __clz(sb & (0xffffffffu >> (31 - lane)))) : -1;
       }
-      cand[v.i0 + k] = (uint8_t)sv;
-    }
-    const bool fg = in && sv != 0;
-    const unsigned m = __ballot_sync(0xffffffffu, fg);
-    // a run starts at a foreground pixel whose left neighbour (same row, same warp) is not foreground
-    const bool starts = fg && (lane == 0 || x == 0 || !((m >> (lane - 1)) & 1u));
-    const unsigned sb = __ballot_sync(0xffffffffu, starts);
-    if (in) {
-      fs[k] = (uint8_t)sv;
-      Ls[k] = fg ? (k - lane) + (31 - __clz(sb & (0xffffffffu >> (31 - lane)))) : -1;
     }
   }
   __syncthreads();

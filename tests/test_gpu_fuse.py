@@ -76,3 +76,29 @@ def test_fused_ops_match_interpreter(shape):
         eng.close()
     assert len(worst) == 5
     assert max(w[0] for w in worst) <= 5e-3, worst
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 320), (1, 320, 192), (1, 1024, 1024), (2, 448, 704)],
+                         ids=["2x256x320", "1x320x192", "1x1024x1024", "2x448x704"])
+def test_segtail_gemm_col2im_equals_conv_form(shape, monkeypatch):
+    """The seg tail as ONE 1x1 GEMM over the 16 kernel positions + col2im epilogue (conv_segtail_kernel, CTD_HALO bit 3)
+    against the 3x3 / 4-phase convolution form (conv_halo_kernel<16>): same fp16 operands, fp32 sums in another order ->
+    the post-sigmoid masks agree to fp32 rounding, and each engine's u8 mask is trunc(255 * its own mask)."""
+    n, h, w = shape
+    prog = cc.compile_checkpoint(get_checkpoint(0, True), fuse=True)
+    pages = _pages(n, h, w, seed=5)
+    res = []
+    for halo in ("7", "15"):
+        monkeypatch.setenv("CTD_HALO", halo)
+        eng = ctd_b200.Engine(prog, precision=PREC_FP16_TC, max_batch=n, max_h=h, max_w=w, skip_postproc=True)
+        try:
+            eng.forward(pages)
+            _, mask, lines = eng.net_outputs(want_blks=False)
+            res.append((mask, lines, eng.mask_u8()))
+        finally:
+            eng.close()
+    (m0, l0, u0), (m1, l1, u1) = res
+    assert np.array_equal(l0, l1)
+    assert np.isfinite(m1).all() and float(np.abs(m0 - m1).max()) <= 1e-5, float(np.abs(m0 - m1).max())
+    assert np.array_equal(u1, (m1 * np.float32(255.0)).astype(np.uint8).reshape(u1.shape))
+    assert int((u0 != u1).sum()) <= u0.size // 10000   # only pixels whose 255*s sits on an integer boundary may flip
