@@ -8,18 +8,16 @@
 //   TMA      : ONE box per tile brings the (8+2) x (16+2) halo block of x (180 pixels x c_ channels, 128B/64B swizzle)
 //   GEMM 1   : t = W1 * x on ALL 180 halo pixels: two M=128 tcgen05.mma row blocks over the plain rows of the box
 //              (rows 180..255 of the second block read whatever follows in shared memory; their results are never used)
-//   epilogue1: tcgen05.ld -> bias + activation -> fp16 -> written with st.shared into the halo block T (over x) in exactly
+//   epilogue1: tcgen05.ld -> bias + activation -> fp16 -> written with st.shared into a second halo block T in exactly
 //              the swizzled K-major layout a TMA load would have produced; pixels outside the image are written as ZERO
 //              (they are the 3x3 convolution's padding, not act(bias)); fence.proxy.async + mbarrier hand-over
 //   GEMM 2   : the nine taps of the 3x3 are matrix-descriptor views into T (start row (dy+1)*10 + (dx+1), SBO = 10 rows),
 //              the same trick as conv_halo_kernel; W1 and the nine W2 tap matrices stay resident in shared memory
-//   epilogue2: bias + activation + residual (x re-read from global = L2) -> fp16 -> TMA store (c_ = 64) or 64-byte rows
+//   epilogue2: bias + activation + residual (x is still in shared memory: centre rows of the halo block) -> fp16 -> TMA
+//              store (c_ = 64) or 64-byte rows (c_ = 32)
 //
-// T overwrites x IN PLACE (GEMM 1 has completed when its accumulator is published) and the same buffer then stages the
-// output tile, so a tile in flight costs one 23 KB / 12 KB buffer.  Four tiles are in flight per CTA (TMEM: 4 x 2 c_
-// columns, GEMM 2 accumulates over the drained columns of GEMM 1's first row block); each epilogue warpgroup owns the
-// tiles of one parity and writes T of its NEXT tile while GEMM 2 of its current tile executes (first version: one tile
-// per warpgroup, 23 % of the samples in the wait for GEMM 2, ncu); the MMA thread issues GEMM 1 three tiles ahead.  Storage points are identical to the unfused path (t is
+// Two tiles are in flight per CTA (one per epilogue warpgroup; TMEM: 2 x (2 c_ + c_) columns), the MMA thread
+// interleaves GEMM 1 of tile i+2 behind GEMM 2 of tile i.  Storage points are identical to the unfused path (t is
 // rounded to fp16 exactly where the unfused engine stores it, accumulation order per output is the same), so the
 // results are BIT-IDENTICAL to the two-kernel sequence (tests/test_gpu_fuse.py).  The destination is a different
 // buffer than the source (neighbouring CTAs read the halo of x while this one writes y).
@@ -48,21 +46,19 @@ struct BnCfg {
   static constexpr int kW2Bytes = 9 * C * kRowBytes;
   static constexpr int kWBytes = (kW1Bytes + kW2Bytes + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = (kHaloRows * kRowBytes + 1023) / 1024 * 1024;
-  static constexpr int kBufs = C == 64 ? 6 : 8;                    // tile buffers: x, then T in place, then the output staging
-  static constexpr int kSlots = 4;                                 // tiles in flight (TMEM: 4 x 2C columns)
-  static constexpr int kTmemCols = kSlots * 2 * C;                 // 512 / 256
+  static constexpr int kXStages = C == 64 ? 3 : 6;
+  static constexpr int kTmemCols = C == 64 ? 512 : 256;            // 2 slots x (2C + C), power of two
   static constexpr int kBarBytes = 512;
-  // layout: buffers | weights | barriers | bias.  The second GEMM-1 row block of the LAST buffer reads 76 rows past
-  // it, i.e. into the weights (the results of those rows are never used).
-  static constexpr size_t kSmem = 1024 + size_t(kBufs) * kStageBytes + size_t(kWBytes) + kBarBytes + 2 * C * 4 + 64;
+  // the second GEMM-1 row block of the LAST x stage reads 76 rows past the stage: the two T blocks follow it
+  static constexpr size_t kSmem = 1024 + size_t(kWBytes) + size_t(kXStages + 2) * kStageBytes + kBarBytes + 2 * C * 4 + 64;
 };
 
 template <int ACT>
 __device__ __forceinline__ float act_fn(float v) {
-  if constexpr (ACT == CTD_ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
+  if constexpr (ACT == CTD_ACT_SILU) return __fdividef(v, 1.0f + exp_neg_fast(v));
   else if constexpr (ACT == CTD_ACT_LEAKY) return fmaxf(v, 0.1f * v);
   else if constexpr (ACT == CTD_ACT_RELU) return fmaxf(v, 0.f);
-  else if constexpr (ACT == CTD_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-v));
+  else if constexpr (ACT == CTD_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + exp_neg_fast(v));
   else return v;
 }
 
@@ -75,6 +71,11 @@ __device__ __forceinline__ uint32_t swz(int r, int j) {
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -124,18 +125,19 @@ template <int C>
 __global__ void __launch_bounds__(kThreads, 1) conv_bneck_kernel(const __grid_constant__ BneckParams p) {
   using Cfg = BnCfg<C>;
   constexpr uint32_t RB = Cfg::kRowBytes;
-  constexpr int NB = Cfg::kBufs, NS = Cfg::kSlots;
+  constexpr int S = Cfg::kXStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t x_base = smem_base;
-  const uint32_t w_base = x_base + NB * Cfg::kStageBytes;
-  const uint32_t bar_base = w_base + Cfg::kWBytes;
-  // barriers: x_full[8] | x_empty[8] | acc1_full[4] | t_full[4] | acc2_full[4] | acc_empty[4] | w | tmem ptr
-  const uint32_t x_full = bar_base, x_empty = bar_base + 64, acc1_full = bar_base + 128, t_full = bar_base + 160;
-  const uint32_t acc2_full = bar_base + 192, acc_empty = bar_base + 224, w_bar = bar_base + 256, tmem_ptr_addr = bar_base + 264;
+  const uint32_t w_base = smem_base;
+  const uint32_t x_base = w_base + Cfg::kWBytes;
+  const uint32_t t_base = x_base + S * Cfg::kStageBytes;
+  const uint32_t bar_base = t_base + 2 * Cfg::kStageBytes;
+  // barriers: x_full[8] | x_empty[8] | acc1_full[2] | t_full[2] | acc2_full[2] | acc_empty[2] | w | tmem ptr
+  const uint32_t x_full = bar_base, x_empty = bar_base + 64, acc1_full = bar_base + 128, t_full = bar_base + 144;
+  const uint32_t acc2_full = bar_base + 160, acc_empty = bar_base + 176, w_bar = bar_base + 192, tmem_ptr_addr = bar_base + 200;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const size_t bar_off = size_t(NB) * Cfg::kStageBytes + size_t(Cfg::kWBytes);
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 264);
+  const size_t bar_off = size_t(Cfg::kWBytes) + size_t(S + 2) * Cfg::kStageBytes;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 200);
   float* bias_s = reinterpret_cast<float*>(smem_gen + bar_off + Cfg::kBarBytes);   // bias1[C] | bias2[C]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -148,11 +150,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_bneck_kernel(const __grid_co
     prefetch_tensormap(&p.w1_map);
     prefetch_tensormap(&p.w2_map);
     if (C == 64) prefetch_tensormap(&p.o_map);
-    for (int s = 0; s < NB; ++s) {
+    for (int s = 0; s < S; ++s) {
       mbar_init(x_full + 8 * s, 1);
-      mbar_init(x_empty + 8 * s, 1);        // the owning warpgroup's leader, once GEMM 2 / the output store has read it
+      mbar_init(x_empty + 8 * s, 1 + 128);   // GEMM 1 commit + the 128 epilogue-2 threads (residual reads)
     }
-    for (int s = 0; s < NS; ++s) {
+    for (int s = 0; s < 2; ++s) {
       mbar_init(acc1_full + 8 * s, 1);
       mbar_init(t_full + 8 * s, 128);
       mbar_init(acc2_full + 8 * s, 1);
@@ -168,8 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_bneck_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
-  auto decode = [&](int ti, int& img, int& y0, int& x0) {
-    const int t = int(blockIdx.x) + ti * int(gridDim.x);
+  auto decode = [&](int t, int& img, int& y0, int& x0) {
     img = t / tiles_per_img;
     const int trem = t - img * tiles_per_img;
     const int ty = trem / p.tiles_x;
@@ -184,13 +185,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_bneck_kernel(const __grid_co
       tma_load_2d(w_base, &p.w1_map, w_bar, 0, 0);
       for (int tap = 0; tap < 9; ++tap)
         tma_load_2d(w_base + uint32_t(Cfg::kW1Bytes) + uint32_t(tap) * uint32_t(C) * RB, &p.w2_map, w_bar, tap * C, 0);
-      for (int ti = 0; ti < my_tiles; ++ti) {
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
         int img, y0, x0;
-        decode(ti, img, y0, x0);
-        const int b = ti % NB;
-        mbar_wait_relaxed(x_empty + 8 * b, ((ti / NB) & 1) ^ 1);
-        mbar_arrive_expect_tx(x_full + 8 * b, uint32_t(kHaloRows) * RB);
-        tma_load_4d(x_base + uint32_t(b) * Cfg::kStageBytes, &p.x_map, x_full + 8 * b, 0, x0 - 1, y0 - 1, img);
+        decode(t, img, y0, x0);
+        const int stage = it % S;
+        mbar_wait_relaxed(x_empty + 8 * stage, ((it / S) & 1) ^ 1);
+        mbar_arrive_expect_tx(x_full + 8 * stage, uint32_t(kHaloRows) * RB);
+        tma_load_4d(x_base + uint32_t(stage) * Cfg::kStageBytes, &p.x_map, x_full + 8 * stage, 0, x0 - 1, y0 - 1, img);
       }
     }
   } else if (warp == 1) {
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_bneck_kernel(const __grid_co
       constexpr int ksteps = C / 16;
       const uint64_t a1_desc0 = make_kmajor_desc(x_base, RB);
       const uint64_t b1_desc = make_kmajor_desc(w_base, RB);
-      const uint64_t a2_desc0 = make_kmajor_desc_ex(x_base, RB, uint32_t(kHW) * RB, 0u);   // T overwrites x in place
+      const uint64_t a2_desc0 = make_kmajor_desc_ex(t_base, RB, uint32_t(kHW) * RB, 0u);
       const uint64_t b2_desc0 = make_kmajor_desc(w_base + Cfg::kW1Bytes, RB);
       uint32_t tap_a[9], tap_b[9];
 #pragma unroll
@@ -211,22 +213,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_bneck_kernel(const __grid_co
       }
       mbar_wait(w_bar, 0);
       auto gemm1 = [&](int ti) {
-        const int slot = ti % NS, b = ti % NB;
-        mbar_wait(acc_empty + 8 * slot, ((ti / NS) & 1) ^ 1);   // epilogue 2 of tile ti-4 has drained the slot
-        mbar_wait(x_full + 8 * b, (ti / NB) & 1);
+        const int slot = ti & 1, stage = ti % S;
+        mbar_wait(x_full + 8 * stage, (ti / S) & 1);
         tc_fence_after();
-        const uint64_t ad = a1_desc0 + uint64_t((uint32_t(b) * Cfg::kStageBytes) >> 4);
-        const uint32_t col = tmem_base + uint32_t(slot * 2 * C);
-        issue_k(col, ad, b1_desc, idesc, 0u, ksteps);
-        issue_k(col + uint32_t(C), ad + uint64_t((128u * RB) >> 4), b1_desc, idesc, 0u, ksteps);
+        // acc1[slot] was drained by epilogue 1 of tile ti-2: this thread has already waited on t_full for it
+        const uint64_t ad = a1_desc0 + uint64_t((uint32_t(stage) * Cfg::kStageBytes) >> 4);
+        issue_k(tmem_base + uint32_t((slot * 3 + 0) * C), ad, b1_desc, idesc, 0u, ksteps);
+        issue_k(tmem_base + uint32_t((slot * 3 + 1) * C), ad + uint64_t((128u * RB) >> 4), b1_desc, idesc, 0u, ksteps);
         umma_commit(acc1_full + 8 * slot);
+        umma_commit(x_empty + 8 * stage);
       };
       auto gemm2 = [&](int ti) {
-        const int slot = ti % NS, b = ti % NB;
-        mbar_wait(t_full + 8 * slot, (ti / NS) & 1);            // T written over x, both GEMM-1 row blocks drained
+        const int slot = ti & 1, use = ti >> 1;
+        mbar_wait(t_full + 8 * slot, use & 1);            // T[slot] written (and acc1[slot] drained)
+        mbar_wait(acc_empty + 8 * slot, (use & 1) ^ 1);   // acc2[slot] drained by epilogue 2 of tile ti-2
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + uint32_t(slot * 2 * C);   // reuses the columns of GEMM 1's first row block
-        const uint64_t ad = a2_desc0 + uint64_t((uint32_t(b) * Cfg::kStageBytes) >> 4);
+        const uint32_t tmem_d = tmem_base + uint32_t((slot * 3 + 2) * C);
+        const uint64_t ad = a2_desc0 + uint64_t((uint32_t(slot) * Cfg::kStageBytes) >> 4);
         uint32_t acc = 0u;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
@@ -235,39 +238,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_bneck_kernel(const __grid_co
         }
         umma_commit(acc2_full + 8 * slot);
       };
-      // GEMM 1 runs three tiles ahead: a warpgroup writes T of its NEXT tile while GEMM 2 of its current tile executes
-      for (int ti = 0; ti < 3 && ti < my_tiles; ++ti) gemm1(ti);
+      if (my_tiles > 0) gemm1(0);
+      if (my_tiles > 1) gemm1(1);
       for (int ti = 0; ti < my_tiles; ++ti) {
         gemm2(ti);
-        if (ti + 3 < my_tiles) gemm1(ti + 3);
+        if (ti + 2 < my_tiles) gemm1(ti + 2);
       }
     }
   } else if (warp >= kEpiWarp0) {
     // =============================== epilogue warpgroups =========================
-    // warpgroup g owns the tiles of parity g; order: E1(t0) E1(t1) E2(t0) E1(t2) E2(t1) ... (E1 = write T, E2 = output)
     const int quad = warp & 3;
-    const int group = (warp - kEpiWarp0) >> 2;
+    const int group = (warp - kEpiWarp0) >> 2;   // tile parity = TMEM slot = T block
     const int row = quad * 32 + lane;
     const uint32_t lane_off = uint32_t(quad * 32) << 16;
     const bool lead = (threadIdx.x & 127) == 0;
+    const uint32_t tblk = t_base + uint32_t(group) * Cfg::kStageBytes;
     const int py = row / kTW, px = row - py * kTW;
-    int store_buf = -1;   // leader: buffer whose output store has been issued but not yet released to the producer
-
-    auto epi1 = [&](int ti) {
+    const int hr_c = (py + 1) * kHW + (px + 1);   // this thread's output pixel inside the halo block
+    int ti = group;
+    for (int t = int(blockIdx.x) + group * int(gridDim.x); t < total_tiles; t += 2 * int(gridDim.x), ti += 2) {
       int img, y0, x0;
-      decode(ti, img, y0, x0);
-      const int slot = ti % NS;
-      const uint32_t blk = x_base + uint32_t(ti % NB) * Cfg::kStageBytes;
-      if constexpr (C == 64) {
-        // release the buffer of this group's previous output store to the producer as early as possible
-        if (lead && store_buf >= 0) {
-          tma_store_wait_read();
-          mbar_arrive(x_empty + 8 * store_buf);
-          store_buf = -1;
-        }
-      }
-      mbar_wait_relaxed(acc1_full + 8 * slot, (ti / NS) & 1);   // GEMM 1 has also finished READING x: overwrite it
+      decode(t, img, y0, x0);
+      const int use = ti >> 1, stage = ti % S;
+      // ---------------- epilogue 1: t = act(W1 x + b1) on the halo pixels -> T block (swizzled, zero outside) -------
+      mbar_wait_relaxed(acc1_full + 8 * group, use & 1);
       tc_fence_after();
+      if (C == 64) {
+        // the T block doubles as the TMA-store staging tile of epilogue 2: the previous store must have read it
+        if (lead) tma_store_wait_read();
+        named_barrier_sync(1 + group, 128);
+      }
 #pragma unroll 1
       for (int m = 0; m < 2; ++m) {
         if (m == 1 && quad * 32 >= kHaloRows - 128) break;   // warp-uniform: rows 128 + 32*quad .. are all >= 180
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_bneck_kernel(const __grid_co
 #pragma unroll 1
         for (int c0 = 0; c0 < C; c0 += 32) {
           uint32_t v[32];
-          tmem_ld_32x32(tmem_base + uint32_t(slot * 2 * C + m * C + c0) + lane_off, v);
+          tmem_ld_32x32(tmem_base + uint32_t((group * 3 + m) * C + c0) + lane_off, v);
           tmem_ld_wait();
           if (!live) continue;
           uint4 o[4];
@@ -296,50 +296,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_bneck_kernel(const __grid_co
             for (int q = 0; q < 4; ++q) o[q] = make_uint4(0u, 0u, 0u, 0u);
           }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) st_shared_v4(blk + swz<C>(hr, (c0 >> 3) + q), o[q].x, o[q].y, o[q].z, o[q].w);
+          for (int q = 0; q < 4; ++q) st_shared_v4(tblk + swz<C>(hr, (c0 >> 3) + q), o[q].x, o[q].y, o[q].z, o[q].w);
         }
       }
       fence_proxy_async();   // generic-proxy writes of T -> visible to the tensor core (async proxy)
       tc_fence_before();
-      mbar_arrive(t_full + 8 * slot);
-    };
-
-    auto epi2 = [&](int ti) {
-      int img, y0, x0;
-      decode(ti, img, y0, x0);
-      const int slot = ti % NS, b = ti % NB;
-      const uint32_t blk = x_base + uint32_t(b) * Cfg::kStageBytes;
+      mbar_arrive(t_full + 8 * group);
+      // ---------------- epilogue 2: y = act(W2 * T + b2) (+ x) ---------------------------------------------------------
       const int gy = y0 + py, gx = x0 + px;
       const bool valid = gy < p.gh && gx < p.gw;
-      const size_t pix = size_t(img) * p.gh * p.gw + size_t(valid ? gy : 0) * p.gw + (valid ? gx : 0);
-      // residual = x at this pixel, from global (L2: the tile was just loaded); issued before the accumulator wait
-      uint4 res[C / 8];
-      if (p.residual) {
-        const __half* rp = p.src + pix * p.src_cstride + p.src_coff;
-#pragma unroll
-        for (int q = 0; q < C / 8; ++q) res[q] = *reinterpret_cast<const uint4*>(rp + q * 8);
-      }
-      if constexpr (C == 64) {
-        // release the buffer of this group's previous output store to the producer
-        if (lead && store_buf >= 0) {
-          tma_store_wait_read();
-          mbar_arrive(x_empty + 8 * store_buf);
-          store_buf = -1;
-        }
-      }
-      mbar_wait_relaxed(acc2_full + 8 * slot, (ti / NS) & 1);   // GEMM 2 complete: T is no longer read either
+      const uint32_t xblk = x_base + uint32_t(stage) * Cfg::kStageBytes;
+      mbar_wait_relaxed(acc2_full + 8 * group, use & 1);
       tc_fence_after();
-      __half* out = p.dst + pix * p.dst_cstride + p.dst_coff;
-#pragma unroll
+      __half* out = p.dst + (size_t(img) * p.gh * p.gw + size_t(valid ? gy : 0) * p.gw + (valid ? gx : 0)) * p.dst_cstride + p.dst_coff;
+#pragma unroll 1
       for (int c0 = 0; c0 < C; c0 += 32) {
+        uint4 res[4];
+        if (p.residual) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) res[q] = ld_shared_v4(xblk + swz<C>(hr_c, (c0 >> 3) + q));
+        }
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + uint32_t(slot * 2 * C + c0) + lane_off, v);
+        tmem_ld_32x32(tmem_base + uint32_t((group * 3 + 2) * C + c0) + lane_off, v);
         tmem_ld_wait();
         uint4 o[4];
-        const uint4 (&rr)[4] = *reinterpret_cast<const uint4(*)[4]>(&res[c0 >> 3]);
-#define CTD_FIN(ACT)                                                          \
-  if (p.residual) finish32<ACT, true>(v, bias_s + C + c0, rr, o);             \
-  else finish32<ACT, false>(v, bias_s + C + c0, rr, o);
+#define CTD_FIN(ACT)                                                           \
+  if (p.residual) finish32<ACT, true>(v, bias_s + C + c0, res, o);             \
+  else finish32<ACT, false>(v, bias_s + C + c0, res, o);
         switch (p.act) {
           case CTD_ACT_SILU: CTD_FIN(CTD_ACT_SILU) break;
           case CTD_ACT_LEAKY: CTD_FIN(CTD_ACT_LEAKY) break;
@@ -348,9 +331,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_bneck_kernel(const __grid_co
         }
 #undef CTD_FIN
         if constexpr (C == 64) {
-          // staging tile = the first 128 rows of the tile's own buffer, 128B swizzle
+          // staging tile = the first 128 rows of this group's T block (GEMM 2 has completed: acc2_full), 128B swizzle
 #pragma unroll
-          for (int q = 0; q < 4; ++q) st_shared_v4(blk + swz<64>(row, (c0 >> 3) + q), o[q].x, o[q].y, o[q].z, o[q].w);
+          for (int q = 0; q < 4; ++q) st_shared_v4(tblk + swz<64>(row, (c0 >> 3) + q), o[q].x, o[q].y, o[q].z, o[q].w);
         } else {
           if (valid) {
 #pragma unroll
@@ -358,28 +341,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_bneck_kernel(const __grid_co
           }
         }
       }
+      // this thread is done with TMEM (tcgen05.wait::ld above) and with the x block
       tc_fence_before();
-      mbar_arrive(acc_empty + 8 * slot);
+      mbar_arrive(acc_empty + 8 * group);
+      mbar_arrive(x_empty + 8 * stage);
       if constexpr (C == 64) {
         fence_proxy_async();
         named_barrier_sync(1 + group, 128);
         if (lead) {
-          tma_store_4d(&p.o_map, blk, 0, x0, y0, img);
+          tma_store_4d(&p.o_map, tblk, 0, x0, y0, img);
           tma_store_commit();
-          store_buf = b;
         }
-      } else {
-        if (lead) mbar_arrive(x_empty + 8 * b);   // nothing reads the buffer after GEMM 2
       }
-    };
-
-    int prev = -1;
-    for (int ti = group; ti < my_tiles; ti += 2) {
-      epi1(ti);
-      if (prev >= 0) epi2(prev);
-      prev = ti;
     }
-    if (prev >= 0) epi2(prev);
     if (C == 64 && lead) tma_store_wait_all();   // shared memory must outlive the bulk stores
   }
   tc_fence_before();
@@ -585,7 +559,6 @@ const char* conv_bneck_plan(BneckPlan& plan, PFN_encodeTiled enc, int n_img, int
   p.tiles_y = (gh + kTH - 1) / kTH;
   p.act = act; p.residual = residual;
   p.dst = dst; p.dst_cstride = dst_cstride; p.dst_coff = dst_coff;
-  p.src = static_cast<const __half*>(src); p.src_cstride = src_cstride; p.src_coff = src_coff;
   p.bias = bias;
   {
     const size_t cs = size_t(src_cstride);

@@ -55,10 +55,10 @@ struct TcCfg {
 
 template <int ACT>
 __device__ __forceinline__ float apply_act(float v) {
-  if constexpr (ACT == CTD_ACT_SILU) return __fdividef(v, 1.0f + __expf(-v));
+  if constexpr (ACT == CTD_ACT_SILU) return __fdividef(v, 1.0f + exp_neg_fast(v));
   else if constexpr (ACT == CTD_ACT_LEAKY) return fmaxf(v, 0.1f * v);
   else if constexpr (ACT == CTD_ACT_RELU) return fmaxf(v, 0.f);
-  else if constexpr (ACT == CTD_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + __expf(-v));
+  else if constexpr (ACT == CTD_ACT_SIGMOID) return __fdividef(1.0f, 1.0f + exp_neg_fast(v));
   else return v;
 }
 
@@ -609,6 +609,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // Detect decode (yolo.py:36-44): columns = anchor*(5+nc) + o
         constexpr int kChunk = BN >= 32 ? 32 : 16;
         const int no = 5 + p.nc;
+        const int no_rcp = 65536 / no + 1;   // col / no == (col * no_rcp) >> 16 for col < 512 (no runtime division per element)
         float* rows = p.blks + (size_t(img) * p.blks_rows_per_img + p.level_row0) * no;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += kChunk) {
@@ -624,7 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int j = 0; j < kChunk; ++j) {
             const int col = nblk * BN + c0 + j;
             if (col < g.cout) {
-              const int a = col / no, o = col - a * no;
+              const int a = (col * no_rcp) >> 16, o = col - a * no;
               const float s = 1.0f / (1.0f + expf(-(__uint_as_float(v[j]) + bias_t[c0 + j])));
               float r;
               if (o == 0) r = (s * 2.0f - 0.5f + float(gx)) * p.det_stride;
@@ -1456,6 +1457,9 @@ const char* conv_tc_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
       }
     }
   int bn = pick_block_n(g.cout_pad);
+  // small grids (the 1/32 and 1/64 layers): a narrower N block spreads the layer over more SMs -- each CTA streams a
+  // quarter of the weights and runs a quarter of the epilogue, which is what the time of a one-tile CTA consists of
+  while (bn > 64 && g.n_img * p.tiles_x * p.tiles_y * (g.cout_pad / bn) * g.n_phase <= g_num_sms / 2) bn /= 2;
   if (split && bn > 64) bn = 64;   // promoted accumulation keeps a BN-float row per epilogue thread in registers
   plan.block_n = bn;
   p.use_tma_store = 0;
@@ -1621,8 +1625,13 @@ const char* conv_hs_plan(ConvTcPlan& plan, PFN_encodeTiled enc, const ConvGeom& 
   plan.halo = 0;
   if (dst == nullptr || g.in_stride != 1) return nullptr;
   if (!((g.n_phase == 1 && g.taps == 9) || (g.n_phase == 4 && g.taps == 4))) return nullptr;
-  const int bn = (g.cout_pad % 256 == 0) ? 256 : ((g.cout_pad % 128 == 0) ? 128 : 0);
+  int bn = (g.cout_pad % 256 == 0) ? 256 : ((g.cout_pad % 128 == 0) ? 128 : 0);
   if (bn == 0 || g.cout_pad > 512 || g.cout % 64 != 0) return nullptr;   // TMA-store epilogue only
+  {
+    // small grids (1/64 layers): N = 128 blocks give twice the CTAs, each with half of the weight stream and epilogue
+    const int sp = g.n_img * ((g.gw + kHaloTileW - 1) / kHaloTileW) * ((g.gh + kHaloTileH - 1) / kHaloTileH) * g.n_phase;
+    if (bn == 256 && sp * (g.cout_pad / 256) <= g_num_sms / 2) bn = 128;
+  }
   for (int s = 0; s < g.n_src; ++s)
     if (g.src_c[s] % 64 != 0 || src_coff[s] % 8 != 0) return nullptr;
   if ((g.dst_coff % 8) != 0 || (g.dst_cstride % 8) != 0) return nullptr;

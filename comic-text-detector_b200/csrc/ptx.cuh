@@ -22,6 +22,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- fast activation math
+// e^-v for the fast SiLU / sigmoid epilogues: ONE ex2.approx.ftz.  `__expf` is ex2.approx WITHOUT .ftz, which the compiler
+// wraps in a denormal guard (FSETP + two predicated FMULs per element: a quarter of the epilogue's instructions, ncu
+// source view).  The guard only matters when e^-v is denormal (v > 87), where 1 + e^-v == 1 either way: the activation
+// values are bit-identical.
+__device__ __forceinline__ float exp_neg_fast(float v) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v * -1.4426950408889634f));
+  return y;
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
 // stream is still running: everything before griddep_wait() (barrier init, TMEM allocation, tensor-map prefetch,

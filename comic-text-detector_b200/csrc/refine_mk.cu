@@ -435,9 +435,12 @@ __device__ __forceinline__ void suf_union(int* L, int a, int b) {
 __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int round) {
   __shared__ int Ls[kChunkPx];
   __shared__ uint8_t fs[kChunkPx];
+  __shared__ unsigned Mw[kChunkPx / 32 + 2];      // foreground bits, 32 pixels per word (+ zero padding)
   const View v = view_of(c, blockIdx.x);
   const WinState& st = c.st[v.w];
   if (round < 4 && round >= st.nproc) return;
+  for (int i = threadIdx.x; i < kChunkPx / 32 + 2; i += kLabelThreads) Mw[i] = 0u;
+  __syncthreads();
   uint8_t* cand = c.cand + v.win.off;
   uint8_t* rootflag = c.tmp + v.win.off;
   int* L = c.L + v.win.off;
@@ -498,6 +501,7 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
       // a run starts at a foreground pixel whose left neighbour (same row, same warp) is not foreground
       const bool starts = fg && (lane == 0 || x == 0 || !((m >> (lane - 1)) & 1u));
       const unsigned sb = __ballot_sync(0xffffffffu, starts);
+      if (lane == 0) Mw[k >> 5] = m;
       if (in) {
         fs[k] = (uint8_t)sv;
         Ls[k] = fg ? (k - lane) + (31 - __clz(sb & (0xffffffffu >> (31 - lane)))) : -1;
@@ -505,21 +509,52 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
     }
   }
   __syncthreads();
-  // pass 2: seams between warps, contacts with the row above inside the chunk
-  for (int k = threadIdx.x; k < v.cnt; k += kLabelThreads) {
-    if (!fs[k]) continue;
-    int yl, x;
-    divmod(k, dv, yl, x);
-    if ((k & 31) == 0 && x > 0 && k > 0 && fs[k - 1]) suf_union(Ls, k, k - 1);
-    if (k < v.rw) continue;
-    const int up = k - v.rw;
-    if (fs[up]) {
-      // only the first pixel of each (current run x upper run) overlap issues the union
-      const bool first = x == 0 || !fs[k - 1] || !fs[up - 1];
-      if (first) suf_union(Ls, k, up);
-    } else {
-      if (x > 0 && fs[up - 1]) suf_union(Ls, k, up - 1);
-      if (x + 1 < v.rw && fs[up + 1]) suf_union(Ls, k, up + 1);
+  // pass 2: seams between warps, contacts with the row above inside the chunk -- on the foreground BIT masks, one
+  // thread per 32-pixel word: the neighbour tests of 32 pixels are a handful of shifts and ANDs, and only the pixels
+  // that really start a (run x upper run) contact walk the union-find (first version: every foreground pixel tested
+  // its four neighbours with byte loads; half of the kernel's instructions, ncu).
+  auto bits_at = [&](int pos) -> unsigned {        // 32 foreground bits starting at pixel `pos` (pixels < 0 read as 0)
+    if (pos <= -32) return 0u;
+    if (pos < 0) return Mw[0] << (-pos);
+    const int w = pos >> 5, sft = pos & 31;
+    return __funnelshift_r(Mw[w], Mw[w + 1], sft);
+  };
+  for (int w = threadIdx.x; w * 32 < v.cnt; w += kLabelThreads) {
+    const unsigned cur = Mw[w];
+    if (!cur) continue;
+    const int k0 = w * 32;
+    int yl, x0;
+    divmod(k0, dv, yl, x0);
+    unsigned rs = 0u;                               // bits whose pixel is the FIRST of its row (x == 0)
+    for (int j = x0 == 0 ? 0 : v.rw - x0; j < 32; j += v.rw) rs |= 1u << j;
+    int xe = x0 + 32;                               // x of the pixel after this word
+    if (xe >= v.rw) xe %= v.rw;
+    const unsigned re = (rs >> 1) | (xe == 0 ? 0x80000000u : 0u);   // bits whose pixel is the LAST of its row
+    const unsigned lft = bits_at(k0 - 1);           // fg(k - 1)
+    // seam: the run labelling of pass 1 restarts at every word
+    if ((cur & 1u) && !(rs & 1u) && (lft & 1u)) suf_union(Ls, k0, k0 - 1);
+    if (k0 + 32 <= v.rw) continue;                  // the whole word lies in the first row of the chunk
+    const unsigned vup = k0 >= v.rw ? 0xffffffffu : (0xffffffffu << (v.rw - k0));   // pixels that have a row above
+    const unsigned up = bits_at(k0 - v.rw), upl = bits_at(k0 - v.rw - 1), upr = bits_at(k0 - v.rw + 1);
+    // pixel and the pixel above are foreground: only the first pixel of each (current run x upper run) overlap unions
+    unsigned f = cur & up & vup & (rs | ~lft | ~upl);
+    while (f) {
+      const int j = __ffs(f) - 1;
+      f &= f - 1u;
+      suf_union(Ls, k0 + j, k0 + j - v.rw);
+    }
+    const unsigned nb = cur & ~up & vup;
+    f = nb & upl & ~rs;                             // diagonal contacts when the pixel above is background
+    while (f) {
+      const int j = __ffs(f) - 1;
+      f &= f - 1u;
+      suf_union(Ls, k0 + j, k0 + j - v.rw - 1);
+    }
+    f = nb & upr & ~re;
+    while (f) {
+      const int j = __ffs(f) - 1;
+      f &= f - 1u;
+      suf_union(Ls, k0 + j, k0 + j - v.rw + 1);
     }
   }
   __syncthreads();

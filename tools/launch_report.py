@@ -41,7 +41,7 @@ def main():
     if len(sys.argv) > 2:
         ops = [l.split() for l in open(sys.argv[2]) if l.startswith("op ")]
         gemm = [o for o in ops if o[3] in ("0", "1", "2", "6", "7", "10")]
-        tc = [(k, t, g) for (k, t, g) in second if "conv_tc" in k or "conv_halo" in k or "conv_hs" in k or "conv_sw" in k or "conv_bneck" in k]
+        tc = [(k, t, g) for (k, t, g) in second if "conv_tc" in k or "conv_halo" in k or "conv_hs" in k or "conv_sw" in k or "conv_bneck" in k or "conv_segtail" in k]
         bs = 16
         print()
         tflop = 0.0
@@ -59,7 +59,7 @@ def main():
             tflop += fl
             bn = re.search(r"conv_(?:tc|halo|hs)_kernel<\(int\)(\d+)>|conv_(?:tc|halo|hs)_kernel<(\d+)>", k)
             print("op%-3s kind %d k%d s%d cin %4d cout %4d /%-2d BN=%-3s grid=%-16s %8.1f us %7.1f TF/s" % (
-                o[1], kind, kk, s, cin, cout, down, ((bn.group(1) or bn.group(2)) + ("h" if "halo" in k else ("s" if "conv_hs" in k else ""))) if bn else ("128w" if "conv_sw" in k else ("fuse" if "conv_bneck" in k else "?")), g, t, fl / t / 1e6))
+                o[1], kind, kk, s, cin, cout, down, ((bn.group(1) or bn.group(2)) + ("h" if "halo" in k else ("s" if "conv_hs" in k else ""))) if bn else ("128w" if "conv_sw" in k else ("fuse" if "conv_bneck" in k else ("tail" if "conv_segtail" in k else "?"))), g, t, fl / t / 1e6))
         ttc = sum(t for _, t, _ in tc)
         print("conv_tc total %.1f us, %.1f GFLOP -> %.1f TF/s" % (ttc, tflop / 1e9, tflop / ttc / 1e6))
 

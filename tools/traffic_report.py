@@ -40,7 +40,7 @@ def main():
     print("%-48s %4s %10s %10s %10s" % ("kernel", "n", "us", "rd MB", "wr MB"))
     for k, (c, t, rdb, wrb) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print("%-48s %4d %10.1f %10.1f %10.1f" % (k[:48], c, t, rdb / 1e6, wrb / 1e6))
-    conv = [d for d in last if any(k in d["name"] for k in ("conv_tc", "conv_halo", "conv_hs", "conv_sw", "conv_bneck"))]
+    conv = [d for d in last if any(k in d["name"] for k in ("conv_tc", "conv_halo", "conv_hs", "conv_sw", "conv_bneck", "conv_segtail"))]
     tot = {"launches": len(conv), "us": sum(d.get("gpu__time_duration.sum", 0.0) for d in conv),
            "dram_read_bytes": sum(d.get("dram__bytes_read.sum", 0.0) for d in conv),
            "dram_write_bytes": sum(d.get("dram__bytes_write.sum", 0.0) for d in conv)}
@@ -52,7 +52,7 @@ def main():
     if len(sys.argv) > 4:
         rows = []
         for k, (c, t, rdb, wrb) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            if any(x in k for x in ("conv_tc", "conv_halo", "conv_hs", "conv_sw", "conv_bneck")):
+            if any(x in k for x in ("conv_tc", "conv_halo", "conv_hs", "conv_sw", "conv_bneck", "conv_segtail")):
                 continue
             rows.append({"kernel": k, "launches": c, "us": round(t, 1), "dram_read_MB": round(rdb / 1e6, 2),
                          "dram_write_MB": round(wrb / 1e6, 2),
