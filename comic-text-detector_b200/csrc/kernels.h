@@ -260,8 +260,9 @@ size_t refine_win_bytes();
 size_t refine_mk_state_bytes(int n_wins);
 size_t refine_mk_chunk_bytes();
 int refine_mk_chunk_px();
+// the first n_multi_chunks records of d_chunks are the chunks of windows that span more than one chunk
 cudaError_t refine_mk_launch(const uint8_t* d_img, const uint8_t* d_mask, int H, int W, const void* d_wins, int n_wins,
-                             const void* d_chunks, int n_chunks, void* d_state, size_t total_px, void* scratch, int refine_mode,
-                             uint8_t* d_out, cudaStream_t s);
+                             const void* d_chunks, int n_chunks, int n_multi_chunks, void* d_state, size_t total_px,
+                             void* scratch, int refine_mode, uint8_t* d_out, cudaStream_t s);
 
 }  // namespace ctd

@@ -95,7 +95,24 @@ int launch_refine(ctd_handle* h, const RefineJob& job, const uint8_t* d_img, con
   int* hidx = reinterpret_cast<int*>(stage + wb);
   if (!job.idx_small.empty()) memcpy(hidx, job.idx_small.data(), job.idx_small.size() * 4);
   if (!job.idx_large.empty()) memcpy(hidx + job.idx_small.size(), job.idx_large.data(), job.idx_large.size() * 4);
-  memcpy(stage + wb + ib, job.chunks.data(), job.chunks.size() * sizeof(HostChunk));
+  // chunk table: the chunks of windows that span SEVERAL chunks first -- only those have chunk borders to unite and
+  // chunk-local roots to re-point (k_union_border / k_flat1 run on that prefix); the kernels are order-agnostic
+  int n_multi = 0;
+  {
+    HostChunk* hc = reinterpret_cast<HostChunk*>(stage + wb + ib);
+    const size_t nc = job.chunks.size();
+    size_t tail = nc;
+    for (size_t i = 0; i < nc;) {
+      size_t j = i;
+      while (j < nc && job.chunks[j].win == job.chunks[i].win) ++j;
+      if (j - i > 1) {
+        for (size_t k = i; k < j; ++k) hc[n_multi++] = job.chunks[k];
+      } else {
+        hc[--tail] = job.chunks[i];
+      }
+      i = j;
+    }
+  }
   CK(cudaMemcpyAsync(base, stage, tb, cudaMemcpyHostToDevice, st));
   if (!pinned) CK(cudaStreamSynchronize(st));   // pageable staging dies with this frame
   const int* d_idx = reinterpret_cast<const int*>(base + wb);
@@ -103,8 +120,8 @@ int launch_refine(ctd_handle* h, const RefineJob& job, const uint8_t* d_img, con
     CK(refine_launch(d_img, d_mask, ih, iw, base, d_idx, int(job.idx_small.size()), d_idx + job.idx_small.size(),
                      int(job.idx_large.size()), job.total_px, base + tb + sb, refine_mode, d_out, st));
   else
-    CK(refine_mk_launch(d_img, d_mask, ih, iw, base, int(job.wins.size()), base + wb + ib, int(job.chunks.size()), base + tb,
-                        job.total_px, base + tb + sb, refine_mode, d_out, st));
+    CK(refine_mk_launch(d_img, d_mask, ih, iw, base, int(job.wins.size()), base + wb + ib, int(job.chunks.size()), n_multi,
+                        base + tb, job.total_px, base + tb + sb, refine_mode, d_out, st));
   return CTD_OK;
 }
 

@@ -832,8 +832,8 @@ int refine_mk_chunk_px() { return kChunkPx; }
 // each unless a single row is longer); d_state: refine_mk_state_bytes(n_wins) bytes (zeroed here); scratch planes as in
 // refine_launch.  img / mask / out hold H*W-pixel planes per page.
 cudaError_t refine_mk_launch(const uint8_t* d_img, const uint8_t* d_mask, int H, int W, const void* d_wins, int n_wins,
-                             const void* d_chunks, int n_chunks, void* d_state, size_t total_px, void* scratch, int refine_mode,
-                             uint8_t* d_out, cudaStream_t s) {
+                             const void* d_chunks, int n_chunks, int n_multi_chunks, void* d_state, size_t total_px,
+                             void* scratch, int refine_mode, uint8_t* d_out, cudaStream_t s) {
   if (n_wins <= 0 || n_chunks <= 0) return cudaSuccess;
   Ctx c;
   c.img_all = d_img; c.mask_all = d_mask; c.out_all = reinterpret_cast<uint32_t*>(d_out);
@@ -862,8 +862,10 @@ cudaError_t refine_mk_launch(const uint8_t* d_img, const uint8_t* d_mask, int H,
       uint8_t* t = c.merged; c.merged = c.tmp; c.tmp = t;   // the dilated plane IS `merged` from here on (no copy back)
     }
     k_label_local<<<g, kLabelThreads, 0, s>>>(c, round);
-    k_union_border<<<g, kThreads, 0, s>>>(c, round);
-    k_flat1<<<g, kThreads, 0, s>>>(c, round);
+    if (n_multi_chunks > 0) {   // single-chunk windows: the chunk-local roots ARE the global roots
+      k_union_border<<<unsigned(n_multi_chunks), kThreads, 0, s>>>(c, round);
+      k_flat1<<<unsigned(n_multi_chunks), kThreads, 0, s>>>(c, round);
+    }
     k_flat2_macc<<<g, kThreads, 0, s>>>(c, round);
     if (round == 4) {
       k_top_a<<<g, kThreads, 0, s>>>(c);
