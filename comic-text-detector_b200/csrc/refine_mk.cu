@@ -314,9 +314,11 @@ __global__ void __launch_bounds__(kThreads) k_xor(Ctx c) {
   int lo[3], hi[3], ot[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) { lo[k] = st.lo[k]; hi[k] = st.hi[k]; ot[k] = st.otsu_t[k]; }
-  unsigned long long loc[12];
+  // per thread <= kChunkPx / kThreads pixels x 255: 32-bit partial sums.  Only the POSITIVE candidates are summed: for
+  // t in {0, 255}, (255 - t) ^ m == 255 - (t ^ m), so the negative's sum is 255 * pixels - the positive's sum.
+  unsigned pos[6], npx = 0;
 #pragma unroll
-  for (int k = 0; k < 12; ++k) loc[k] = 0ull;
+  for (int k = 0; k < 6; ++k) pos[k] = 0u;
   const DivW dv = make_div(v.rw, v.rw * v.rh);
   for (int k0 = 0; k0 < v.cnt; k0 += kThreads * kU) {
     int mk[kU], gr[kU], ch[kU][3];
@@ -337,24 +339,29 @@ __global__ void __launch_bounds__(kThreads) k_xor(Ctx c) {
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       if (mk[u] < 0) continue;
+      ++npx;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        if (k < ncol) {
-          const int t = (gr[u] >= lo[k] && gr[u] <= hi[k]) ? 255 : 0;
-          loc[2 * k] += (unsigned)(t ^ mk[u]);
-          loc[2 * k + 1] += (unsigned)((255 - t) ^ mk[u]);
-        }
+        const int t = (gr[u] >= lo[k] && gr[u] <= hi[k]) ? 255 : 0;     // only read for k < ncol
+        pos[k] += (unsigned)(t ^ mk[u]);
         const int t2 = ch[u][k] > ot[k] ? 255 : 0;
-        loc[6 + 2 * k] += (unsigned)(t2 ^ mk[u]);
-        loc[6 + 2 * k + 1] += (unsigned)((255 - t2) ^ mk[u]);
+        pos[3 + k] += (unsigned)(t2 ^ mk[u]);
       }
     }
   }
 #pragma unroll
-  for (int k = 0; k < 12; ++k) {
-    unsigned long long s = loc[k];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0 && s) atomicAdd(&sx[k], s);
+  for (int k = 0; k < 6; ++k) {
+    const bool used = k >= 3 || k < ncol;
+    unsigned long long sp = used ? pos[k] : 0ull, sn = used ? 255ull * npx - pos[k] : 0ull;
+    for (int o = 16; o > 0; o >>= 1) {
+      sp += __shfl_down_sync(0xffffffffu, sp, o);
+      sn += __shfl_down_sync(0xffffffffu, sn, o);
+    }
+    // xs layout: [2k] positive, [2k+1] negative for the 3 colours, then the 3 channels
+    if ((threadIdx.x & 31) == 0) {
+      if (sp) atomicAdd(&sx[2 * k], sp);
+      if (sn) atomicAdd(&sx[2 * k + 1], sn);
+    }
   }
   __syncthreads();
   if (threadIdx.x < 12 && sx[threadIdx.x]) atomicAdd(&c.st[v.w].xs[threadIdx.x], sx[threadIdx.x]);
@@ -436,6 +443,7 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
   __shared__ int Ls[kChunkPx];
   __shared__ uint8_t fs[kChunkPx];
   __shared__ unsigned Mw[kChunkPx / 32 + 2];      // foreground bits, 32 pixels per word (+ zero padding)
+  __shared__ unsigned Sw[kChunkPx / 32];          // run-start bits (the only nodes of the chunk-local forest)
   const View v = view_of(c, blockIdx.x);
   const WinState& st = c.st[v.w];
   if (round < 4 && round >= st.nproc) return;
@@ -501,7 +509,7 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
       // a run starts at a foreground pixel whose left neighbour (same row, same warp) is not foreground
       const bool starts = fg && (lane == 0 || x == 0 || !((m >> (lane - 1)) & 1u));
       const unsigned sb = __ballot_sync(0xffffffffu, starts);
-      if (lane == 0) Mw[k >> 5] = m;
+      if (lane == 0) { Mw[k >> 5] = m; Sw[k >> 5] = sb; }
       if (in) {
         fs[k] = (uint8_t)sv;
         Ls[k] = fg ? (k - lane) + (31 - __clz(sb & (0xffffffffu >> (31 - lane)))) : -1;
@@ -519,9 +527,12 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
     const int w = pos >> 5, sft = pos & 31;
     return __funnelshift_r(Mw[w], Mw[w + 1], sft);
   };
-  for (int w = threadIdx.x; w * 32 < v.cnt; w += kLabelThreads) {
+  // two threads per word (16 pixels each): all 512 threads of the CTA take part
+  for (int hw = threadIdx.x; hw * 16 < v.cnt; hw += kLabelThreads) {
+    const int w = hw >> 1;
+    const unsigned half = (hw & 1) ? 0xffff0000u : 0x0000ffffu;
     const unsigned cur = Mw[w];
-    if (!cur) continue;
+    if (!(cur & half)) continue;
     const int k0 = w * 32;
     int yl, x0;
     divmod(k0, dv, yl, x0);
@@ -532,9 +543,9 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
     const unsigned re = (rs >> 1) | (xe == 0 ? 0x80000000u : 0u);   // bits whose pixel is the LAST of its row
     const unsigned lft = bits_at(k0 - 1);           // fg(k - 1)
     // seam: the run labelling of pass 1 restarts at every word
-    if ((cur & 1u) && !(rs & 1u) && (lft & 1u)) suf_union(Ls, k0, k0 - 1);
+    if (!(hw & 1) && (cur & 1u) && !(rs & 1u) && (lft & 1u)) suf_union(Ls, k0, k0 - 1);
     if (k0 + 32 <= v.rw) continue;                  // the whole word lies in the first row of the chunk
-    const unsigned vup = k0 >= v.rw ? 0xffffffffu : (0xffffffffu << (v.rw - k0));   // pixels that have a row above
+    const unsigned vup = (k0 >= v.rw ? 0xffffffffu : (0xffffffffu << (v.rw - k0))) & half;   // pixels that have a row above
     const unsigned up = bits_at(k0 - v.rw), upl = bits_at(k0 - v.rw - 1), upr = bits_at(k0 - v.rw + 1);
     // pixel and the pixel above are foreground: only the first pixel of each (current run x upper run) overlap unions
     unsigned f = cur & up & vup & (rs | ~lft | ~upl);
@@ -558,11 +569,25 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
     }
   }
   __syncthreads();
+  // pass 3a: flatten the forest.  Its nodes are the run starts only (every other foreground pixel points at its run
+  // start and is never re-parented): after this pass every run start points straight at its root, so the root of ANY
+  // foreground pixel is Ls[Ls[k]] -- two loads instead of a walk (the walks were 10 hops on average, ncu).
+  for (int hw = threadIdx.x; hw * 16 < v.cnt; hw += kLabelThreads) {
+    unsigned f = Sw[hw >> 1] & ((hw & 1) ? 0xffff0000u : 0x0000ffffu);
+    const int k0 = (hw >> 1) * 32;
+    while (f) {
+      const int s0 = k0 + __ffs(f) - 1;
+      f &= f - 1u;
+      const int r = suf_find(Ls, s0);
+      if (r != s0) atomicMin(&Ls[s0], r);
+    }
+  }
+  __syncthreads();
   // pass 3: chunk-local roots to global memory (window-local pixel indices)
   for (int k = threadIdx.x; k < v.cnt; k += kLabelThreads) {
     const int i = v.i0 + k;
     int r = -1;
-    if (fs[k]) r = suf_find(Ls, k);
+    if (fs[k]) r = Ls[Ls[k]];
     L[i] = r < 0 ? -1 : v.i0 + r;
     rootflag[i] = (r == k) ? 1 : 0;
     // every global root is one of these chunk-local roots: their per-label sums start at zero here, so that the
