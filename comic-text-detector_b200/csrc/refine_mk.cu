@@ -452,7 +452,6 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
   if (round < 4 && round >= st.nproc) return;
   for (int i = threadIdx.x; i < kChunkPx / 32 + 2; i += kLabelThreads) Mw[i] = 0u;
   __syncthreads();
-  uint8_t* cand = c.cand + v.win.off;
   uint8_t* rootflag = c.tmp + v.win.off;
   int* L = c.L + v.win.off;
   int* acc = c.acc + 4 * v.win.off;
@@ -505,7 +504,6 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
           const int tv = kind < 3 ? ((raw[u] >= lo && raw[u] <= hi) ? 255 : 0) : (raw[u] > ot ? 255 : 0);
           sv = neg ? 255 - tv : tv;
         }
-        cand[v.i0 + k] = (uint8_t)sv;
       }
       const bool fg = in && sv != 0;
       const unsigned m = __ballot_sync(0xffffffffu, fg);
@@ -603,18 +601,17 @@ __global__ void __launch_bounds__(kThreads) k_union_border(Ctx c, int round) {
   const View v = view_of(c, blockIdx.x);
   if (round < 4 && round >= c.st[v.w].nproc) return;
   if (v.y0 == 0) return;
-  const uint8_t* src = c.cand + v.win.off;
-  int* L = c.L + v.win.off;
+  int* L = c.L + v.win.off;   // foreground <=> L >= 0 (written for every pixel by k_label_local)
   for (int x = threadIdx.x; x < v.rw; x += kThreads) {
     const int i = v.i0 + x;
-    if (!src[i]) continue;
+    if (__ldcg(L + i) < 0) continue;
     const int up = i - v.rw;
-    if (src[up]) {
-      const bool first = x == 0 || !src[i - 1] || !src[up - 1];
+    if (__ldcg(L + up) >= 0) {
+      const bool first = x == 0 || __ldcg(L + i - 1) < 0 || __ldcg(L + up - 1) < 0;
       if (first) uf_union(L, i, up);
     } else {
-      if (x > 0 && src[up - 1]) uf_union(L, i, up - 1);
-      if (x + 1 < v.rw && src[up + 1]) uf_union(L, i, up + 1);
+      if (x > 0 && __ldcg(L + up - 1) >= 0) uf_union(L, i, up - 1);
+      if (x + 1 < v.rw && __ldcg(L + up + 1) >= 0) uf_union(L, i, up + 1);
     }
   }
 }
@@ -679,8 +676,10 @@ __global__ void __launch_bounds__(kThreads) k_flat2_macc(Ctx c, int round) {
       if (rr >= 0 && rr != p[u]) L[i] = rr;
       const bool un = rr >= 0 && mg[u] == 0;
       const bool pg = un && pd[u] != 0;
-      const unsigned peers = __match_any_sync(0xffffffffu, rr);
       const unsigned bg = __ballot_sync(0xffffffffu, pg), bl = __ballot_sync(0xffffffffu, un && !pg);
+      // the 32 consecutive pixels of a warp mostly lie in ONE component (or all in the background): no match.any then
+      const int rr0 = __shfl_sync(0xffffffffu, rr, 0);
+      const unsigned peers = __all_sync(0xffffffffu, rr == rr0) ? 0xffffffffu : __match_any_sync(0xffffffffu, rr);
       if (rr >= 0 && lane == __ffs(peers) - 1) {
         atomicAdd(&area[rr], __popc(peers));
         atomicMax(&maxi[rr], i - lane + 31 - __clz(peers));
