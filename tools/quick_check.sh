@@ -9,7 +9,7 @@ timeout 900 python -m pytest "$@" -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
 rc=$?
 echo "pytest rc=$rc"; tail -15 $OUT/${TAG}_pytest.log
 if [ $rc -ne 0 ]; then exit $rc; fi
-timeout 600 python bench.py --steps 20 --warmup 5 --no-extras --no-cpu-baseline > $OUT/${TAG}_bench_line.json 2> $OUT/${TAG}_bench.err
+timeout 600 python bench.py --steps 20 --warmup 5 --no-extras --no-cpu-baseline --sustain-steps 0 > $OUT/${TAG}_bench_line.json 2> $OUT/${TAG}_bench.err
 echo "bench rc=$?"; python - <<PY
 import json
 d = json.load(open("$OUT/${TAG}_bench_line.json"))
