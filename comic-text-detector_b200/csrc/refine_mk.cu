@@ -444,20 +444,25 @@ __device__ __forceinline__ void suf_union(int* L, int a, int b) {
 
 __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int round) {
   __shared__ int Ls[kChunkPx];
-  __shared__ uint8_t fs[kChunkPx];
   __shared__ unsigned Mw[kChunkPx / 32 + 2];      // foreground bits, 32 pixels per word (+ zero padding)
   __shared__ unsigned Sw[kChunkPx / 32];          // run-start bits (the only nodes of the chunk-local forest)
+  __shared__ unsigned Gw[kChunkPx / 32];          // foreground & not yet merged & predicted     ("gain" pixels)
+  __shared__ unsigned Bw[kChunkPx / 32];          // foreground & not yet merged & not predicted ("loss" pixels)
+  __shared__ int s_fg;
   const View v = view_of(c, blockIdx.x);
-  const WinState& st = c.st[v.w];
+  WinState& st = c.st[v.w];
   if (round < 4 && round >= st.nproc) return;
   for (int i = threadIdx.x; i < kChunkPx / 32 + 2; i += kLabelThreads) Mw[i] = 0u;
+  if (threadIdx.x == 0) s_fg = 0;
   __syncthreads();
   uint8_t* rootflag = c.tmp + v.win.off;
   int* L = c.L + v.win.off;
   int* acc = c.acc + 4 * v.win.off;
   const int n = v.rw * v.rh;
+  int* area = acc; int* gain = acc + n; int* loss = acc + 2 * n; int* maxi = acc + 3 * n;
   const uint8_t* grey = c.grey + v.win.off;
   const uint8_t* merged = c.merged + v.win.off;
+  const uint8_t* predm = c.predm + v.win.off;
   int kind = 0, neg = 0, lo = 0, hi = 0, ot = 0;
   if (round < 4) {
     kind = st.proc_kind[round]; neg = st.proc_neg[round];
@@ -466,20 +471,22 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
   const int lane = threadIdx.x & 31;
   const DivW dv = make_div(v.rw, kChunkPx + 1);   // chunk-local indices: k = row * rw + x, k < kChunkPx
   constexpr int kIt = kChunkPx / kLabelThreads;    // 16 pixels per thread
-  // pass 1: source value per pixel (coalesced; ALL loads of the thread issued before the first use), then run starts
-  // inside each warp's 32 consecutive pixels
-  constexpr int kB = 8;                            // loads in flight per thread (two batches of 8 keep 3 CTAs / SM)
+  // pass 1: source value, `merged` and `pred` of every pixel (coalesced; the loads of a batch are issued before their
+  // first use) -> foreground / gain / loss BIT masks and the run starts inside each warp's 32 consecutive pixels
+  constexpr int kB = 4;
 #pragma unroll 1
   for (int ub = 0; ub < kIt; ub += kB) {
     if (ub * kLabelThreads >= v.cnt) break;        // CTA-uniform
-    int raw[kB];
+    int raw[kB], mg[kB], pd[kB];
 #pragma unroll
     for (int u = 0; u < kB; ++u) {
       const int k = (ub + u) * kLabelThreads + threadIdx.x;
-      raw[u] = 0;
+      raw[u] = 0; mg[u] = 1; pd[u] = 0;
       if (k < v.cnt) {
         const int i = v.i0 + k;
-        if (round == 4) raw[u] = merged[i];
+        mg[u] = merged[i];
+        pd[u] = predm[i];
+        if (round == 4) raw[u] = mg[u];
         else if (kind < 3) raw[u] = grey[i];
         else {
           int yl, x;
@@ -506,20 +513,20 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
         }
       }
       const bool fg = in && sv != 0;
+      const bool un = fg && mg[u] == 0;
       const unsigned m = __ballot_sync(0xffffffffu, fg);
+      const unsigned gb = __ballot_sync(0xffffffffu, un && pd[u] != 0);
+      const unsigned lb = __ballot_sync(0xffffffffu, un && pd[u] == 0);
       // a run starts at a foreground pixel whose left neighbour (same row, same warp) is not foreground
       const bool starts = fg && (lane == 0 || x == 0 || !((m >> (lane - 1)) & 1u));
       const unsigned sb = __ballot_sync(0xffffffffu, starts);
-      if (lane == 0) { Mw[k >> 5] = m; Sw[k >> 5] = sb; }
-      if (in) {
-        fs[k] = (uint8_t)sv;
-        Ls[k] = fg ? (k - lane) + (31 - __clz(sb & (0xffffffffu >> (31 - lane)))) : -1;
-      }
+      if (lane == 0) { Mw[k >> 5] = m; Sw[k >> 5] = sb; Gw[k >> 5] = gb; Bw[k >> 5] = lb; }
+      if (in) Ls[k] = fg ? (k - lane) + (31 - __clz(sb & (0xffffffffu >> (31 - lane)))) : -1;
     }
   }
   __syncthreads();
-  // pass 2: seams between warps, contacts with the row above inside the chunk -- on the foreground BIT masks, one
-  // thread per 32-pixel word: the neighbour tests of 32 pixels are a handful of shifts and ANDs, and only the pixels
+  // pass 2: seams between warps, contacts with the row above inside the chunk -- on the foreground BIT masks, two
+  // threads per 32-pixel word: the neighbour tests of 32 pixels are a handful of shifts and ANDs, and only the pixels
   // that really start a (run x upper run) contact walk the union-find (first version: every foreground pixel tested
   // its four neighbours with byte loads; half of the kernel's instructions, ncu).
   auto bits_at = [&](int pos) -> unsigned {        // 32 foreground bits starting at pixel `pos` (pixels < 0 read as 0)
@@ -528,7 +535,6 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
     const int w = pos >> 5, sft = pos & 31;
     return __funnelshift_r(Mw[w], Mw[w + 1], sft);
   };
-  // two threads per word (16 pixels each): all 512 threads of the CTA take part
   for (int hw = threadIdx.x; hw * 16 < v.cnt; hw += kLabelThreads) {
     const int w = hw >> 1;
     const unsigned half = (hw & 1) ? 0xffff0000u : 0x0000ffffu;
@@ -572,28 +578,65 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
   __syncthreads();
   // pass 3a: flatten the forest.  Its nodes are the run starts only (every other foreground pixel points at its run
   // start and is never re-parented): after this pass every run start points straight at its root, so the root of ANY
-  // foreground pixel is Ls[Ls[k]] -- two loads instead of a walk (the walks were 10 hops on average, ncu).
+  // foreground pixel is Ls[Ls[k]] -- two loads instead of a walk (the walks were 10 hops on average, ncu).  The roots
+  // zero their per-label sums here (area, gain, loss, max pixel index).
+  int fgc = 0;
   for (int hw = threadIdx.x; hw * 16 < v.cnt; hw += kLabelThreads) {
-    unsigned f = Sw[hw >> 1] & ((hw & 1) ? 0xffff0000u : 0x0000ffffu);
+    const unsigned half = (hw & 1) ? 0xffff0000u : 0x0000ffffu;
+    unsigned f = Sw[hw >> 1] & half;
+    fgc += __popc(Mw[hw >> 1] & half);
     const int k0 = (hw >> 1) * 32;
     while (f) {
       const int s0 = k0 + __ffs(f) - 1;
       f &= f - 1u;
       const int r = suf_find(Ls, s0);
-      if (r != s0) atomicMin(&Ls[s0], r);
+      if (r != s0) {
+        atomicMin(&Ls[s0], r);
+      } else {
+        const int gi = v.i0 + s0;
+        area[gi] = 0; gain[gi] = 0; loss[gi] = 0; maxi[gi] = -1;
+      }
     }
   }
+  if (round == 4) {   // label 0 of the inverse = the pixels already in `merged`
+    for (int o = 16; o > 0; o >>= 1) fgc += __shfl_down_sync(0xffffffffu, fgc, o);
+    if (lane == 0 && fgc) atomicAdd(&s_fg, fgc);
+  }
   __syncthreads();
-  // pass 3: chunk-local roots to global memory (window-local pixel indices)
+  if (round == 4 && threadIdx.x == 0) {
+    const int a0 = v.cnt - s_fg;
+    if (a0) atomicAdd(&st.area0, a0);
+  }
+  // pass 3b: chunk-local root of every pixel to global memory (window-local pixel indices; -1 = background)
   for (int k = threadIdx.x; k < v.cnt; k += kLabelThreads) {
-    const int i = v.i0 + k;
-    int r = -1;
-    if (fs[k]) r = Ls[Ls[k]];
-    L[i] = r < 0 ? -1 : v.i0 + r;
-    rootflag[i] = (r == k) ? 1 : 0;
-    // every global root is one of these chunk-local roots: their per-label sums start at zero here, so that the
-    // flatten pass can accumulate right away
-    if (r == k) { acc[i] = 0; acc[n + i] = 0; acc[2 * n + i] = 0; acc[3 * n + i] = -1; }   // area, gain, loss, maxi
+    const int p = Ls[k];
+    const int r = p < 0 ? -1 : Ls[p];
+    L[v.i0 + k] = r < 0 ? -1 : v.i0 + r;
+    rootflag[v.i0 + k] = (r == k) ? 1 : 0;
+  }
+  // pass 3c: per-label sums, one update per RUN (popcounts of the run's bits in the foreground / gain / loss masks) into
+  // the sums of its chunk-local root.  k_flat1 adds the sums of the chunk roots of a multi-chunk window to their global
+  // root; there is no per-pixel accumulation sweep any more.
+  for (int hw = threadIdx.x; hw * 16 < v.cnt; hw += kLabelThreads) {
+    const int w = hw >> 1;
+    const unsigned M = Mw[w], S = Sw[w];
+    unsigned f = S & ((hw & 1) ? 0xffff0000u : 0x0000ffffu);
+    if (!f) continue;
+    const unsigned G = Gw[w], B = Bw[w];
+    const int k0 = w * 32;
+    while (f) {
+      const int sbit = __ffs(f) - 1;
+      f &= f - 1u;
+      const unsigned stop = (~M | S) & (0xfffffffeu << sbit);          // first position after the run
+      const int e = stop ? __ffs(stop) - 2 : 31;                       // last pixel of the run
+      const unsigned rm = (e == 31 ? 0xffffffffu : ((2u << e) - 1u)) & ~((1u << sbit) - 1u);
+      const int gi = v.i0 + Ls[k0 + sbit];
+      atomicAdd(&area[gi], __popc(rm));
+      atomicMax(&maxi[gi], v.i0 + k0 + e);
+      const int g_ = __popc(rm & G), l_ = __popc(rm & B);
+      if (g_) atomicAdd(&gain[gi], g_);
+      if (l_) atomicAdd(&loss[gi], l_);
+    }
   }
 }
 // level 2: the first row of every chunk against the last row of the chunk above
@@ -621,6 +664,9 @@ __global__ void __launch_bounds__(kThreads) k_flat1(Ctx c, int round) {
   if (round < 4 && round >= c.st[v.w].nproc) return;
   const uint8_t* rootflag = c.tmp + v.win.off;
   int* L = c.L + v.win.off;
+  int* acc = c.acc + 4 * v.win.off;
+  const int n = v.rw * v.rh;
+  int* area = acc; int* gain = acc + n; int* loss = acc + 2 * n; int* maxi = acc + 3 * n;
   constexpr int U = 8;
   for (int k0 = 0; k0 < v.cnt; k0 += kThreads * U) {
     uint8_t rf[U];
@@ -630,71 +676,22 @@ __global__ void __launch_bounds__(kThreads) k_flat1(Ctx c, int round) {
       rf[u] = k < v.cnt ? rootflag[v.i0 + k] : 0;
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (rf[u]) uf_find_compress(L, v.i0 + k0 + u * kThreads + threadIdx.x);
-  }
-}
-// ---- merge step (textmask.py:92-108 / 118-131): per-label sums, then the labels that lower xor(merged, pred) -----------
-// level 3b fused with the accumulation: every pixel takes its root, writes it back and adds itself to the root's sums
-// (warp-aggregated: the 32 consecutive pixels of a warp mostly share a label).  After k_flat1 every chunk-local root
-// points straight at its global root, and every pixel's L is a chunk-local root (k_label_local pass 3), so the root of
-// pixel i is L[L[i]]: two dependent loads, issued for kU pixels at a time.
-__global__ void __launch_bounds__(kThreads) k_flat2_macc(Ctx c, int round) {
-  const View v = view_of(c, blockIdx.x);
-  WinState& st = c.st[v.w];
-  if (round < 4 && round >= st.nproc) return;
-  int* L = c.L + v.win.off;
-  const uint8_t* predm = c.predm + v.win.off;
-  const uint8_t* merged = c.merged + v.win.off;
-  int* acc = c.acc + 4 * v.win.off;
-  const int n = v.rw * v.rh;
-  int* area = acc; int* gain = acc + n; int* loss = acc + 2 * n; int* maxi = acc + 3 * n;
-  constexpr int kF = 4;   // pixels in flight per thread (8 measured slower: 55 registers, fewer resident warps)
-  const int lane = threadIdx.x & 31;
-  int a0 = 0;
-  for (int k0 = 0; k0 < v.cnt; k0 += kThreads * kF) {
-    int p[kF], r[kF];
-    uint8_t mg[kF], pd[kF];
-#pragma unroll
-    for (int u = 0; u < kF; ++u) {
-      const int k = k0 + u * kThreads + threadIdx.x;
-      p[u] = -2; mg[u] = 1; pd[u] = 0;
-      if (k < v.cnt) {
-        const int i = v.i0 + k;
-        p[u] = __ldcg(L + i);
-        mg[u] = merged[i];
-        pd[u] = predm[i];
+    for (int u = 0; u < U; ++u) {
+      if (!rf[u]) continue;
+      // chunk-local root: point it straight at its global root and hand its sums (complete since k_label_local) over
+      const int cr = v.i0 + k0 + u * kThreads + threadIdx.x;
+      const int g = uf_find_compress(L, cr);
+      if (g != cr) {
+        atomicAdd(&area[g], area[cr]);
+        atomicMax(&maxi[g], maxi[cr]);
+        const int g_ = gain[cr], l_ = loss[cr];
+        if (g_) atomicAdd(&gain[g], g_);
+        if (l_) atomicAdd(&loss[g], l_);
       }
     }
-#pragma unroll
-    for (int u = 0; u < kF; ++u) r[u] = p[u] >= 0 ? __ldcg(L + p[u]) : (p[u] == -2 ? -2 : -1);
-#pragma unroll
-    for (int u = 0; u < kF; ++u) {
-      if (k0 + u * kThreads >= v.cnt) break;      // CTA-uniform
-      const int i = v.i0 + k0 + u * kThreads + threadIdx.x;
-      const int rr = r[u];
-      if (rr >= 0 && rr != p[u]) L[i] = rr;
-      const bool un = rr >= 0 && mg[u] == 0;
-      const bool pg = un && pd[u] != 0;
-      const unsigned bg = __ballot_sync(0xffffffffu, pg), bl = __ballot_sync(0xffffffffu, un && !pg);
-      // the 32 consecutive pixels of a warp mostly lie in ONE component (or all in the background): no match.any then
-      const int rr0 = __shfl_sync(0xffffffffu, rr, 0);
-      const unsigned peers = __all_sync(0xffffffffu, rr == rr0) ? 0xffffffffu : __match_any_sync(0xffffffffu, rr);
-      if (rr >= 0 && lane == __ffs(peers) - 1) {
-        atomicAdd(&area[rr], __popc(peers));
-        atomicMax(&maxi[rr], i - lane + 31 - __clz(peers));
-        const int g_ = __popc(peers & bg), l_ = __popc(peers & bl);
-        if (g_) atomicAdd(&gain[rr], g_);
-        if (l_) atomicAdd(&loss[rr], l_);
-      }
-      if (rr == -1) ++a0;
-    }
-  }
-  if (round == 4) {   // label 0 of the inverse = the pixels already in `merged`
-    for (int o = 16; o > 0; o >>= 1) a0 += __shfl_down_sync(0xffffffffu, a0, o);
-    if ((threadIdx.x & 31) == 0 && a0) atomicAdd(&st.area0, a0);
   }
 }
+// ---- merge step (textmask.py:92-108 / 118-131) -------------------------------------------------------------------------
 // hole filling only: the two largest areas over all labels incl. label 0, as a multiset (max1 with its multiplicity, max2)
 __global__ void __launch_bounds__(kThreads) k_top_a(Ctx c) {
   const View v = view_of(c, blockIdx.x);
@@ -767,8 +764,11 @@ __global__ void __launch_bounds__(kThreads) k_mapply(Ctx c, int round) {
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const int k = k0 + u * kThreads + threadIdx.x;
-      r[u] = k < v.cnt ? L[v.i0 + k] : -1;
+      r[u] = k < v.cnt ? L[v.i0 + k] : -1;      // chunk-local root of the pixel ...
     }
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (r[u] >= 0) r[u] = L[r[u]];             // ... which points straight at the global root (k_flat1)
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       a[u] = 0; g[u] = 0; l[u] = 0; mx[u] = 0;
@@ -909,7 +909,6 @@ cudaError_t refine_mk_launch(const uint8_t* d_img, const uint8_t* d_mask, int H,
       k_union_border<<<unsigned(n_multi_chunks), kThreads, 0, s>>>(c, round);
       k_flat1<<<unsigned(n_multi_chunks), kThreads, 0, s>>>(c, round);
     }
-    k_flat2_macc<<<g, kThreads, 0, s>>>(c, round);
     if (round == 4) {
       k_top_a<<<g, kThreads, 0, s>>>(c);
       k_top_b<<<g, kThreads, 0, s>>>(c);
