@@ -120,8 +120,8 @@ __device__ __forceinline__ void hist_add(int* hist, int bin) {
     if ((threadIdx.x & 31) == 0 && bin >= 0) atomicAdd(&hist[bin], 32);
     return;
   }
-  const unsigned peers = __match_any_sync(0xffffffffu, bin);
-  if (bin >= 0 && int(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+  // mixed warp: plain shared-memory atomics (the hardware serialises equal bins; measured faster than a match.any vote)
+  if (bin >= 0) atomicAdd(&hist[bin], 1);
 }
 
 // i = q * d + r for 0 <= i < 2^24 (exact in float; |q error| <= 1 before the correction), else integer division.
@@ -142,40 +142,77 @@ __device__ __forceinline__ void divmod(int i, const DivW& dv, int& q, int& r) {
 
 // ---- phase 0: grey, pred mask (cross erosion > 60), merged = 0, histograms ------------------------------------------
 constexpr int kU = 4;   // pixels per thread and outer iteration: the loads of all kU pixels are issued before the first use
+constexpr int kChunkPxFwd = 8192;                       // = kChunkPx (defined with the labelling kernels below)
+constexpr int kExtWords = (3 * kChunkPxFwd) / 32 + 4;   // chunk (<= kChunkPx) + one halo row above and below
+__device__ __forceinline__ unsigned bits_from(const unsigned* M, int pos) {   // 32 bits starting at pixel `pos` (< 0 reads 0)
+  if (pos <= -32) return 0u;
+  if (pos < 0) return M[0] << (-pos);
+  const int w = pos >> 5, sft = pos & 31;
+  return __funnelshift_r(M[w], M[w + 1], sft);
+}
+// The two erosions of the mask crop are threshold tests of a minimum: min over the cross > 60 <=> NO pixel of the cross is
+// <= 60.  So the chunk's rows plus one row above and below are packed into two "bad pixel" bit masks (mask <= 60,
+// mask <= 127) by warp ballots -- ONE mask load per pixel instead of nine bounds-checked ones -- and one thread per
+// 32-pixel word ORs the 5 / 9 shifted views (row ends masked; outside the window reads 0 = not bad = BORDER_CONSTANT +inf).
 __global__ void __launch_bounds__(kThreads) k_phase0(Ctx c) {
   __shared__ int sh[4][256];
+  __shared__ unsigned N60[kExtWords], N127[kExtWords];
+  __shared__ unsigned F60[kChunkPxFwd / 32 + 1], F127[kChunkPxFwd / 32 + 1];
   const View v = view_of(c, blockIdx.x);
   for (int i = threadIdx.x; i < 1024; i += kThreads) (&sh[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < kExtWords; i += kThreads) { N60[i] = 0u; N127[i] = 0u; }
   __syncthreads();
   uint8_t* grey = c.grey + v.win.off;
   uint8_t* predm = c.predm + v.win.off;
   uint8_t* merged = c.merged + v.win.off;
-  const DivW dv = make_div(v.rw, v.rw * v.rh);
+  const DivW dv = make_div(v.rw, 3 * kChunkPxFwd + 1);
+  const int ystart = v.y0 > 0 ? v.y0 - 1 : 0;
+  const int yend = min(v.y0 + v.rows + 1, v.rh);
+  const int ext = (yend - ystart) * v.rw;
+  const int off = (v.y0 - ystart) * v.rw;
+  for (int e0 = 0; e0 < ext; e0 += kThreads) {
+    const int e = e0 + threadIdx.x;
+    int mv = 255;
+    if (e < ext) {
+      int ye, xe;
+      divmod(e, dv, ye, xe);
+      mv = v.mask[size_t(v.win.y1 + ystart + ye) * c.W + v.win.x1 + xe];
+    }
+    const unsigned b60 = __ballot_sync(0xffffffffu, mv <= 60), b127 = __ballot_sync(0xffffffffu, mv <= 127);
+    if ((threadIdx.x & 31) == 0) { N60[e >> 5] = b60; N127[e >> 5] = b127; }
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w * 32 < v.cnt; w += kThreads) {
+    const int k0 = w * 32;
+    int yl, x0;
+    divmod(k0, dv, yl, x0);
+    unsigned rs = 0u;
+    for (int j = x0 == 0 ? 0 : v.rw - x0; j < 32; j += v.rw) rs |= 1u << j;
+    int xe = x0 + 32;
+    if (xe >= v.rw) xe %= v.rw;
+    const unsigned re = (rs >> 1) | (xe == 0 ? 0x80000000u : 0u);
+    const int p = k0 + off;
+    // cross (textmask.py:86-89, MORPH_CROSS 3x3) on the <= 60 mask
+    F60[w] = bits_from(N60, p) | bits_from(N60, p - v.rw) | bits_from(N60, p + v.rw) | (bits_from(N60, p - 1) & ~rs) |
+             (bits_from(N60, p + 1) & ~re);
+    // full 3x3 (textmask.py:60, the eroded mask of get_topk_color) on the <= 127 mask
+    F127[w] = bits_from(N127, p) | bits_from(N127, p - v.rw) | bits_from(N127, p + v.rw) |
+              ((bits_from(N127, p - 1) | bits_from(N127, p - v.rw - 1) | bits_from(N127, p + v.rw - 1)) & ~rs) |
+              ((bits_from(N127, p + 1) | bits_from(N127, p - v.rw + 1) | bits_from(N127, p + v.rw + 1)) & ~re);
+  }
+  __syncthreads();
+  const DivW dvw = make_div(v.rw, v.rw * v.rh);
   for (int k0 = 0; k0 < v.cnt; k0 += kThreads * kU) {
-    int b[kU], g[kU], r[kU], m3[kU], mc[kU];
+    int b[kU], g[kU], r[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       const int k = k0 + u * kThreads + threadIdx.x;
-      b[u] = -1; g[u] = -1; r[u] = -1; m3[u] = 255; mc[u] = 255;
+      b[u] = -1; g[u] = -1; r[u] = -1;
       if (k < v.cnt) {
         int y, x;
-        divmod(v.i0 + k, dv, y, x);
+        divmod(v.i0 + k, dvw, y, x);
         const size_t gp = size_t(v.win.y1 + y) * c.W + v.win.x1 + x;
         b[u] = v.img[gp * 3]; g[u] = v.img[gp * 3 + 1]; r[u] = v.img[gp * 3 + 2];
-        // erosions of the mask CROP (window borders ignore the outside: BORDER_CONSTANT with +inf)
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-          const int yy = y + dy;
-          if (yy < 0 || yy >= v.rh) continue;
-#pragma unroll
-          for (int dx = -1; dx <= 1; ++dx) {
-            const int xx = x + dx;
-            if (xx < 0 || xx >= v.rw) continue;
-            const int mv = v.mask[size_t(v.win.y1 + yy) * c.W + v.win.x1 + xx];
-            m3[u] = min(m3[u], mv);
-            if (dx == 0 || dy == 0) mc[u] = min(mc[u], mv);
-          }
-        }
       }
     }
 #pragma unroll
@@ -183,18 +220,20 @@ __global__ void __launch_bounds__(kThreads) k_phase0(Ctx c) {
       const int k = k0 + u * kThreads + threadIdx.x;
       const bool in = k < v.cnt;
       int gr = 0;
+      bool core = false;
       if (in) {
         const int i = v.i0 + k;
         gr = (b[u] * 1868 + g[u] * 9617 + r[u] * 4899 + 8192) >> 14;  // cv2.COLOR_BGR2GRAY, 8u fixed point
         grey[i] = (uint8_t)gr;
-        predm[i] = mc[u] > 60 ? 255 : 0;                  // textmask.py:86-89
+        predm[i] = ((F60[k >> 5] >> (k & 31)) & 1u) ? 0 : 255;          // cross erosion > 60 (textmask.py:86-89)
         merged[i] = 0;
+        core = !((F127[k >> 5] >> (k & 31)) & 1u);                       // 3x3 erosion > 127 (textmask.py:60)
       }
-      if (k0 + u * kThreads < v.cnt) {   // warp-uniform: skip the histogram votes of fully idle warps
+      if (k0 + u * kThreads < v.cnt) {   // CTA-uniform: skip the histogram votes of iterations past the chunk
         hist_add(sh[1], b[u]);
         hist_add(sh[2], g[u]);
         hist_add(sh[3], r[u]);
-        hist_add(sh[0], (in && m3[u] > 127) ? gr : -1);     // textmask.py:60
+        hist_add(sh[0], core ? gr : -1);
       }
     }
   }
@@ -413,6 +452,7 @@ __global__ void k_decide2(Ctx c, int n_wins) {
 // the global forest).  Level 2: only the first row of every chunk issues global unions with the row above it.
 // Level 3: compress from the chain nodes, then every pixel takes its (chunk-local) parent's root.
 constexpr int kChunkPx = 8192;
+static_assert(kChunkPx == kChunkPxFwd, "kChunkPxFwd mirrors kChunkPx");
 constexpr int kLabelThreads = 512;
 
 __device__ __forceinline__ int suf_find(const int* L, int a) {
@@ -698,19 +738,21 @@ __global__ void __launch_bounds__(kThreads) k_top_a(Ctx c) {
   WinState& st = c.st[v.w];
   const int* L = c.L + v.win.off;
   const int* area = c.acc + 4 * v.win.off;
+  const uint8_t* rootflag = c.tmp + v.win.off;
   int m = -1;
   constexpr int U = 8;
   for (int k0 = 0; k0 < v.cnt; k0 += kThreads * U) {
-    int l[U], a[U];
+    uint8_t rf[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int k = k0 + u * kThreads + threadIdx.x;
-      l[u] = -1; a[u] = -1;
-      if (k < v.cnt) { l[u] = L[v.i0 + k] - (v.i0 + k); a[u] = area[v.i0 + k]; }   // l == 0: the pixel is a root
+      rf[u] = k < v.cnt ? rootflag[v.i0 + k] : 0;     // chunk-local roots: the only candidates for a global root
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (l[u] == 0) m = max(m, a[u]);
+    for (int u = 0; u < U; ++u) {
+      const int i = v.i0 + k0 + u * kThreads + threadIdx.x;
+      if (rf[u] && L[i] == i) m = max(m, area[i]);
+    }
   }
   if (v.y0 == 0 && threadIdx.x == 0) m = max(m, st.area0);
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_down_sync(0xffffffffu, m, o));
@@ -721,21 +763,23 @@ __global__ void __launch_bounds__(kThreads) k_top_b(Ctx c) {
   WinState& st = c.st[v.w];
   const int* L = c.L + v.win.off;
   const int* area = c.acc + 4 * v.win.off;
+  const uint8_t* rootflag = c.tmp + v.win.off;
   const int m1 = st.max1;
   int m2 = -1, c1 = 0;
   auto push = [&](int a) { if (a == m1) ++c1; else m2 = max(m2, a); };
   constexpr int U = 8;
   for (int k0 = 0; k0 < v.cnt; k0 += kThreads * U) {
-    int l[U], a[U];
+    uint8_t rf[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int k = k0 + u * kThreads + threadIdx.x;
-      l[u] = -1; a[u] = -1;
-      if (k < v.cnt) { l[u] = L[v.i0 + k] - (v.i0 + k); a[u] = area[v.i0 + k]; }
+      rf[u] = k < v.cnt ? rootflag[v.i0 + k] : 0;
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (l[u] == 0) push(a[u]);
+    for (int u = 0; u < U; ++u) {
+      const int i = v.i0 + k0 + u * kThreads + threadIdx.x;
+      if (rf[u] && L[i] == i) push(area[i]);
+    }
   }
   if (v.y0 == 0 && threadIdx.x == 0) push(st.area0);
   for (int o = 16; o > 0; o >>= 1) {
@@ -796,12 +840,6 @@ __global__ void __launch_bounds__(kThreads) k_mapply(Ctx c, int round) {
 // per 32-pixel word ORs the nine views (row ends masked), and the bytes are written back coalesced: ~25 instructions per
 // pixel instead of ~120 (nine bounds-checked byte loads).
 constexpr int kDilWords = (3 * kChunkPx) / 32 + 4;   // chunk (<= kChunkPx) + two halo rows (a row is <= kChunkPx pixels)
-__device__ __forceinline__ unsigned bits_from(const unsigned* M, int pos) {   // 32 bits starting at pixel `pos` (< 0 reads 0)
-  if (pos <= -32) return 0u;
-  if (pos < 0) return M[0] << (-pos);
-  const int w = pos >> 5, sft = pos & 31;
-  return __funnelshift_r(M[w], M[w + 1], sft);
-}
 __global__ void __launch_bounds__(kThreads) k_dilate(Ctx c) {
   __shared__ unsigned Mw[kDilWords];
   __shared__ unsigned Ow[kChunkPx / 32 + 1];
