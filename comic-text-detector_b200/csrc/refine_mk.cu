@@ -463,11 +463,23 @@ __device__ __forceinline__ int suf_find(const int* L, int a) {
   }
   return a;
 }
+// find with path halving: every visited node is re-pointed at its grandparent (atomicMin: parents have smaller indices
+// than their children, and concurrent unions only ever lower a root's entry).  The walks of the union phase were ~10 hops.
+__device__ __forceinline__ int suf_find_halve(int* L, int a) {
+  int p = L[a];
+  while (p != a) {
+    const int gp = L[p];
+    if (gp != p) atomicMin(&L[a], gp);
+    a = p;
+    p = gp;
+  }
+  return a;
+}
 __device__ __forceinline__ void suf_union(int* L, int a, int b) {
   bool done;
   do {
-    a = suf_find(L, a);
-    b = suf_find(L, b);
+    a = suf_find_halve(L, a);
+    b = suf_find_halve(L, b);
     if (a < b) {
       const int old = atomicMin(&L[b], a);
       done = old == b;
@@ -514,6 +526,12 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
   // pass 1: source value, `merged` and `pred` of every pixel (coalesced; the loads of a batch are issued before their
   // first use) -> foreground / gain / loss BIT masks and the run starts inside each warp's 32 consecutive pixels
   constexpr int kB = 4;
+  int xrun, xstep;                                 // x = k % rw without a division per pixel: k advances by kLabelThreads
+  {
+    int q;
+    divmod(int(threadIdx.x), dv, q, xrun);
+    divmod(kLabelThreads, dv, q, xstep);
+  }
 #pragma unroll 1
   for (int ub = 0; ub < kIt; ub += kB) {
     if (ub * kLabelThreads >= v.cnt) break;        // CTA-uniform
@@ -541,10 +559,11 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
       if (k0 >= v.cnt) break;                       // CTA-uniform
       const int k = k0 + threadIdx.x;
       const bool in = k < v.cnt;
-      int sv = 0, x = 0;
+      int sv = 0;
+      const int x = xrun;                           // x of pixel k, carried from iteration to iteration
+      xrun += xstep;
+      if (xrun >= v.rw) xrun -= v.rw;
       if (in) {
-        int yl;
-        divmod(k, dv, yl, x);
         if (round == 4) {
           sv = raw[u] ? 0 : 255;
         } else {
