@@ -699,12 +699,13 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
   }
 }
 // level 2: the first row of every chunk against the last row of the chunk above
-__global__ void __launch_bounds__(kThreads) k_union_border(Ctx c, int round) {
+constexpr int kBorderThreads = 256;  // (64-thread CTAs measured 3x slower: a window row is up to thousands of pixels)
+__global__ void __launch_bounds__(kBorderThreads) k_union_border(Ctx c, int round) {
   const View v = view_of(c, blockIdx.x);
   if (round < 4 && round >= c.st[v.w].nproc) return;
   if (v.y0 == 0) return;
   int* L = c.L + v.win.off;   // foreground <=> L >= 0 (written for every pixel by k_label_local)
-  for (int x = threadIdx.x; x < v.rw; x += kThreads) {
+  for (int x = threadIdx.x; x < v.rw; x += int(blockDim.x)) {
     const int i = v.i0 + x;
     if (__ldcg(L + i) < 0) continue;
     const int up = i - v.rw;
@@ -963,7 +964,7 @@ cudaError_t refine_mk_launch(const uint8_t* d_img, const uint8_t* d_mask, int H,
     }
     k_label_local<<<g, kLabelThreads, 0, s>>>(c, round);
     if (n_multi_chunks > 0) {   // single-chunk windows: the chunk-local roots ARE the global roots
-      k_union_border<<<unsigned(n_multi_chunks), kThreads, 0, s>>>(c, round);
+      k_union_border<<<unsigned(n_multi_chunks), kBorderThreads, 0, s>>>(c, round);
       k_flat1<<<unsigned(n_multi_chunks), kThreads, 0, s>>>(c, round);
     }
     if (round == 4) {
