@@ -42,15 +42,19 @@ template <int BN>
 struct TcCfg {
   static constexpr int kABytes = 128 * 128;  // per stage (worst case 128-byte rows)
   static constexpr int kBBytes = BN * 128;
-  // one persistent CTA per SM: fill ~200 KB with pipeline stages
-  static constexpr int kStages = BN >= 256 ? 3 : (BN >= 128 ? 5 : 7);
+  // one persistent CTA per SM.  The streamed-operand layers run at (bytes in flight per SM) / (loaded L2 latency, ~2 us):
+  // the operand ring takes every byte the other regions leave (192 KB: 4 x 48 KB at BN = 256, was 3), which is why the
+  // layout below has no alignment slack (the dynamic shared-memory base is 1024-byte aligned, checked at kernel start)
+  static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : (BN >= 64 ? 8 : 10));
   static constexpr int kStoreBytes = BN >= 64 ? 2 * 128 * 128 : 0;      // one 128x64 fp16 staging tile per epilogue warpgroup
   // TMEM accumulator stages (512 columns per SM): small tiles get a deep ring so that two epilogue warpgroups
   // can drain two tiles at once while the MMA warp runs ahead
   static constexpr int kAccStages = BN >= 256 ? 2 : (BN >= 128 ? 4 : 8);
   static constexpr int kTmemCols = BN * kAccStages < 32 ? 32 : BN * kAccStages;   // power of two >= 32
   static constexpr int kBiasFloats = 512;
-  static constexpr size_t kSmem = 1024 /*align slack*/ + size_t(kStages) * (kABytes + kBBytes) + 512 + kBiasFloats * 4 + kStoreBytes + 1024;
+  // operand ring | store staging (1024-aligned: the ring is a multiple of 1024) | barriers (512 B) | bias
+  static constexpr size_t kSmem = size_t(kStages) * (kABytes + kBBytes) + kStoreBytes + 512 + kBiasFloats * 4;
+  static_assert(kSmem <= 227 * 1024, "conv_tc_kernel: shared memory");
 };
 
 template <int ACT>
@@ -285,23 +289,24 @@ __device__ __forceinline__ void issue_kblock(uint32_t tmem_d, uint64_t ad, uint6
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   using Cfg = TcCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_tc[];
+  uint8_t* const smem_raw = smem_tc;
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();   // the layout has no alignment slack
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + Cfg::kStages * Cfg::kABytes;
-  const uint32_t bar_base = b_base + Cfg::kStages * Cfg::kBBytes;
+  const uint32_t store_base = b_base + Cfg::kStages * Cfg::kBBytes;
+  const uint32_t bar_base = store_base + Cfg::kStoreBytes;
   // barriers (8 B each): full[S] | empty[S] | tmem_full[A] | tmem_empty[A] | tmem ptr   (<= 512 bytes)
   const uint32_t full_bar = bar_base, empty_bar = bar_base + 8 * Cfg::kStages;
   const uint32_t tmem_full_bar = bar_base + 16 * Cfg::kStages;
   const uint32_t tmem_empty_bar = tmem_full_bar + 8 * Cfg::kAccStages;
   const uint32_t tmem_ptr_addr = tmem_empty_bar + 8 * Cfg::kAccStages;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const size_t bar_off = size_t(Cfg::kStages) * (Cfg::kABytes + Cfg::kBBytes);
+  const size_t bar_off = size_t(Cfg::kStages) * (Cfg::kABytes + Cfg::kBBytes) + Cfg::kStoreBytes;
   volatile uint32_t* tmem_ptr_gen =
       reinterpret_cast<volatile uint32_t*>(smem_gen + bar_off + 16 * Cfg::kStages + 16 * Cfg::kAccStages);
   float* bias_s = reinterpret_cast<float*>(smem_gen + bar_off + 512);
-  // staging tiles of the TMA-store epilogue: 1024-byte aligned, one per epilogue warpgroup
-  const uint32_t store_base = (bar_base + 512u + uint32_t(Cfg::kBiasFloats) * 4u + 1023u) & ~1023u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom& g = p.g;
