@@ -7,9 +7,13 @@
 // the batch: the windows are cut into chunks of whole rows (<= kChunkPx pixels, table built by the host, which knows
 // the window sizes), one CTA per chunk, so a giant window is spread over the whole GPU and the kernel boundary is the
 // barrier.  Per-window reductions (histograms, xor sums, the two largest hole areas) go through a small per-window
-// state record in global memory; per-window scalar decisions are one-CTA-per-window kernels.  Same arithmetic, same
-// scratch planes and the same union-find (global atomics) as refine.cu -- results are bit-identical
-// (tests/test_gpu_refine.py runs both).
+// state record in global memory; per-window scalar decisions are one-CTA-per-window kernels.  Results are bit-identical to
+// refine.cu and to the oracle (tests/test_gpu_refine.py runs all three).
+//
+// The sweeps are instruction-issue bound, not memory bound (ncu, profiles/r02_refine_full_summary.txt), so the binary planes
+// are handled as BIT masks wherever a neighbourhood is involved: warp ballots pack 32 pixels per shared-memory word and one
+// thread per (half) word does the work of 16 - 32 pixels with funnel shifts, ANDs and popcounts -- the erosions of phase 0,
+// the dilation, the run contacts of the labelling and the per-label sums (one update per RUN, not per pixel).
 #include <cuda_runtime.h>
 #include <limits.h>
 #include <math.h>
@@ -49,7 +53,7 @@ struct Ctx {
   // planes (window-pixel indexed)
   int* L;
   int* acc;
-  uint8_t *grey, *cand, *predm, *merged, *tmp;
+  uint8_t *grey, *cand, *predm, *merged, *tmp;   // cand: unused here (kept: the scratch layout is shared with refine.cu)
 };
 
 struct View {
