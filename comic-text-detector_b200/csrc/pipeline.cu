@@ -50,8 +50,10 @@ void RefineJob::add(int x1, int y1, int x2, int y2, int page, int iw, int ih) {
   const int wi = int(wins.size());
   (a > size_t(refine_large_px()) ? idx_large : idx_small).push_back(wi);
   const int rw = x2 - x1, rh = y2 - y1;
-  const int rows_per = std::max(1, refine_mk_chunk_px() / rw);
-  for (int y0 = 0; y0 < rh; y0 += rows_per) chunks.push_back(HostChunk{wi, y0, std::min(rows_per, rh - y0), 0});
+  int rows_per = std::max(1, refine_mk_chunk_px() / rw);
+  if (rows_per >= 8) rows_per &= ~3;   // chunk starts on multiples of 4 rows -> 4-byte aligned in the window planes
+  for (int y0 = 0; y0 < rh; y0 += rows_per)   // pad bit 0: aligned start (the labelling kernel then loads 4 pixels per thread)
+    chunks.push_back(HostChunk{wi, y0, std::min(rows_per, rh - y0), ((long long)y0 * rw) % 4 == 0 ? 1 : 0});
   wins.push_back(w);
   total_px = (total_px + a + 3) / 4 * 4;
 }

@@ -58,7 +58,7 @@ struct Ctx {
 
 struct View {
   RefineWin win;
-  int w, rw, rh, y0, rows, i0, cnt;
+  int w, rw, rh, y0, rows, i0, cnt, aligned;   // aligned: the chunk starts on a 4-byte boundary of the window planes
   const uint8_t* img;
   const uint8_t* mask;
 };
@@ -74,6 +74,7 @@ __device__ __forceinline__ View view_of(const Ctx& c, int chunk) {
   v.rows = ch.rows;
   v.i0 = ch.y0 * v.rw;
   v.cnt = ch.rows * v.rw;
+  v.aligned = ch.pad & 1;
   v.img = c.img_all + size_t(v.win.page) * c.H * c.W * 3;
   v.mask = c.mask_all + size_t(v.win.page) * c.H * c.W;
   return v;
@@ -529,62 +530,134 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
   constexpr int kIt = kChunkPx / kLabelThreads;    // 16 pixels per thread
   // pass 1: source value, `merged` and `pred` of every pixel (coalesced; the loads of a batch are issued before their
   // first use) -> foreground / gain / loss BIT masks and the run starts inside each warp's 32 consecutive pixels
-  constexpr int kB = 4;
-  int xrun, xstep;                                 // x = k % rw without a division per pixel: k advances by kLabelThreads
-  {
-    int q;
-    divmod(int(threadIdx.x), dv, q, xrun);
-    divmod(kLabelThreads, dv, q, xstep);
-  }
+  if (v.aligned) {
+    // pass 1, vector form (the chunk starts on a 4-byte boundary of the byte planes): FOUR consecutive pixels per thread from
+    // one 32-bit load per plane; the three 4-bit results of 8 lanes are OR-reduced into the 32-pixel words (redux.sync) --
+    // a quarter of the loads / address arithmetic and no per-pixel ballots or shared-memory stores.
+    const uint32_t* mg32 = reinterpret_cast<const uint32_t*>(merged + v.i0);
+    const uint32_t* pd32 = reinterpret_cast<const uint32_t*>(predm + v.i0);
+    const uint32_t* gr32 = reinterpret_cast<const uint32_t*>(grey + v.i0);
+    const int sh = 4 * (lane & 7);
+    const unsigned grp = 0xffu << (8 * (lane >> 3));
 #pragma unroll 1
-  for (int ub = 0; ub < kIt; ub += kB) {
-    if (ub * kLabelThreads >= v.cnt) break;        // CTA-uniform
-    int raw[kB], mg[kB], pd[kB];
-#pragma unroll
-    for (int u = 0; u < kB; ++u) {
-      const int k = (ub + u) * kLabelThreads + threadIdx.x;
-      raw[u] = 0; mg[u] = 1; pd[u] = 0;
+    for (int it = 0; it < kChunkPx / (4 * kLabelThreads); ++it) {
+      if (it * 4 * kLabelThreads >= v.cnt) break;      // CTA-uniform
+      const int k = 4 * (it * kLabelThreads + int(threadIdx.x));
+      unsigned fg4 = 0u, g4 = 0u, b4 = 0u;
       if (k < v.cnt) {
-        const int i = v.i0 + k;
-        mg[u] = merged[i];
-        pd[u] = predm[i];
-        if (round == 4) raw[u] = mg[u];
-        else if (kind < 3) raw[u] = grey[i];
-        else {
-          int yl, x;
-          divmod(k, dv, yl, x);
-          raw[u] = v.img[(size_t(v.win.y1 + v.y0 + yl) * c.W + v.win.x1 + x) * 3 + (kind - 3)];
+        const unsigned m4 = mg32[k >> 2], p4 = pd32[k >> 2];
+        unsigned s4 = m4;
+        if (round < 4) {
+          if (kind < 3) {
+            s4 = gr32[k >> 2];
+          } else {
+            s4 = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (k + j < v.cnt) {
+                int yl, x;
+                divmod(k + j, dv, yl, x);
+                s4 |= unsigned(v.img[(size_t(v.win.y1 + v.y0 + yl) * c.W + v.win.x1 + x) * 3 + (kind - 3)]) << (8 * j);
+              }
+            }
+          }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (k + j < v.cnt) {
+            const int sbv = int((s4 >> (8 * j)) & 0xffu), mb = int((m4 >> (8 * j)) & 0xffu), pb = int((p4 >> (8 * j)) & 0xffu);
+            bool fg;
+            if (round == 4) {
+              fg = sbv == 0;
+            } else {
+              const bool t = kind < 3 ? (sbv >= lo && sbv <= hi) : (sbv > ot);
+              fg = neg ? !t : t;
+            }
+            const bool un = fg && mb == 0;
+            fg4 |= unsigned(fg) << j;
+            g4 |= unsigned(un && pb != 0) << j;
+            b4 |= unsigned(un && pb == 0) << j;
+          }
+        }
+      }
+      const unsigned M = __reduce_or_sync(grp, fg4 << sh), G = __reduce_or_sync(grp, g4 << sh), B = __reduce_or_sync(grp, b4 << sh);
+      if ((lane & 7) == 0) { const int w = k >> 5; Mw[w] = M; Gw[w] = G; Bw[w] = B; }
+    }
+    __syncthreads();
+    // run starts: a foreground pixel whose left neighbour in the same row AND word is not foreground
+    for (int w = threadIdx.x; w * 32 < v.cnt; w += kLabelThreads) {
+      const unsigned M = Mw[w];
+      int yl, x0;
+      divmod(w * 32, dv, yl, x0);
+      unsigned rs = 0u;
+      for (int j = x0 == 0 ? 0 : v.rw - x0; j < 32; j += v.rw) rs |= 1u << j;
+      const unsigned S = M & (~(M << 1) | rs);
+      Sw[w] = S;
+      unsigned f = S;
+      while (f) {
+        const int k = w * 32 + __ffs(f) - 1;
+        f &= f - 1u;
+        Ls[k] = k;
       }
     }
-#pragma unroll
-    for (int u = 0; u < kB; ++u) {
-      const int k0 = (ub + u) * kLabelThreads;
-      if (k0 >= v.cnt) break;                       // CTA-uniform
-      const int k = k0 + threadIdx.x;
-      const bool in = k < v.cnt;
-      int sv = 0;
-      const int x = xrun;                           // x of pixel k, carried from iteration to iteration
-      xrun += xstep;
-      if (xrun >= v.rw) xrun -= v.rw;
-      if (in) {
-        if (round == 4) {
-          sv = raw[u] ? 0 : 255;
-        } else {
-          const int tv = kind < 3 ? ((raw[u] >= lo && raw[u] <= hi) ? 255 : 0) : (raw[u] > ot ? 255 : 0);
-          sv = neg ? 255 - tv : tv;
+  } else {
+    constexpr int kB = 4;
+    int xrun, xstep;                                 // x = k % rw without a division per pixel: k advances by kLabelThreads
+    {
+      int q;
+      divmod(int(threadIdx.x), dv, q, xrun);
+      divmod(kLabelThreads, dv, q, xstep);
+    }
+  #pragma unroll 1
+    for (int ub = 0; ub < kIt; ub += kB) {
+      if (ub * kLabelThreads >= v.cnt) break;        // CTA-uniform
+      int raw[kB], mg[kB], pd[kB];
+  #pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const int k = (ub + u) * kLabelThreads + threadIdx.x;
+        raw[u] = 0; mg[u] = 1; pd[u] = 0;
+        if (k < v.cnt) {
+          const int i = v.i0 + k;
+          mg[u] = merged[i];
+          pd[u] = predm[i];
+          if (round == 4) raw[u] = mg[u];
+          else if (kind < 3) raw[u] = grey[i];
+          else {
+            int yl, x;
+            divmod(k, dv, yl, x);
+            raw[u] = v.img[(size_t(v.win.y1 + v.y0 + yl) * c.W + v.win.x1 + x) * 3 + (kind - 3)];
+          }
         }
       }
-      const bool fg = in && sv != 0;
-      const bool un = fg && mg[u] == 0;
-      const unsigned m = __ballot_sync(0xffffffffu, fg);
-      const unsigned gb = __ballot_sync(0xffffffffu, un && pd[u] != 0);
-      const unsigned lb = __ballot_sync(0xffffffffu, un && pd[u] == 0);
-      // a run starts at a foreground pixel whose left neighbour (same row, same warp) is not foreground
-      const bool starts = fg && (lane == 0 || x == 0 || !((m >> (lane - 1)) & 1u));
-      const unsigned sb = __ballot_sync(0xffffffffu, starts);
-      if (lane == 0) { Mw[k >> 5] = m; Sw[k >> 5] = sb; Gw[k >> 5] = gb; Bw[k >> 5] = lb; }
-      if (in) Ls[k] = fg ? (k - lane) + (31 - __clz(sb & (0xffffffffu >> (31 - lane)))) : -1;
+  #pragma unroll
+      for (int u = 0; u < kB; ++u) {
+        const int k0 = (ub + u) * kLabelThreads;
+        if (k0 >= v.cnt) break;                       // CTA-uniform
+        const int k = k0 + threadIdx.x;
+        const bool in = k < v.cnt;
+        int sv = 0;
+        const int x = xrun;                           // x of pixel k, carried from iteration to iteration
+        xrun += xstep;
+        if (xrun >= v.rw) xrun -= v.rw;
+        if (in) {
+          if (round == 4) {
+            sv = raw[u] ? 0 : 255;
+          } else {
+            const int tv = kind < 3 ? ((raw[u] >= lo && raw[u] <= hi) ? 255 : 0) : (raw[u] > ot ? 255 : 0);
+            sv = neg ? 255 - tv : tv;
+          }
+        }
+        const bool fg = in && sv != 0;
+        const bool un = fg && mg[u] == 0;
+        const unsigned m = __ballot_sync(0xffffffffu, fg);
+        const unsigned gb = __ballot_sync(0xffffffffu, un && pd[u] != 0);
+        const unsigned lb = __ballot_sync(0xffffffffu, un && pd[u] == 0);
+        // a run starts at a foreground pixel whose left neighbour (same row, same warp) is not foreground
+        const bool starts = fg && (lane == 0 || x == 0 || !((m >> (lane - 1)) & 1u));
+        const unsigned sb = __ballot_sync(0xffffffffu, starts);
+        if (lane == 0) { Mw[k >> 5] = m; Sw[k >> 5] = sb; Gw[k >> 5] = gb; Bw[k >> 5] = lb; }
+        if (starts) Ls[k] = k;    // forest nodes = run starts; any other foreground pixel maps to its run start via start_of()
+      }
     }
   }
   __syncthreads();
@@ -592,6 +665,10 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
   // threads per 32-pixel word: the neighbour tests of 32 pixels are a handful of shifts and ANDs, and only the pixels
   // that really start a (run x upper run) contact walk the union-find (first version: every foreground pixel tested
   // its four neighbours with byte loads; half of the kernel's instructions, ncu).
+  // run start of foreground pixel p: the highest run-start bit at or below p in its word (runs restart at every word)
+  auto start_of = [&](int pos) -> int {
+    return (pos & ~31) + 31 - __clz(Sw[pos >> 5] & (0xffffffffu >> (31 - (pos & 31))));
+  };
   auto bits_at = [&](int pos) -> unsigned {        // 32 foreground bits starting at pixel `pos` (pixels < 0 read as 0)
     if (pos <= -32) return 0u;
     if (pos < 0) return Mw[0] << (-pos);
@@ -613,7 +690,7 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
     const unsigned re = (rs >> 1) | (xe == 0 ? 0x80000000u : 0u);   // bits whose pixel is the LAST of its row
     const unsigned lft = bits_at(k0 - 1);           // fg(k - 1)
     // seam: the run labelling of pass 1 restarts at every word
-    if (!(hw & 1) && (cur & 1u) && !(rs & 1u) && (lft & 1u)) suf_union(Ls, k0, k0 - 1);
+    if (!(hw & 1) && (cur & 1u) && !(rs & 1u) && (lft & 1u)) suf_union(Ls, k0, start_of(k0 - 1));
     if (k0 + 32 <= v.rw) continue;                  // the whole word lies in the first row of the chunk
     const unsigned vup = (k0 >= v.rw ? 0xffffffffu : (0xffffffffu << (v.rw - k0))) & half;   // pixels that have a row above
     const unsigned up = bits_at(k0 - v.rw), upl = bits_at(k0 - v.rw - 1), upr = bits_at(k0 - v.rw + 1);
@@ -622,20 +699,20 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
     while (f) {
       const int j = __ffs(f) - 1;
       f &= f - 1u;
-      suf_union(Ls, k0 + j, k0 + j - v.rw);
+      suf_union(Ls, start_of(k0 + j), start_of(k0 + j - v.rw));
     }
     const unsigned nb = cur & ~up & vup;
     f = nb & upl & ~rs;                             // diagonal contacts when the pixel above is background
     while (f) {
       const int j = __ffs(f) - 1;
       f &= f - 1u;
-      suf_union(Ls, k0 + j, k0 + j - v.rw - 1);
+      suf_union(Ls, start_of(k0 + j), start_of(k0 + j - v.rw - 1));
     }
     f = nb & upr & ~re;
     while (f) {
       const int j = __ffs(f) - 1;
       f &= f - 1u;
-      suf_union(Ls, k0 + j, k0 + j - v.rw + 1);
+      suf_union(Ls, start_of(k0 + j), start_of(k0 + j - v.rw + 1));
     }
   }
   __syncthreads();
@@ -672,8 +749,7 @@ __global__ void __launch_bounds__(kLabelThreads, 3) k_label_local(Ctx c, int rou
   }
   // pass 3b: chunk-local root of every pixel to global memory (window-local pixel indices; -1 = background)
   for (int k = threadIdx.x; k < v.cnt; k += kLabelThreads) {
-    const int p = Ls[k];
-    const int r = p < 0 ? -1 : Ls[p];
+    const int r = ((Mw[k >> 5] >> (k & 31)) & 1u) ? Ls[start_of(k)] : -1;
     L[v.i0 + k] = r < 0 ? -1 : v.i0 + r;
     rootflag[v.i0 + k] = (r == k) ? 1 : 0;
   }
