@@ -471,7 +471,7 @@ def extras(line, args, ck, prog, pages, local):
             t0 = time.perf_counter()
             nblk = 0
             for i in range(n):
-                _m, _r, bl = det(pages[i % B].copy())
+                _m, _r, bl = det(pages[i % B])
                 nblk += len(bl)
             dt = time.perf_counter() - t0
             fwd = []
