@@ -411,7 +411,8 @@ def main():
                        "in_flight": "%d batches per GPU (%d workspaces x 2 slots)" % (2 * n_eng, n_eng),
                        "multi_gpu": ("pages sharded B per rank; one NCCL gather of each rank's complete result arena to rank 0 per step"
                                      if world > 1 else "single GPU")},
-            "gpu_launches": (eng.last_launch_count() + 6) * args.steps,
+            # forward graph (convs + thin ops + NMS / CCL / contour kernels) + copies + the 29 refine_mask launches of a batch
+            "gpu_launches": (eng.last_launch_count() + 6 + 29) * args.steps,
             "clocks": clocks,
             "conv_roofline_frac_of_nominal": net_val / world * GFLOP_PER_PAGE_1024 * 1e9 / 2.25e15,
             "e2e": {"value": e2e_val, "unit": "pages/s", "h2d_bytes_per_step": int(B * H * W * 3), "d2h_bytes_per_step": d2h,
